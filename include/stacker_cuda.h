@@ -1,0 +1,177 @@
+/*
+ * stacker_cuda.h — C ABI of the B200 (sm_100a) align-and-stack library.
+ *
+ * This is the drop-in boundary for libstacker's ECC align-and-stack hot path.  The reference crate
+ * (eadf/libstacker.rs) has no FFI of its own for this path: it reaches OpenCV through the `opencv`
+ * crate's generated bindings.  Each entry point below replaces one group of those OpenCV calls; the
+ * reference call site it stands for is cited as  file:line  into /root/reference.
+ *
+ * Conventions
+ *   - every function returns an int status (STK_OK == 0); stk_last_error() returns a thread-local,
+ *     human-readable description of the last failure on the calling thread.
+ *   - the caller owns every host buffer; the library owns every device buffer.
+ *   - plain pointers and sizes only; no C++/torch/OpenCV types.
+ *   - images are 8-bit, interleaved, row-major, `pitch` bytes per row (cv::Mat::step), channel order
+ *     as decoded by OpenCV (B,G,R[,A]).
+ *   - a context is bound to ONE CUDA device.  Multi-GPU stacking = one context per device, each fed
+ *     its shard of the frames, plus one sum-reduce of the partial stacks (NCCL) between
+ *     stk_ecc_partial() and stk_ecc_finish_from() — see INTEGRATION.md.
+ *   - there is NO CPU fallback: without a usable CUDA device every call fails with STK_ERR_CUDA.
+ */
+#ifndef STACKER_CUDA_H_
+#define STACKER_CUDA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STK_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------------------------- */
+enum {
+  STK_OK = 0,
+  STK_ERR_BAD_ARG = 1,      /* -> StackerError::InvalidParams            (src/lib.rs:41-42)        */
+  STK_ERR_CUDA = 2,         /* -> StackerError::ProcessingError          (src/lib.rs:43-44)        */
+  STK_ERR_NOT_ENOUGH = 3,   /* -> StackerError::NotEnoughFiles           (src/lib.rs:31-32)        */
+  STK_ERR_ECC_NOCONV = 4,   /* cv::Error::StsNoConv from findTransformECC -> StackerError::OpenCvError
+                               (src/lib.rs:777 `?`): lambda denominator <= 0                       */
+  STK_ERR_ECC_NAN = 5,      /* same, "NaN encountered"                                             */
+  STK_ERR_CRITERIA = 6,     /* neither COUNT nor EPS set: CV_Assert in findTransformECC
+                               -> StackerError::OpenCvError (src/utils.rs:159-170)                 */
+  STK_ERR_STATE = 7,        /* call order violated (e.g. submit before set_reference)             */
+  STK_ERR_UNSUPPORTED = 8,  /* -> StackerError::NotImplemented           (src/lib.rs:33-34)        */
+  STK_ERR_NOMEM = 9
+};
+
+/* MotionType discriminants == opencv::video::MOTION_*            (src/lib.rs:603-609) */
+enum { STK_MOTION_TRANSLATION = 0, STK_MOTION_EUCLIDEAN = 1, STK_MOTION_AFFINE = 2, STK_MOTION_HOMOGRAPHY = 3 };
+
+/* TermCriteria_Type bits                                          (src/utils.rs:159-170) */
+enum { STK_TERM_COUNT = 1, STK_TERM_EPS = 2 };
+
+/* cv::BorderTypes accepted by the warp-only path                  (src/lib.rs:297-298) */
+enum { STK_BORDER_CONSTANT = 0 };
+
+typedef struct stk_ecc_ctx stk_ecc_ctx;
+
+/* EccMatchParameters + TermCriteria + frame geometry            (src/lib.rs:611-623, src/utils.rs:159-170) */
+typedef struct stk_ecc_config {
+  int32_t width, height;      /* frame size; every frame of a stack has the size of frame 0        */
+  int32_t channels;           /* 3 (BGR) or 4 (BGRA)                                               */
+  int32_t motion_type;        /* STK_MOTION_*                                                      */
+  int32_t criteria_type;      /* STK_TERM_COUNT | STK_TERM_EPS as built by src/utils.rs:161-168    */
+  int32_t max_count;          /* used when COUNT is set, else OpenCV's 200                          */
+  double  epsilon;            /* used when EPS is set, else -1 (run every iteration)                */
+  int32_t gauss_filt_size;    /* odd, >= 1                                                         */
+  int32_t device;             /* CUDA device ordinal, -1 = current device                          */
+  int32_t lanes;              /* concurrent frame pipelines (streams) on the device; 0 = default   */
+  int32_t seed_reference;     /* 1: the stack accumulator starts as the unwarped reference frame
+                                 (src/lib.rs:752-754); 0 on the non-root shards of a multi-GPU stack */
+  int32_t align;              /* 1: ECC alignment (ecc_match); 0: warp-only context (keypoint_match
+                                 tail, src/lib.rs:289-350) — no reference planes are built          */
+} stk_ecc_config;
+
+/* per-frame outcome of findTransformECC                          (src/lib.rs:769-777) */
+typedef struct stk_frame_result {
+  int64_t tag;                /* caller's frame id                                                 */
+  float   warp[9];            /* row-major 3x3; rows 0-1 are the 2x3 matrix for non-homography     */
+  double  rho;                /* final correlation coefficient (the reference discards it)         */
+  int32_t iterations;
+  int32_t status;             /* STK_OK | STK_ERR_ECC_NOCONV | STK_ERR_ECC_NAN                     */
+} stk_frame_result;
+
+/* ---- library ------------------------------------------------------------------------------ */
+int         stk_abi_version(void);
+const char* stk_last_error(void);
+int         stk_device_count(int* count);
+
+/* pinned host memory for decode targets: "JPEG decode stays on the host and feeds pinned,
+   asynchronous uploads".  Replaces the Mat allocation inside imgcodecs::imread (src/utils.rs:132). */
+int stk_pinned_alloc(void** ptr, size_t bytes);
+int stk_pinned_free(void* ptr);
+
+/* ---- ecc_match: context per (stack, device)            replaces src/lib.rs:719-847 ------------ */
+int stk_ecc_create(const stk_ecc_config* cfg, stk_ecc_ctx** out);
+int stk_ecc_destroy(stk_ecc_ctx* ctx);
+
+/* frame 0: cvt_color + (inside find_transform_ecc) GaussianBlur + gradients of the INPUT image,
+   done once per stack instead of once per call          (src/lib.rs:731-738, :769-772)
+   *_device variants take a device pointer on the context's device. */
+int stk_ecc_set_reference(stk_ecc_ctx* ctx, const uint8_t* bgr, size_t pitch);
+int stk_ecc_set_reference_device(stk_ecc_ctx* ctx, const uint8_t* d_bgr, size_t pitch);
+
+/* one non-reference frame: read_grey_and_f32's conversions, find_transform_ecc, warp_affine |
+   warp_perspective, acc + warped                         (src/lib.rs:756-814)
+   Asynchronous: returns once the frame is queued on a lane.  The host buffer may be reused as soon as
+   the call returns unless it is pinned (stk_pinned_alloc), in which case it must stay valid until
+   stk_ecc_sync()/finish.  Thread-safe. */
+int stk_ecc_submit_frame(stk_ecc_ctx* ctx, const uint8_t* bgr, size_t pitch, int64_t tag);
+int stk_ecc_submit_frame_pinned(stk_ecc_ctx* ctx, const uint8_t* pinned_bgr, size_t pitch, int64_t tag);
+int stk_ecc_submit_frame_device(stk_ecc_ctx* ctx, const uint8_t* d_bgr, size_t pitch, int64_t tag);
+
+/* keypoint_match tail: warp_perspective(img_f32, H, size, INTER_LINEAR, border_mode, border_value)
+   + accumulate                                           (src/lib.rs:289-316)
+   h is the 3x3 f64 matrix from find_homography (forward map, inverted internally like OpenCV). */
+int stk_ecc_submit_warp(stk_ecc_ctx* ctx, const uint8_t* bgr, size_t pitch, const double h[9],
+                        int border_mode, const double border_value[4], int64_t tag);
+int stk_ecc_submit_warp_device(stk_ecc_ctx* ctx, const uint8_t* d_bgr, size_t pitch, const double h[9],
+                               int border_mode, const double border_value[4], int64_t tag);
+
+/* wait for every queued frame; returns the first per-frame error (STK_ERR_ECC_*) or STK_OK */
+int stk_ecc_sync(stk_ecc_ctx* ctx);
+
+/* per-frame results in submission order; *count receives how many were written (<= capacity) */
+int stk_ecc_results(stk_ecc_ctx* ctx, stk_frame_result* out, int capacity, int* count);
+
+/* Rayon try_reduce of the per-thread partial sums + `/ n`  (src/lib.rs:819-839, :339-346)
+   stk_ecc_finish   : single-device stack: sum lanes, scale by 1/divisor, copy to host (out_pitch
+                      bytes per row, width*channels floats per row).
+   stk_ecc_partial  : multi-device: sum lanes in place and hand out the device pointer of this
+                      device's partial stack (height*width*channels contiguous floats) so the caller's
+                      plumbing can sum-reduce it across devices (ncclReduce / torch.distributed).
+   stk_ecc_finish_from : scale `d_sum` (device, same layout; NULL = this context's partial) by
+                      1/divisor and copy to host. */
+int stk_ecc_finish(stk_ecc_ctx* ctx, int divisor, float* out, size_t out_pitch);
+int stk_ecc_partial(stk_ecc_ctx* ctx, float** d_partial, size_t* n_floats);
+int stk_ecc_finish_from(stk_ecc_ctx* ctx, const float* d_sum, int divisor, float* out, size_t out_pitch);
+/* same, result left on the device (d_out: height*width*channels floats) */
+int stk_ecc_finish_device(stk_ecc_ctx* ctx, const float* d_sum, int divisor, float* d_out);
+
+/* start a new stack on the same context (same geometry/parameters): clears accumulators/results */
+int stk_ecc_reset(stk_ecc_ctx* ctx);
+
+/* counters for benchmarks: kernels launched by this context since creation / last reset */
+int stk_ecc_launch_count(stk_ecc_ctx* ctx, int64_t* launches);
+
+/* ---- single stages, exposed for verification and for callers that want one step only --------------- */
+/* cvt_color(BGR2GRAY) + convertTo(f32) + GaussianBlur(k x k, sigma 0): the template/input plane
+   findTransformECC builds from an 8-bit frame (src/utils.rs:136-142 + src/lib.rs:769).  Host in, host out
+   (out_pitch bytes per row, width floats). */
+int stk_prep_grey_blur(const uint8_t* bgr, size_t pitch, int width, int height, int channels, int ksize,
+                       int device, float* out, size_t out_pitch);
+/* ONE ECC iteration of `frame` (host, 8-bit) against the context's reference, starting from `warp_in`
+   (row-major 3x3 f32): returns the kernel's reduced sums (layout documented in csrc/ecc_iter.cuh,
+   *nv values written, capacity `cap`), the updated warp, rho and the loop status.  Does not touch the
+   accumulators.  Test hook for the parity suite. */
+int stk_ecc_debug_iteration(stk_ecc_ctx* ctx, const uint8_t* bgr, size_t pitch, const float warp_in[9],
+                            double* totals, int cap, int* nv, float warp_out[9], double* rho, int* status);
+
+/* ---- sharpness_tenengrad                               replaces src/lib.rs:1101-1147 ---------- */
+/* grey: single-channel 8-bit (channels == 1) — or BGR/BGRA (channels 3/4), converted with
+   cvt_color(BGR2GRAY) on the fly.  ksize in {1,3,5,7} else STK_ERR_BAD_ARG (src/lib.rs:1103-1107).
+   *out = mean(gx^2 + gy^2), bit-identical to the CV_64F OpenCV pipeline. */
+int stk_tenengrad(const uint8_t* img, size_t pitch, int width, int height, int channels, int ksize,
+                  int device, double* out);
+int stk_tenengrad_device(const uint8_t* d_img, size_t pitch, int width, int height, int channels,
+                         int ksize, int device, double* out);
+/* n same-sized frames resident on the device, frame i at d_imgs + i*frame_stride; out[n] */
+int stk_tenengrad_batch_device(const uint8_t* d_imgs, size_t frame_stride, size_t pitch, int width,
+                               int height, int channels, int ksize, int n, int device, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STACKER_CUDA_H_ */

@@ -1,0 +1,449 @@
+"""Host-side mirror of the libstacker public API (/root/reference/src/lib.rs) over the C ABI.
+
+The reference is a Rust crate; Rust is not available in this image, so this module (and the C++ mirror
+in host/, and the uncompiled Rust crate in rust/) drive the SAME extern "C" entry points the Rust
+wrappers bind.  What stays on the host is what the reference keeps on the host: file decode
+(imgcodecs::imread) and, for keypoint_match, the ORB / BFMatcher / findHomography stages — both through
+OpenCV (`cv2`), which the crate links as well.  Everything numeric on the ECC align-and-stack path runs
+in the CUDA library; there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+import os
+from concurrent.futures import ThreadPoolExecutor
+from dataclasses import dataclass
+from typing import Iterable, Optional, Sequence
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import lib
+
+BORDER_CONSTANT = 0          # opencv::core::BORDER_CONSTANT
+RANSAC = 8                   # opencv::calib3d::RANSAC
+LMEDS = 4
+
+
+# ---- errors: /root/reference/src/lib.rs:27-45 -----------------------------------------------------
+class StackerError(Exception):
+    """Base of the crate's error enum."""
+
+
+class OpenCvError(StackerError):
+    """StackerError::OpenCvError — any failure the reference gets from OpenCV, including
+    findTransformECC's StsNoConv (src/lib.rs:777)."""
+
+
+class NotEnoughFiles(StackerError):
+    def __init__(self):
+        super().__init__("Not enough files")
+
+
+class NotImplementedError_(StackerError):
+    """StackerError::NotImplemented."""
+
+
+class InvalidPathEncoding(StackerError):
+    pass
+
+
+class InvalidParams(StackerError):
+    def __init__(self, msg):
+        super().__init__(f"Invalid parameter(s) {msg}")
+
+
+class ProcessingError(StackerError):
+    def __init__(self, msg):
+        super().__init__(f"Internal error {msg}")
+
+
+def _raise(rc: int):
+    msg = _ffi.last_error()
+    if rc in (_ffi.STK_ERR_ECC_NOCONV, _ffi.STK_ERR_ECC_NAN, _ffi.STK_ERR_CRITERIA):
+        raise OpenCvError(msg)
+    if rc == _ffi.STK_ERR_BAD_ARG:
+        raise InvalidParams(msg)
+    if rc == _ffi.STK_ERR_NOT_ENOUGH:
+        raise NotEnoughFiles()
+    if rc == _ffi.STK_ERR_UNSUPPORTED:
+        raise NotImplementedError_(msg)
+    raise ProcessingError(msg)
+
+
+def _check(rc: int):
+    if rc != _ffi.STK_OK:
+        _raise(rc)
+
+
+# ---- parameter types: src/lib.rs:48-73, :603-623 -----------------------------------------------------
+class MotionType(enum.IntEnum):
+    """Discriminants are OpenCV's MOTION_* (src/lib.rs:603-609)."""
+    Translation = 0
+    Euclidean = 1
+    Affine = 2
+    Homography = 3
+
+
+@dataclass(frozen=True)
+class EccMatchParameters:
+    motion_type: MotionType
+    max_count: Optional[int]
+    epsilon: Optional[float]
+    gauss_filt_size: int
+
+
+@dataclass(frozen=True)
+class KeyPointMatchParameters:
+    """Defaults are `impl Default` at src/utils.rs:250-261."""
+    method: int = RANSAC
+    ransac_reproj_threshold: float = 3.0
+    match_keep_ratio: float = 0.75
+    match_ratio: float = 0.8
+    border_mode: int = BORDER_CONSTANT
+    border_value: Sequence[float] = (0.0, 0.0, 0.0, 0.0)
+
+
+def term_criteria(params: EccMatchParameters):
+    """From<EccMatchParameters> for Result<TermCriteria> (src/utils.rs:159-170): (typ, max_count, epsilon);
+    unset fields stay at TermCriteria::default() == 0."""
+    typ, mc, eps = 0, 0, 0.0
+    if params.max_count is not None:
+        typ |= _ffi.STK_TERM_COUNT
+        mc = int(params.max_count)
+    if params.epsilon is not None:
+        typ |= _ffi.STK_TERM_EPS
+        eps = float(params.epsilon)
+    return typ, mc, eps
+
+
+# ---- low-level stack context ---------------------------------------------------------------------------
+def _device_view(obj):
+    """(ptr, pitch_bytes) of an array living on the GPU (anything with __cuda_array_interface__, e.g. a
+    torch CUDA tensor of shape HxWxC uint8), or None for host arrays."""
+    iface = getattr(obj, "__cuda_array_interface__", None)
+    if iface is None:
+        return None
+    shape = iface["shape"]
+    strides = iface.get("strides")
+    pitch = strides[0] if strides else int(np.prod(shape[1:]))
+    return int(iface["data"][0]), int(pitch)
+
+
+class EccStack:
+    """One stack on one CUDA device: wraps stk_ecc_ctx.  `params=None` makes a warp-only context
+    (keypoint_match tail)."""
+
+    def __init__(self, width: int, height: int, channels: int = 3, params: Optional[EccMatchParameters] = None,
+                 device: int = -1, lanes: int = 0, seed_reference: bool = True):
+        cfg = _ffi.EccConfig()
+        cfg.width, cfg.height, cfg.channels = int(width), int(height), int(channels)
+        cfg.device, cfg.lanes = int(device), int(lanes)
+        cfg.seed_reference = 1 if seed_reference else 0
+        if params is not None:
+            typ, mc, eps = term_criteria(params)
+            cfg.align = 1
+            cfg.motion_type = int(params.motion_type)
+            cfg.criteria_type, cfg.max_count, cfg.epsilon = typ, mc, eps
+            cfg.gauss_filt_size = int(params.gauss_filt_size)
+        else:
+            cfg.align = 0
+        self.width, self.height, self.channels = cfg.width, cfg.height, cfg.channels
+        self._ctx = C.c_void_p()
+        self._keep = []          # host arrays that must outlive asynchronous copies
+        _check(lib.stk_ecc_create(C.byref(cfg), C.byref(self._ctx)))
+
+    # -- lifetime
+    def close(self):
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            lib.stk_ecc_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- frames
+    def _host_frame(self, frame: np.ndarray):
+        if frame.dtype != np.uint8 or frame.ndim != 3 or frame.shape[2] != self.channels:
+            raise OpenCvError(f"frame must be 8-bit HxWx{self.channels} (got {frame.dtype} {frame.shape})")
+        if frame.shape[0] != self.height or frame.shape[1] != self.width:
+            raise OpenCvError(f"frame size {frame.shape[1]}x{frame.shape[0]} differs from the stack's "
+                              f"{self.width}x{self.height}")
+        if frame.strides[2] != 1 or frame.strides[1] != self.channels:
+            frame = np.ascontiguousarray(frame)
+        return frame, frame.ctypes.data, frame.strides[0]
+
+    def set_reference(self, frame):
+        dv = _device_view(frame)
+        if dv is not None:
+            _check(lib.stk_ecc_set_reference_device(self._ctx, dv[0], dv[1]))
+            self._keep.append(frame)
+        else:
+            f, ptr, pitch = self._host_frame(frame)
+            _check(lib.stk_ecc_set_reference(self._ctx, ptr, pitch))
+
+    def submit(self, frame, tag: int = 0, pinned: bool = False):
+        dv = _device_view(frame)
+        if dv is not None:
+            self._keep.append(frame)
+            _check(lib.stk_ecc_submit_frame_device(self._ctx, dv[0], dv[1], int(tag)))
+            return
+        f, ptr, pitch = self._host_frame(frame)
+        if pinned:
+            self._keep.append(f)
+            _check(lib.stk_ecc_submit_frame_pinned(self._ctx, ptr, pitch, int(tag)))
+        else:
+            _check(lib.stk_ecc_submit_frame(self._ctx, ptr, pitch, int(tag)))
+
+    def submit_warp(self, frame, h, border_mode: int = BORDER_CONSTANT, border_value=(0, 0, 0, 0), tag: int = 0):
+        hm = (C.c_double * 9)(*np.asarray(h, np.float64).reshape(9))
+        bv = (C.c_double * 4)(*[float(v) for v in border_value])
+        dv = _device_view(frame)
+        if dv is not None:
+            self._keep.append(frame)
+            _check(lib.stk_ecc_submit_warp_device(self._ctx, dv[0], dv[1], hm, int(border_mode), bv, int(tag)))
+            return
+        f, ptr, pitch = self._host_frame(frame)
+        _check(lib.stk_ecc_submit_warp(self._ctx, ptr, pitch, hm, int(border_mode), bv, int(tag)))
+
+    # -- completion
+    def sync(self):
+        rc = lib.stk_ecc_sync(self._ctx)
+        self._keep.clear()
+        _check(rc)
+
+    def results(self):
+        n = C.c_int(0)
+        cap = 1 << 16
+        buf = (_ffi.FrameResult * cap)()
+        _check(lib.stk_ecc_results(self._ctx, buf, cap, C.byref(n)))
+        out = []
+        for i in range(n.value):
+            r = buf[i]
+            out.append(dict(tag=r.tag, warp=np.array(r.warp[:], np.float32).reshape(3, 3), rho=r.rho,
+                            iterations=r.iterations, status=r.status))
+        return out
+
+    def finish(self, divisor: int) -> np.ndarray:
+        out = np.empty((self.height, self.width, self.channels), np.float32)
+        _check(lib.stk_ecc_finish(self._ctx, int(divisor), out.ctypes.data, out.strides[0]))
+        self._keep.clear()
+        return out
+
+    def partial(self):
+        """(device pointer, n_floats) of this device's partial stack, lanes already summed."""
+        ptr, n = C.c_void_p(), C.c_size_t()
+        _check(lib.stk_ecc_partial(self._ctx, C.byref(ptr), C.byref(n)))
+        return ptr.value, n.value
+
+    def finish_from(self, d_sum_ptr: Optional[int], divisor: int) -> np.ndarray:
+        out = np.empty((self.height, self.width, self.channels), np.float32)
+        _check(lib.stk_ecc_finish_from(self._ctx, d_sum_ptr, int(divisor), out.ctypes.data, out.strides[0]))
+        self._keep.clear()
+        return out
+
+    def finish_device(self, d_sum_ptr: Optional[int], divisor: int, d_out_ptr: int):
+        _check(lib.stk_ecc_finish_device(self._ctx, d_sum_ptr, int(divisor), d_out_ptr))
+
+    def debug_iteration(self, frame: np.ndarray, warp_in):
+        """One ECC iteration from `warp_in` (3x3): (totals f64[NV], warp_out 3x3 f32, rho, status)."""
+        f, ptr, pitch = self._host_frame(frame)
+        win = (C.c_float * 9)(*np.asarray(warp_in, np.float32).reshape(9))
+        tot = (C.c_double * 128)()
+        nv, rho, status = C.c_int(), C.c_double(), C.c_int()
+        wout = (C.c_float * 9)()
+        _check(lib.stk_ecc_debug_iteration(self._ctx, ptr, pitch, win, tot, 128, C.byref(nv), wout, C.byref(rho),
+                                           C.byref(status)))
+        return (np.array(tot[:nv.value]), np.array(wout[:], np.float32).reshape(3, 3), rho.value, status.value)
+
+    def reset(self):
+        _check(lib.stk_ecc_reset(self._ctx))
+        self._keep.clear()
+
+    def launch_count(self) -> int:
+        n = C.c_int64()
+        _check(lib.stk_ecc_launch_count(self._ctx, C.byref(n)))
+        return n.value
+
+
+def prep_grey_blur(frame: np.ndarray, ksize: int, device: int = -1) -> np.ndarray:
+    """The f32 plane findTransformECC builds from an 8-bit BGR frame: grey -> f32 -> GaussianBlur(k)."""
+    frame = np.ascontiguousarray(frame)
+    h, w, ch = frame.shape
+    out = np.empty((h, w), np.float32)
+    _check(lib.stk_prep_grey_blur(frame.ctypes.data, frame.strides[0], w, h, ch, int(ksize), device,
+                                  out.ctypes.data, out.strides[0]))
+    return out
+
+
+# ---- decode (host; stays OpenCV like the reference) -----------------------------------------------------
+def imread(path, flags=None):
+    """utils::imread (src/utils.rs:111-117)."""
+    import cv2
+    p = os.fspath(path)
+    if not isinstance(p, str):
+        raise InvalidPathEncoding(repr(path))
+    img = cv2.imread(p, cv2.IMREAD_UNCHANGED if flags is None else flags)
+    if img is None:
+        # OpenCV returns an empty Mat; the first OpenCV call on it fails -> OpenCvError in the reference
+        raise OpenCvError(f"imread failed for {p}")
+    return img
+
+
+def _load(item):
+    return item if isinstance(item, np.ndarray) else imread(item)
+
+
+def _check_colour_frame(img: np.ndarray):
+    if img.dtype != np.uint8:
+        raise OpenCvError("findTransformECC: images must have 8uC1 type after cvtColor (got a non-8-bit file)")
+    if img.ndim != 3 or img.shape[2] not in (3, 4):
+        raise OpenCvError("cvtColor(BGR2GRAY): input must have 3 or 4 channels")
+
+
+# ---- ecc_match: src/lib.rs:702-847 ----------------------------------------------------------------------
+def ecc_match(files: Iterable, params: EccMatchParameters, scale_down_width: Optional[float] = None, *,
+              device: int = -1, workers: Optional[int] = None, return_details: bool = False):
+    """Align every frame to the first with ECC and average them.
+
+    `files`: paths (decoded on host threads with cv2.imread(IMREAD_UNCHANGED), as
+    utils::read_grey_and_f32 does) or already-decoded HxWxC uint8 arrays.
+    Returns the stacked image, float32 HxWxC in [0,1] (the reference's CV_32FC3 Mat).
+    Errors: NotEnoughFiles (empty input); OpenCvError (no COUNT/EPS criteria, ECC non-convergence, bad
+    image type); InvalidParams (scale_down_width out of range)."""
+    items = list(files)
+    if not items:
+        raise NotEnoughFiles()
+    if scale_down_width is not None:
+        # ecc_match_scaling_down (src/lib.rs:849-1028) is row N1 of SURVEY.md §8(f): next, not yet built
+        raise NotImplementedError_("ecc_match with scale_down_width is not implemented yet")
+    typ, _, _ = term_criteria(params)
+    first = _load(items[0])
+    _check_colour_frame(first)
+    if not typ:
+        raise OpenCvError("findTransformECC: criteria.type must have COUNT or EPS set")
+    h, w, ch = first.shape
+    with EccStack(w, h, ch, params, device=device) as st:
+        st.set_reference(first)
+        n_workers = workers or min(8, os.cpu_count() or 1)
+        rest = items[1:]
+        if rest:
+            if all(isinstance(i, np.ndarray) for i in rest):
+                for k, fr in enumerate(rest):
+                    _check_colour_frame(fr)
+                    st.submit(fr, tag=k + 1)
+            else:
+                with ThreadPoolExecutor(max_workers=n_workers) as ex:      # Rayon: one task per frame
+                    for k, fr in enumerate(ex.map(_load, rest)):
+                        _check_colour_frame(fr)
+                        st.submit(fr, tag=k + 1)
+        out = st.finish(len(items))
+        if return_details:
+            return out, st.results()
+        return out
+
+
+# ---- keypoint_match: src/lib.rs:129-353 -----------------------------------------------------------------
+def _orb(grey):
+    import cv2
+    return cv2.ORB_create().detectAndCompute(grey, None)      # utils::orb_detect_and_compute
+
+
+def _frame_homography(kp0, des0, img, params: KeyPointMatchParameters):
+    """Host stages of src/lib.rs:200-287; None == the reference drops the frame."""
+    import cv2
+    grey = cv2.cvtColor(img, cv2.COLOR_BGR2GRAY)
+    kp, des = _orb(grey)
+    if des is None or des0 is None:
+        return None
+    knn = cv2.BFMatcher(cv2.NORM_HAMMING, False).knnMatch(des0, des, k=2)
+    good = [m[0] for m in knn
+            if len(m) == 2 and m[0].distance < np.float32(params.match_ratio) * m[1].distance]
+    good.sort(key=lambda m: m.distance)
+    keep = int(round(float(np.float32(len(good)) * np.float32(params.match_keep_ratio))))
+    good = good[:keep]
+    if len(good) < 5:
+        return None
+    src = np.float32([kp0[m.queryIdx].pt for m in good]).reshape(-1, 1, 2)
+    dst = np.float32([kp[m.trainIdx].pt for m in good]).reshape(-1, 1, 2)
+    try:
+        hm, _ = cv2.findHomography(dst, src, params.method, params.ransac_reproj_threshold)
+    except cv2.error:
+        return None
+    if hm is None or hm.shape != (3, 3) or abs(np.linalg.det(hm)) < 1e-6:
+        return None
+    return hm
+
+
+def keypoint_match(files: Iterable, params: KeyPointMatchParameters = KeyPointMatchParameters(),
+                   scale_down_width: Optional[float] = None, *, device: int = -1,
+                   workers: Optional[int] = None):
+    """Returns (dropped, stacked f32 HxWxC).  ORB / BFMatcher / findHomography stay on the host (OpenCV),
+    the final warp_perspective + accumulate + divide run on the GPU.
+
+    Deviation, documented: when frames are dropped the reference's result depends on how Rayon split the
+    index range (src/lib.rs:307 seeds a worker's accumulator with a copy of frame 0); here dropped frames
+    are simply left out and the sum is divided by n - dropped."""
+    import cv2
+    items = list(files)
+    if not items:
+        raise NotEnoughFiles()
+    if scale_down_width is not None:
+        raise NotImplementedError_("keypoint_match with scale_down_width is not implemented yet")
+    first = _load(items[0])
+    _check_colour_frame(first)
+    h, w, ch = first.shape
+    kp0, des0 = _orb(cv2.cvtColor(first, cv2.COLOR_BGR2GRAY))
+    dropped = 0
+    with EccStack(w, h, ch, None, device=device) as st:
+        st.set_reference(first)
+
+        def work(item):
+            img = _load(item)
+            _check_colour_frame(img)
+            return img, _frame_homography(kp0, des0, img, params)
+
+        n_workers = workers or min(8, os.cpu_count() or 1)
+        with ThreadPoolExecutor(max_workers=n_workers) as ex:
+            for k, (img, hm) in enumerate(ex.map(work, items[1:])):
+                if hm is None:
+                    dropped += 1
+                    continue
+                if img.shape[:2] != (h, w):
+                    raise NotImplementedError_("frames of differing size")
+                st.submit_warp(img, hm, params.border_mode, params.border_value, tag=k + 1)
+        if len(items) - dropped <= 0:
+            raise InvalidParams("All images discarded: try modifying KeyPointMatchParameters::match_distance_threshold")
+        return dropped, st.finish(len(items) - dropped)
+
+
+# ---- sharpness_tenengrad: src/lib.rs:1101-1147 ----------------------------------------------------------
+def sharpness_tenengrad(src_grey_mat, k_size: int, *, device: int = -1) -> float:
+    if k_size not in (1, 3, 5, 7):
+        raise InvalidParams("Kernel size must be 1, 3, 5, or 7")
+    out = C.c_double()
+    dv = _device_view(src_grey_mat)
+    if dv is not None:
+        shape = src_grey_mat.__cuda_array_interface__["shape"]
+        ch = 1 if len(shape) == 2 else shape[2]
+        _check(lib.stk_tenengrad_device(dv[0], dv[1], shape[1], shape[0], ch, k_size, device, C.byref(out)))
+        return out.value
+    a = np.asarray(src_grey_mat)
+    if a.dtype != np.uint8:
+        raise NotImplementedError_("sharpness_tenengrad: only 8-bit input is implemented on the GPU path")
+    if a.ndim != 2:
+        raise OpenCvError("sharpness_tenengrad expects a single-channel image")
+    if a.strides[1] != 1:
+        a = np.ascontiguousarray(a)
+    _check(lib.stk_tenengrad(a.ctypes.data, a.strides[0], a.shape[1], a.shape[0], 1, k_size, device, C.byref(out)))
+    return out.value

@@ -1,0 +1,889 @@
+// C ABI of the sm_100a align-and-stack library (see include/stacker_cuda.h).
+//
+// Host-side orchestration only: contexts, lanes (one CUDA stream + one CUDA graph with a device-driven
+// WHILE loop per lane), pinned staging and result records.  All arithmetic is in the kernels included
+// below; there is no CPU fallback.
+#include "../../include/stacker_cuda.h"
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "ecc_iter.cuh"
+#include "prep.cuh"
+#include "tenengrad.cuh"
+#include "warp_acc.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU(expr)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (expr);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(STK_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+// getGaussianKernel(k, sigma <= 0, CV_32F): tabulated dyadic taps for k <= 9 (as cv2 4.13 returns them),
+// sampled Gaussian otherwise.
+void gaussian_taps(int k, float* taps) {
+  static const float t1[] = {1.f};
+  static const float t3[] = {0.25f, 0.5f, 0.25f};
+  static const float t5[] = {0.0625f, 0.25f, 0.375f, 0.25f, 0.0625f};
+  static const float t7[] = {0.03125f, 0.109375f, 0.21875f, 0.28125f, 0.21875f, 0.109375f, 0.03125f};
+  static const float t9[] = {0.015625f, 0.05078125f, 0.1171875f, 0.19921875f, 0.234375f,
+                             0.19921875f, 0.1171875f, 0.05078125f, 0.015625f};
+  const float* tab = k == 1 ? t1 : k == 3 ? t3 : k == 5 ? t5 : k == 7 ? t7 : k == 9 ? t9 : nullptr;
+  if (tab) { for (int i = 0; i < k; ++i) taps[i] = tab[i]; return; }
+  const double sigma = 0.3 * ((k - 1) * 0.5 - 1) + 0.8;
+  const double scale2x = -0.5 / (sigma * sigma);
+  std::vector<double> v(k);
+  double sum = 0;
+  for (int i = 0; i < k; ++i) { const double x = i - (k - 1) * 0.5; v[i] = std::exp(scale2x * x * x); sum += v[i]; }
+  for (int i = 0; i < k; ++i) taps[i] = (float)(v[i] / sum);
+}
+
+// OpenCV's inverse of the forward map, f64, same operation order as imgwarp.cpp / cv::invert 3x3.
+// Compiled for the host without FMA contraction (x86-64 baseline), like the OpenCV it mirrors.
+void invert_perspective_host(const double* s, double* o) {
+  auto det2 = [](double a, double b, double c, double d) { return a * d - b * c; };
+  double d = s[0] * det2(s[4], s[5], s[7], s[8]) - s[1] * det2(s[3], s[5], s[6], s[8]) +
+             s[2] * det2(s[3], s[4], s[6], s[7]);
+  if (d == 0.0) { for (int i = 0; i < 9; ++i) o[i] = 0.0; return; }
+  d = 1.0 / d;
+  o[0] = det2(s[4], s[5], s[7], s[8]) * d;
+  o[1] = det2(s[2], s[1], s[8], s[7]) * d;
+  o[2] = det2(s[1], s[2], s[4], s[5]) * d;
+  o[3] = det2(s[5], s[3], s[8], s[6]) * d;
+  o[4] = det2(s[0], s[2], s[6], s[8]) * d;
+  o[5] = det2(s[2], s[0], s[5], s[3]) * d;
+  o[6] = det2(s[3], s[4], s[6], s[7]) * d;
+  o[7] = det2(s[1], s[0], s[7], s[6]) * d;
+  o[8] = det2(s[0], s[1], s[3], s[4]) * d;
+}
+
+struct Lane {
+  cudaStream_t stream = nullptr;
+  float* tmpl = nullptr;            // T plane
+  uint8_t* d_frame = nullptr;       // device staging for host-submitted frames
+  uint8_t* h_stage = nullptr;       // pinned staging for pageable host buffers
+  cudaEvent_t stage_free = nullptr; // H2D out of h_stage finished
+  stk::EccState* st = nullptr;
+  double* partials = nullptr;
+  float* acc = nullptr;
+  bool acc_used = false;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  cudaGraphConditionalHandle handle = 0;
+};
+
+struct ResultSlot {
+  int64_t tag;
+  stk::EccState* host;      // pinned copy of the frame's final state (null for warp-only frames)
+};
+
+}  // namespace
+
+struct stk_ecc_ctx {
+  stk_ecc_config cfg;
+  int device = 0;
+  int sm_count = 0;
+  int n_lanes = 0;
+  std::vector<Lane> lanes;
+  float* img = nullptr;             // I plane (blurred reference grey)
+  uint8_t* d_ref = nullptr;         // device copy of the reference frame when it came from the host
+  float* d_out = nullptr;           // scaled result before D2H
+  int pitch_f = 0;                  // floats per row of I / T
+  size_t frame_bytes = 0;           // width*channels*height (dense staging)
+  size_t acc_floats = 0;
+  // ECC tiling
+  int n_strips = 0, n_bands = 0, rows_per_tile = 0, n_tiles = 0, nv = 0;
+  int max_iter = 0;
+  double eps = 0;
+  bool host_loop = false;
+  bool have_ref = false;
+  stk::PrepParams prep_proto;
+  std::mutex mu;
+  int next_lane = 0;
+  std::vector<ResultSlot> results;
+  std::vector<stk::EccState*> state_chunks;   // pinned, kChunk states each
+  size_t states_used = 0;
+  std::atomic<int64_t> launches{0};
+  int64_t iter_launches_counted = 0;
+  static constexpr size_t kChunk = 256;
+};
+
+namespace {
+
+template <int MOTION> void* iter_kernel_ptr() { return (void*)stk::ecc_iter_kernel<MOTION>; }
+
+void* iter_kernel(int motion) {
+  switch (motion) {
+    case STK_MOTION_TRANSLATION: return iter_kernel_ptr<stk::kTranslation>();
+    case STK_MOTION_EUCLIDEAN: return iter_kernel_ptr<stk::kEuclidean>();
+    case STK_MOTION_AFFINE: return iter_kernel_ptr<stk::kAffine>();
+    default: return iter_kernel_ptr<stk::kHomography>();
+  }
+}
+
+int model_nv(int motion) {
+  switch (motion) {
+    case STK_MOTION_TRANSLATION: return stk::Layout<stk::kTranslation>::NV;
+    case STK_MOTION_EUCLIDEAN: return stk::Layout<stk::kEuclidean>::NV;
+    case STK_MOTION_AFFINE: return stk::Layout<stk::kAffine>::NV;
+    default: return stk::Layout<stk::kHomography>::NV;
+  }
+}
+
+stk::EccIterParams iter_params(stk_ecc_ctx* c, Lane& ln, bool use_handle) {
+  stk::EccIterParams p;
+  p.img = c->img;
+  p.tmpl = ln.tmpl;
+  p.pitch = c->pitch_f;
+  p.width = c->cfg.width;
+  p.height = c->cfg.height;
+  p.rows_per_tile = c->rows_per_tile;
+  p.n_strips = c->n_strips;
+  p.n_bands = c->n_bands;
+  p.partials = ln.partials;
+  p.st = ln.st;
+  p.handle = ln.handle;
+  p.use_handle = use_handle ? 1 : 0;
+  p.totals_out = nullptr;
+  return p;
+}
+
+// graph per lane:  init -> WHILE(handle) { ecc_iter_kernel }
+int build_lane_graph(stk_ecc_ctx* c, Lane& ln) {
+  const bool persp = c->cfg.motion_type == STK_MOTION_HOMOGRAPHY;
+  CU(cudaGraphCreate(&ln.graph, 0));
+  CU(cudaGraphConditionalHandleCreate(&ln.handle, ln.graph, 1, cudaGraphCondAssignDefault));
+
+  cudaGraphNode_t init_node, cond_node, iter_node;
+  {
+    stk::EccState* st = ln.st;
+    int persp_i = persp ? 1 : 0, max_iter = c->max_iter, use = 1;
+    double eps = c->eps;
+    cudaGraphConditionalHandle h = ln.handle;
+    void* args[] = {&st, &persp_i, &max_iter, &eps, &h, &use};
+    cudaKernelNodeParams kp = {};
+    kp.func = (void*)stk::ecc_init_kernel;
+    kp.gridDim = dim3(1);
+    kp.blockDim = dim3(32);
+    kp.kernelParams = args;
+    CU(cudaGraphAddKernelNode(&init_node, ln.graph, nullptr, 0, &kp));
+  }
+  {
+    cudaGraphNodeParams np = {};
+    np.type = cudaGraphNodeTypeConditional;
+    np.conditional.handle = ln.handle;
+    np.conditional.type = cudaGraphCondTypeWhile;
+    np.conditional.size = 1;
+    CU(cudaGraphAddNode(&cond_node, ln.graph, &init_node, 1, &np));
+    cudaGraph_t body = np.conditional.phGraph_out[0];
+    stk::EccIterParams ip = iter_params(c, ln, true);
+    void* args[] = {&ip};
+    cudaKernelNodeParams kp = {};
+    kp.func = iter_kernel(c->cfg.motion_type);
+    kp.gridDim = dim3(c->n_tiles);
+    kp.blockDim = dim3(stk::kEccThreads);
+    kp.kernelParams = args;
+    CU(cudaGraphAddKernelNode(&iter_node, body, nullptr, 0, &kp));
+  }
+  CU(cudaGraphInstantiate(&ln.exec, ln.graph, 0));
+  return STK_OK;
+}
+
+int launch_prep(stk_ecc_ctx* c, const uint8_t* d_src, size_t pitch, float* dst, cudaStream_t s) {
+  stk::PrepParams p = c->prep_proto;
+  p.src = d_src;
+  p.src_pitch = pitch;
+  p.dst = dst;
+  const int r = p.radius;
+  const size_t smem = (size_t)((stk::kPrepTW + 2 * r) * (stk::kPrepTH + 2 * r) + (stk::kPrepTH + 2 * r) * stk::kPrepTW) * sizeof(float);
+  dim3 grid((c->cfg.width + stk::kPrepTW - 1) / stk::kPrepTW, (c->cfg.height + stk::kPrepTH - 1) / stk::kPrepTH);
+  stk::prep_grey_blur_kernel<<<grid, stk::kPrepThreads, smem, s>>>(p);
+  c->launches++;
+  CU(cudaGetLastError());
+  return STK_OK;
+}
+
+int launch_warp(stk_ecc_ctx* c, Lane& ln, const uint8_t* d_src, size_t pitch, bool persp,
+                const double* inv_host, const float* border, bool from_state) {
+  stk::WarpAccParams p = {};
+  p.src = d_src;
+  p.src_pitch = pitch;
+  p.acc = ln.acc;
+  p.width = c->cfg.width;
+  p.height = c->cfg.height;
+  p.src_width = c->cfg.width;
+  p.src_height = c->cfg.height;
+  p.inv_ptr = from_state ? ln.st->inv : nullptr;   // device address arithmetic only
+  p.status_ptr = from_state ? &ln.st->status : nullptr;
+  if (inv_host) for (int i = 0; i < 9; ++i) p.inv[i] = inv_host[i];
+  for (int i = 0; i < 4; ++i) p.border[i] = border ? border[i] : 0.f;
+  p.store = ln.acc_used ? 0 : 1;
+  dim3 block(stk::kWarpBX, stk::kWarpBY);
+  dim3 grid((p.width + stk::kWarpBX - 1) / stk::kWarpBX, (p.height + stk::kWarpBY - 1) / stk::kWarpBY);
+  const int ch = c->cfg.channels;
+  if (ch == 3) {
+    if (persp) stk::warp_accumulate_kernel<3, true><<<grid, block, 0, ln.stream>>>(p);
+    else stk::warp_accumulate_kernel<3, false><<<grid, block, 0, ln.stream>>>(p);
+  } else {
+    if (persp) stk::warp_accumulate_kernel<4, true><<<grid, block, 0, ln.stream>>>(p);
+    else stk::warp_accumulate_kernel<4, false><<<grid, block, 0, ln.stream>>>(p);
+  }
+  c->launches++;
+  CU(cudaGetLastError());
+  ln.acc_used = true;
+  return STK_OK;
+}
+
+int alloc_result_state(stk_ecc_ctx* c, stk::EccState** out) {
+  const size_t chunk = c->states_used / stk_ecc_ctx::kChunk, off = c->states_used % stk_ecc_ctx::kChunk;
+  if (chunk >= c->state_chunks.size()) {
+    stk::EccState* p = nullptr;
+    CU(cudaHostAlloc((void**)&p, sizeof(stk::EccState) * stk_ecc_ctx::kChunk, cudaHostAllocDefault));
+    memset(p, 0, sizeof(stk::EccState) * stk_ecc_ctx::kChunk);
+    c->state_chunks.push_back(p);
+  }
+  *out = c->state_chunks[chunk] + off;
+  c->states_used++;
+  return STK_OK;
+}
+
+// Stage a host frame into the lane's device buffer (dense rows).  `pinned` = the caller's buffer is
+// page-locked and stays valid until sync, so it is copied from directly.
+int upload_frame(stk_ecc_ctx* c, Lane& ln, const uint8_t* host, size_t pitch, bool pinned) {
+  const size_t row = (size_t)c->cfg.width * c->cfg.channels;
+  if (pinned) {
+    CU(cudaMemcpy2DAsync(ln.d_frame, row, host, pitch, row, c->cfg.height, cudaMemcpyHostToDevice, ln.stream));
+    return STK_OK;
+  }
+  CU(cudaEventSynchronize(ln.stage_free));
+  if (pitch == row) {
+    memcpy(ln.h_stage, host, row * c->cfg.height);
+  } else {
+    for (int y = 0; y < c->cfg.height; ++y) memcpy(ln.h_stage + (size_t)y * row, host + (size_t)y * pitch, row);
+  }
+  CU(cudaMemcpyAsync(ln.d_frame, ln.h_stage, row * c->cfg.height, cudaMemcpyHostToDevice, ln.stream));
+  CU(cudaEventRecord(ln.stage_free, ln.stream));
+  return STK_OK;
+}
+
+Lane& pick_lane(stk_ecc_ctx* c) {
+  Lane& ln = c->lanes[c->next_lane];
+  c->next_lane = (c->next_lane + 1) % c->n_lanes;
+  return ln;
+}
+
+// the ECC part of one frame on its lane: prep -> device loop -> warp+accumulate -> result record
+int enqueue_align(stk_ecc_ctx* c, Lane& ln, const uint8_t* d_src, size_t pitch, int64_t tag) {
+  int rc = launch_prep(c, d_src, pitch, ln.tmpl, ln.stream);
+  if (rc) return rc;
+  const bool persp = c->cfg.motion_type == STK_MOTION_HOMOGRAPHY;
+  if (!c->host_loop) {
+    CU(cudaGraphLaunch(ln.exec, ln.stream));
+    c->launches++;   // init kernel; the iteration launches are added from the result records
+  } else {
+    // host-driven fallback (STK_LOOP_MODE=host): same kernels, convergence polled every few iterations
+    stk::ecc_init_kernel<<<1, 32, 0, ln.stream>>>(ln.st, persp ? 1 : 0, c->max_iter, c->eps, 0, 0);
+    c->launches++;
+    CU(cudaGetLastError());
+    stk::EccIterParams ip = iter_params(c, ln, false);
+    void* args[] = {&ip};
+    int done_iters = 0;
+    int* h_cont = nullptr;
+    CU(cudaHostAlloc((void**)&h_cont, sizeof(int), cudaHostAllocDefault));
+    *h_cont = 1;
+    while (*h_cont && done_iters < c->max_iter) {
+      const int chunk = std::min(4, c->max_iter - done_iters);
+      for (int i = 0; i < chunk; ++i)
+        CU(cudaLaunchKernel(iter_kernel(c->cfg.motion_type), dim3(c->n_tiles), dim3(stk::kEccThreads), args, 0, ln.stream));
+      done_iters += chunk;
+      CU(cudaMemcpyAsync(h_cont, &ln.st->cont, sizeof(int), cudaMemcpyDeviceToHost, ln.stream));
+      CU(cudaStreamSynchronize(ln.stream));
+    }
+    cudaFreeHost(h_cont);
+  }
+  rc = launch_warp(c, ln, d_src, pitch, persp, nullptr, nullptr, true);
+  if (rc) return rc;
+  stk::EccState* hs = nullptr;
+  rc = alloc_result_state(c, &hs);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(hs, ln.st, sizeof(stk::EccState), cudaMemcpyDeviceToHost, ln.stream));
+  c->results.push_back({tag, hs});
+  return STK_OK;
+}
+
+int sync_all(stk_ecc_ctx* c) {
+  for (auto& ln : c->lanes) CU(cudaStreamSynchronize(ln.stream));
+  // account for the device-launched iteration kernels and surface per-frame failures
+  int first_err = STK_OK;
+  int64_t iters = 0;
+  for (auto& r : c->results) {
+    if (!r.host) continue;
+    iters += r.host->iters;
+    if (r.host->status != 0 && first_err == STK_OK) first_err = r.host->status;
+  }
+  c->launches += iters - c->iter_launches_counted;
+  c->iter_launches_counted = iters;
+  if (first_err == STK_ERR_ECC_NOCONV)
+    return fail(first_err, "findTransformECC: the algorithm stopped before its convergence (lambda denominator <= 0)");
+  if (first_err == STK_ERR_ECC_NAN) return fail(first_err, "findTransformECC: NaN encountered");
+  return first_err;
+}
+
+int lane_sum(stk_ecc_ctx* c, float* out, const float* const* extra, int n_extra, bool scale, int divisor,
+             cudaStream_t s) {
+  stk::LaneSumParams p = {};
+  int n = 0;
+  for (int i = 0; i < n_extra; ++i) p.lanes[n++] = extra[i];
+  p.n_lanes = n;
+  p.out = out;
+  p.n = c->acc_floats;
+  p.apply_scale = scale ? 1 : 0;
+  p.scale = scale ? (float)(1.0 / (double)divisor) : 1.f;
+  const int blocks = c->sm_count * 8;
+  stk::lane_sum_scale_kernel<<<blocks, 256, 0, s>>>(p);
+  c->launches++;
+  CU(cudaGetLastError());
+  return STK_OK;
+}
+
+int check_ctx(stk_ecc_ctx* c) {
+  if (!c) return fail(STK_ERR_BAD_ARG, "null context");
+  CU(cudaSetDevice(c->device));
+  return STK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int stk_abi_version(void) { return STK_ABI_VERSION; }
+const char* stk_last_error(void) { return g_err.c_str(); }
+
+int stk_device_count(int* count) {
+  if (!count) return fail(STK_ERR_BAD_ARG, "null count");
+  CU(cudaGetDeviceCount(count));
+  return STK_OK;
+}
+
+int stk_pinned_alloc(void** ptr, size_t bytes) {
+  if (!ptr) return fail(STK_ERR_BAD_ARG, "null ptr");
+  CU(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
+  return STK_OK;
+}
+int stk_pinned_free(void* ptr) {
+  CU(cudaFreeHost(ptr));
+  return STK_OK;
+}
+
+int stk_ecc_create(const stk_ecc_config* cfg, stk_ecc_ctx** out) {
+  if (!cfg || !out) return fail(STK_ERR_BAD_ARG, "null argument");
+  *out = nullptr;
+  if (cfg->width <= 0 || cfg->height <= 0) return fail(STK_ERR_BAD_ARG, "bad frame size %dx%d", cfg->width, cfg->height);
+  if (cfg->width > 32766 || cfg->height > 32766) return fail(STK_ERR_BAD_ARG, "frame larger than OpenCV's remap limit (32767)");
+  if (cfg->channels != 3 && cfg->channels != 4) return fail(STK_ERR_UNSUPPORTED, "channels must be 3 or 4 (got %d)", cfg->channels);
+  if (cfg->align) {
+    if (cfg->motion_type < 0 || cfg->motion_type > 3) return fail(STK_ERR_BAD_ARG, "bad motion type %d", cfg->motion_type);
+    if (!(cfg->criteria_type & (STK_TERM_COUNT | STK_TERM_EPS)))
+      return fail(STK_ERR_CRITERIA, "TermCriteria needs COUNT or EPS (findTransformECC asserts)");
+    if (cfg->gauss_filt_size < 1 || cfg->gauss_filt_size % 2 == 0 || cfg->gauss_filt_size / 2 > stk::kMaxGaussRadius)
+      return fail(STK_ERR_BAD_ARG, "gauss_filt_size must be odd, in [1, %d]", 2 * stk::kMaxGaussRadius + 1);
+  }
+  int dev = cfg->device;
+  if (dev < 0) CU(cudaGetDevice(&dev));
+  CU(cudaSetDevice(dev));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10)
+    return fail(STK_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor);
+
+  stk_ecc_ctx* c = new (std::nothrow) stk_ecc_ctx();
+  if (!c) return fail(STK_ERR_NOMEM, "out of host memory");
+  c->cfg = *cfg;
+  c->device = dev;
+  c->sm_count = prop.multiProcessorCount;
+  c->n_lanes = cfg->lanes > 0 ? std::min(cfg->lanes, 16) : 4;
+  c->pitch_f = (cfg->width + 31) / 32 * 32;
+  c->frame_bytes = (size_t)cfg->width * cfg->channels * cfg->height;
+  c->acc_floats = (size_t)cfg->width * cfg->channels * cfg->height;
+  c->max_iter = (cfg->criteria_type & STK_TERM_COUNT) ? cfg->max_count : 200;
+  c->eps = (cfg->criteria_type & STK_TERM_EPS) ? cfg->epsilon : -1.0;
+  const char* lm = getenv("STK_LOOP_MODE");
+  c->host_loop = lm && strcmp(lm, "host") == 0;
+
+  int rc = STK_OK;
+  auto cleanup = [&](int code) { stk_ecc_destroy(c); return code; };
+
+  if (cfg->align) {
+    // tiling: 128-column strips x bands; as many tiles as resident blocks (2 per SM by launch bounds),
+    // never fewer than 32 rows per tile so the per-tile fold/reduction stays amortised
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)iter_kernel(cfg->motion_type), stk::kEccThreads, 0) != cudaSuccess || occ < 1) occ = 1;
+    const int slots = c->sm_count * occ;
+    c->n_strips = (cfg->width + stk::kEccStripW - 1) / stk::kEccStripW;
+    int bands = std::max(1, slots / c->n_strips);
+    int rows = (cfg->height + bands - 1) / bands;
+    rows = std::max(rows, 32);
+    rows = (rows + 1) & ~1;
+    c->rows_per_tile = rows;
+    c->n_bands = (cfg->height + rows - 1) / rows;
+    c->n_tiles = c->n_strips * c->n_bands;
+    c->nv = model_nv(cfg->motion_type);
+    stk::PrepParams& pp = c->prep_proto;
+    memset(&pp, 0, sizeof pp);
+    pp.dst_pitch = c->pitch_f;
+    pp.width = cfg->width;
+    pp.height = cfg->height;
+    pp.channels = cfg->channels;
+    pp.radius = cfg->gauss_filt_size / 2;
+    gaussian_taps(cfg->gauss_filt_size, pp.taps);
+    const int r = pp.radius;
+    const size_t smem = (size_t)((stk::kPrepTW + 2 * r) * (stk::kPrepTH + 2 * r) + (stk::kPrepTH + 2 * r) * stk::kPrepTW) * sizeof(float);
+    if (smem > 48 * 1024) {
+      if (cudaFuncSetAttribute(stk::prep_grey_blur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return cleanup(fail(STK_ERR_CUDA, "cannot reserve %zu bytes of shared memory for the blur", smem));
+    }
+    if (cudaMalloc((void**)&c->img, (size_t)c->pitch_f * cfg->height * sizeof(float)) != cudaSuccess)
+      return cleanup(fail(STK_ERR_NOMEM, "cudaMalloc(I plane) failed"));
+  }
+  c->lanes.resize(c->n_lanes);
+  for (auto& ln : c->lanes) {
+    if (cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking) != cudaSuccess) return cleanup(fail(STK_ERR_CUDA, "cudaStreamCreate failed"));
+    if (cudaEventCreateWithFlags(&ln.stage_free, cudaEventDisableTiming) != cudaSuccess) return cleanup(fail(STK_ERR_CUDA, "cudaEventCreate failed"));
+    if (cudaMalloc((void**)&ln.acc, c->acc_floats * sizeof(float)) != cudaSuccess) return cleanup(fail(STK_ERR_NOMEM, "cudaMalloc(accumulator) failed"));
+    if (cfg->align) {
+      if (cudaMalloc((void**)&ln.tmpl, (size_t)c->pitch_f * cfg->height * sizeof(float)) != cudaSuccess) return cleanup(fail(STK_ERR_NOMEM, "cudaMalloc(T plane) failed"));
+      if (cudaMalloc((void**)&ln.st, sizeof(stk::EccState)) != cudaSuccess) return cleanup(fail(STK_ERR_NOMEM, "cudaMalloc(state) failed"));
+      if (cudaMemsetAsync(ln.st, 0, sizeof(stk::EccState), ln.stream) != cudaSuccess ||
+          cudaStreamSynchronize(ln.stream) != cudaSuccess) return cleanup(fail(STK_ERR_CUDA, "cudaMemset failed"));
+      if (cudaMalloc((void**)&ln.partials, (size_t)c->n_tiles * c->nv * sizeof(double)) != cudaSuccess) return cleanup(fail(STK_ERR_NOMEM, "cudaMalloc(partials) failed"));
+      if (!c->host_loop) {
+        rc = build_lane_graph(c, ln);
+        if (rc) return cleanup(rc);
+      }
+    }
+  }
+  *out = c;
+  return STK_OK;
+}
+
+int stk_ecc_destroy(stk_ecc_ctx* c) {
+  if (!c) return STK_OK;
+  cudaSetDevice(c->device);
+  for (auto& ln : c->lanes) {
+    if (ln.stream) cudaStreamSynchronize(ln.stream);
+    if (ln.exec) cudaGraphExecDestroy(ln.exec);
+    if (ln.graph) cudaGraphDestroy(ln.graph);
+    cudaFree(ln.tmpl); cudaFree(ln.d_frame); cudaFree(ln.st); cudaFree(ln.partials); cudaFree(ln.acc);
+    if (ln.h_stage) cudaFreeHost(ln.h_stage);
+    if (ln.stage_free) cudaEventDestroy(ln.stage_free);
+    if (ln.stream) cudaStreamDestroy(ln.stream);
+  }
+  cudaFree(c->img); cudaFree(c->d_ref); cudaFree(c->d_out);
+  for (auto* p : c->state_chunks) cudaFreeHost(p);
+  delete c;
+  return STK_OK;
+}
+
+static int ensure_host_staging(stk_ecc_ctx* c, Lane& ln, bool need_pinned_stage) {
+  if (!ln.d_frame) CU(cudaMalloc((void**)&ln.d_frame, c->frame_bytes));
+  if (need_pinned_stage && !ln.h_stage) CU(cudaHostAlloc((void**)&ln.h_stage, c->frame_bytes, cudaHostAllocDefault));
+  return STK_OK;
+}
+
+static int set_reference_impl(stk_ecc_ctx* c, const uint8_t* d_bgr, size_t pitch) {
+  Lane& l0 = c->lanes[0];
+  if (c->cfg.align) {
+    int rc = launch_prep(c, d_bgr, pitch, c->img, l0.stream);
+    if (rc) return rc;
+  }
+  if (c->cfg.seed_reference) {
+    const int row = c->cfg.width * c->cfg.channels;
+    dim3 grid((row + 255) / 256, c->cfg.height);
+    stk::seed_accumulator_kernel<<<grid, 256, 0, l0.stream>>>(d_bgr, pitch, l0.acc, row, c->cfg.height);
+    c->launches++;
+    CU(cudaGetLastError());
+    l0.acc_used = true;
+  }
+  CU(cudaStreamSynchronize(l0.stream));
+  c->have_ref = true;
+  return STK_OK;
+}
+
+int stk_ecc_set_reference(stk_ecc_ctx* c, const uint8_t* bgr, size_t pitch) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  if (!bgr) return fail(STK_ERR_BAD_ARG, "null frame");
+  const size_t row = (size_t)c->cfg.width * c->cfg.channels;
+  if (pitch < row) return fail(STK_ERR_BAD_ARG, "pitch %zu < row bytes %zu", pitch, row);
+  std::lock_guard<std::mutex> g(c->mu);
+  if (!c->d_ref) CU(cudaMalloc((void**)&c->d_ref, c->frame_bytes));
+  // stream-ordered on lane 0: a blocking cudaMemcpy from pageable memory may return before the DMA has
+  // landed and is ordered only against the legacy stream, which the (non-blocking) lane streams ignore
+  CU(cudaMemcpy2DAsync(c->d_ref, row, bgr, pitch, row, c->cfg.height, cudaMemcpyHostToDevice, c->lanes[0].stream));
+  return set_reference_impl(c, c->d_ref, row);
+}
+
+int stk_ecc_set_reference_device(stk_ecc_ctx* c, const uint8_t* d_bgr, size_t pitch) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  if (!d_bgr) return fail(STK_ERR_BAD_ARG, "null frame");
+  if (pitch < (size_t)c->cfg.width * c->cfg.channels) return fail(STK_ERR_BAD_ARG, "pitch too small");
+  std::lock_guard<std::mutex> g(c->mu);
+  return set_reference_impl(c, d_bgr, pitch);
+}
+
+static int submit_align(stk_ecc_ctx* c, const uint8_t* buf, size_t pitch, int64_t tag, int kind) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  if (!buf) return fail(STK_ERR_BAD_ARG, "null frame");
+  if (!c->cfg.align) return fail(STK_ERR_STATE, "context was created with align = 0");
+  const size_t row = (size_t)c->cfg.width * c->cfg.channels;
+  if (pitch < row) return fail(STK_ERR_BAD_ARG, "pitch %zu < row bytes %zu", pitch, row);
+  std::lock_guard<std::mutex> g(c->mu);
+  if (!c->have_ref) return fail(STK_ERR_STATE, "stk_ecc_set_reference must come first");
+  Lane& ln = pick_lane(c);
+  if (kind == 2) return enqueue_align(c, ln, buf, pitch, tag);
+  rc = ensure_host_staging(c, ln, kind == 0);
+  if (rc) return rc;
+  rc = upload_frame(c, ln, buf, pitch, kind == 1);
+  if (rc) return rc;
+  return enqueue_align(c, ln, ln.d_frame, row, tag);
+}
+
+int stk_ecc_submit_frame(stk_ecc_ctx* c, const uint8_t* bgr, size_t pitch, int64_t tag) { return submit_align(c, bgr, pitch, tag, 0); }
+int stk_ecc_submit_frame_pinned(stk_ecc_ctx* c, const uint8_t* bgr, size_t pitch, int64_t tag) { return submit_align(c, bgr, pitch, tag, 1); }
+int stk_ecc_submit_frame_device(stk_ecc_ctx* c, const uint8_t* d_bgr, size_t pitch, int64_t tag) { return submit_align(c, d_bgr, pitch, tag, 2); }
+
+static int submit_warp(stk_ecc_ctx* c, const uint8_t* buf, size_t pitch, const double* h, int border_mode,
+                       const double* border_value, int64_t tag, bool device) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  if (!buf || !h) return fail(STK_ERR_BAD_ARG, "null argument");
+  if (border_mode != STK_BORDER_CONSTANT) return fail(STK_ERR_UNSUPPORTED, "border mode %d: only BORDER_CONSTANT is implemented", border_mode);
+  const size_t row = (size_t)c->cfg.width * c->cfg.channels;
+  if (pitch < row) return fail(STK_ERR_BAD_ARG, "pitch %zu < row bytes %zu", pitch, row);
+  double inv[9];
+  invert_perspective_host(h, inv);
+  float border[4] = {0, 0, 0, 0};
+  if (border_value) for (int i = 0; i < 4; ++i) border[i] = (float)border_value[i];
+  std::lock_guard<std::mutex> g(c->mu);
+  Lane& ln = pick_lane(c);
+  const uint8_t* d_src = buf;
+  size_t d_pitch = pitch;
+  if (!device) {
+    rc = ensure_host_staging(c, ln, true);
+    if (rc) return rc;
+    rc = upload_frame(c, ln, buf, pitch, false);
+    if (rc) return rc;
+    d_src = ln.d_frame;
+    d_pitch = row;
+  }
+  rc = launch_warp(c, ln, d_src, d_pitch, true, inv, border, false);
+  if (rc) return rc;
+  c->results.push_back({tag, nullptr});
+  return STK_OK;
+}
+
+int stk_ecc_submit_warp(stk_ecc_ctx* c, const uint8_t* bgr, size_t pitch, const double h[9], int border_mode,
+                        const double border_value[4], int64_t tag) {
+  return submit_warp(c, bgr, pitch, h, border_mode, border_value, tag, false);
+}
+int stk_ecc_submit_warp_device(stk_ecc_ctx* c, const uint8_t* d_bgr, size_t pitch, const double h[9], int border_mode,
+                               const double border_value[4], int64_t tag) {
+  return submit_warp(c, d_bgr, pitch, h, border_mode, border_value, tag, true);
+}
+
+int stk_ecc_sync(stk_ecc_ctx* c) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> g(c->mu);
+  return sync_all(c);
+}
+
+int stk_ecc_results(stk_ecc_ctx* c, stk_frame_result* out, int capacity, int* count) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  if (!count || (capacity > 0 && !out)) return fail(STK_ERR_BAD_ARG, "null argument");
+  std::lock_guard<std::mutex> g(c->mu);
+  for (auto& ln : c->lanes) CU(cudaStreamSynchronize(ln.stream));
+  int n = 0;
+  for (auto& r : c->results) {
+    if (n >= capacity) break;
+    stk_frame_result& o = out[n++];
+    memset(&o, 0, sizeof o);
+    o.tag = r.tag;
+    if (r.host) {
+      for (int i = 0; i < 9; ++i) o.warp[i] = r.host->m[i];
+      o.rho = r.host->rho;
+      o.iterations = r.host->iters;
+      o.status = r.host->status;
+    } else {
+      o.warp[0] = o.warp[4] = o.warp[8] = 1.f;
+    }
+  }
+  *count = n;
+  return STK_OK;
+}
+
+int stk_ecc_partial(stk_ecc_ctx* c, float** d_partial, size_t* n_floats) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  if (!d_partial) return fail(STK_ERR_BAD_ARG, "null argument");
+  std::lock_guard<std::mutex> g(c->mu);
+  rc = sync_all(c);
+  if (rc) return rc;
+  const float* used[16];
+  int n = 0;
+  for (auto& ln : c->lanes) if (ln.acc_used) used[n++] = ln.acc;
+  Lane& l0 = c->lanes[0];
+  if (!(n == 1 && used[0] == l0.acc)) {
+    // lane 0 first so that `out` aliasing lanes[0] is read before it is written by the same thread
+    const float* ordered[16];
+    int m = 0;
+    if (l0.acc_used) ordered[m++] = l0.acc;
+    for (auto& ln : c->lanes) if (ln.acc_used && ln.acc != l0.acc) ordered[m++] = ln.acc;
+    rc = lane_sum(c, l0.acc, ordered, m, false, 1, l0.stream);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(l0.stream));
+  }
+  for (auto& ln : c->lanes) ln.acc_used = false;
+  l0.acc_used = true;
+  *d_partial = l0.acc;
+  if (n_floats) *n_floats = c->acc_floats;
+  return STK_OK;
+}
+
+int stk_ecc_finish_device(stk_ecc_ctx* c, const float* d_sum, int divisor, float* d_out) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  if (divisor <= 0) return fail(STK_ERR_BAD_ARG, "divisor must be positive (got %d)", divisor);
+  if (!d_out) return fail(STK_ERR_BAD_ARG, "null output");
+  std::lock_guard<std::mutex> g(c->mu);
+  const float* src = d_sum ? d_sum : c->lanes[0].acc;
+  rc = lane_sum(c, d_out, &src, 1, true, divisor, c->lanes[0].stream);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(c->lanes[0].stream));
+  return STK_OK;
+}
+
+int stk_ecc_finish_from(stk_ecc_ctx* c, const float* d_sum, int divisor, float* out, size_t out_pitch) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  if (!out) return fail(STK_ERR_BAD_ARG, "null output");
+  const size_t row = (size_t)c->cfg.width * c->cfg.channels * sizeof(float);
+  if (out_pitch < row) return fail(STK_ERR_BAD_ARG, "out_pitch %zu < row bytes %zu", out_pitch, row);
+  {
+    std::lock_guard<std::mutex> g(c->mu);
+    if (!c->d_out) CU(cudaMalloc((void**)&c->d_out, c->acc_floats * sizeof(float)));
+  }
+  rc = stk_ecc_finish_device(c, d_sum, divisor, c->d_out);
+  if (rc) return rc;
+  CU(cudaMemcpy2D(out, out_pitch, c->d_out, row, row, c->cfg.height, cudaMemcpyDeviceToHost));
+  return STK_OK;
+}
+
+int stk_ecc_finish(stk_ecc_ctx* c, int divisor, float* out, size_t out_pitch) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  if (divisor <= 0) return fail(STK_ERR_BAD_ARG, "divisor must be positive (got %d)", divisor);
+  if (!out) return fail(STK_ERR_BAD_ARG, "null output");
+  const size_t row = (size_t)c->cfg.width * c->cfg.channels * sizeof(float);
+  if (out_pitch < row) return fail(STK_ERR_BAD_ARG, "out_pitch %zu < row bytes %zu", out_pitch, row);
+  {
+    std::lock_guard<std::mutex> g(c->mu);
+    rc = sync_all(c);
+    if (rc) return rc;
+    if (!c->d_out) CU(cudaMalloc((void**)&c->d_out, c->acc_floats * sizeof(float)));
+    const float* used[16];
+    int n = 0;
+    for (auto& ln : c->lanes) if (ln.acc_used) used[n++] = ln.acc;
+    rc = lane_sum(c, c->d_out, used, n, true, divisor, c->lanes[0].stream);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(c->lanes[0].stream));
+  }
+  CU(cudaMemcpy2D(out, out_pitch, c->d_out, row, row, c->cfg.height, cudaMemcpyDeviceToHost));
+  return STK_OK;
+}
+
+int stk_ecc_reset(stk_ecc_ctx* c) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> g(c->mu);
+  for (auto& ln : c->lanes) { CU(cudaStreamSynchronize(ln.stream)); ln.acc_used = false; }
+  c->results.clear();
+  c->states_used = 0;
+  c->iter_launches_counted = 0;
+  c->launches = 0;
+  c->next_lane = 0;
+  c->have_ref = false;
+  return STK_OK;
+}
+
+int stk_ecc_launch_count(stk_ecc_ctx* c, int64_t* launches) {
+  if (!c || !launches) return fail(STK_ERR_BAD_ARG, "null argument");
+  *launches = c->launches.load();
+  return STK_OK;
+}
+
+/* ---- single stages ----------------------------------------------------------------------------------- */
+int stk_prep_grey_blur(const uint8_t* bgr, size_t pitch, int width, int height, int channels, int ksize,
+                       int device, float* out, size_t out_pitch) {
+  if (!bgr || !out) return fail(STK_ERR_BAD_ARG, "null argument");
+  stk_ecc_config cfg = {};
+  cfg.width = width; cfg.height = height; cfg.channels = channels;
+  cfg.motion_type = STK_MOTION_TRANSLATION; cfg.criteria_type = STK_TERM_COUNT; cfg.max_count = 1;
+  cfg.gauss_filt_size = ksize; cfg.device = device; cfg.lanes = 1; cfg.seed_reference = 0; cfg.align = 1;
+  if (out_pitch < (size_t)width * sizeof(float)) return fail(STK_ERR_BAD_ARG, "out_pitch too small");
+  stk_ecc_ctx* c = nullptr;
+  int rc = stk_ecc_create(&cfg, &c);
+  if (rc) return rc;
+  rc = stk_ecc_set_reference(c, bgr, pitch);
+  if (rc == STK_OK) {
+    cudaError_t e = cudaMemcpy2D(out, out_pitch, c->img, (size_t)c->pitch_f * sizeof(float),
+                                 (size_t)width * sizeof(float), height, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = fail(STK_ERR_CUDA, "prep readback: %s", cudaGetErrorString(e));
+  }
+  stk_ecc_destroy(c);
+  return rc;
+}
+
+int stk_ecc_debug_iteration(stk_ecc_ctx* c, const uint8_t* bgr, size_t pitch, const float warp_in[9],
+                            double* totals, int cap, int* nv, float warp_out[9], double* rho, int* status) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  if (!bgr || !warp_in || !totals || !nv) return fail(STK_ERR_BAD_ARG, "null argument");
+  if (!c->cfg.align) return fail(STK_ERR_STATE, "context was created with align = 0");
+  if (cap < c->nv) return fail(STK_ERR_BAD_ARG, "totals capacity %d < %d", cap, c->nv);
+  std::lock_guard<std::mutex> g(c->mu);
+  if (!c->have_ref) return fail(STK_ERR_STATE, "stk_ecc_set_reference must come first");
+  Lane& ln = c->lanes[0];
+  rc = ensure_host_staging(c, ln, true);
+  if (rc) return rc;
+  rc = upload_frame(c, ln, bgr, pitch, false);
+  if (rc) return rc;
+  const size_t row = (size_t)c->cfg.width * c->cfg.channels;
+  rc = launch_prep(c, ln.d_frame, row, ln.tmpl, ln.stream);
+  if (rc) return rc;
+  const bool persp = c->cfg.motion_type == STK_MOTION_HOMOGRAPHY;
+  stk::ecc_init_kernel<<<1, 32, 0, ln.stream>>>(ln.st, persp ? 1 : 0, 1 << 30, -1.0, 0, 0);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(ln.st->m, warp_in, 9 * sizeof(float), cudaMemcpyHostToDevice, ln.stream));
+  double* d_tot = nullptr;
+  CU(cudaMalloc((void**)&d_tot, sizeof(double) * c->nv));
+  stk::EccIterParams ip = iter_params(c, ln, false);
+  ip.totals_out = d_tot;
+  void* args[] = {&ip};
+  cudaError_t e = cudaLaunchKernel(iter_kernel(c->cfg.motion_type), dim3(c->n_tiles), dim3(stk::kEccThreads), args, 0, ln.stream);
+  stk::EccState hs;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(totals, d_tot, sizeof(double) * c->nv, cudaMemcpyDeviceToHost, ln.stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&hs, ln.st, sizeof hs, cudaMemcpyDeviceToHost, ln.stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ln.stream);
+  cudaFree(d_tot);
+  if (e != cudaSuccess) return fail(STK_ERR_CUDA, "debug iteration: %s", cudaGetErrorString(e));
+  *nv = c->nv;
+  if (warp_out) for (int i = 0; i < 9; ++i) warp_out[i] = hs.m[i];
+  if (rho) *rho = hs.rho;
+  if (status) *status = hs.status;
+  return STK_OK;
+}
+
+/* ---- Tenengrad ------------------------------------------------------------------------------------ */
+static int tenengrad_taps(int ksize, stk::TenengradParams& p) {
+  memset(p.dtap, 0, sizeof p.dtap);
+  memset(p.stap, 0, sizeof p.stap);
+  switch (ksize) {   // getDerivKernels(dx = 1, dy = 0, ksize)
+    case 1: { const int d[] = {-1, 0, 1}, s[] = {0, 1, 0}; p.radius = 1; memcpy(p.dtap, d, sizeof d); memcpy(p.stap, s, sizeof s); break; }
+    case 3: { const int d[] = {-1, 0, 1}, s[] = {1, 2, 1}; p.radius = 1; memcpy(p.dtap, d, sizeof d); memcpy(p.stap, s, sizeof s); break; }
+    case 5: { const int d[] = {-1, -2, 0, 2, 1}, s[] = {1, 4, 6, 4, 1}; p.radius = 2; memcpy(p.dtap, d, sizeof d); memcpy(p.stap, s, sizeof s); break; }
+    case 7: { const int d[] = {-1, -4, -5, 0, 5, 4, 1}, s[] = {1, 6, 15, 20, 15, 6, 1}; p.radius = 3; memcpy(p.dtap, d, sizeof d); memcpy(p.stap, s, sizeof s); break; }
+    default: return fail(STK_ERR_BAD_ARG, "Kernel size must be 1, 3, 5, or 7");
+  }
+  return STK_OK;
+}
+
+int stk_tenengrad_batch_device(const uint8_t* d_imgs, size_t frame_stride, size_t pitch, int width, int height,
+                               int channels, int ksize, int n, int device, double* out) {
+  stk::TenengradParams p = {};
+  int rc = tenengrad_taps(ksize, p);
+  if (rc) return rc;
+  if (!d_imgs || !out || n <= 0) return fail(STK_ERR_BAD_ARG, "null/empty argument");
+  if (width <= 0 || height <= 0) return fail(STK_ERR_BAD_ARG, "bad size");
+  if (channels != 1 && channels != 3 && channels != 4) return fail(STK_ERR_UNSUPPORTED, "channels must be 1, 3 or 4");
+  if (pitch < (size_t)width * channels) return fail(STK_ERR_BAD_ARG, "pitch too small");
+  if (device >= 0) CU(cudaSetDevice(device));
+  unsigned long long* d_sums = nullptr;
+  CU(cudaMalloc((void**)&d_sums, sizeof(unsigned long long) * n));
+  cudaError_t e = cudaMemset(d_sums, 0, sizeof(unsigned long long) * n);
+  std::vector<unsigned long long> h(n);
+  if (e == cudaSuccess) {
+    p.src = d_imgs; p.frame_stride = frame_stride; p.pitch = pitch;
+    p.width = width; p.height = height; p.channels = channels; p.sums = d_sums;
+    for (int z0 = 0; z0 < n && e == cudaSuccess; z0 += 32768) {
+      stk::TenengradParams q = p;
+      q.src = d_imgs + (size_t)z0 * frame_stride;
+      q.sums = d_sums + z0;
+      dim3 grid((width + stk::kTenTW - 1) / stk::kTenTW, (height + stk::kTenTH - 1) / stk::kTenTH, std::min(32768, n - z0));
+      stk::tenengrad_kernel<<<grid, stk::kTenThreads>>>(q);
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(h.data(), d_sums, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost);
+  }
+  cudaFree(d_sums);
+  if (e != cudaSuccess) return fail(STK_ERR_CUDA, "tenengrad: %s", cudaGetErrorString(e));
+  const double scale = 1.0 / ((double)width * (double)height);
+  for (int i = 0; i < n; ++i) out[i] = (double)h[i] * scale;   // cv::mean: exact integer sum * (1.0 / N)
+  return STK_OK;
+}
+
+int stk_tenengrad_device(const uint8_t* d_img, size_t pitch, int width, int height, int channels, int ksize,
+                         int device, double* out) {
+  return stk_tenengrad_batch_device(d_img, 0, pitch, width, height, channels, ksize, 1, device, out);
+}
+
+int stk_tenengrad(const uint8_t* img, size_t pitch, int width, int height, int channels, int ksize, int device,
+                  double* out) {
+  stk::TenengradParams p = {};
+  int rc = tenengrad_taps(ksize, p);
+  if (rc) return rc;
+  if (!img || !out) return fail(STK_ERR_BAD_ARG, "null argument");
+  if (width <= 0 || height <= 0) return fail(STK_ERR_BAD_ARG, "bad size");
+  if (channels != 1 && channels != 3 && channels != 4) return fail(STK_ERR_UNSUPPORTED, "channels must be 1, 3 or 4");
+  const size_t row = (size_t)width * channels;
+  if (pitch < row) return fail(STK_ERR_BAD_ARG, "pitch too small");
+  if (device >= 0) CU(cudaSetDevice(device));
+  uint8_t* d = nullptr;
+  CU(cudaMalloc((void**)&d, row * height));
+  cudaError_t e = cudaMemcpy2D(d, row, img, pitch, row, height, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(d); return fail(STK_ERR_CUDA, "tenengrad upload: %s", cudaGetErrorString(e)); }
+  rc = stk_tenengrad_batch_device(d, 0, row, width, height, channels, ksize, 1, -1, out);
+  cudaFree(d);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,151 @@
+// K4 — final warp + accumulate, and K5 — lane sum + scale.
+//
+// K4 replaces, per frame, Mat::convert_to(CV_32F, 1/255) (/root/reference/src/utils.rs:133),
+// imgproc::warp_affine | warp_perspective(INTER_LINEAR, BORDER_CONSTANT) and the MatExpr `acc + warped`
+// (/root/reference/src/lib.rs:780-814; keypoint_match tail :289-316).  The f32 colour frame and the
+// warped frame are never materialised: the kernel gathers the 8-bit source, converts the four taps,
+// interpolates and adds into the f32 accumulator.  Algorithmic traffic 3N (u8 gather) + 12N + 12N.
+//
+// Bit-exactness vs OpenCV (oracle/restate.py::warp_linear, pinned against cv2): destination -> source
+// coordinates in f64 with OpenCV's operation order (no FMA contraction), quantised to 1/32 px
+// (perspective: round-half-even of 32*u, 64-px column blocks; affine: 10-bit fixed point), weights
+// from the 5-bit fractions, value = s00*w00 + s01*w01 + s10*w10 + s11*w11 summed left to right in f32,
+// taps outside the source replaced by the border value.
+//
+// K5 replaces Rayon's try_reduce of the per-thread partial sums and the final MatExpr `/ n`
+// (/root/reference/src/lib.rs:819-839, :339-346): out = (sum over lanes) * float(1/n).
+#pragma once
+#include "common.cuh"
+
+namespace stk {
+
+struct WarpAccParams {
+  const uint8_t* src;     // u8 interleaved
+  size_t src_pitch;
+  float* acc;             // f32 interleaved, width*channels floats per row, dense
+  int width, height;      // destination size (== accumulator size)
+  int src_width, src_height;
+  const double* inv_ptr;  // device pointer to the inverse map (ECC path), or null -> inv[]
+  const int* status_ptr;  // device pointer to the frame's ECC status (skip when != 0), or null
+  double inv[9];
+  float border[4];
+  int store;              // 1: acc = v (first frame on this lane), 0: acc += v
+};
+
+constexpr int kWarpBX = 32, kWarpBY = 8;
+
+template <int C, bool PERSP>
+__global__ void __launch_bounds__(kWarpBX * kWarpBY) warp_accumulate_kernel(const WarpAccParams p) {
+  if (p.status_ptr && *p.status_ptr != 0) return;
+  const int x = blockIdx.x * kWarpBX + threadIdx.x;
+  const int y = blockIdx.y * kWarpBY + threadIdx.y;
+  if (x >= p.width || y >= p.height) return;
+  double m[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) m[i] = p.inv_ptr ? p.inv_ptr[i] : p.inv[i];
+
+  int xq, yq;
+  if (PERSP) {
+    // WarpPerspectiveInvoker: X0/Y0/W0 at the start of the 64-px column block, then + M*x1
+    const int bw = min(64, p.width);
+    const int xb = (x / bw) * bw;
+    const double xbd = (double)xb, x1 = (double)(x - xb), yd = (double)y;
+    const double X0 = __dadd_rn(__dadd_rn(__dmul_rn(m[0], xbd), __dmul_rn(m[1], yd)), m[2]);
+    const double Y0 = __dadd_rn(__dadd_rn(__dmul_rn(m[3], xbd), __dmul_rn(m[4], yd)), m[5]);
+    const double W0 = __dadd_rn(__dadd_rn(__dmul_rn(m[6], xbd), __dmul_rn(m[7], yd)), m[8]);
+    double W = __dadd_rn(W0, __dmul_rn(m[6], x1));
+    W = (W != 0.0) ? __ddiv_rn((double)kInterTab, W) : 0.0;
+    const double fX = fmax(-2147483648.0, fmin(2147483647.0, __dmul_rn(__dadd_rn(X0, __dmul_rn(m[0], x1)), W)));
+    const double fY = fmax(-2147483648.0, fmin(2147483647.0, __dmul_rn(__dadd_rn(Y0, __dmul_rn(m[3], x1)), W)));
+    xq = __double2int_rn(fX);
+    yq = __double2int_rn(fY);
+  } else {
+    const double xd = (double)x, yd = (double)y;
+    const int adelta = __double2int_rn(__dmul_rn(__dmul_rn(m[0], xd), kAbScale));
+    const int bdelta = __double2int_rn(__dmul_rn(__dmul_rn(m[3], xd), kAbScale));
+    const int X0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(m[1], yd), m[2]), kAbScale)) + 16;
+    const int Y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(m[4], yd), m[5]), kAbScale)) + 16;
+    xq = (int)((unsigned)X0 + (unsigned)adelta) >> (kAbBits - kInterBits);
+    yq = (int)((unsigned)Y0 + (unsigned)bdelta) >> (kAbBits - kInterBits);
+  }
+  // integer part is stored as short in OpenCV's map (saturate_cast<short>)
+  const int sx = max(-32768, min(32767, xq >> kInterBits));
+  const int sy = max(-32768, min(32767, yq >> kInterBits));
+  const float ax = (float)(xq & (kInterTab - 1)) * (1.f / kInterTab);
+  const float ay = (float)(yq & (kInterTab - 1)) * (1.f / kInterTab);
+  const float w00 = __fmul_rn(1.f - ay, 1.f - ax), w01 = __fmul_rn(1.f - ay, ax);
+  const float w10 = __fmul_rn(ay, 1.f - ax), w11 = __fmul_rn(ay, ax);
+
+  const int sw = p.src_width, sh = p.src_height;
+  float v[C];
+  if (sx >= sw || sx + 1 < 0 || sy >= sh || sy + 1 < 0) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) v[c] = p.border[c];
+  } else {
+    const bool x0in = (unsigned)sx < (unsigned)sw, x1in = (unsigned)(sx + 1) < (unsigned)sw;
+    const bool y0in = (unsigned)sy < (unsigned)sh, y1in = (unsigned)(sy + 1) < (unsigned)sh;
+    const uint8_t* r0 = p.src + (ptrdiff_t)sy * (ptrdiff_t)p.src_pitch + (ptrdiff_t)sx * C;
+    const uint8_t* r1 = r0 + p.src_pitch;
+    const float k255 = (float)(1.0 / 255.0);
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float s00 = (y0in && x0in) ? __fmul_rn((float)__ldg(r0 + c), k255) : p.border[c];
+      const float s01 = (y0in && x1in) ? __fmul_rn((float)__ldg(r0 + C + c), k255) : p.border[c];
+      const float s10 = (y1in && x0in) ? __fmul_rn((float)__ldg(r1 + c), k255) : p.border[c];
+      const float s11 = (y1in && x1in) ? __fmul_rn((float)__ldg(r1 + C + c), k255) : p.border[c];
+      v[c] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s00, w00), __fmul_rn(s01, w01)), __fmul_rn(s10, w10)),
+                       __fmul_rn(s11, w11));
+    }
+  }
+  float* a = p.acc + ((size_t)y * p.width + x) * C;
+  if (p.store) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) a[c] = v[c];
+  } else {
+#pragma unroll
+    for (int c = 0; c < C; ++c) a[c] = __fadd_rn(a[c], v[c]);
+  }
+}
+
+// frame 0 enters the stack unwarped: acc = u8 * (1/255)        (/root/reference/src/lib.rs:752-754)
+__global__ void seed_accumulator_kernel(const uint8_t* src, size_t src_pitch, float* acc, int row_elems,
+                                        int height) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (i >= row_elems || y >= height) return;
+  acc[(size_t)y * row_elems + i] = __fmul_rn((float)__ldg(src + (size_t)y * src_pitch + i), (float)(1.0 / 255.0));
+}
+
+struct LaneSumParams {
+  const float* lanes[16];
+  int n_lanes;
+  float* out;
+  size_t n;         // floats
+  float scale;      // float(1/divisor), or 1
+  int apply_scale;
+};
+
+// out[i] = ((l0[i] + l1[i]) + l2[i] ...) [* scale]; n_lanes may be 0 (zeros).  `out` may alias lanes[0].
+__global__ void lane_sum_scale_kernel(const LaneSumParams p) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t n4 = p.n / 4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.n_lanes > 0) s = reinterpret_cast<const float4*>(p.lanes[0])[i];
+    for (int l = 1; l < p.n_lanes; ++l) {
+      const float4 t = reinterpret_cast<const float4*>(p.lanes[l])[i];
+      s.x = __fadd_rn(s.x, t.x); s.y = __fadd_rn(s.y, t.y); s.z = __fadd_rn(s.z, t.z); s.w = __fadd_rn(s.w, t.w);
+    }
+    if (p.apply_scale) { s.x = __fmul_rn(s.x, p.scale); s.y = __fmul_rn(s.y, p.scale); s.z = __fmul_rn(s.z, p.scale); s.w = __fmul_rn(s.w, p.scale); }
+    reinterpret_cast<float4*>(p.out)[i] = s;
+  }
+  // tail
+  for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += stride) {
+    float s = p.n_lanes > 0 ? p.lanes[0][i] : 0.f;
+    for (int l = 1; l < p.n_lanes; ++l) s = __fadd_rn(s, p.lanes[l][i]);
+    if (p.apply_scale) s = __fmul_rn(s, p.scale);
+    p.out[i] = s;
+  }
+}
+
+}  // namespace stk

@@ -467,7 +467,7 @@ def _sep_corr_int(img: np.ndarray, kx, ky) -> np.ndarray:
 
 def sharpness_tenengrad(grey_u8: np.ndarray, ksize: int) -> float:
     """Sobel dx, dy in CV_64F, mean(gx^2 + gy^2).  All values are integers < 2^53 so the f64 result is
-    exact: uint64 sum / N."""
+    exact; cv::mean multiplies it by the rounded reciprocal: sum * (1.0 / N)."""
     if ksize not in SOBEL_KERNELS:
         raise ValueError("Kernel size must be 1, 3, 5, or 7")      # StackerError::InvalidParams
     d, s = SOBEL_KERNELS[ksize]
@@ -475,7 +475,7 @@ def sharpness_tenengrad(grey_u8: np.ndarray, ksize: int) -> float:
     gx = _sep_corr_int(g, d, s)
     gy = _sep_corr_int(g, s, d)
     total = int((gx * gx + gy * gy).sum())
-    return float(total) / float(grey_u8.size)
+    return float(total) * (1.0 / float(grey_u8.size))
 
 
 def rank_by_sharpness(values):

@@ -1,0 +1,55 @@
+"""Generates tests/golden/*.npz with the REAL OpenCV (cv2) on seeded synthetic inputs.
+
+Run in a container that has cv2 (this image: 4.13.0; the reference pins OpenCV 4.12.0):
+    python tests/golden/make_golden.py
+The vectors pin the oracle (oracle/restate.py) where cv2 is unavailable, and are used by the GPU suite
+as a second, committed reference.  Inputs are regenerated from the seeds by oracle/synth.py, so only the
+cv2 OUTPUTS are stored."""
+import os
+import sys
+
+import numpy as np
+import cv2
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from oracle import synth, cvref  # noqa: E402
+
+
+def ecc_cases():
+    out = {}
+    for motion in (0, 1, 2, 3):
+        st = synth.Stack(256, 192, 3, motion, seed=100 + motion)
+        frames = st.frames()
+        stack, warps, rhos = cvref.ecc_match(frames, motion, 5000, 1e-5, 5, workers=1)
+        out[f"m{motion}_warps"] = np.stack([np.vstack([w, [0, 0, 1]]) if w.shape[0] == 2 else w for w in warps[1:]]).astype(np.float32)
+        out[f"m{motion}_rhos"] = np.array(rhos[1:], np.float64)
+        out[f"m{motion}_stack8"] = np.rint(stack * 255.0).astype(np.uint8)
+    return out
+
+
+def primitive_cases():
+    out = {}
+    st = synth.Stack(200, 150, 2, 3, seed=55)
+    f0, f1 = st.frames()
+    out["grey"] = cv2.cvtColor(f0, cv2.COLOR_BGR2GRAY)
+    for k in (3, 5, 7, 9):
+        out[f"blur{k}"] = cv2.GaussianBlur(out["grey"].astype(np.float32), (k, k), 0)
+    rng = np.random.default_rng(8)
+    hm = synth.random_warp(rng, 3, 200, 150)
+    hm[:2, 2] += (13.3, -7.7)
+    am = synth.random_warp(rng, 2, 200, 150)[:2]
+    f32 = f1.astype(np.float32) * np.float32(1 / 255.0)
+    out["H"] = hm
+    out["A"] = am
+    out["warp_persp"] = cv2.warpPerspective(f32, hm, (200, 150), flags=cv2.INTER_LINEAR)
+    out["warp_affine"] = cv2.warpAffine(f32, am, (200, 150), flags=cv2.INTER_LINEAR)
+    for k in (1, 3, 5, 7):
+        out[f"teng{k}"] = np.float64(cvref.sharpness_tenengrad(out["grey"], k))
+    return out
+
+
+if __name__ == "__main__":
+    np.savez_compressed(os.path.join(HERE, "ecc_256x192.npz"), **ecc_cases())
+    np.savez_compressed(os.path.join(HERE, "primitives_200x150.npz"), **primitive_cases())
+    print("cv2", cv2.__version__, "golden vectors written")

@@ -1,0 +1,314 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle (oracle/restate.py,
+itself pinned to cv2) and against cv2 directly where it is installed.
+
+Bars (BASELINE.json north_star): warp matrices within 0.05 px corner displacement, 8-bit stack
+max-abs-diff <= 1 (PSNR >= 50 dB), identical sharpness ordering; byte/integer/sampling work bit-exact."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import restate as R
+from oracle import synth
+from parity_util import assert_stack_parity, psnr8
+
+pytestmark = pytest.mark.gpu
+
+MOTIONS = [0, 1, 2, 3]
+
+
+# ---- K1: grey + blur, bit-exact ------------------------------------------------------------------------
+@pytest.mark.parametrize("size", [(320, 240), (257, 131), (64, 40), (1000, 37)])
+@pytest.mark.parametrize("k", [1, 3, 5, 7, 9])
+def test_prep_bit_exact(pkg, size, k):
+    w, h = size
+    rng = np.random.default_rng(w * 31 + k)
+    frame = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    got = pkg.prep_grey_blur(frame, k, device=0)
+    want = R.gaussian_blur_f32(R.bgr2gray_u8(frame).astype(np.float32), k)
+    assert np.array_equal(got, want)
+
+
+def test_prep_large_kernel_close(pkg):
+    rng = np.random.default_rng(5)
+    frame = rng.integers(0, 256, (96, 160, 3), dtype=np.uint8)
+    for k in (11, 15, 31):
+        got = pkg.prep_grey_blur(frame, k, device=0)
+        want = R.gaussian_blur_f32(R.bgr2gray_u8(frame).astype(np.float32), k)
+        assert np.abs(got - want).max() <= 1e-4
+
+
+def test_prep_bgra(pkg):
+    rng = np.random.default_rng(6)
+    frame = rng.integers(0, 256, (50, 70, 4), dtype=np.uint8)
+    got = pkg.prep_grey_blur(frame, 5, device=0)
+    want = R.gaussian_blur_f32(R.bgr2gray_u8(frame[..., :3]).astype(np.float32), 5)
+    assert np.array_equal(got, want)
+
+
+# ---- K4: final warp + accumulate, bit-exact ------------------------------------------------------------
+def _rand_h(rng, w, h, big=False):
+    g = synth.random_warp(rng, 3, w, h)
+    if big:
+        g[:2, 2] += rng.uniform(-0.4, 0.4, 2) * (w, h)
+        g[:2, :2] += rng.uniform(-0.1, 0.1, (2, 2))
+    return g
+
+
+@pytest.mark.parametrize("size", [(320, 240), (333, 97), (64, 64), (31, 200)])
+@pytest.mark.parametrize("big", [False, True])
+def test_warp_only_matches_oracle_bit_exact(pkg, size, big):
+    """keypoint_match tail: frame 0 unwarped + warpPerspective(frame_i, H_i f64) summed, / n."""
+    w, h = size
+    rng = np.random.default_rng(w + h + big)
+    frames = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for _ in range(4)]
+    hs = [_rand_h(rng, w, h, big) for _ in range(3)]
+    with pkg.EccStack(w, h, 3, None, device=0, lanes=1) as st:     # one lane: fixed summation order
+        st.set_reference(frames[0])
+        for f, hm in zip(frames[1:], hs):
+            st.submit_warp(f, hm)
+        got = st.finish(4)
+    acc = R.to_f32_unit(frames[0])
+    for f, hm in zip(frames[1:], hs):
+        acc = acc + R.warp_linear(R.to_f32_unit(f), hm, w, h, perspective=True, inverse_map=False)
+    want = acc * np.float32(1.0 / 4)
+    assert np.array_equal(got, want)
+
+
+def test_warp_only_border_value_and_bgra(pkg):
+    w, h = 120, 90
+    rng = np.random.default_rng(3)
+    frames = [rng.integers(0, 256, (h, w, 4), dtype=np.uint8) for _ in range(2)]
+    hm = _rand_h(rng, w, h, True)
+    bv = (0.25, 0.5, 0.75, 1.0)
+    with pkg.EccStack(w, h, 4, None, device=0, lanes=1) as st:
+        st.set_reference(frames[0])
+        st.submit_warp(frames[1], hm, pkg.BORDER_CONSTANT, bv)
+        got = st.finish(2)
+    want = (R.to_f32_unit(frames[0]) +
+            R.warp_linear(R.to_f32_unit(frames[1]), hm, w, h, True, False, border_value=np.array(bv))) * np.float32(0.5)
+    assert np.array_equal(got, want)
+
+
+def test_warp_only_vs_cv2(pkg, have_cv2):
+    if not have_cv2:
+        pytest.skip("cv2 not installed")
+    import cv2
+    w, h = 400, 300
+    rng = np.random.default_rng(9)
+    frames = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for _ in range(3)]
+    hs = [_rand_h(rng, w, h, i == 1) for i in range(2)]
+    with pkg.EccStack(w, h, 3, None, device=0, lanes=1) as st:
+        st.set_reference(frames[0])
+        for f, hm in zip(frames[1:], hs):
+            st.submit_warp(f, hm)
+        got = st.finish(3)
+    acc = frames[0].astype(np.float32) * np.float32(1 / 255.0)
+    for f, hm in zip(frames[1:], hs):
+        acc = acc + cv2.warpPerspective(f.astype(np.float32) * np.float32(1 / 255.0), hm, (w, h), flags=cv2.INTER_LINEAR)
+    assert np.array_equal(got, acc * np.float32(1.0 / 3))
+
+
+# ---- K2: one iteration's reductions against the oracle ---------------------------------------------------
+def _expected_totals(motion, tmpl, img, m32):
+    """The NV sums in the kernel's layout (csrc/ecc_iter.cuh Layout<>), from the oracle's planes in f64."""
+    hs, ws = tmpl.shape
+    persp = motion == 3
+    gxp, gyp = R.central_gradients(img)
+    w_ = R.warp_linear(img, m32, ws, hs, persp, True).astype(np.float64)
+    gx = R.warp_linear(gxp, m32, ws, hs, persp, True).astype(np.float64)
+    gy = R.warp_linear(gyp, m32, ws, hs, persp, True).astype(np.float64)
+    mk = R.warp_mask_nearest(m32, ws, hs, img.shape[1], img.shape[0], persp).astype(np.float64)
+    t_ = tmpl.astype(np.float64)
+    X = np.broadcast_to(np.arange(ws, dtype=np.float64)[None, :], (hs, ws))
+    Y = np.broadcast_to(np.arange(hs, dtype=np.float64)[:, None], (hs, ws))
+    m = np.asarray(m32, np.float64)
+    if motion == 0:
+        g, kron = [gx, gy], False
+    elif motion == 1:
+        c, s = m[0, 0], m[1, 0]
+        g, kron = [gx * (-X * s - Y * c) + gy * (X * c - Y * s), gx, gy], False
+    elif motion == 2:
+        g, kron = [gx, gy], True
+    else:
+        den = X * m[2, 0] + Y * m[2, 1] + 1.0
+        hx = -(X * m[0, 0] + Y * m[0, 1] + m[0, 2]) / den
+        hy = -(X * m[1, 0] + Y * m[1, 1] + m[1, 2]) / den
+        a, b = gx / den, gy / den
+        g, kron = [a, b, hx * a + hy * b], True
+    out = [mk.sum(), (mk * w_).sum(), (mk * w_ * w_).sum(), (mk * t_).sum(), (mk * t_ * t_).sum(), (mk * w_ * t_).sum()]
+    qm = [np.ones_like(X), X, Y, X * X, X * Y, Y * Y] if kron else [np.ones_like(X)]
+    zm = [np.ones_like(X), X, Y] if kron else [np.ones_like(X)]
+    for i in range(len(g)):
+        for j in range(i, len(g)):
+            out += [(g[i] * g[j] * q).sum() for q in qm]
+    for z in (w_, mk, mk * t_):
+        for gi in g:
+            out += [(gi * z * q).sum() for q in zm]
+    return np.array(out)
+
+
+@pytest.mark.parametrize("motion", MOTIONS)
+@pytest.mark.parametrize("size", [(320, 240), (389, 211)])
+def test_iteration_sums_match_oracle(pkg, motion, size):
+    w, h = size
+    st_ = synth.Stack(w, h, 2, motion, seed=20 + motion)
+    f0, f1 = st_.frames()
+    # a matrix near (not at) the truth, so the warp leaves the frame on one side
+    rng = np.random.default_rng(motion)
+    g = st_.truth[1].copy()
+    g[:2, 2] += rng.uniform(-1.5, 1.5, 2)
+    m32 = g.astype(np.float32)
+    if motion != 3:
+        m32[2] = (0, 0, 1)
+    if motion == 1:   # keep it a rotation
+        th = math.asin(float(m32[1, 0]))
+        m32[0, 0] = m32[1, 1] = np.float32(math.cos(th)); m32[0, 1] = -m32[1, 0]
+    params = pkg.EccMatchParameters(pkg.MotionType(motion), 50, 1e-5, 5)
+    with pkg.EccStack(w, h, 3, params, device=0, lanes=1) as st:
+        st.set_reference(f0)
+        tot, m_out, rho, status = st.debug_iteration(f1, m32)
+    tmpl = R.gaussian_blur_f32(R.bgr2gray_u8(f1).astype(np.float32), 5)
+    img = R.gaussian_blur_f32(R.bgr2gray_u8(f0).astype(np.float32), 5)
+    mm = m32 if motion == 3 else m32[:2]
+    want = _expected_totals(motion, tmpl, img, mm)
+    assert tot.shape == want.shape
+    scale = np.maximum(np.abs(want), 1e-3 * np.abs(want).max() if motion < 2 else 0) + 1e-12
+    rel = np.abs(tot - want) / np.maximum(np.abs(want), 1e-30)
+    assert tot[0] == want[0], (tot[0], want[0])       # the masked pixel count is exact
+    big = np.abs(want) > 1e-6 * np.abs(want).max()
+    assert rel[big].max() < 2e-4, (np.argmax(rel * big), rel[big].max())
+    # and the update the kernel derives from its own sums equals the oracle's epilogue on the oracle's sums
+    sums = R.ecc_sums(motion, tmpl, img, *R.central_gradients(img), mm)
+    rho_want, m_want = R.ecc_epilogue(motion, sums, mm)
+    assert status == 0
+    assert abs(rho - rho_want) < 1e-6
+    assert synth.corner_displacement(m_out if motion == 3 else m_out[:2], m_want, w, h) < 2e-3
+
+
+# ---- the whole path: ecc_match vs oracle / cv2 -----------------------------------------------------------
+@pytest.mark.parametrize("motion", MOTIONS)
+def test_ecc_match_small_vs_oracle(pkg, motion):
+    w, h = 320, 240
+    stack = synth.Stack(w, h, 4, motion, seed=47 + motion)
+    frames = stack.frames()
+    params = pkg.EccMatchParameters(pkg.MotionType(motion), 5000, 1e-5, 5)
+    got, res = pkg.ecc_match(frames, params, None, device=0, return_details=True)
+    want, warps, iters = R.ecc_match(frames, motion, 5000, 1e-5, 5)
+    assert [r["status"] for r in res] == [0, 0, 0]
+    for r, wm, it in zip(res, warps[1:], iters[1:]):
+        mine = r["warp"] if motion == 3 else r["warp"][:2]
+        assert synth.corner_displacement(mine, wm, w, h) <= 0.05
+        assert it > 40 or abs(r["iterations"] - it) <= 2
+    assert_stack_parity(got, want, warps, motion, 4)
+
+
+def test_ecc_match_config1_vs_cv2(pkg, have_cv2):
+    """BASELINE config 1: Homography, 5 x 1024x768, max_count 5000, eps 1e-5, gauss 5 (examples/main.rs:105-114)."""
+    if not have_cv2:
+        pytest.skip("cv2 not installed")
+    from oracle import cvref
+    stack = synth.config_stack(1)
+    frames = stack.frames()
+    params = pkg.EccMatchParameters(pkg.MotionType.Homography, 5000, 1e-5, 5)
+    got, res = pkg.ecc_match(frames, params, None, device=0, return_details=True)
+    want, warps, _ = cvref.ecc_match(frames, 3, 5000, 1e-5, 5)
+    for r, wm in zip(res, warps[1:]):
+        assert synth.corner_displacement(r["warp"], wm, 1024, 768) <= 0.05
+    g8, w8 = np.rint(got * 255.0), np.rint(want * 255.0)
+    assert np.abs(g8 - w8).max() <= 1
+    assert psnr8(g8, w8) >= 50.0
+
+
+def test_ecc_match_config2_shape_vs_cv2(pkg, have_cv2):
+    """BASELINE config 2 (Euclidean 1920x1080) on 4 of its 16 frames."""
+    if not have_cv2:
+        pytest.skip("cv2 not installed")
+    from oracle import cvref
+    frames = synth.config_stack(2, n_frames=4).frames()
+    params = pkg.EccMatchParameters(pkg.MotionType.Euclidean, 5000, 1e-5, 5)
+    got, res = pkg.ecc_match(frames, params, None, device=0, return_details=True)
+    want, warps, _ = cvref.ecc_match(frames, 1, 5000, 1e-5, 5)
+    for r, wm in zip(res, warps[1:]):
+        assert synth.corner_displacement(r["warp"][:2], wm, 1920, 1080) <= 0.05
+    assert_stack_parity(got, want, warps, 1, 4)
+
+
+def test_fixed_iteration_count_and_eps_only(pkg):
+    """TermCriteria flag semantics (src/utils.rs:159-170): COUNT only -> exactly max_count iterations;
+    EPS only -> OpenCV's 200-iteration cap with the eps test."""
+    w, h = 256, 192
+    frames = synth.Stack(w, h, 2, 2, seed=77).frames()
+    _, res = pkg.ecc_match(frames, pkg.EccMatchParameters(pkg.MotionType.Affine, 7, None, 3), None, device=0, return_details=True)
+    assert res[0]["iterations"] == 7
+    _, res = pkg.ecc_match(frames, pkg.EccMatchParameters(pkg.MotionType.Affine, None, 1e-3, 3), None, device=0, return_details=True)
+    _, _, it = R.find_transform_ecc(R.bgr2gray_u8(frames[1]), R.bgr2gray_u8(frames[0]), 2, R.term_criteria(None, 1e-3), 3)
+    assert abs(res[0]["iterations"] - it) <= 1 and res[0]["iterations"] < 200
+
+
+def test_ecc_errors(pkg):
+    w, h = 128, 96
+    frames = synth.Stack(w, h, 2, 0, seed=5).frames()
+    with pytest.raises(pkg.NotEnoughFiles):
+        pkg.ecc_match([], pkg.EccMatchParameters(pkg.MotionType.Affine, 10, 1e-4, 5))
+    with pytest.raises(pkg.OpenCvError):      # neither COUNT nor EPS: CV_Assert inside findTransformECC
+        pkg.ecc_match(frames, pkg.EccMatchParameters(pkg.MotionType.Affine, None, None, 5), device=0)
+    # uncorrelated images: OpenCV raises StsNoConv -> the whole call fails (src/lib.rs:777)
+    rng = np.random.default_rng(0)
+    flat = np.full((h, w, 3), 7, np.uint8)
+    with pytest.raises(pkg.OpenCvError):
+        pkg.ecc_match([frames[0], flat], pkg.EccMatchParameters(pkg.MotionType.Translation, 20, 1e-4, 5), device=0)
+    # a single frame is legal: the stack is frame 0 itself
+    out = pkg.ecc_match(frames[:1], pkg.EccMatchParameters(pkg.MotionType.Translation, 20, 1e-4, 5), device=0)
+    assert np.array_equal(out, R.to_f32_unit(frames[0]))
+
+
+def test_lanes_and_device_resident_input(pkg):
+    """Same stack through 1 lane / 4 lanes, host and device-resident frames: identical warps, stack equal
+    up to f32 summation order."""
+    import torch
+    w, h = 320, 240
+    frames = synth.Stack(w, h, 6, 3, seed=91).frames()
+    params = pkg.EccMatchParameters(pkg.MotionType.Homography, 5000, 1e-5, 5)
+    outs, warps = [], []
+    for lanes, dev in ((1, False), (4, False), (3, True)):
+        with pkg.EccStack(w, h, 3, params, device=0, lanes=lanes) as st:
+            src = [torch.from_numpy(f).cuda() for f in frames] if dev else frames
+            st.set_reference(src[0])
+            for k, f in enumerate(src[1:]):
+                st.submit(f, tag=k + 1)
+            outs.append(st.finish(len(frames)))
+            warps.append([r["warp"] for r in st.results()])
+    for ws in warps[1:]:
+        for a, b in zip(warps[0], ws):
+            assert np.array_equal(a, b)
+    for o in outs[1:]:
+        assert np.abs(o - outs[0]).max() <= 1e-6
+
+
+# ---- K6: Tenengrad, bit-identical ------------------------------------------------------------------------
+@pytest.mark.parametrize("k", [1, 3, 5, 7])
+@pytest.mark.parametrize("size", [(320, 240), (65, 33), (1000, 701)])
+def test_tenengrad_exact(pkg, k, size):
+    w, h = size
+    rng = np.random.default_rng(w + k)
+    grey = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    assert pkg.sharpness_tenengrad(grey, k, device=0) == R.sharpness_tenengrad(grey, k)
+
+
+def test_tenengrad_vs_cv2_and_ordering(pkg, have_cv2):
+    """config 3's ranking step: identical sharpness ORDER (ties included) as the reference."""
+    if not have_cv2:
+        pytest.skip("cv2 not installed")
+    from oracle import cvref
+    stack = synth.config_stack(3, n_frames=8, width=640, height=360)
+    greys = [R.bgr2gray_u8(f) for f in stack.frames()]
+    mine = [pkg.sharpness_tenengrad(g, 3, device=0) for g in greys]
+    ref = [cvref.sharpness_tenengrad(g, 3) for g in greys]
+    assert mine == ref
+    assert R.rank_by_sharpness(mine) == R.rank_by_sharpness(ref)
+
+
+def test_tenengrad_invalid_k(pkg):
+    with pytest.raises(pkg.InvalidParams):
+        pkg.sharpness_tenengrad(np.zeros((8, 8), np.uint8), 4)

@@ -1,0 +1,91 @@
+"""Host-side logic and the C-ABI surface, no GPU needed."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_term_criteria_doctest(pkg):
+    """The reference's only executed test on this path (/root/reference/src/utils.rs:148-158):
+    max_count None, epsilon Some(0.1) -> epsilon == 0.1, typ == EPS."""
+    p = pkg.EccMatchParameters(pkg.MotionType.Euclidean, None, 0.1, 3)
+    typ, mc, eps = pkg.term_criteria(p)
+    assert eps == 0.1 and typ == 2 and mc == 0
+    assert pkg.term_criteria(pkg.EccMatchParameters(pkg.MotionType.Affine, 5000, 1e-5, 5)) == (3, 5000, 1e-5)
+    assert pkg.term_criteria(pkg.EccMatchParameters(pkg.MotionType.Affine, 7, None, 5)) == (1, 7, 0.0)
+    assert pkg.term_criteria(pkg.EccMatchParameters(pkg.MotionType.Affine, None, None, 5))[0] == 0
+
+
+def test_motion_type_discriminants(pkg):
+    # opencv::video::MOTION_* (/root/reference/src/lib.rs:603-609)
+    assert [int(pkg.MotionType.Translation), int(pkg.MotionType.Euclidean), int(pkg.MotionType.Affine),
+            int(pkg.MotionType.Homography)] == [0, 1, 2, 3]
+
+
+def test_keypoint_defaults(pkg):
+    # impl Default (/root/reference/src/utils.rs:250-261)
+    d = pkg.KeyPointMatchParameters()
+    assert (d.method, d.ransac_reproj_threshold, d.match_keep_ratio, d.match_ratio, d.border_mode) == (8, 3.0, 0.75, 0.8, 0)
+    assert tuple(d.border_value) == (0.0, 0.0, 0.0, 0.0)
+
+
+def test_abi_exports_every_declared_symbol(pkg):
+    header = open(os.path.join(ROOT, "include", "stacker_cuda.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(stk_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 25
+    lib = ctypes.CDLL(pkg._ffi.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/stacker_cuda.h but not exported"
+    assert declared == set(pkg._ffi.SYMBOLS), declared ^ set(pkg._ffi.SYMBOLS)
+    assert lib.stk_abi_version() == 1
+
+
+def test_struct_layout_matches_header(pkg):
+    # stk_ecc_config: 6 int32, double, 5 int32 -> 8-byte aligned; stk_frame_result: i64, 9 f32, f64, 2 i32
+    assert ctypes.sizeof(pkg._ffi.EccConfig) == 56
+    assert pkg._ffi.EccConfig.epsilon.offset == 24
+    assert ctypes.sizeof(pkg._ffi.FrameResult) == 64
+    assert pkg._ffi.FrameResult.rho.offset == 48
+
+
+def test_errors_before_any_gpu_work(pkg):
+    with pytest.raises(pkg.NotEnoughFiles):
+        pkg.ecc_match([], pkg.EccMatchParameters(pkg.MotionType.Homography, 10, 1e-3, 5))
+    with pytest.raises(pkg.NotEnoughFiles):
+        pkg.keypoint_match([])
+    with pytest.raises(pkg.InvalidParams):
+        pkg.sharpness_tenengrad(np.zeros((8, 8), np.uint8), 2)
+    with pytest.raises(pkg.StackerError):
+        pkg.ecc_match(["/nonexistent/a.jpg"], pkg.EccMatchParameters(pkg.MotionType.Homography, 10, 1e-3, 5))
+
+
+def test_no_cpu_fallback_without_gpu(pkg):
+    """On a box without a CUDA device the product path must fail loudly, not compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(pkg.ProcessingError):
+        pkg.sharpness_tenengrad(np.zeros((16, 16), np.uint8), 3)
+    frames = [np.zeros((32, 32, 3), np.uint8)] * 2
+    with pytest.raises(pkg.ProcessingError):
+        pkg.ecc_match(frames, pkg.EccMatchParameters(pkg.MotionType.Affine, 5, 1e-3, 3))
+
+
+def test_product_package_never_imports_oracle():
+    pkg_dir = os.path.join(ROOT, "libstacker.rs_b200")
+    for dirpath, _, files in os.walk(pkg_dir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h", ".rs")):
+                src = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "import oracle" not in src and "from oracle" not in src and "oracle/" not in src.replace("oracle/restate.py", "").replace("oracle/", "oracle_") or f.endswith((".cu", ".cuh")), f
+
+
+def test_rank_by_sharpness_order():
+    from oracle import restate as R
+    # examples/main.rs:53-64: ascending sort, drop the worst, reverse -> sharpest first
+    assert R.rank_by_sharpness([5.0, 1.0, 9.0, 3.0]) == [2, 0, 3]

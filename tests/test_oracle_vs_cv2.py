@@ -1,0 +1,135 @@
+"""Pins the oracle (oracle/restate.py) to the reference's numeric engine, OpenCV, (a) live through cv2
+when it is installed and (b) through the committed cv2-generated vectors in tests/golden/.
+
+The reference's own tests hold no numeric vectors for this path; this file is what makes
+the oracle trustworthy."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import restate as R
+from oracle import synth
+from parity_util import assert_stack_parity
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def cv2():
+    return pytest.importorskip("cv2")
+
+
+# ---- golden vectors (run everywhere) -----------------------------------------------------------------------
+def test_golden_primitives():
+    g = np.load(os.path.join(GOLD, "primitives_200x150.npz"))
+    f0, f1 = synth.Stack(200, 150, 2, 3, seed=55).frames()
+    grey = R.bgr2gray_u8(f0)
+    assert np.array_equal(grey, g["grey"])
+    for k in (3, 5, 7, 9):
+        assert np.array_equal(R.gaussian_blur_f32(grey.astype(np.float32), k), g[f"blur{k}"])
+    f32 = R.to_f32_unit(f1)
+    assert np.array_equal(R.warp_linear(f32, g["H"], 200, 150, True, False), g["warp_persp"])
+    assert np.array_equal(R.warp_linear(f32, g["A"], 200, 150, False, False), g["warp_affine"])
+    for k in (1, 3, 5, 7):
+        assert R.sharpness_tenengrad(grey, k) == float(g[f"teng{k}"])
+
+
+@pytest.mark.parametrize("motion", [0, 1, 2, 3])
+def test_golden_ecc_match(motion):
+    g = np.load(os.path.join(GOLD, "ecc_256x192.npz"))
+    frames = synth.Stack(256, 192, 3, motion, seed=100 + motion).frames()
+    stack, warps, _ = R.ecc_match(frames, motion, 5000, 1e-5, 5)
+    for mine, ref in zip(warps[1:], g[f"m{motion}_warps"]):
+        assert synth.corner_displacement(mine, ref if motion == 3 else ref[:2], 256, 192) <= 5e-3
+    assert_stack_parity(stack, g[f"m{motion}_stack8"].astype(np.float32) / np.float32(255.0), warps, motion, 3)
+
+
+# ---- live cv2 checks -----------------------------------------------------------------------------------------
+def test_grey_blur_gradients_exact(cv2):
+    rng = np.random.default_rng(1)
+    bgr = rng.integers(0, 256, (97, 131, 3), dtype=np.uint8)
+    grey = R.bgr2gray_u8(bgr)
+    assert np.array_equal(grey, cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY))
+    gf = grey.astype(np.float32)
+    for k in (1, 3, 5, 7, 9):
+        assert np.array_equal(R.gaussian_taps(k), cv2.getGaussianKernel(k, 0, cv2.CV_32F).ravel())
+        assert np.array_equal(R.gaussian_blur_f32(gf, k), cv2.GaussianBlur(gf, (k, k), 0))
+    for k in (11, 15):
+        assert np.abs(R.gaussian_blur_f32(gf, k) - cv2.GaussianBlur(gf, (k, k), 0)).max() < 1e-4
+    img = R.gaussian_blur_f32(gf, 5)
+    gx, gy = R.central_gradients(img)
+    dx = np.array([[-0.5, 0, 0.5]], np.float32)
+    assert np.array_equal(gx, cv2.filter2D(img, -1, dx))
+    assert np.array_equal(gy, cv2.filter2D(img, -1, dx.T))
+
+
+@pytest.mark.parametrize("motion", [0, 1, 2, 3])
+def test_warps_bit_exact(cv2, motion):
+    rng = np.random.default_rng(10 + motion)
+    w, h = 173, 119
+    f32 = R.to_f32_unit(rng.integers(0, 256, (h, w, 3), dtype=np.uint8))
+    plane = rng.uniform(0, 255, (h, w)).astype(np.float32)
+    ones = np.ones((h, w), np.uint8)
+    for t in range(4):
+        g = synth.random_warp(rng, motion, w, h)
+        if t >= 2:
+            g[:2, 2] += rng.uniform(-60, 60, 2)
+        if motion == 3:
+            m = g.astype(np.float32)
+            assert np.array_equal(R.warp_linear(f32, m, w, h, True, False), cv2.warpPerspective(f32, m, (w, h), flags=cv2.INTER_LINEAR))
+            assert np.array_equal(R.warp_linear(plane, m, w, h, True, True),
+                                  cv2.warpPerspective(plane, m, (w, h), flags=cv2.INTER_LINEAR | cv2.WARP_INVERSE_MAP))
+            mk = cv2.warpPerspective(ones, m, (w, h), flags=cv2.INTER_NEAREST | cv2.WARP_INVERSE_MAP)
+            assert np.array_equal(R.warp_mask_nearest(m, w, h, w, h, True), mk > 0)
+            # f64 homography (keypoint_match tail)
+            assert np.array_equal(R.warp_linear(f32, g, w, h, True, False), cv2.warpPerspective(f32, g, (w, h), flags=cv2.INTER_LINEAR))
+        else:
+            m = g[:2].astype(np.float32)
+            assert np.array_equal(R.warp_linear(f32, m, w, h, False, False), cv2.warpAffine(f32, m, (w, h), flags=cv2.INTER_LINEAR))
+            assert np.array_equal(R.warp_linear(plane, m, w, h, False, True),
+                                  cv2.warpAffine(plane, m, (w, h), flags=cv2.INTER_LINEAR | cv2.WARP_INVERSE_MAP))
+            mk = cv2.warpAffine(ones, m, (w, h), flags=cv2.INTER_NEAREST | cv2.WARP_INVERSE_MAP)
+            assert np.array_equal(R.warp_mask_nearest(m, w, h, w, h, False), mk > 0)
+
+
+@pytest.mark.parametrize("motion", [0, 1, 2, 3])
+@pytest.mark.parametrize("crit", [(5000, 1e-5), (12, None)])
+def test_find_transform_ecc_vs_cv2(cv2, motion, crit):
+    from oracle import cvref
+    frames = synth.Stack(240, 180, 2, motion, seed=30 + motion).frames()
+    g0, g1 = R.bgr2gray_u8(frames[0]), R.bgr2gray_u8(frames[1])
+    rho_c, m_c = cvref.align_frame(g1, g0, motion, cvref.term_criteria(*crit), 5)
+    rho_r, m_r, _ = R.find_transform_ecc(g1, g0, motion, R.term_criteria(*crit), 5)
+    assert synth.corner_displacement(m_c, m_r, 240, 180) <= 2e-3
+    assert abs(rho_c - rho_r) < 1e-4
+
+
+def test_tenengrad_exact_vs_cv2(cv2):
+    from oracle import cvref
+    rng = np.random.default_rng(2)
+    grey = rng.integers(0, 256, (120, 200), dtype=np.uint8)
+    for k in (1, 3, 5, 7):
+        assert R.sharpness_tenengrad(grey, k) == cvref.sharpness_tenengrad(grey, k)
+    with pytest.raises(ValueError):
+        R.sharpness_tenengrad(grey, 4)
+
+
+def test_ecc_match_restatement_vs_cv2_stack(cv2):
+    from oracle import cvref
+    frames = synth.Stack(200, 150, 3, 3, seed=3).frames()
+    a, wa, _ = R.ecc_match(frames, 3, 5000, 1e-5, 5)
+    b, wb, _ = cvref.ecc_match(frames, 3, 5000, 1e-5, 5, workers=1)
+    for x, y in zip(wa[1:], wb[1:]):
+        assert synth.corner_displacement(x, y, 200, 150) <= 5e-3
+    assert_stack_parity(a, b, wb, 3, 3)
+
+
+def test_noconv_raises_like_opencv(cv2):
+    rng = np.random.default_rng(4)
+    a = rng.integers(0, 256, (64, 64), dtype=np.uint8)
+    flat = np.full((64, 64), 9, np.uint8)
+    with pytest.raises(cv2.error):
+        cv2.findTransformECC(flat, a, np.eye(2, 3, dtype=np.float32), 0, (3, 20, 1e-4), None, 5)
+    with pytest.raises(R.EccNoConvergence):
+        R.find_transform_ecc(flat, a, 0, (3, 20, 1e-4), 5)
