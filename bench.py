@@ -1,0 +1,398 @@
+#!/usr/bin/env python
+"""Benchmark of the ECC align-and-stack hot path (BASELINE.json metric: ECC-aligned+stacked frames/s at 4K).
+
+  python bench.py --gpus N --steps K --warmup W          this repo's CUDA path
+  python bench.py --impl reference ...                   the reference's CPU path (OpenCV through cv2, driven
+                                                         call-for-call like /root/reference/src/lib.rs:719-847)
+
+A "step" = one whole stack: BASELINE configs[3] — ecc_match MotionType::Homography, max_count 5000, eps 1e-5,
+gauss_filt_size 5, on 64 synthetic 3840x2160 BGR frames (oracle/synth.py, seeds fixed) — reference prep + seed,
+63 x {prep, device ECC loop, final warp + accumulate}, lane sum, [reduce over ranks], divide.
+`value`  : frames/s with every frame already resident in HBM as u8 BGR (CUDA-event time, max over ranks).
+`e2e`    : the same through the host-facing API with frames in pinned HOST memory and the stacked image copied
+           back to the host every step.
+N > 1    : the 64 frames are sharded over the ranks (strong scaling), one NCCL sum-reduce of the partial stacks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "ECC-aligned+stacked frames/s at 4K"
+UNIT = "frames/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    # workload overrides (anything but the defaults is reported in config and is not the headline)
+    ap.add_argument("--frames", type=int, default=64)
+    ap.add_argument("--width", type=int, default=3840)
+    ap.add_argument("--height", type=int, default=2160)
+    ap.add_argument("--motion", type=int, default=3)
+    ap.add_argument("--lanes", type=int, default=int(os.environ.get("STK_LANES", "4")))
+    ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="frames in the CPU sample (0 = one per core, <= 32)")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    base = (f"ecc_match MotionType::{['Translation', 'Euclidean', 'Affine', 'Homography'][a.motion]}, "
+            f"{a.frames} synthetic {a.width}x{a.height} BGR frames, max_count 5000, eps 1e-5, gauss_filt_size 5")
+    if (a.frames, a.width, a.height, a.motion) == (64, 3840, 2160, 3):
+        return "BASELINE configs[3]: " + base
+    return "NON-HEADLINE override: " + base
+
+
+def make_stack(a):
+    from oracle import synth
+    return synth.Stack(a.width, a.height, a.frames, a.motion, seed=4)
+
+
+# ---- clocks -----------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU while the timed region runs (NVML, 20 ms period)."""
+
+    def __init__(self, device_index: int):
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thr = None
+        self._h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            import torch
+            uuid = torch.cuda.get_device_properties(device_index).uuid
+            self._nv = pynvml
+            try:
+                self._h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+            except Exception:
+                self._h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._h = None
+
+    def _loop(self):
+        nv = self._nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                try:
+                    bits = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                except Exception:
+                    bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for bit, name in names.items():
+                    if bits & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def start(self):
+        if self._h is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+        return {
+            "sm_mhz": statistics.median(self.samples) if self.samples else None,
+            "sm_max_mhz": self.max_mhz,
+            "reasons": sorted(self.reasons),
+            "samples": len(self.samples),
+        }
+
+
+# ---- CPU reference arm --------------------------------------------------------------------------------------
+def cpu_sample_run(a, n_sample: int):
+    """The reference's CPU path on a bounded sample of the workload: frame 0 + (n_sample-1) frames of the
+    same stack, one task per frame on all host cores.  Returns (frames/s, seconds, workers, n_sample)."""
+    import cv2  # noqa: F401
+    from oracle import cvref
+    stack = make_stack(a)
+    frames = [stack.frame(i) for i in range(n_sample)]
+    workers = min(os.cpu_count() or 1, max(1, n_sample - 1))
+    t0 = time.perf_counter()
+    cvref.ecc_match(frames, a.motion, 5000, 1e-5, 5, workers=workers)
+    dt = time.perf_counter() - t0
+    return n_sample / dt, dt, workers, n_sample
+
+
+def default_cpu_sample(a):
+    if a.cpu_sample > 0:
+        return a.cpu_sample
+    return min(a.frames, min(os.cpu_count() or 1, 32) + 1)
+
+
+def run_reference(a, rank, world):
+    if rank != 0:
+        return
+    try:
+        import cv2
+    except Exception as e:  # pragma: no cover
+        print(json.dumps({"impl": "reference", "unavailable": f"cv2 (the reference's OpenCV engine) not importable: {e}"}))
+        return
+    n_sample = default_cpu_sample(a)
+    vals, secs, workers = [], [], 1
+    for i in range(a.warmup + a.steps):
+        v, dt, workers, _ = cpu_sample_run(a, n_sample)
+        if i >= a.warmup:
+            vals.append(v)
+            secs.append(dt)
+    value = len(vals) * n_sample / sum(secs)
+    sample = (f"frame 0 + {n_sample - 1} of the {a.frames} frames of the workload per step, frames in host memory, "
+              f"ThreadPool({workers}) one task per frame + OpenCV's own pool ({cv2.getNumThreads()} threads), cv2 {cv2.__version__}")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "host_cores": os.cpu_count()},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample,
+                         "note": "the Rust crate cannot be built here (no rustc/cargo, no C++ OpenCV); this is the same "
+                                 "OpenCV engine (cv2) driven call-for-call as src/lib.rs:719-847 drives it"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ---- this repo's arm ------------------------------------------------------------------------------------------
+def run_b200(a, rank, local_rank, world):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    from oracle import synth
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    pkg = ge.load_package()
+    D = pkg.distributed
+
+    n, w, h = a.frames, a.width, a.height
+    n_px = w * h
+    stack_src = make_stack(a)
+    mine = D.shard_frames(n, rank, world)
+    host = {0: stack_src.frame(0)}
+    for i in mine:
+        host[i] = stack_src.frame(i)
+    dev_frames = {i: torch.from_numpy(f).to(dev) for i, f in host.items()}
+    pinned = {i: torch.from_numpy(f).pin_memory() for i, f in host.items()}
+    pinned_np = {i: t.numpy() for i, t in pinned.items()}
+    params = pkg.EccMatchParameters(pkg.MotionType(a.motion), 5000, 1e-5, 5)
+    st = pkg.EccStack(w, h, 3, params, device=local_rank, lanes=a.lanes, seed_reference=(rank == 0))
+    out_dev = torch.empty(h, w, 3, dtype=torch.float32, device=dev)
+    out_host = torch.empty(h, w, 3, dtype=torch.float32).pin_memory()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step_resident():
+        st.reset()
+        st.set_reference(dev_frames[0])
+        for i in mine:
+            st.submit(dev_frames[i], tag=i)
+        ptr, nfl = st.partial()
+        if world > 1:
+            part = torch.as_tensor(D.DevicePtrArray(ptr, nfl), device=dev)
+            D.reduce_partial_stack(part, 0)
+            torch.cuda.synchronize()
+        if rank == 0:
+            st.finish_device(ptr, n, out_dev.data_ptr())
+
+    def step_e2e():
+        st.reset()
+        st.set_reference(pinned_np[0])
+        for i in mine:
+            st.submit(pinned_np[i], tag=i, pinned=True)
+        ptr, nfl = st.partial()
+        if world > 1:
+            part = torch.as_tensor(D.DevicePtrArray(ptr, nfl), device=dev)
+            D.reduce_partial_stack(part, 0)
+            torch.cuda.synchronize()
+        if rank == 0:
+            st.finish_device(ptr, n, out_dev.data_ptr())
+            out_host.copy_(out_dev, non_blocking=False)
+
+    def timed(fn, steps, warmup, sample_clocks):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        sampler = ClockSampler(local_rank) if sample_clocks else None
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = st.launch_count()
+        e0.record()
+        t0 = time.perf_counter()
+        launches = 0
+        for _ in range(steps):
+            fn()
+            launches += st.launch_count()     # reset() zeroes the counter at the start of every step
+        torch.cuda.synchronize()
+        e1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        clocks = sampler.stop() if sampler else None
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        del l0
+        return float(ms.item()), wall * 1e3, launches, clocks
+
+    ms, wall_ms, launches, clocks = timed(step_resident, a.steps, a.warmup, True)
+    value = n * a.steps / (ms / 1e3)
+    res = st.results()
+    iters = [r["iterations"] for r in res]
+    # the run must have aligned the frames for real: recovered warps vs the ground truth of the generator
+    truth_err = max((synth.corner_displacement(r["warp"] if a.motion == 3 else r["warp"][:2],
+                                               stack_src.truth[r["tag"]], w, h) for r in res), default=0.0)
+    statuses = sorted({r["status"] for r in res})
+
+    e2e = None
+    if not a.skip_e2e:
+        ems, _, _, _ = timed(step_e2e, a.steps, min(a.warmup, 1), False)
+        h2d = sum(pinned_np[i].nbytes for i in [0] + mine)
+        e2e = {"value": n * a.steps / (ems / 1e3), "unit": UNIT, "ms_per_step": ems / a.steps,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(out_host.numel() * 4) if rank == 0 else 0,
+               "api": "EccStack.set_reference/submit(pinned host frames)/partial/finish_device + D2H of the stack"}
+        if world > 1:
+            tot = torch.tensor([float(h2d)], dtype=torch.float64, device=dev)
+            dist.all_reduce(tot)
+            e2e["h2d_bytes_per_step"] = int(tot.item())
+
+    # ---- roofline of the dominant kernel (ecc_iter_kernel), measured alone: 1 lane, CUDA events per stage ----
+    st.close()
+    roof = stages = None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    if rank == 0:
+        with pkg.EccStack(w, h, 3, params, device=local_rank, lanes=1, seed_reference=True) as s1:
+            for rep in range(2):          # first pass warms up
+                s1.reset()
+                s1.set_profiling(rep == 1)
+                s1.set_reference(dev_frames[0])
+                for i in mine[:16]:
+                    s1.submit(dev_frames[i], tag=i)
+                s1.sync()
+            t = s1.stage_times()
+        if t["frames"] and t["iterations"]:
+            per_iter_ms = t["loop_ms"] / t["iterations"]
+            achieved = 8.0 * n_px / (per_iter_ms * 1e-3) / 1e9
+            traffic = None
+            try:
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "ecc_iter_traffic.json"))).get("dram_bytes_per_launch")
+            except Exception:
+                pass
+            roof = {"bound": "hbm", "kernel": "ecc_iter_kernel<Homography>" if a.motion == 3 else f"ecc_iter_kernel<{a.motion}>",
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                    "algorithmic_bytes_per_launch": 8 * n_px, "us_per_launch": per_iter_ms * 1e3,
+                    "peak_source": peak_src,
+                    "how": "1 lane, CUDA events on the lane stream around each frame's device loop (init + all "
+                           "iterations of the graph WHILE node, relaunch gaps included) / iterations; "
+                           f"{t['frames']} frames, {t['iterations']} iterations"}
+            stages = {
+                "prep": {"ms_per_frame": t["prep_ms"] / t["frames"], "GBps": 7.0 * n_px / (t["prep_ms"] / t["frames"] * 1e-3) / 1e9},
+                "ecc_loop": {"ms_per_frame": t["loop_ms"] / t["frames"], "iterations_per_frame": t["iterations"] / t["frames"]},
+                "warp_accumulate": {"ms_per_frame": t["warp_ms"] / t["frames"], "GBps": 27.0 * n_px / (t["warp_ms"] / t["frames"] * 1e-3) / 1e9},
+            }
+
+    if world > 1:
+        it_t = torch.tensor([float(sum(iters))], dtype=torch.float64, device=dev)
+        dist.all_reduce(it_t)
+        total_iters = int(it_t.item())
+        l_t = torch.tensor([float(launches)], dtype=torch.float64, device=dev)
+        dist.all_reduce(l_t)
+        launches = int(l_t.item())
+    else:
+        total_iters = sum(iters)
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.skip_cpu:
+        try:
+            import cv2
+            n_sample = default_cpu_sample(a)
+            v, dt, workers, _ = cpu_sample_run(a, n_sample)
+            cpu = {"value": v, "unit": UNIT, "cores": workers, "kind": "port",
+                   "sample": f"frame 0 + {n_sample - 1} frames of the same stack in {dt:.1f} s, one task per frame on "
+                             f"{workers} threads + OpenCV pool ({cv2.getNumThreads()}), cv2 {cv2.__version__}; "
+                             f"host has {os.cpu_count()} cores"}
+        except Exception as e:  # pragma: no cover
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+
+    if rank == 0:
+        # algorithmic bytes of the whole step: per frame (34 + 8K)N, per stack 43N per GPU
+        alg_bytes = (34 * (n - 1) + 8 * total_iters + 43 * world) * n_px
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(a), "lanes": a.lanes,
+                       "l2": "inputs larger than L2: every step reads all frames (%.2f GB u8) from HBM" % (n * n_px * 3 / 1e9),
+                       "parallelism": f"frames sharded over {world} GPU(s), one NCCL reduce" if world > 1 else "1 GPU",
+                       "ecc_iterations_per_step": total_iters, "wall_ms_per_step": wall_ms / a.steps},
+            "whole_step": {"algorithmic_GBps_per_gpu": alg_bytes / (ms / a.steps * 1e-3) / 1e9 / world,
+                           "frac_of_hbm_peak": alg_bytes / (ms / a.steps * 1e-3) / 1e9 / world / peak},
+            "roofline": roof, "stages": stages, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": launches, "clocks": clocks,
+            "check": {"max_corner_error_vs_ground_truth_px": truth_err, "ecc_status_codes": statuses,
+                      "stack_mean": float(out_dev.mean().item())},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.gpus > 1 and world == 1 and "RANK" not in os.environ:
+        # convenience: re-launch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={a.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29511"),
+               os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    if a.impl == "reference":
+        run_reference(a, rank, world)
+    else:
+        run_b200(a, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -145,6 +145,11 @@ int stk_ecc_reset(stk_ecc_ctx* ctx);
 
 /* counters for benchmarks: kernels launched by this context since creation / last reset */
 int stk_ecc_launch_count(stk_ecc_ctx* ctx, int64_t* launches);
+/* per-stage device times.  With profiling on, every align submission is bracketed by CUDA events on its
+   lane's stream: [prep | device ECC loop | warp+accumulate].  stk_ecc_stage_times (after a sync) returns the
+   summed milliseconds per stage, the number of frames and the total ECC iterations they cover. */
+int stk_ecc_set_profiling(stk_ecc_ctx* ctx, int enabled);
+int stk_ecc_stage_times(stk_ecc_ctx* ctx, double ms[3], int64_t* frames, int64_t* iterations);
 
 /* ---- single stages, exposed for verification and for callers that want one step only --------------- */
 /* cvt_color(BGR2GRAY) + convertTo(f32) + GaussianBlur(k x k, sigma 0): the template/input plane
@@ -158,6 +163,13 @@ int stk_prep_grey_blur(const uint8_t* bgr, size_t pitch, int width, int height, 
    accumulators.  Test hook for the parity suite. */
 int stk_ecc_debug_iteration(stk_ecc_ctx* ctx, const uint8_t* bgr, size_t pitch, const float warp_in[9],
                             double* totals, int cap, int* nv, float warp_out[9], double* rho, int* status);
+
+/* Same call, but instead of the sums it returns %globaltimer stamps (ns) of the iteration kernel:
+   for each tile [start, pixels done, partial written, -] then [cross-tile sum done, solve done, end,
+   last block id]; *n_tiles receives the tile count.  `iters` launches are made back to back and the
+   stamps of the last one are returned.  Profiling hook. */
+int stk_ecc_debug_timing(stk_ecc_ctx* ctx, const uint8_t* bgr, size_t pitch, const float warp_in[9], int iters,
+                         uint64_t* stamps, int cap, int* n_tiles);
 
 /* ---- sharpness_tenengrad                               replaces src/lib.rs:1101-1147 ---------- */
 /* grey: single-channel 8-bit (channels == 1) — or BGR/BGRA (channels 3/4), converted with

@@ -14,7 +14,7 @@ from .api import (  # noqa: F401
     ecc_match, keypoint_match, sharpness_tenengrad, term_criteria, EccStack, imread,
     BORDER_CONSTANT, RANSAC, prep_grey_blur,
 )
-from . import _ffi  # noqa: F401
+from . import _ffi, distributed  # noqa: F401
 
 prelude = ("EccMatchParameters", "KeyPointMatchParameters", "MotionType", "StackerError", "ecc_match",
            "keypoint_match")   # /root/reference/src/lib.rs:1168-1173

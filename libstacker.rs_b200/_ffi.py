@@ -58,9 +58,12 @@ SYMBOLS = {
     "stk_ecc_finish_device": (C.c_int, [_P, _P, C.c_int, _P]),
     "stk_ecc_reset": (C.c_int, [_P]),
     "stk_ecc_launch_count": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+    "stk_ecc_set_profiling": (C.c_int, [_P, C.c_int]),
+    "stk_ecc_stage_times": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "stk_prep_grey_blur": (C.c_int, [_P, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_size_t]),
     "stk_ecc_debug_iteration": (C.c_int, [_P, _P, C.c_size_t, C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_int,
                                           C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    "stk_ecc_debug_timing": (C.c_int, [_P, _P, C.c_size_t, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_uint64), C.c_int, C.POINTER(C.c_int)]),
     "stk_tenengrad": (C.c_int, [_P, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "stk_tenengrad_device": (C.c_int, [_P, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "stk_tenengrad_batch_device": (C.c_int, [_P, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),

@@ -255,6 +255,17 @@ class EccStack:
     def finish_device(self, d_sum_ptr: Optional[int], divisor: int, d_out_ptr: int):
         _check(lib.stk_ecc_finish_device(self._ctx, d_sum_ptr, int(divisor), d_out_ptr))
 
+    def set_profiling(self, enabled: bool):
+        _check(lib.stk_ecc_set_profiling(self._ctx, 1 if enabled else 0))
+
+    def stage_times(self):
+        """dict(prep_ms, loop_ms, warp_ms, frames, iterations) summed over the frames submitted with
+        profiling on."""
+        ms = (C.c_double * 3)()
+        nf, it = C.c_int64(), C.c_int64()
+        _check(lib.stk_ecc_stage_times(self._ctx, ms, C.byref(nf), C.byref(it)))
+        return dict(prep_ms=ms[0], loop_ms=ms[1], warp_ms=ms[2], frames=nf.value, iterations=it.value)
+
     def debug_iteration(self, frame: np.ndarray, warp_in):
         """One ECC iteration from `warp_in` (3x3): (totals f64[NV], warp_out 3x3 f32, rho, status)."""
         f, ptr, pitch = self._host_frame(frame)
@@ -265,6 +276,18 @@ class EccStack:
         _check(lib.stk_ecc_debug_iteration(self._ctx, ptr, pitch, win, tot, 128, C.byref(nv), wout, C.byref(rho),
                                            C.byref(status)))
         return (np.array(tot[:nv.value]), np.array(wout[:], np.float32).reshape(3, 3), rho.value, status.value)
+
+    def debug_timing(self, frame: np.ndarray, warp_in, iters: int = 3):
+        """%globaltimer stamps (ns) of the last of `iters` back-to-back iteration kernels:
+        (tiles[n_tiles, 4], tail[4])."""
+        f, ptr, pitch = self._host_frame(frame)
+        win = (C.c_float * 9)(*np.asarray(warp_in, np.float32).reshape(9))
+        cap = 4 * 65536 + 4
+        buf = (C.c_uint64 * cap)()
+        nt = C.c_int()
+        _check(lib.stk_ecc_debug_timing(self._ctx, ptr, pitch, win, int(iters), buf, cap, C.byref(nt)))
+        a = np.frombuffer(buf, dtype=np.uint64, count=nt.value * 4 + 4).copy()
+        return a[:nt.value * 4].reshape(nt.value, 4), a[nt.value * 4:]
 
     def reset(self):
         _check(lib.stk_ecc_reset(self._ctx))

@@ -5,6 +5,7 @@
 // below; there is no CPU fallback.
 #include "../../include/stacker_cuda.h"
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -83,6 +84,33 @@ void invert_perspective_host(const double* s, double* o) {
   o[8] = det2(s[0], s[1], s[3], s[4]) * d;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point table (no link-time libcuda dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_plane_tensor_map(CUtensorMap* tm, const float* base, int width, int height, int pitch_floats, int box_w,
+                          int box_h) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !ptr)
+      return fail(STK_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    fn = (EncodeTiledFn)ptr;
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)width, (cuuint64_t)height};
+  const cuuint64_t gstride[1] = {(cuuint64_t)pitch_floats * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(STK_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return STK_OK;
+}
+
 struct Lane {
   cudaStream_t stream = nullptr;
   float* tmpl = nullptr;            // T plane
@@ -96,11 +124,13 @@ struct Lane {
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
   cudaGraphConditionalHandle handle = 0;
+  CUtensorMap tm_tmpl;
 };
 
 struct ResultSlot {
   int64_t tag;
   stk::EccState* host;      // pinned copy of the frame's final state (null for warp-only frames)
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // profiling: prep | loop | warp boundaries
 };
 
 }  // namespace
@@ -121,6 +151,8 @@ struct stk_ecc_ctx {
   int n_strips = 0, n_bands = 0, rows_per_tile = 0, n_tiles = 0, nv = 0;
   int max_iter = 0;
   double eps = 0;
+  CUtensorMap tm_img;
+  bool exact_coords = false;
   bool host_loop = false;
   bool have_ref = false;
   stk::PrepParams prep_proto;
@@ -131,19 +163,20 @@ struct stk_ecc_ctx {
   size_t states_used = 0;
   std::atomic<int64_t> launches{0};
   int64_t iter_launches_counted = 0;
+  bool profiling = false;
   static constexpr size_t kChunk = 256;
 };
 
 namespace {
 
-template <int MOTION> void* iter_kernel_ptr() { return (void*)stk::ecc_iter_kernel<MOTION>; }
-
-void* iter_kernel(int motion) {
+// homography has two instantiations: FastPersp coordinates (default) and exact f64 (STK_ECC_EXACT_COORDS=1)
+void* iter_kernel_for(int motion, bool exact) {
   switch (motion) {
-    case STK_MOTION_TRANSLATION: return iter_kernel_ptr<stk::kTranslation>();
-    case STK_MOTION_EUCLIDEAN: return iter_kernel_ptr<stk::kEuclidean>();
-    case STK_MOTION_AFFINE: return iter_kernel_ptr<stk::kAffine>();
-    default: return iter_kernel_ptr<stk::kHomography>();
+    case STK_MOTION_TRANSLATION: return (void*)stk::ecc_iter_kernel<stk::kTranslation, true>;
+    case STK_MOTION_EUCLIDEAN: return (void*)stk::ecc_iter_kernel<stk::kEuclidean, true>;
+    case STK_MOTION_AFFINE: return (void*)stk::ecc_iter_kernel<stk::kAffine, true>;
+    default: return exact ? (void*)stk::ecc_iter_kernel<stk::kHomography, true>
+                          : (void*)stk::ecc_iter_kernel<stk::kHomography, false>;
   }
 }
 
@@ -158,6 +191,9 @@ int model_nv(int motion) {
 
 stk::EccIterParams iter_params(stk_ecc_ctx* c, Lane& ln, bool use_handle) {
   stk::EccIterParams p;
+  memset(&p, 0, sizeof p);
+  p.tm_img = c->tm_img;
+  p.tm_tmpl = ln.tm_tmpl;
   p.img = c->img;
   p.tmpl = ln.tmpl;
   p.pitch = c->pitch_f;
@@ -167,10 +203,12 @@ stk::EccIterParams iter_params(stk_ecc_ctx* c, Lane& ln, bool use_handle) {
   p.n_strips = c->n_strips;
   p.n_bands = c->n_bands;
   p.partials = ln.partials;
+  p.tiles_pad = (c->n_tiles + 31) / 32 * 32;
   p.st = ln.st;
   p.handle = ln.handle;
   p.use_handle = use_handle ? 1 : 0;
   p.totals_out = nullptr;
+  p.timing_out = nullptr;
   return p;
 }
 
@@ -205,9 +243,10 @@ int build_lane_graph(stk_ecc_ctx* c, Lane& ln) {
     stk::EccIterParams ip = iter_params(c, ln, true);
     void* args[] = {&ip};
     cudaKernelNodeParams kp = {};
-    kp.func = iter_kernel(c->cfg.motion_type);
+    kp.func = iter_kernel_for(c->cfg.motion_type, c->exact_coords);
     kp.gridDim = dim3(c->n_tiles);
     kp.blockDim = dim3(stk::kEccThreads);
+    kp.sharedMemBytes = stk::kEccDynSmem;
     kp.kernelParams = args;
     CU(cudaGraphAddKernelNode(&iter_node, body, nullptr, 0, &kp));
   }
@@ -300,8 +339,20 @@ Lane& pick_lane(stk_ecc_ctx* c) {
 
 // the ECC part of one frame on its lane: prep -> device loop -> warp+accumulate -> result record
 int enqueue_align(stk_ecc_ctx* c, Lane& ln, const uint8_t* d_src, size_t pitch, int64_t tag) {
-  int rc = launch_prep(c, d_src, pitch, ln.tmpl, ln.stream);
+  ResultSlot slot;
+  slot.tag = tag;
+  slot.host = nullptr;
+  auto mark = [&](int i) -> int {
+    if (!c->profiling) return STK_OK;
+    CU(cudaEventCreate(&slot.ev[i]));
+    CU(cudaEventRecord(slot.ev[i], ln.stream));
+    return STK_OK;
+  };
+  int rc = mark(0);
   if (rc) return rc;
+  rc = launch_prep(c, d_src, pitch, ln.tmpl, ln.stream);
+  if (rc) return rc;
+  if ((rc = mark(1))) return rc;
   const bool persp = c->cfg.motion_type == STK_MOTION_HOMOGRAPHY;
   if (!c->host_loop) {
     CU(cudaGraphLaunch(ln.exec, ln.stream));
@@ -320,20 +371,21 @@ int enqueue_align(stk_ecc_ctx* c, Lane& ln, const uint8_t* d_src, size_t pitch, 
     while (*h_cont && done_iters < c->max_iter) {
       const int chunk = std::min(4, c->max_iter - done_iters);
       for (int i = 0; i < chunk; ++i)
-        CU(cudaLaunchKernel(iter_kernel(c->cfg.motion_type), dim3(c->n_tiles), dim3(stk::kEccThreads), args, 0, ln.stream));
+        CU(cudaLaunchKernel(iter_kernel_for(c->cfg.motion_type, c->exact_coords), dim3(c->n_tiles), dim3(stk::kEccThreads), args, stk::kEccDynSmem, ln.stream));
       done_iters += chunk;
       CU(cudaMemcpyAsync(h_cont, &ln.st->cont, sizeof(int), cudaMemcpyDeviceToHost, ln.stream));
       CU(cudaStreamSynchronize(ln.stream));
     }
     cudaFreeHost(h_cont);
   }
+  if ((rc = mark(2))) return rc;
   rc = launch_warp(c, ln, d_src, pitch, persp, nullptr, nullptr, true);
   if (rc) return rc;
-  stk::EccState* hs = nullptr;
-  rc = alloc_result_state(c, &hs);
+  if ((rc = mark(3))) return rc;
+  rc = alloc_result_state(c, &slot.host);
   if (rc) return rc;
-  CU(cudaMemcpyAsync(hs, ln.st, sizeof(stk::EccState), cudaMemcpyDeviceToHost, ln.stream));
-  c->results.push_back({tag, hs});
+  CU(cudaMemcpyAsync(slot.host, ln.st, sizeof(stk::EccState), cudaMemcpyDeviceToHost, ln.stream));
+  c->results.push_back(slot);
   return STK_OK;
 }
 
@@ -433,6 +485,8 @@ int stk_ecc_create(const stk_ecc_config* cfg, stk_ecc_ctx** out) {
   c->acc_floats = (size_t)cfg->width * cfg->channels * cfg->height;
   c->max_iter = (cfg->criteria_type & STK_TERM_COUNT) ? cfg->max_count : 200;
   c->eps = (cfg->criteria_type & STK_TERM_EPS) ? cfg->epsilon : -1.0;
+  const char* ec = getenv("STK_ECC_EXACT_COORDS");
+  c->exact_coords = ec && strcmp(ec, "1") == 0;
   const char* lm = getenv("STK_LOOP_MODE");
   c->host_loop = lm && strcmp(lm, "host") == 0;
 
@@ -440,16 +494,21 @@ int stk_ecc_create(const stk_ecc_config* cfg, stk_ecc_ctx** out) {
   auto cleanup = [&](int code) { stk_ecc_destroy(c); return code; };
 
   if (cfg->align) {
-    // tiling: 128-column strips x bands; as many tiles as resident blocks (2 per SM by launch bounds),
-    // never fewer than 32 rows per tile so the per-tile fold/reduction stays amortised
+    // tiling: 128-column strips x bands of R rows (R a multiple of the 16-row chunk); as many tiles as
+    // resident blocks, never fewer than 32 rows per tile so the per-tile fold/reduction stays amortised
+    if (cudaFuncSetAttribute((const void*)iter_kernel_for(cfg->motion_type, c->exact_coords), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             stk::kEccDynSmem) != cudaSuccess)
+      return cleanup(fail(STK_ERR_CUDA, "cannot reserve %d bytes of dynamic shared memory for the ECC kernel", stk::kEccDynSmem));
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)iter_kernel(cfg->motion_type), stk::kEccThreads, 0) != cudaSuccess || occ < 1) occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)iter_kernel_for(cfg->motion_type, c->exact_coords), stk::kEccThreads,
+                                                      stk::kEccDynSmem) != cudaSuccess || occ < 1) occ = 1;
     const int slots = c->sm_count * occ;
     c->n_strips = (cfg->width + stk::kEccStripW - 1) / stk::kEccStripW;
     int bands = std::max(1, slots / c->n_strips);
     int rows = (cfg->height + bands - 1) / bands;
     rows = std::max(rows, 32);
-    rows = (rows + 1) & ~1;
+    rows = (rows + stk::kChunkH - 1) / stk::kChunkH * stk::kChunkH;
+    rows = std::min(rows, stk::kMaxChunks * stk::kChunkH);
     c->rows_per_tile = rows;
     c->n_bands = (cfg->height + rows - 1) / rows;
     c->n_tiles = c->n_strips * c->n_bands;
@@ -470,6 +529,9 @@ int stk_ecc_create(const stk_ecc_config* cfg, stk_ecc_ctx** out) {
     }
     if (cudaMalloc((void**)&c->img, (size_t)c->pitch_f * cfg->height * sizeof(float)) != cudaSuccess)
       return cleanup(fail(STK_ERR_NOMEM, "cudaMalloc(I plane) failed"));
+    rc = make_plane_tensor_map(&c->tm_img, c->img, cfg->width, cfg->height, c->pitch_f, stk::kBoxW, stk::kBoxH);
+    if (rc) return cleanup(rc);
+
   }
   c->lanes.resize(c->n_lanes);
   for (auto& ln : c->lanes) {
@@ -478,10 +540,12 @@ int stk_ecc_create(const stk_ecc_config* cfg, stk_ecc_ctx** out) {
     if (cudaMalloc((void**)&ln.acc, c->acc_floats * sizeof(float)) != cudaSuccess) return cleanup(fail(STK_ERR_NOMEM, "cudaMalloc(accumulator) failed"));
     if (cfg->align) {
       if (cudaMalloc((void**)&ln.tmpl, (size_t)c->pitch_f * cfg->height * sizeof(float)) != cudaSuccess) return cleanup(fail(STK_ERR_NOMEM, "cudaMalloc(T plane) failed"));
+      rc = make_plane_tensor_map(&ln.tm_tmpl, ln.tmpl, cfg->width, cfg->height, c->pitch_f, stk::kEccStripW, stk::kChunkH);
+      if (rc) return cleanup(rc);
       if (cudaMalloc((void**)&ln.st, sizeof(stk::EccState)) != cudaSuccess) return cleanup(fail(STK_ERR_NOMEM, "cudaMalloc(state) failed"));
       if (cudaMemsetAsync(ln.st, 0, sizeof(stk::EccState), ln.stream) != cudaSuccess ||
           cudaStreamSynchronize(ln.stream) != cudaSuccess) return cleanup(fail(STK_ERR_CUDA, "cudaMemset failed"));
-      if (cudaMalloc((void**)&ln.partials, (size_t)c->n_tiles * c->nv * sizeof(double)) != cudaSuccess) return cleanup(fail(STK_ERR_NOMEM, "cudaMalloc(partials) failed"));
+      if (cudaMalloc((void**)&ln.partials, (size_t)((c->n_tiles + 31) / 32 * 32) * c->nv * sizeof(double)) != cudaSuccess) return cleanup(fail(STK_ERR_NOMEM, "cudaMalloc(partials) failed"));
       if (!c->host_loop) {
         rc = build_lane_graph(c, ln);
         if (rc) return cleanup(rc);
@@ -504,6 +568,7 @@ int stk_ecc_destroy(stk_ecc_ctx* c) {
     if (ln.stage_free) cudaEventDestroy(ln.stage_free);
     if (ln.stream) cudaStreamDestroy(ln.stream);
   }
+  for (auto& r : c->results) for (auto& e : r.ev) if (e) cudaEventDestroy(e);
   cudaFree(c->img); cudaFree(c->d_ref); cudaFree(c->d_out);
   for (auto* p : c->state_chunks) cudaFreeHost(p);
   delete c;
@@ -606,7 +671,7 @@ static int submit_warp(stk_ecc_ctx* c, const uint8_t* buf, size_t pitch, const d
   }
   rc = launch_warp(c, ln, d_src, d_pitch, true, inv, border, false);
   if (rc) return rc;
-  c->results.push_back({tag, nullptr});
+  { ResultSlot slot; slot.tag = tag; slot.host = nullptr; c->results.push_back(slot); }
   return STK_OK;
 }
 
@@ -736,6 +801,7 @@ int stk_ecc_reset(stk_ecc_ctx* c) {
   if (rc) return rc;
   std::lock_guard<std::mutex> g(c->mu);
   for (auto& ln : c->lanes) { CU(cudaStreamSynchronize(ln.stream)); ln.acc_used = false; }
+  for (auto& r : c->results) for (auto& e : r.ev) if (e) cudaEventDestroy(e);
   c->results.clear();
   c->states_used = 0;
   c->iter_launches_counted = 0;
@@ -748,6 +814,36 @@ int stk_ecc_reset(stk_ecc_ctx* c) {
 int stk_ecc_launch_count(stk_ecc_ctx* c, int64_t* launches) {
   if (!c || !launches) return fail(STK_ERR_BAD_ARG, "null argument");
   *launches = c->launches.load();
+  return STK_OK;
+}
+
+int stk_ecc_set_profiling(stk_ecc_ctx* c, int enabled) {
+  if (!c) return fail(STK_ERR_BAD_ARG, "null context");
+  std::lock_guard<std::mutex> g(c->mu);
+  c->profiling = enabled != 0;
+  return STK_OK;
+}
+
+int stk_ecc_stage_times(stk_ecc_ctx* c, double ms[3], int64_t* frames, int64_t* iterations) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  if (!ms) return fail(STK_ERR_BAD_ARG, "null argument");
+  std::lock_guard<std::mutex> g(c->mu);
+  for (auto& ln : c->lanes) CU(cudaStreamSynchronize(ln.stream));
+  ms[0] = ms[1] = ms[2] = 0.0;
+  int64_t nf = 0, it = 0;
+  for (auto& r : c->results) {
+    if (!r.ev[0] || !r.ev[3]) continue;
+    for (int k = 0; k < 3; ++k) {
+      float t = 0.f;
+      CU(cudaEventElapsedTime(&t, r.ev[k], r.ev[k + 1]));
+      ms[k] += t;
+    }
+    ++nf;
+    if (r.host) it += r.host->iters;
+  }
+  if (frames) *frames = nf;
+  if (iterations) *iterations = it;
   return STK_OK;
 }
 
@@ -799,7 +895,7 @@ int stk_ecc_debug_iteration(stk_ecc_ctx* c, const uint8_t* bgr, size_t pitch, co
   stk::EccIterParams ip = iter_params(c, ln, false);
   ip.totals_out = d_tot;
   void* args[] = {&ip};
-  cudaError_t e = cudaLaunchKernel(iter_kernel(c->cfg.motion_type), dim3(c->n_tiles), dim3(stk::kEccThreads), args, 0, ln.stream);
+  cudaError_t e = cudaLaunchKernel(iter_kernel_for(c->cfg.motion_type, c->exact_coords), dim3(c->n_tiles), dim3(stk::kEccThreads), args, stk::kEccDynSmem, ln.stream);
   stk::EccState hs;
   if (e == cudaSuccess) e = cudaMemcpyAsync(totals, d_tot, sizeof(double) * c->nv, cudaMemcpyDeviceToHost, ln.stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(&hs, ln.st, sizeof hs, cudaMemcpyDeviceToHost, ln.stream);
@@ -810,6 +906,44 @@ int stk_ecc_debug_iteration(stk_ecc_ctx* c, const uint8_t* bgr, size_t pitch, co
   if (warp_out) for (int i = 0; i < 9; ++i) warp_out[i] = hs.m[i];
   if (rho) *rho = hs.rho;
   if (status) *status = hs.status;
+  return STK_OK;
+}
+
+int stk_ecc_debug_timing(stk_ecc_ctx* c, const uint8_t* bgr, size_t pitch, const float warp_in[9], int iters,
+                         uint64_t* stamps, int cap, int* n_tiles) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  if (!bgr || !warp_in || !stamps || !n_tiles) return fail(STK_ERR_BAD_ARG, "null argument");
+  if (!c->cfg.align) return fail(STK_ERR_STATE, "context was created with align = 0");
+  const int need = c->n_tiles * 4 + 4;
+  if (cap < need) return fail(STK_ERR_BAD_ARG, "stamps capacity %d < %d", cap, need);
+  std::lock_guard<std::mutex> g(c->mu);
+  if (!c->have_ref) return fail(STK_ERR_STATE, "stk_ecc_set_reference must come first");
+  Lane& ln = c->lanes[0];
+  rc = ensure_host_staging(c, ln, true);
+  if (rc) return rc;
+  rc = upload_frame(c, ln, bgr, pitch, false);
+  if (rc) return rc;
+  const size_t row = (size_t)c->cfg.width * c->cfg.channels;
+  rc = launch_prep(c, ln.d_frame, row, ln.tmpl, ln.stream);
+  if (rc) return rc;
+  const bool persp = c->cfg.motion_type == STK_MOTION_HOMOGRAPHY;
+  stk::ecc_init_kernel<<<1, 32, 0, ln.stream>>>(ln.st, persp ? 1 : 0, 1 << 30, -1.0, 0, 0);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(ln.st->m, warp_in, 9 * sizeof(float), cudaMemcpyHostToDevice, ln.stream));
+  unsigned long long* d_t = nullptr;
+  CU(cudaMalloc((void**)&d_t, sizeof(unsigned long long) * need));
+  stk::EccIterParams ip = iter_params(c, ln, false);
+  ip.timing_out = d_t;
+  void* args[] = {&ip};
+  cudaError_t e = cudaSuccess;
+  for (int i = 0; i < std::max(1, iters) && e == cudaSuccess; ++i)
+    e = cudaLaunchKernel(iter_kernel_for(c->cfg.motion_type, c->exact_coords), dim3(c->n_tiles), dim3(stk::kEccThreads), args, stk::kEccDynSmem, ln.stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(stamps, d_t, sizeof(unsigned long long) * need, cudaMemcpyDeviceToHost, ln.stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ln.stream);
+  cudaFree(d_t);
+  if (e != cudaSuccess) return fail(STK_ERR_CUDA, "debug timing: %s", cudaGetErrorString(e));
+  *n_tiles = c->n_tiles;
   return STK_OK;
 }
 
