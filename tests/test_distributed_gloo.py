@@ -1,0 +1,82 @@
+"""N > 1 host logic on CPU: frame sharding + the single sum-reduce + divide (world_size 2, gloo).
+
+The per-rank compute is stood in by the oracle (tests may call it); what is under test is the plumbing in
+libstacker.rs_b200/distributed.py that bench.py and a multi-GPU caller use unchanged with the nccl backend."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, n_frames, q):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as ge
+    from oracle import restate as R, synth
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    D = ge.load_package().distributed
+    w, h, motion = 96, 64, 0
+    frames = synth.Stack(w, h, n_frames, motion, seed=21).frames()
+    grey0 = R.bgr2gray_u8(frames[0])
+    # rank 0 seeds its partial stack with the unwarped reference frame (src/lib.rs:752-754)
+    acc = R.to_f32_unit(frames[0]) if rank == 0 else np.zeros((h, w, 3), np.float32)
+    mine = D.shard_frames(n_frames, rank, world)
+    for i in mine:
+        _, m, _ = R.find_transform_ecc(R.bgr2gray_u8(frames[i]), grey0, motion, R.term_criteria(30, 1e-4), 5)
+        acc = acc + R.final_warp(frames[i], m, motion)
+    part = torch.from_numpy(acc.reshape(-1).copy())
+    D.reduce_partial_stack(part, 0)
+    if rank == 0:
+        out = (part.numpy() * np.float32(1.0 / n_frames)).reshape(h, w, 3)
+        q.put((mine, out))
+    else:
+        q.put((mine, None))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_frames", [5, 2])
+def test_two_rank_stack_equals_single_rank(n_frames):
+    import torch.multiprocessing as mp
+    from oracle import restate as R, synth
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_frames, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    shards = sorted(sum((r[0] for r in results), []))
+    assert shards == list(range(1, n_frames))            # every non-reference frame exactly once
+    out = next(r[1] for r in results if r[1] is not None)
+    frames = synth.Stack(96, 64, n_frames, 0, seed=21).frames()
+    want, _, _ = R.ecc_match(frames, 0, 30, 1e-4, 5)
+    assert np.abs(out - want).max() <= 1e-6              # f32 summation order only
+
+
+def test_shard_frames_partition(pkg):
+    D = pkg.distributed
+    for n in (1, 2, 7, 64):
+        for world in (1, 2, 4, 8):
+            got = sorted(sum((D.shard_frames(n, r, world) for r in range(world)), []))
+            assert got == list(range(1, n))
+            sizes = [len(D.shard_frames(n, r, world)) for r in range(world)]
+            assert max(sizes) - min(sizes) <= 1
