@@ -11,10 +11,11 @@
 // (template = frame i, input = frame 0, identity init, no mask).  Restated on the CPU in
 // oracle/restate.py (ecc_sums / ecc_epilogue), which is pinned against cv2.findTransformECC.
 //
-// Work decomposition ("column owner"): a tile is 128 columns x R rows, one 256-thread block per tile;
-// every thread keeps ONE column x for the whole tile.  Because X is constant per thread, the Kronecker
+// Work decomposition ("column owner"): the frame is cut into 128-column strips of 16-row chunks and the
+// chunk list is dealt evenly to one persistent 256-thread block per resident slot (2 per SM); within a run
+// of chunks of one strip every thread keeps ONE column x.  Because X is constant per thread, the Kronecker
 // structure of the affine / homography Jacobians ( J = g (x) [X, Y, 1] ) lets a pixel accumulate only
-// g_i*g_j*{1,Y,Y^2} and g_i*z*{1,Y}; the X factors are folded in once per tile.
+// g_i*g_j*{1,Y,Y^2} and g_i*z*{1,Y}; the X factors are folded in once per run.
 //
 // Data movement: the tile is walked in chunks of 16 rows.  The bounding boxes of all chunks' sample
 // positions are computed up front (one thread per chunk); an elected lane then keeps four stages of TMA
@@ -42,7 +43,7 @@ constexpr int kChunkRowsPerThread = kChunkH / kEccRowParts;
 constexpr int kBoxW = 144;          // I box: 128 columns + drift/halo margin
 constexpr int kBoxH = 32;           // I box: 16 rows + drift/halo margin
 constexpr int kEccStages = 4;
-constexpr int kMaxChunks = 128;      // rows_per_tile <= kMaxChunks * kChunkH
+constexpr int kMaxChunks = 128;      // chunks per run (box table size); longer runs are split
 constexpr int kImgStageBytes = kBoxW * kBoxH * 4;          // 18432
 constexpr int kTmplStageBytes = kEccStripW * kChunkH * 4;  // 8192
 constexpr int kStageBytes = kImgStageBytes + kTmplStageBytes;
@@ -71,10 +72,10 @@ struct alignas(64) EccIterParams {
   const float* tmpl;
   int pitch;                // floats, both planes
   int width, height;        // template size == image size on this path
-  int rows_per_tile;        // R (multiple of kChunkH)
-  int n_strips, n_bands;
-  double* partials;         // [NV][tiles_pad]: value-major so the cross-tile sum reads coalesced
-  int tiles_pad;            // n_tiles rounded up to 32
+  int n_strips;             // 128-column strips
+  int chunks_per_strip;     // ceil(height / kChunkH)
+  double* partials;         // [NV][tiles_pad]: value-major so the cross-block sum reads coalesced
+  int tiles_pad;            // gridDim.x rounded up to 32
   EccState* st;
   cudaGraphConditionalHandle handle;
   int use_handle;
@@ -618,8 +619,50 @@ __device__ __noinline__ void ecc_epilogue_warp(const double* tot, EccState* st, 
   __syncwarp();
 }
 
+// ---- warp reduction of a register vector -----------------------------------------------------------
+// Butterfly "transpose-reduce": 64 values per lane are summed across the 32 lanes in 62 shuffles (each
+// stage halves the values a lane still carries) instead of 64 x 5; lane l ends with the totals of values
+// 2l and 2l+1.  Values beyond 64 (and vectors shorter than 32) take the plain 5-step butterfly.
+template <int NV>
+__device__ __forceinline__ void warp_reduce_vector(float (&v)[NV], int lane, float* out /* [NV] in smem */) {
+  if constexpr (NV >= 32) {
+    float r[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) r[i] = i < NV ? v[i] : 0.f;
+#pragma unroll
+    for (int half = 32, o = 16; half >= 2; half >>= 1, o >>= 1) {
+      const bool up = (lane & o) != 0;
+#pragma unroll
+      for (int i = 0; i < half; ++i) {
+        const float lo = r[i], hi = r[i + half];
+        const float send = up ? lo : hi;
+        const float keep = up ? hi : lo;
+        r[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+      }
+    }
+    if (2 * lane < NV) out[2 * lane] = r[0];
+    if (2 * lane + 1 < NV) out[2 * lane + 1] = r[1];
+#pragma unroll
+    for (int i = 64; i < NV; ++i) {
+      const float t = warp_sum(v[i]);
+      if (lane == 0) out[i] = t;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float t = warp_sum(v[i]);
+      if (lane == 0) out[i] = t;
+    }
+  }
+}
+
 // ---- the iteration kernel ----------------------------------------------------------------------------
 // EXACT = false (homography only): FastPersp coordinates for the boxed pixels; true: f64 everywhere.
+//
+// Persistent, balanced: the frame is cut into 128-column strips of 16-row chunks; the chunk list (strip
+// major) is split evenly over the resident blocks, so every block owns a contiguous run of chunks — one
+// or two "segments" (a run that crosses into the next strip).  Per segment the thread's column is fixed;
+// at a segment end the block folds its sums into an f64 shared accumulator.
 template <int MOTION, bool EXACT>
 __global__ void __launch_bounds__(kEccThreads, 2) ecc_iter_kernel(const __grid_constant__ EccIterParams p) {
   using L = Layout<MOTION>;
@@ -632,6 +675,7 @@ __global__ void __launch_bounds__(kEccThreads, 2) ecc_iter_kernel(const __grid_c
   __shared__ alignas(8) uint64_t s_full[kEccStages];
   __shared__ alignas(8) uint64_t s_empty[kEccStages];
   __shared__ float s_red[kWarps][NV];
+  __shared__ double s_accum[NV];
   __shared__ int s_last;
   __shared__ double s_tot[NV];
 
@@ -641,197 +685,208 @@ __global__ void __launch_bounds__(kEccThreads, 2) ecc_iter_kernel(const __grid_c
 
   const int tid = threadIdx.x;
   const int lane = tid & 31, wid = tid >> 5;
-  const int strip = blockIdx.x % p.n_strips, band = blockIdx.x / p.n_strips;
-  const int x0 = strip * kEccStripW;
-  const int x1 = min(x0 + kEccStripW, p.width) - 1;       // inclusive
-  const int y0 = band * p.rows_per_tile;
-  const int y1 = min(y0 + p.rows_per_tile, p.height);     // exclusive
-  const int n_chunks = (y1 - y0 + kChunkH - 1) / kChunkH;
-
   if (p.timing_out && tid == 0) p.timing_out[(size_t)blockIdx.x * 4 + 0] = global_ns();
   if (tid < 9) s_m[tid] = st->m[tid];
+  if (tid < NV) s_accum[tid] = 0.0;
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < kEccStages; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], kWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncthreads();
 
-  // box table: for each chunk, where its 144x32 window of I starts — or "no box" when the sample
-  // positions of the chunk do not fit one.  TMA zero-fills whatever part of a box lies outside the image;
-  // pixels whose taps touch the border are routed to the general path one by one (see `safe` below).
-  if (tid < n_chunks) {
-    const int cy0 = y0 + tid * kChunkH;
-    const int cy1 = min(cy0 + kChunkH, y1) - 1;
-    double umin, umax, vmin, vmax;
-    bool ok = chunk_bounds<Md::persp>(s_m, x0, x1, cy0, cy1, umin, umax, vmin, vmax);
-    int xlo = 0, ylo = 0;
-    if (ok) ok = fabs(umin) < 1e8 && fabs(umax) < 1e8 && fabs(vmin) < 1e8 && fabs(vmax) < 1e8;
-    if (ok) {
-      // the innermost TMA coordinate must land on a 16-byte boundary (4 floats): an unaligned start raises
-      // "illegal instruction" on sm_100 (measured, scripts/tma_probe3.cu)
-      xlo = ((int)floor(umin) - 2) & ~3;
-      ylo = (int)floor(vmin) - 2;
-      ok = ((int)floor(umax) + 3 - xlo < kBoxW) && ((int)floor(vmax) + 3 - ylo < kBoxH);
-    }
-    s_box[tid][0] = ok ? xlo : INT_MIN;
-    s_box[tid][1] = ylo;
-  }
-  __syncthreads();
-
-  // producer (warp 0, lane 0): TMA issue for chunk c into stage c % kEccStages
-  auto issue = [&](int c) {
-    const int s = c % kEccStages;
-    const int xlo = s_box[c][0], ylo = s_box[c][1];
-    const bool boxed = xlo != INT_MIN;
-    unsigned char* stage = dyn + s * kStageBytes;
-    mbar_expect_tx(&s_full[s], (boxed ? kImgStageBytes : 0) + kTmplStageBytes);
-    if (boxed) tma_load_2d(stage, &p.tm_img, xlo, ylo, &s_full[s]);
-    tma_load_2d(stage + kImgStageBytes, &p.tm_tmpl, x0, y0 + c * kChunkH, &s_full[s]);
-  };
-  if (tid == 0) {
-    for (int c = 0; c < kEccStages - 1 && c < n_chunks; ++c) issue(c);
-  }
+  const int cps = p.chunks_per_strip;
+  const long long total = (long long)p.n_strips * cps;
+  int g0 = (int)((long long)blockIdx.x * total / gridDim.x);
+  const int g1 = (int)((long long)(blockIdx.x + 1) * total / gridDim.x);
+  int cc = 0;                       // chunks this block has consumed so far: drives stage and phase
 
   const int col = tid & (kEccStripW - 1);
   const int part = tid / kEccStripW;
-  const int x = x0 + col;
-  const float xf = (float)x;
-  const bool col_ok = x < p.width;
-
-  Accum<MOTION> acc;
-  acc.clear();
-  int n_safe = 0;
   constexpr bool fast_coords = Md::persp && !EXACT;
-  FastPersp fp;
-  if (fast_coords) fp.init(s_m, x);
 
-  // general path for one pixel: exact coordinates, every border rule, nearest-neighbour mask
-  auto slow_pixel = [&](int y, float t_) {
-    Coord<Md::persp> co;
-    Jac<MOTION> jac;
-    co.init(s_m, x);
-    jac.init(s_m, xf);
-    int xq, yq, xn, yn;
-    const bool ok = co.at_with_nearest(y, xq, yq, xn, yn);
-    Sample smp; smp.w = 0.f; smp.gx2 = 0.f; smp.gy2 = 0.f;
-    float mk = 0.f;
-    if (ok) {
-      const int sx = xq >> kInterBits, sy = yq >> kInterBits;
-      if (sx >= -1 && sx < p.width && sy >= -1 && sy < p.height) {
-        const float ax = (float)(xq & (kInterTab - 1)) * (1.f / kInterTab);
-        const float ay = (float)(yq & (kInterTab - 1)) * (1.f / kInterTab);
-        smp = sample_general(p.img, p.pitch, p.width, p.height, sx, sy, ax, ay);
+  while (g0 < g1) {
+    // ---- segment: chunks [c_first, c_first + nseg) of one strip ---------------------------------
+    const int strip = g0 / cps, c_first = g0 - strip * cps;
+    const int nseg = min(min(cps - c_first, g1 - g0), kMaxChunks);
+    const int x0 = strip * kEccStripW;
+    const int x1 = min(x0 + kEccStripW, p.width) - 1;       // inclusive
+    const int y0 = c_first * kChunkH;
+    const int y1 = min(y0 + nseg * kChunkH, p.height);      // exclusive
+    __syncthreads();    // s_m / barriers ready (first pass); previous segment fully consumed (later passes)
+
+    // box table: for each chunk, where its 144x32 window of I starts — or "no box" when the sample
+    // positions of the chunk do not fit one.  TMA zero-fills whatever part of a box lies outside the
+    // image; pixels whose taps touch the border are handled by the careful variant (see `safe` below).
+    if (tid < nseg) {
+      const int cy0 = y0 + tid * kChunkH;
+      const int cy1 = min(cy0 + kChunkH, y1) - 1;
+      double umin, umax, vmin, vmax;
+      bool ok = chunk_bounds<Md::persp>(s_m, x0, x1, cy0, cy1, umin, umax, vmin, vmax);
+      int xlo = 0, ylo = 0;
+      if (ok) ok = fabs(umin) < 1e8 && fabs(umax) < 1e8 && fabs(vmin) < 1e8 && fabs(vmax) < 1e8;
+      if (ok) {
+        // the innermost TMA coordinate must land on a 16-byte boundary (4 floats): an unaligned start
+        // raises "illegal instruction" on sm_100 (measured, scripts/tma_probe3.cu)
+        xlo = ((int)floor(umin) - 2) & ~3;
+        ylo = (int)floor(vmin) - 2;
+        ok = ((int)floor(umax) + 3 - xlo < kBoxW) && ((int)floor(vmax) + 3 - ylo < kBoxH);
       }
-      // OpenCV warps an all-ones mask with INTER_NEAREST: 1 where the rounded position is inside
-      mk = ((unsigned)xn < (unsigned)p.width && (unsigned)yn < (unsigned)p.height) ? 1.f : 0.f;
+      s_box[tid][0] = ok ? xlo : INT_MIN;
+      s_box[tid][1] = ylo;
     }
-    float g[G];
-    const float yf = (float)y;
-    jac.eval(smp, yf, g);
-    acc.template add<false>(g, smp.w, t_, mk, yf);
-  };
+    __syncthreads();
 
-  for (int c = 0; c < n_chunks; ++c) {
-    const int s = c % kEccStages;
-    if (tid == 0 && c + kEccStages - 1 < n_chunks) {
-      // the stage being refilled held chunk c-1: wait until all warps have released it
-      if (c >= 1) mbar_wait(&s_empty[(c - 1) % kEccStages], (unsigned)((c - 1) / kEccStages) & 1u);
-      issue(c + kEccStages - 1);
+    // producer (thread 0): TMA issue for local chunk c (global sequence number cc + c)
+    auto issue = [&](int c) {
+      const int gc = cc + c;
+      const int s = gc % kEccStages;
+      // the stage last held sequence number gc - kEccStages: wait until every warp has released it
+      if (gc >= kEccStages) mbar_wait(&s_empty[s], (unsigned)(gc / kEccStages - 1) & 1u);
+      const int xlo = s_box[c][0], ylo = s_box[c][1];
+      const bool boxed = xlo != INT_MIN;
+      unsigned char* stage = dyn + s * kStageBytes;
+      mbar_expect_tx(&s_full[s], (boxed ? kImgStageBytes : 0) + kTmplStageBytes);
+      if (boxed) tma_load_2d(stage, &p.tm_img, xlo, ylo, &s_full[s]);
+      tma_load_2d(stage + kImgStageBytes, &p.tm_tmpl, x0, y0 + c * kChunkH, &s_full[s]);
+    };
+    if (tid == 0) {
+      for (int c = 0; c < kEccStages - 1 && c < nseg; ++c) issue(c);
     }
-    __syncwarp();
-    mbar_wait(&s_full[s], (unsigned)(c / kEccStages) & 1u);
-    const float* box = reinterpret_cast<const float*>(dyn + s * kStageBytes);
-    const float* tbox = reinterpret_cast<const float*>(dyn + s * kStageBytes + kImgStageBytes);
-    const int xlo = s_box[c][0], ylo = s_box[c][1];
-    const bool boxed = xlo != INT_MIN;
-    const int cy0 = y0 + c * kChunkH;
-    const int ya = cy0 + part * kChunkRowsPerThread;
-    const int yb = min(ya + kChunkRowsPerThread, y1);
-    // lanes beyond the image width sit the chunk out; warp votes below use the mask of the lanes that work
-    const unsigned wmask = __ballot_sync(0xffffffffu, col_ok && ya < yb);
-    if (col_ok && ya < yb) {
-      const float* trow = tbox + (ya - cy0) * kEccStripW + col;
-      if (boxed) {
-        float yf = (float)ya;
-        Coord<Md::persp> co;
-        Jac<MOTION> jac;
-        if (!fast_coords) { co.init(s_m, x); jac.init(s_m, xf); }
-#pragma unroll 2
-        for (int y = ya; y < yb; ++y, yf += 1.0f) {
-          float g[G];
-          Sample smp;
-          const float t_ = trow[(y - ya) * kEccStripW];
-          int sx, sy, xn = 0, yn = 0;   // integer sample position / nearest position in the image
-          float ax, ay, du = 0.f, dv = 0.f, rw = 0.f;
-          if (fast_coords) {
-            int qx, qy;
-            fp.at(yf, qx, qy, du, dv, rw);
-            sx = x + (qx >> kInterBits);
-            sy = y + (qy >> kInterBits);
-            ax = (float)(qx & (kInterTab - 1)) * (1.f / kInterTab);
-            ay = (float)(qy & (kInterTab - 1)) * (1.f / kInterTab);
-          } else {
-            int xq, yq;
-            co.at_with_nearest(y, xq, yq, xn, yn);
-            sx = xq >> kInterBits;
-            sy = yq >> kInterBits;
-            ax = (float)(xq & (kInterTab - 1)) * (1.f / kInterTab);
-            ay = (float)(yq & (kInterTab - 1)) * (1.f / kInterTab);
-          }
-          // safe: the four bilinear taps and their gradient stencils stay off the border rows/columns, so
-          // no border rule applies and the mask is 1.  The branch is taken warp-wide: a warp on the rim
-          // runs the careful variant for all its lanes (no divergence), every other warp the plain one.
-          const bool safe = (unsigned)(sx - 1) <= (unsigned)(p.width - 4) && (unsigned)(sy - 1) <= (unsigned)(p.height - 4);
-          const float* bp = box + (sy - ylo) * kBoxW + (sx - xlo);
-          const bool all_safe = __all_sync(wmask, safe);
-          float mk = 1.f;
-          if (all_safe) {
-            smp = sample_box(bp, ax, ay);
-          } else {
-            smp = sample_box_rules(bp, ax, ay, sx, sy, p.width, p.height);
-            if (fast_coords) { FastPersp::nearest(du, dv, xn, yn); xn += x; yn += y; }
-            // OpenCV warps an all-ones mask with INTER_NEAREST: 1 where the rounded position is inside
-            mk = ((unsigned)xn < (unsigned)p.width && (unsigned)yn < (unsigned)p.height) ? 1.f : 0.f;
-          }
-          if (fast_coords) {
-            // a = gx / den, b = gy / den, t = hatX a + hatY b with hatX = -u, hatY = -v, den = w
-            const float hr = 0.5f * rw;
-            g[0] = smp.gx2 * hr; g[1] = smp.gy2 * hr;
-            g[G - 1] = -fmaf(xf + du, g[0], (yf + dv) * g[1]);
-          } else {
-            jac.eval(smp, yf, g);
-          }
-          if (all_safe) { acc.template add<true>(g, smp.w, t_, 1.f, yf); ++n_safe; }
-          else acc.template add<false>(g, smp.w, t_, mk, yf);
+
+    const int x = x0 + col;
+    const float xf = (float)x;
+    const bool col_ok = x < p.width;
+    Accum<MOTION> acc;
+    acc.clear();
+    int n_safe = 0;
+    FastPersp fp;
+    if (fast_coords) fp.init(s_m, x);
+
+    // general path for one pixel: exact coordinates, every border rule, nearest-neighbour mask
+    auto slow_pixel = [&](int y, float t_) {
+      Coord<Md::persp> co;
+      Jac<MOTION> jac;
+      co.init(s_m, x);
+      jac.init(s_m, xf);
+      int xq, yq, xn, yn;
+      const bool ok = co.at_with_nearest(y, xq, yq, xn, yn);
+      Sample smp; smp.w = 0.f; smp.gx2 = 0.f; smp.gy2 = 0.f;
+      float mk = 0.f;
+      if (ok) {
+        const int sx = xq >> kInterBits, sy = yq >> kInterBits;
+        if (sx >= -1 && sx < p.width && sy >= -1 && sy < p.height) {
+          const float ax = (float)(xq & (kInterTab - 1)) * (1.f / kInterTab);
+          const float ay = (float)(yq & (kInterTab - 1)) * (1.f / kInterTab);
+          smp = sample_general(p.img, p.pitch, p.width, p.height, sx, sy, ax, ay);
         }
-      } else {
-        for (int y = ya; y < yb; ++y) slow_pixel(y, trow[(y - ya) * kEccStripW]);
+        // OpenCV warps an all-ones mask with INTER_NEAREST: 1 where the rounded position is inside
+        mk = ((unsigned)xn < (unsigned)p.width && (unsigned)yn < (unsigned)p.height) ? 1.f : 0.f;
       }
+      float g[G];
+      const float yf = (float)y;
+      jac.eval(smp, yf, g);
+      acc.template add<false>(g, smp.w, t_, mk, yf);
+    };
+
+    for (int c = 0; c < nseg; ++c) {
+      const int gc = cc + c;
+      const int s = gc % kEccStages;
+      if (tid == 0 && c + kEccStages - 1 < nseg) issue(c + kEccStages - 1);
+      __syncwarp();
+      mbar_wait(&s_full[s], (unsigned)(gc / kEccStages) & 1u);
+      const float* box = reinterpret_cast<const float*>(dyn + s * kStageBytes);
+      const float* tbox = reinterpret_cast<const float*>(dyn + s * kStageBytes + kImgStageBytes);
+      const int xlo = s_box[c][0], ylo = s_box[c][1];
+      const bool boxed = xlo != INT_MIN;
+      const int cy0 = y0 + c * kChunkH;
+      const int ya = cy0 + part * kChunkRowsPerThread;
+      const int yb = min(ya + kChunkRowsPerThread, y1);
+      // lanes beyond the image width sit the chunk out; warp votes below use the mask of the lanes that work
+      const unsigned wmask = __ballot_sync(0xffffffffu, col_ok && ya < yb);
+      if (col_ok && ya < yb) {
+        const float* trow = tbox + (ya - cy0) * kEccStripW + col;
+        if (boxed) {
+          float yf = (float)ya;
+          Coord<Md::persp> co;
+          Jac<MOTION> jac;
+          if (!fast_coords) { co.init(s_m, x); jac.init(s_m, xf); }
+#pragma unroll 2
+          for (int y = ya; y < yb; ++y, yf += 1.0f) {
+            float g[G];
+            Sample smp;
+            const float t_ = trow[(y - ya) * kEccStripW];
+            int sx, sy, xn = 0, yn = 0;   // integer sample position / nearest position in the image
+            float ax, ay, du = 0.f, dv = 0.f, rw = 0.f;
+            if (fast_coords) {
+              int qx, qy;
+              fp.at(yf, qx, qy, du, dv, rw);
+              sx = x + (qx >> kInterBits);
+              sy = y + (qy >> kInterBits);
+              ax = (float)(qx & (kInterTab - 1)) * (1.f / kInterTab);
+              ay = (float)(qy & (kInterTab - 1)) * (1.f / kInterTab);
+            } else {
+              int xq, yq;
+              co.at_with_nearest(y, xq, yq, xn, yn);
+              sx = xq >> kInterBits;
+              sy = yq >> kInterBits;
+              ax = (float)(xq & (kInterTab - 1)) * (1.f / kInterTab);
+              ay = (float)(yq & (kInterTab - 1)) * (1.f / kInterTab);
+            }
+            // safe: the four bilinear taps and their gradient stencils stay off the border rows/columns,
+            // so no border rule applies and the mask is 1.  The branch is taken warp-wide: a warp on the
+            // rim runs the careful variant for all its lanes (no divergence), every other warp the plain one.
+            const bool safe = (unsigned)(sx - 1) <= (unsigned)(p.width - 4) && (unsigned)(sy - 1) <= (unsigned)(p.height - 4);
+            const float* bp = box + (sy - ylo) * kBoxW + (sx - xlo);
+            const bool all_safe = __all_sync(wmask, safe);
+            float mk = 1.f;
+            if (all_safe) {
+              smp = sample_box(bp, ax, ay);
+            } else {
+              smp = sample_box_rules(bp, ax, ay, sx, sy, p.width, p.height);
+              if (fast_coords) { FastPersp::nearest(du, dv, xn, yn); xn += x; yn += y; }
+              // OpenCV warps an all-ones mask with INTER_NEAREST: 1 where the rounded position is inside
+              mk = ((unsigned)xn < (unsigned)p.width && (unsigned)yn < (unsigned)p.height) ? 1.f : 0.f;
+            }
+            if (fast_coords) {
+              // a = gx / den, b = gy / den, t = hatX a + hatY b with hatX = -u, hatY = -v, den = w
+              const float hr = 0.5f * rw;
+              g[0] = smp.gx2 * hr; g[1] = smp.gy2 * hr;
+              g[G - 1] = -fmaf(xf + du, g[0], (yf + dv) * g[1]);
+            } else {
+              jac.eval(smp, yf, g);
+            }
+            if (all_safe) { acc.template add<true>(g, smp.w, t_, 1.f, yf); ++n_safe; }
+            else acc.template add<false>(g, smp.w, t_, mk, yf);
+          }
+        } else {
+          for (int y = ya; y < yb; ++y) slow_pixel(y, trow[(y - ya) * kEccStripW]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[s]);      // this warp is done with stage s
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&s_empty[s]);      // this warp is done with stage s
+    acc.n += (float)n_safe;
+
+    // ---- segment end: registers -> warp transpose-reduce -> smem -> f64 block accumulator ----------
+    {
+      float v[NV];
+      acc.emit(xf, v);
+      warp_reduce_vector<NV>(v, lane, s_red[wid]);
+    }
+    __syncthreads();
+    if (tid < NV) {
+      double sres = 0.0;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) sres += (double)s_red[w][tid];
+      s_accum[tid] += sres;
+    }
+    cc += nseg;
+    g0 += nseg;
   }
-  acc.n += (float)n_safe;
   if (p.timing_out && tid == 0) p.timing_out[(size_t)blockIdx.x * 4 + 1] = global_ns();
+  if (tid < NV) p.partials[(size_t)tid * p.tiles_pad + blockIdx.x] = s_accum[tid];
 
-  // ---- block reduction: registers -> warp shuffle -> smem -> f64 partial of this tile -------------
-  float v[NV];
-  acc.emit(xf, v);
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const float sres = warp_sum(v[i]);
-    if (lane == 0) s_red[wid][i] = sres;
-  }
-  __syncthreads();
-  if (tid < NV) {
-    double sres = 0.0;
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) sres += (double)s_red[w][tid];
-    p.partials[(size_t)tid * p.tiles_pad + blockIdx.x] = sres;
-  }
-
-  // ---- last block: deterministic cross-tile sum + solve --------------------------------------------
+  // ---- last block: deterministic cross-block sum + solve --------------------------------------------
   __threadfence();
   __syncthreads();
   if (p.timing_out && tid == 0) p.timing_out[(size_t)blockIdx.x * 4 + 2] = global_ns();
@@ -842,9 +897,9 @@ __global__ void __launch_bounds__(kEccThreads, 2) ecc_iter_kernel(const __grid_c
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  // value-major partials: lane l of a warp reads tiles l, l+32, ... of one value — 16 independent coalesced
+  // value-major partials: lane l of a warp reads blocks l, l+32, ... of one value — 16 independent coalesced
   // loads in flight per lane and two values per round, so the whole sum costs a few L2 round trips
-  // instead of one per tile (measured: 26 us -> ~3 us at 270 tiles).  Fixed order => deterministic.
+  // instead of one per block (measured: 26 us -> ~5 us at 270 partials).  Fixed order => deterministic.
   const int n_tiles = gridDim.x;
   for (int i = wid; i < NV; i += 2 * kWarps) {
     const int i2 = i + kWarps;
@@ -869,7 +924,7 @@ __global__ void __launch_bounds__(kEccThreads, 2) ecc_iter_kernel(const __grid_c
   __syncthreads();
   if (p.totals_out && tid < NV) p.totals_out[tid] = s_tot[tid];
   unsigned long long* tail = p.timing_out ? p.timing_out + (size_t)gridDim.x * 4 : nullptr;
-  if (tail && tid == 0) tail[0] = global_ns();        // cross-tile sum done
+  if (tail && tid == 0) tail[0] = global_ns();        // cross-block sum done
   if (wid == 0) {
     ecc_epilogue_warp<MOTION>(s_tot, st, lane);
     if (tail && lane == 0) tail[1] = global_ns();     // solve + update done

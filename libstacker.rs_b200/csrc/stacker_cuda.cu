@@ -148,7 +148,7 @@ struct stk_ecc_ctx {
   size_t frame_bytes = 0;           // width*channels*height (dense staging)
   size_t acc_floats = 0;
   // ECC tiling
-  int n_strips = 0, n_bands = 0, rows_per_tile = 0, n_tiles = 0, nv = 0;
+  int n_strips = 0, chunks_per_strip = 0, n_tiles = 0, nv = 0;   // n_tiles = persistent blocks of the ECC kernel
   int max_iter = 0;
   double eps = 0;
   CUtensorMap tm_img;
@@ -199,9 +199,8 @@ stk::EccIterParams iter_params(stk_ecc_ctx* c, Lane& ln, bool use_handle) {
   p.pitch = c->pitch_f;
   p.width = c->cfg.width;
   p.height = c->cfg.height;
-  p.rows_per_tile = c->rows_per_tile;
   p.n_strips = c->n_strips;
-  p.n_bands = c->n_bands;
+  p.chunks_per_strip = c->chunks_per_strip;
   p.partials = ln.partials;
   p.tiles_pad = (c->n_tiles + 31) / 32 * 32;
   p.st = ln.st;
@@ -259,8 +258,7 @@ int launch_prep(stk_ecc_ctx* c, const uint8_t* d_src, size_t pitch, float* dst, 
   p.src = d_src;
   p.src_pitch = pitch;
   p.dst = dst;
-  const int r = p.radius;
-  const size_t smem = (size_t)((stk::kPrepTW + 2 * r) * (stk::kPrepTH + 2 * r) + (stk::kPrepTH + 2 * r) * stk::kPrepTW) * sizeof(float);
+  const size_t smem = stk::prep_smem_bytes(p.radius);
   dim3 grid((c->cfg.width + stk::kPrepTW - 1) / stk::kPrepTW, (c->cfg.height + stk::kPrepTH - 1) / stk::kPrepTH);
   stk::prep_grey_blur_kernel<<<grid, stk::kPrepThreads, smem, s>>>(p);
   c->launches++;
@@ -494,8 +492,7 @@ int stk_ecc_create(const stk_ecc_config* cfg, stk_ecc_ctx** out) {
   auto cleanup = [&](int code) { stk_ecc_destroy(c); return code; };
 
   if (cfg->align) {
-    // tiling: 128-column strips x bands of R rows (R a multiple of the 16-row chunk); as many tiles as
-    // resident blocks, never fewer than 32 rows per tile so the per-tile fold/reduction stays amortised
+    // work split: 128-column strips x 16-row chunks, dealt evenly to one persistent block per resident slot
     if (cudaFuncSetAttribute((const void*)iter_kernel_for(cfg->motion_type, c->exact_coords), cudaFuncAttributeMaxDynamicSharedMemorySize,
                              stk::kEccDynSmem) != cudaSuccess)
       return cleanup(fail(STK_ERR_CUDA, "cannot reserve %d bytes of dynamic shared memory for the ECC kernel", stk::kEccDynSmem));
@@ -504,14 +501,10 @@ int stk_ecc_create(const stk_ecc_config* cfg, stk_ecc_ctx** out) {
                                                       stk::kEccDynSmem) != cudaSuccess || occ < 1) occ = 1;
     const int slots = c->sm_count * occ;
     c->n_strips = (cfg->width + stk::kEccStripW - 1) / stk::kEccStripW;
-    int bands = std::max(1, slots / c->n_strips);
-    int rows = (cfg->height + bands - 1) / bands;
-    rows = std::max(rows, 32);
-    rows = (rows + stk::kChunkH - 1) / stk::kChunkH * stk::kChunkH;
-    rows = std::min(rows, stk::kMaxChunks * stk::kChunkH);
-    c->rows_per_tile = rows;
-    c->n_bands = (cfg->height + rows - 1) / rows;
-    c->n_tiles = c->n_strips * c->n_bands;
+    c->chunks_per_strip = (cfg->height + stk::kChunkH - 1) / stk::kChunkH;
+    const long long total_chunks = (long long)c->n_strips * c->chunks_per_strip;
+    // at least two chunks per block so the per-run fold/reduction stays amortised on small frames
+    c->n_tiles = (int)std::max(1LL, std::min<long long>(slots, total_chunks / 2));
     c->nv = model_nv(cfg->motion_type);
     stk::PrepParams& pp = c->prep_proto;
     memset(&pp, 0, sizeof pp);
@@ -521,8 +514,7 @@ int stk_ecc_create(const stk_ecc_config* cfg, stk_ecc_ctx** out) {
     pp.channels = cfg->channels;
     pp.radius = cfg->gauss_filt_size / 2;
     gaussian_taps(cfg->gauss_filt_size, pp.taps);
-    const int r = pp.radius;
-    const size_t smem = (size_t)((stk::kPrepTW + 2 * r) * (stk::kPrepTH + 2 * r) + (stk::kPrepTH + 2 * r) * stk::kPrepTW) * sizeof(float);
+    const size_t smem = stk::prep_smem_bytes(pp.radius);
     if (smem > 48 * 1024) {
       if (cudaFuncSetAttribute(stk::prep_grey_blur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return cleanup(fail(STK_ERR_CUDA, "cannot reserve %zu bytes of shared memory for the blur", smem));

@@ -34,76 +34,124 @@ struct WarpAccParams {
 
 constexpr int kWarpBX = 32, kWarpBY = 8;
 
+// One thread per destination pixel (32 x 8 tile per block).  The C interpolated values of the tile are
+// staged in shared memory and the accumulator read-modify-write is done as coalesced 128-bit accesses
+// (a tile row is 32*C contiguous floats), so the 24N bytes of accumulator traffic move at full line width.
 template <int C, bool PERSP>
 __global__ void __launch_bounds__(kWarpBX * kWarpBY) warp_accumulate_kernel(const WarpAccParams p) {
+  __shared__ __align__(16) float s_val[kWarpBY][kWarpBX * C];
   if (p.status_ptr && *p.status_ptr != 0) return;
   const int x = blockIdx.x * kWarpBX + threadIdx.x;
   const int y = blockIdx.y * kWarpBY + threadIdx.y;
-  if (x >= p.width || y >= p.height) return;
-  double m[9];
-#pragma unroll
-  for (int i = 0; i < 9; ++i) m[i] = p.inv_ptr ? p.inv_ptr[i] : p.inv[i];
-
-  int xq, yq;
-  if (PERSP) {
-    // WarpPerspectiveInvoker: X0/Y0/W0 at the start of the 64-px column block, then + M*x1
-    const int bw = min(64, p.width);
-    const int xb = (x / bw) * bw;
-    const double xbd = (double)xb, x1 = (double)(x - xb), yd = (double)y;
-    const double X0 = __dadd_rn(__dadd_rn(__dmul_rn(m[0], xbd), __dmul_rn(m[1], yd)), m[2]);
-    const double Y0 = __dadd_rn(__dadd_rn(__dmul_rn(m[3], xbd), __dmul_rn(m[4], yd)), m[5]);
-    const double W0 = __dadd_rn(__dadd_rn(__dmul_rn(m[6], xbd), __dmul_rn(m[7], yd)), m[8]);
-    double W = __dadd_rn(W0, __dmul_rn(m[6], x1));
-    W = (W != 0.0) ? __ddiv_rn((double)kInterTab, W) : 0.0;
-    const double fX = fmax(-2147483648.0, fmin(2147483647.0, __dmul_rn(__dadd_rn(X0, __dmul_rn(m[0], x1)), W)));
-    const double fY = fmax(-2147483648.0, fmin(2147483647.0, __dmul_rn(__dadd_rn(Y0, __dmul_rn(m[3], x1)), W)));
-    xq = __double2int_rn(fX);
-    yq = __double2int_rn(fY);
-  } else {
-    const double xd = (double)x, yd = (double)y;
-    const int adelta = __double2int_rn(__dmul_rn(__dmul_rn(m[0], xd), kAbScale));
-    const int bdelta = __double2int_rn(__dmul_rn(__dmul_rn(m[3], xd), kAbScale));
-    const int X0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(m[1], yd), m[2]), kAbScale)) + 16;
-    const int Y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(m[4], yd), m[5]), kAbScale)) + 16;
-    xq = (int)((unsigned)X0 + (unsigned)adelta) >> (kAbBits - kInterBits);
-    yq = (int)((unsigned)Y0 + (unsigned)bdelta) >> (kAbBits - kInterBits);
-  }
-  // integer part is stored as short in OpenCV's map (saturate_cast<short>)
-  const int sx = max(-32768, min(32767, xq >> kInterBits));
-  const int sy = max(-32768, min(32767, yq >> kInterBits));
-  const float ax = (float)(xq & (kInterTab - 1)) * (1.f / kInterTab);
-  const float ay = (float)(yq & (kInterTab - 1)) * (1.f / kInterTab);
-  const float w00 = __fmul_rn(1.f - ay, 1.f - ax), w01 = __fmul_rn(1.f - ay, ax);
-  const float w10 = __fmul_rn(ay, 1.f - ax), w11 = __fmul_rn(ay, ax);
-
-  const int sw = p.src_width, sh = p.src_height;
+  const bool inside = x < p.width && y < p.height;
   float v[C];
-  if (sx >= sw || sx + 1 < 0 || sy >= sh || sy + 1 < 0) {
 #pragma unroll
-    for (int c = 0; c < C; ++c) v[c] = p.border[c];
-  } else {
-    const bool x0in = (unsigned)sx < (unsigned)sw, x1in = (unsigned)(sx + 1) < (unsigned)sw;
-    const bool y0in = (unsigned)sy < (unsigned)sh, y1in = (unsigned)(sy + 1) < (unsigned)sh;
-    const uint8_t* r0 = p.src + (ptrdiff_t)sy * (ptrdiff_t)p.src_pitch + (ptrdiff_t)sx * C;
-    const uint8_t* r1 = r0 + p.src_pitch;
-    const float k255 = (float)(1.0 / 255.0);
+  for (int c = 0; c < C; ++c) v[c] = 0.f;
+  if (inside) {
+    double m[9];
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
-      const float s00 = (y0in && x0in) ? __fmul_rn((float)__ldg(r0 + c), k255) : p.border[c];
-      const float s01 = (y0in && x1in) ? __fmul_rn((float)__ldg(r0 + C + c), k255) : p.border[c];
-      const float s10 = (y1in && x0in) ? __fmul_rn((float)__ldg(r1 + c), k255) : p.border[c];
-      const float s11 = (y1in && x1in) ? __fmul_rn((float)__ldg(r1 + C + c), k255) : p.border[c];
-      v[c] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s00, w00), __fmul_rn(s01, w01)), __fmul_rn(s10, w10)),
-                       __fmul_rn(s11, w11));
+    for (int i = 0; i < 9; ++i) m[i] = p.inv_ptr ? p.inv_ptr[i] : p.inv[i];
+
+    int xq, yq;
+    if (PERSP) {
+      // WarpPerspectiveInvoker: X0/Y0/W0 at the start of the 64-px column block, then + M*x1
+      const int bw = min(64, p.width);
+      const int xb = (x / bw) * bw;
+      const double xbd = (double)xb, x1 = (double)(x - xb), yd = (double)y;
+      const double X0 = __dadd_rn(__dadd_rn(__dmul_rn(m[0], xbd), __dmul_rn(m[1], yd)), m[2]);
+      const double Y0 = __dadd_rn(__dadd_rn(__dmul_rn(m[3], xbd), __dmul_rn(m[4], yd)), m[5]);
+      const double W0 = __dadd_rn(__dadd_rn(__dmul_rn(m[6], xbd), __dmul_rn(m[7], yd)), m[8]);
+      double W = __dadd_rn(W0, __dmul_rn(m[6], x1));
+      W = (W != 0.0) ? __ddiv_rn((double)kInterTab, W) : 0.0;
+      const double fX = fmax(-2147483648.0, fmin(2147483647.0, __dmul_rn(__dadd_rn(X0, __dmul_rn(m[0], x1)), W)));
+      const double fY = fmax(-2147483648.0, fmin(2147483647.0, __dmul_rn(__dadd_rn(Y0, __dmul_rn(m[3], x1)), W)));
+      xq = __double2int_rn(fX);
+      yq = __double2int_rn(fY);
+    } else {
+      const double xd = (double)x, yd = (double)y;
+      const int adelta = __double2int_rn(__dmul_rn(__dmul_rn(m[0], xd), kAbScale));
+      const int bdelta = __double2int_rn(__dmul_rn(__dmul_rn(m[3], xd), kAbScale));
+      const int X0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(m[1], yd), m[2]), kAbScale)) + 16;
+      const int Y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(m[4], yd), m[5]), kAbScale)) + 16;
+      xq = (int)((unsigned)X0 + (unsigned)adelta) >> (kAbBits - kInterBits);
+      yq = (int)((unsigned)Y0 + (unsigned)bdelta) >> (kAbBits - kInterBits);
+    }
+    // integer part is stored as short in OpenCV's map (saturate_cast<short>)
+    const int sx = max(-32768, min(32767, xq >> kInterBits));
+    const int sy = max(-32768, min(32767, yq >> kInterBits));
+    const float ax = (float)(xq & (kInterTab - 1)) * (1.f / kInterTab);
+    const float ay = (float)(yq & (kInterTab - 1)) * (1.f / kInterTab);
+    const float w00 = __fmul_rn(1.f - ay, 1.f - ax), w01 = __fmul_rn(1.f - ay, ax);
+    const float w10 = __fmul_rn(ay, 1.f - ax), w11 = __fmul_rn(ay, ax);
+
+    const int sw = p.src_width, sh = p.src_height;
+    if (sx >= sw || sx + 1 < 0 || sy >= sh || sy + 1 < 0) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) v[c] = p.border[c];
+    } else {
+      const bool x0in = (unsigned)sx < (unsigned)sw, x1in = (unsigned)(sx + 1) < (unsigned)sw;
+      const bool y0in = (unsigned)sy < (unsigned)sh, y1in = (unsigned)(sy + 1) < (unsigned)sh;
+      const uint8_t* r0 = p.src + (ptrdiff_t)sy * (ptrdiff_t)p.src_pitch + (ptrdiff_t)sx * C;
+      const uint8_t* r1 = r0 + p.src_pitch;
+      const float k255 = (float)(1.0 / 255.0);
+      // issue all tap loads first (independent), then convert and blend
+      unsigned t00[C], t01[C], t10[C], t11[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        t00[c] = (y0in && x0in) ? __ldg(r0 + c) : 0u;
+        t01[c] = (y0in && x1in) ? __ldg(r0 + C + c) : 0u;
+        t10[c] = (y1in && x0in) ? __ldg(r1 + c) : 0u;
+        t11[c] = (y1in && x1in) ? __ldg(r1 + C + c) : 0u;
+      }
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float s00 = (y0in && x0in) ? __fmul_rn((float)t00[c], k255) : p.border[c];
+        const float s01 = (y0in && x1in) ? __fmul_rn((float)t01[c], k255) : p.border[c];
+        const float s10 = (y1in && x0in) ? __fmul_rn((float)t10[c], k255) : p.border[c];
+        const float s11 = (y1in && x1in) ? __fmul_rn((float)t11[c], k255) : p.border[c];
+        v[c] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s00, w00), __fmul_rn(s01, w01)), __fmul_rn(s10, w10)),
+                         __fmul_rn(s11, w11));
+      }
     }
   }
-  float* a = p.acc + ((size_t)y * p.width + x) * C;
-  if (p.store) {
 #pragma unroll
-    for (int c = 0; c < C; ++c) a[c] = v[c];
+  for (int c = 0; c < C; ++c) s_val[threadIdx.y][threadIdx.x * C + c] = v[c];
+  __syncthreads();
+
+  // coalesced accumulate: the tile row y holds floats [x_tile0*C, x_tile0*C + 32*C) of accumulator row y
+  const int tx0 = blockIdx.x * kWarpBX;
+  const int row_elems = min(kWarpBX, p.width - tx0) * C;        // valid floats in this tile row
+  const size_t row_base = (size_t)tx0 * C;                       // float offset of the tile inside a row
+  const bool vec_ok = (((size_t)p.width * C) % 4 == 0) && (row_base % 4 == 0);
+  const int tid = threadIdx.y * kWarpBX + threadIdx.x;
+  if (vec_ok) {
+    constexpr int kVecPerRow = kWarpBX * C / 4;
+    for (int i = tid; i < kWarpBY * kVecPerRow; i += kWarpBX * kWarpBY) {
+      const int r = i / kVecPerRow, q = i - r * kVecPerRow;
+      const int yy = blockIdx.y * kWarpBY + r;
+      if (yy >= p.height || q * 4 >= row_elems) continue;
+      float* a = p.acc + (size_t)yy * p.width * C + row_base + q * 4;
+      const float4 nv = *reinterpret_cast<const float4*>(&s_val[r][q * 4]);
+      if (q * 4 + 4 <= row_elems) {
+        float4 o = nv;
+        if (!p.store) {
+          const float4 cur = *reinterpret_cast<const float4*>(a);
+          o.x = __fadd_rn(cur.x, nv.x); o.y = __fadd_rn(cur.y, nv.y); o.z = __fadd_rn(cur.z, nv.z); o.w = __fadd_rn(cur.w, nv.w);
+        }
+        *reinterpret_cast<float4*>(a) = o;
+      } else {
+        const float e[4] = {nv.x, nv.y, nv.z, nv.w};
+        for (int k = 0; k < 4 && q * 4 + k < row_elems; ++k) a[k] = p.store ? e[k] : __fadd_rn(a[k], e[k]);
+      }
+    }
   } else {
-#pragma unroll
-    for (int c = 0; c < C; ++c) a[c] = __fadd_rn(a[c], v[c]);
+    for (int i = tid; i < kWarpBY * kWarpBX * C; i += kWarpBX * kWarpBY) {
+      const int r = i / (kWarpBX * C), q = i - r * (kWarpBX * C);
+      const int yy = blockIdx.y * kWarpBY + r;
+      if (yy >= p.height || q >= row_elems) continue;
+      float* a = p.acc + (size_t)yy * p.width * C + row_base + q;
+      *a = p.store ? s_val[r][q] : __fadd_rn(*a, s_val[r][q]);
+    }
   }
 }
 

@@ -1,0 +1,223 @@
+//! libstacker — same public API as eadf/libstacker.rs, with the ECC align-and-stack path (and the Tenengrad
+//! metric and the final warp/accumulate of `keypoint_match`) running on an NVIDIA B200 through the C ABI in
+//! `include/stacker_cuda.h`.  File decode and the ORB / BFMatcher / findHomography stages stay on the host
+//! in OpenCV, exactly where the reference has them.
+//!
+//! This crate is provided as the binding a maintainer adds; it is not compiled in this repository (no Rust
+//! toolchain in the build image).  The C++ (`../host`) and Python (`../api.py`) mirrors drive the same ABI
+//! and are what the test-suite runs.
+pub mod ffi;
+pub mod utils;
+
+pub use opencv;
+use opencv::core::{self, Mat, Point2f, Vector};
+use opencv::{calib3d, features2d, imgproc, prelude::*};
+use rayon::prelude::*;
+use std::path::PathBuf;
+use thiserror::Error;
+
+#[derive(Error, Debug)]
+pub enum StackerError {
+    #[error(transparent)]
+    OpenCvError(#[from] opencv::Error),
+    #[error("Not enough files")]
+    NotEnoughFiles,
+    #[error("Not implemented")]
+    NotImplemented,
+    #[error(transparent)]
+    IoError(#[from] std::io::Error),
+    #[error("Invalid path encoding {0}")]
+    InvalidPathEncoding(PathBuf),
+    #[error("Invalid parameter(s) {0}")]
+    InvalidParams(String),
+    #[error("Internal error {0}")]
+    ProcessingError(String),
+}
+
+/// Status code of the CUDA library -> the variant the reference would have produced at that point.
+fn check(rc: i32) -> Result<(), StackerError> {
+    use ffi::*;
+    match rc {
+        STK_OK => Ok(()),
+        // findTransformECC's StsNoConv / CV_Assert surface as opencv::Error in the reference (src/lib.rs:777)
+        STK_ERR_ECC_NOCONV | STK_ERR_ECC_NAN | STK_ERR_CRITERIA => Err(StackerError::OpenCvError(opencv::Error::new(
+            core::StsNoConv, last_error()))),
+        STK_ERR_BAD_ARG => Err(StackerError::InvalidParams(last_error())),
+        STK_ERR_NOT_ENOUGH => Err(StackerError::NotEnoughFiles),
+        STK_ERR_UNSUPPORTED => Err(StackerError::NotImplemented),
+        _ => Err(StackerError::ProcessingError(last_error())),
+    }
+}
+
+#[derive(Debug, Clone, Copy)]
+pub struct KeyPointMatchParameters {
+    pub method: i32,
+    pub ransac_reproj_threshold: f64,
+    pub match_keep_ratio: f32,
+    pub match_ratio: f32,
+    pub border_mode: i32,
+    pub border_value: core::Scalar,
+}
+
+#[derive(Debug, Copy, Clone, PartialEq, Eq)]
+pub enum MotionType {
+    Homography = opencv::video::MOTION_HOMOGRAPHY as isize,
+    Affine = opencv::video::MOTION_AFFINE as isize,
+    Euclidean = opencv::video::MOTION_EUCLIDEAN as isize,
+    Translation = opencv::video::MOTION_TRANSLATION as isize,
+}
+
+#[derive(Debug, Copy, Clone)]
+pub struct EccMatchParameters {
+    pub motion_type: MotionType,
+    pub max_count: Option<i32>,
+    pub epsilon: Option<f64>,
+    pub gauss_filt_size: i32,
+}
+
+fn new_ctx(first: &Mat, ecc: Option<(EccMatchParameters, core::TermCriteria)>) -> Result<ffi::Ctx, StackerError> {
+    let mut cfg = ffi::stk_ecc_config {
+        width: first.cols(), height: first.rows(), channels: first.channels(),
+        device: -1, lanes: 0, seed_reference: 1, ..Default::default()
+    };
+    if let Some((p, c)) = ecc {
+        cfg.align = 1;
+        cfg.motion_type = p.motion_type as i32;
+        cfg.criteria_type = c.typ;
+        cfg.max_count = c.max_count;
+        cfg.epsilon = c.epsilon;
+        cfg.gauss_filt_size = p.gauss_filt_size;
+    }
+    let mut raw = std::ptr::null_mut();
+    check(unsafe { ffi::stk_ecc_create(&cfg, &mut raw) })?;
+    Ok(ffi::Ctx(raw))
+}
+
+fn finish(ctx: &ffi::Ctx, first: &Mat, divisor: usize) -> Result<Mat, StackerError> {
+    let typ = core::CV_MAKETYPE(core::CV_32F, first.channels());
+    let mut out = unsafe { Mat::new_rows_cols(first.rows(), first.cols(), typ)? };
+    let pitch = out.mat_step().get(0);
+    check(unsafe { ffi::stk_ecc_finish(ctx.0, divisor as i32, out.data_mut() as *mut f32, pitch) })?;
+    Ok(out)
+}
+
+/// Aligns every image to the first with ECC and averages them.  Same contract as the reference
+/// (`src/lib.rs:702-717`): `Ok(Mat)` is CV_32FC3 in [0, 1]; `scale_down_width` selects the scaled variant.
+pub fn ecc_match<I, P>(files: I, params: EccMatchParameters, scale_down_width: Option<f32>) -> Result<Mat, StackerError>
+where
+    I: IntoIterator<Item = P>,
+    P: AsRef<std::path::Path>,
+{
+    let files: Vec<PathBuf> = files.into_iter().map(|p| p.as_ref().to_path_buf()).collect();
+    if scale_down_width.is_some() {
+        return Err(StackerError::NotImplemented); // next
+    }
+    if files.is_empty() {
+        return Err(StackerError::NotEnoughFiles);
+    }
+    let criteria = Result::<core::TermCriteria, StackerError>::from(params)?;
+    let first = utils::read_frame(&files[0])?;
+    let ctx = new_ctx(&first, Some((params, criteria)))?;
+    check(unsafe { ffi::stk_ecc_set_reference(ctx.0, first.data(), first.mat_step().get(0)) })?;
+    // decode on the Rayon pool, one task per frame (reference: src/lib.rs:746-749); submission is thread-safe,
+    // asynchronous, and copies the frame into pinned staging before returning
+    (1..files.len()).into_par_iter().with_min_len(1).try_for_each(|i| -> Result<(), StackerError> {
+        let img = utils::read_frame(&files[i])?;
+        if img.size()? != first.size()? || img.channels() != first.channels() {
+            return Err(StackerError::InvalidParams(format!("{:?}: size differs from the first frame", files[i])));
+        }
+        check(unsafe { ffi::stk_ecc_submit_frame(ctx.0, img.data(), img.mat_step().get(0), i as i64) })
+    })?;
+    finish(&ctx, &first, files.len())
+}
+
+/// Feature-based alignment: ORB / BFMatcher / findHomography on the host exactly as the reference
+/// (`src/lib.rs:146-287`), final `warp_perspective` + accumulate + divide on the GPU (`:289-350`).
+pub fn keypoint_match<I, P>(files: I, params: KeyPointMatchParameters, scale_down_width: Option<f32>) -> Result<(i32, Mat), StackerError>
+where
+    I: IntoIterator<Item = P>,
+    P: AsRef<std::path::Path>,
+{
+    let files: Vec<PathBuf> = files.into_iter().map(|p| p.as_ref().to_path_buf()).collect();
+    if scale_down_width.is_some() {
+        return Err(StackerError::NotImplemented);
+    }
+    if files.is_empty() {
+        return Err(StackerError::NotEnoughFiles);
+    }
+    let first = utils::read_frame(&files[0])?;
+    let grey = |img: &Mat| -> Result<Mat, StackerError> {
+        let mut g = Mat::default();
+        imgproc::cvt_color(img, &mut g, imgproc::COLOR_BGR2GRAY, 0, core::AlgorithmHint::ALGO_HINT_DEFAULT)?;
+        Ok(g)
+    };
+    let orb = |g: &Mat| -> Result<(Vector<core::KeyPoint>, Mat), StackerError> {
+        let mut orb = features2d::ORB::create_def()?;
+        let (mut kp, mut des) = (Vector::new(), Mat::default());
+        orb.detect_and_compute(g, &Mat::default(), &mut kp, &mut des, false)?;
+        Ok((kp, des))
+    };
+    let (kp0, des0) = orb(&grey(&first)?)?;
+    let ctx = new_ctx(&first, None)?;
+    check(unsafe { ffi::stk_ecc_set_reference(ctx.0, first.data(), first.mat_step().get(0)) })?;
+    let border = [params.border_value[0], params.border_value[1], params.border_value[2], params.border_value[3]];
+    let dropped: i32 = (1..files.len()).into_par_iter().with_min_len(1).map(|i| -> Result<i32, StackerError> {
+        let img = utils::read_frame(&files[i])?;
+        let (kp, des) = orb(&grey(&img)?)?;
+        let mut matcher = features2d::BFMatcher::create(core::NORM_HAMMING, false)?;
+        matcher.add(&des)?;
+        let mut knn = Vector::<Vector<core::DMatch>>::new();
+        matcher.knn_match(&des0, &mut knn, 2, &Mat::default(), false)?;
+        let mut good: Vec<core::DMatch> = knn.iter()
+            .filter_map(|m| (m.len() == 2 && m.get(0).unwrap().distance < params.match_ratio * m.get(1).unwrap().distance)
+                .then(|| m.get(0).unwrap()))
+            .collect();
+        good.sort_by(|a, b| a.distance.partial_cmp(&b.distance).unwrap_or(std::cmp::Ordering::Equal));
+        good.truncate((good.len() as f32 * params.match_keep_ratio).round() as usize);
+        if good.len() < 5 {
+            return Ok(1);
+        }
+        let mut src = Vector::<Point2f>::with_capacity(good.len());
+        let mut dst = Vector::<Point2f>::with_capacity(good.len());
+        for m in &good {
+            src.push(kp0.get(m.query_idx as usize)?.pt());
+            dst.push(kp.get(m.train_idx as usize)?.pt());
+        }
+        let h = match calib3d::find_homography(&dst, &src, &mut Mat::default(), params.method, params.ransac_reproj_threshold) {
+            Ok(h) => h,
+            Err(_) => return Ok(1),
+        };
+        if h.empty() || h.rows() != 3 || h.cols() != 3 || core::determinant(&h)?.abs() < 1e-6 {
+            return Ok(1);
+        }
+        let hv: Vec<f64> = h.data_typed::<f64>()?.to_vec();
+        check(unsafe {
+            ffi::stk_ecc_submit_warp(ctx.0, img.data(), img.mat_step().get(0), hv.as_ptr(), params.border_mode, border.as_ptr(), i as i64)
+        })?;
+        Ok(0)
+    }).try_reduce(|| 0, |a, b| Ok(a + b))?;
+    if files.len() as i32 - dropped <= 0 {
+        return Err(StackerError::InvalidParams("All images discarded: try modifying KeyPointMatchParameters::match_distance_threshold".into()));
+    }
+    Ok((dropped, finish(&ctx, &first, files.len() - dropped as usize)?))
+}
+
+/// Tenengrad sharpness (Krotkov86) of an 8-bit single-channel image; bit-identical to the reference's
+/// CV_64F Sobel pipeline (`src/lib.rs:1101-1147`).
+pub fn sharpness_tenengrad(src_grey_mat: &Mat, k_size: i32) -> Result<f64, StackerError> {
+    if ![1, 3, 5, 7].contains(&k_size) {
+        return Err(StackerError::InvalidParams("Kernel size must be 1, 3, 5, or 7".into()));
+    }
+    if src_grey_mat.depth() != core::CV_8U || src_grey_mat.channels() != 1 {
+        return Err(StackerError::NotImplemented);
+    }
+    let mut out = 0f64;
+    check(unsafe {
+        ffi::stk_tenengrad(src_grey_mat.data(), src_grey_mat.mat_step().get(0), src_grey_mat.cols(), src_grey_mat.rows(), 1, k_size, -1, &mut out)
+    })?;
+    Ok(out)
+}
+
+pub mod prelude {
+    pub use super::{EccMatchParameters, KeyPointMatchParameters, MotionType, StackerError, ecc_match, keypoint_match};
+}

@@ -1,0 +1,63 @@
+//! Host-side helpers kept from the reference crate's `utils` module (same signatures): checked `imread`,
+//! the `EccMatchParameters -> TermCriteria` conversion and the `KeyPointMatchParameters` defaults.
+use crate::{EccMatchParameters, StackerError};
+use opencv::{imgcodecs, prelude::*};
+
+/// `imread` with a checked path (reference: src/utils.rs:111-117).
+#[inline(always)]
+pub fn imread<P: AsRef<std::path::Path>>(path: P, imread_flags: i32) -> Result<Mat, StackerError> {
+    let path_str = path
+        .as_ref()
+        .to_str()
+        .ok_or_else(|| StackerError::InvalidPathEncoding(path.as_ref().to_path_buf()))?;
+    Ok(imgcodecs::imread(path_str, imread_flags)?)
+}
+
+/// Decode as-is (IMREAD_UNCHANGED) and check what the device path needs: 8-bit, 3 or 4 channels, continuous.
+/// The grey conversion and the `* 1/255` of the reference's `read_grey_and_f32` happen on the GPU.
+pub(crate) fn read_frame(path: &std::path::Path) -> Result<Mat, StackerError> {
+    let img = imread(path, imgcodecs::IMREAD_UNCHANGED)?;
+    if img.depth() != opencv::core::CV_8U || !(img.channels() == 3 || img.channels() == 4) {
+        // the reference fails here too: cvtColor(BGR2GRAY) / findTransformECC reject anything else
+        return Err(StackerError::InvalidParams(format!(
+            "unsupported image type (depth {}, {} channels) in {:?}", img.depth(), img.channels(), path
+        )));
+    }
+    if img.is_continuous() { Ok(img) } else { Ok(img.try_clone()?) }
+}
+
+impl From<EccMatchParameters> for Result<opencv::core::TermCriteria, StackerError> {
+    /// ```
+    /// # use libstacker::{prelude::*, opencv::core::TermCriteria_Type};
+    /// let t: Result<opencv::core::TermCriteria, StackerError> = EccMatchParameters {
+    ///     motion_type: MotionType::Euclidean, max_count: None, epsilon: Some(0.1), gauss_filt_size: 3 }.into();
+    /// let t = t.unwrap();
+    /// assert_eq!(t.epsilon, 0.1);
+    /// assert_eq!(t.typ, TermCriteria_Type::EPS as i32);
+    /// ```
+    fn from(r: EccMatchParameters) -> Result<opencv::core::TermCriteria, StackerError> {
+        let mut rv = opencv::core::TermCriteria::default()?;
+        if let Some(max_count) = r.max_count {
+            rv.typ |= opencv::core::TermCriteria_Type::COUNT as i32;
+            rv.max_count = max_count;
+        }
+        if let Some(epsilon) = r.epsilon {
+            rv.typ |= opencv::core::TermCriteria_Type::EPS as i32;
+            rv.epsilon = epsilon;
+        }
+        Ok(rv)
+    }
+}
+
+impl Default for crate::KeyPointMatchParameters {
+    fn default() -> Self {
+        Self {
+            method: opencv::calib3d::RANSAC,
+            ransac_reproj_threshold: 3.0,
+            match_keep_ratio: 0.75,
+            match_ratio: 0.8,
+            border_mode: opencv::core::BORDER_CONSTANT,
+            border_value: opencv::core::Scalar::default(),
+        }
+    }
+}
