@@ -38,37 +38,71 @@ inline size_t prep_smem_bytes(int r) {
   return (size_t)((kPrepTH + 2 * r) * prep_grey_pitch(r) + (kPrepTH + 2 * r) * kPrepTW) * sizeof(float);
 }
 
-// dynamic smem: grey[(TH+2r)][gp] floats + tmp[(TH+2r)][TW] floats
+// dynamic smem: tmp[(TH+2r)][TW] floats + grey[(TH+2r)][gp] floats
+// R > 0: compile-time radius (loops unrolled, taps in registers); R == 0: runtime radius p.radius.
+template <int R>
 __global__ void __launch_bounds__(kPrepThreads) prep_grey_blur_kernel(const PrepParams p) {
   extern __shared__ __align__(16) float prep_smem[];
-  const int r = p.radius;
+  const int r = R > 0 ? R : p.radius;
   const int gw = kPrepTW + 2 * r, gh = kPrepTH + 2 * r, gp = prep_grey_pitch(r);
   float* tmp = prep_smem;                       // [gh][TW], 16-byte aligned rows
   float* grey = prep_smem + gh * kPrepTW;       // [gh][gp]
   const int x0 = blockIdx.x * kPrepTW, y0 = blockIdx.y * kPrepTH;
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
   const int ch = p.channels;
+  constexpr int kWarps = kPrepThreads / 32;
 
-  // 1. grey tile with reflected halo
-  for (int ty = wrp; ty < gh; ty += kPrepThreads / 32) {
-    const int sy = reflect101(y0 + ty - r, p.height);
-    const uint8_t* row = p.src + (size_t)sy * p.src_pitch;
-    for (int tx = lane; tx < gw; tx += 32) {
-      const int sx = reflect101(x0 + tx - r, p.width);
-      const uint8_t* px = row + (size_t)sx * ch;
-      grey[ty * gp + tx] = (float)bgr2gray(__ldg(px), __ldg(px + 1), __ldg(px + 2));
+  // 1. grey tile with halo; tiles whose halo stays inside the image skip the BORDER_REFLECT_101 index math
+  const bool interior = x0 - r >= 0 && x0 + kPrepTW + r <= p.width && y0 - r >= 0 && y0 + kPrepTH + r <= p.height;
+  if (interior) {
+    const uint8_t* base = p.src + (size_t)(y0 - r) * p.src_pitch + (size_t)(x0 - r) * ch;
+    // all byte loads of a row are issued before the first conversion (memory-level parallelism)
+    constexpr int kCols = (kPrepTW + 2 * (R > 0 ? R : kMaxGaussRadius) + 31) / 32;
+    for (int ty = wrp; ty < gh; ty += kWarps) {
+      const uint8_t* row = base + (size_t)ty * p.src_pitch;
+      unsigned b[kCols], g[kCols], rch[kCols];
+#pragma unroll
+      for (int q = 0; q < kCols; ++q) {
+        const int tx = lane + 32 * q;
+        if (tx < gw) { const uint8_t* px = row + tx * ch; b[q] = __ldg(px); g[q] = __ldg(px + 1); rch[q] = __ldg(px + 2); }
+      }
+#pragma unroll
+      for (int q = 0; q < kCols; ++q) {
+        const int tx = lane + 32 * q;
+        if (tx < gw) grey[ty * gp + tx] = (float)bgr2gray(b[q], g[q], rch[q]);
+      }
+    }
+  } else {
+    for (int ty = wrp; ty < gh; ty += kWarps) {
+      const int sy = reflect101(y0 + ty - r, p.height);
+      const uint8_t* row = p.src + (size_t)sy * p.src_pitch;
+      for (int tx = lane; tx < gw; tx += 32) {
+        const int sx = reflect101(x0 + tx - r, p.width);
+        const uint8_t* px = row + (size_t)sx * ch;
+        grey[ty * gp + tx] = (float)bgr2gray(__ldg(px), __ldg(px + 1), __ldg(px + 2));
+      }
     }
   }
   __syncthreads();
 
-  // 2. horizontal pass (symmetric taps: centre + pairs)
-  for (int ty = wrp; ty < gh; ty += kPrepThreads / 32) {
+  // taps (symmetric: centre + pairs) — registers when R is a template constant
+  float tap[(R > 0 ? R : kMaxGaussRadius) + 1];
+#pragma unroll
+  for (int k = 0; k <= (R > 0 ? R : kMaxGaussRadius); ++k) tap[k] = (k <= r) ? p.taps[r + k] : 0.f;
+
+  // 2. horizontal pass
+  for (int ty = wrp; ty < gh; ty += kWarps) {
 #pragma unroll
     for (int q = 0; q < kPrepTW / 32; ++q) {
       const int tx = lane + 32 * q;
       const float* c = grey + ty * gp + tx + r;
-      float s = p.taps[r] * c[0];
-      for (int k = 1; k <= r; ++k) s += p.taps[r + k] * (c[-k] + c[k]);
+      float s = tap[0] * c[0];
+      if (R > 0) {
+#pragma unroll
+        for (int k = 1; k <= R; ++k) s += tap[k] * (c[-k] + c[k]);
+      } else {
+        for (int k = 1; k <= r; ++k) s += p.taps[r + k] * (c[-k] + c[k]);
+      }
       tmp[ty * kPrepTW + tx] = s;
     }
   }
@@ -77,18 +111,22 @@ __global__ void __launch_bounds__(kPrepThreads) prep_grey_blur_kernel(const Prep
   // 3. vertical pass: each thread 4 consecutive columns, 128-bit smem loads and global stores
   const int cx = lane * 4;                       // 32 lanes x 4 = 128 columns
   const bool full4 = x0 + cx + 3 < p.width;
-  for (int ty = wrp; ty < kPrepTH; ty += kPrepThreads / 32) {
+  for (int ty = wrp; ty < kPrepTH; ty += kWarps) {
     const int y = y0 + ty;
     if (y >= p.height || x0 + cx >= p.width) continue;
     const float* c = tmp + (ty + r) * kPrepTW + cx;
     const float4 v0 = *reinterpret_cast<const float4*>(c);
-    const float t0 = p.taps[r];
-    float4 s = make_float4(t0 * v0.x, t0 * v0.y, t0 * v0.z, t0 * v0.w);
-    for (int k = 1; k <= r; ++k) {
+    float4 s = make_float4(tap[0] * v0.x, tap[0] * v0.y, tap[0] * v0.z, tap[0] * v0.w);
+    auto acc_pair = [&](int k, float t) {
       const float4 a = *reinterpret_cast<const float4*>(c - k * kPrepTW);
       const float4 b = *reinterpret_cast<const float4*>(c + k * kPrepTW);
-      const float t = p.taps[r + k];
       s.x += t * (a.x + b.x); s.y += t * (a.y + b.y); s.z += t * (a.z + b.z); s.w += t * (a.w + b.w);
+    };
+    if (R > 0) {
+#pragma unroll
+      for (int k = 1; k <= R; ++k) acc_pair(k, tap[k]);
+    } else {
+      for (int k = 1; k <= r; ++k) acc_pair(k, p.taps[r + k]);
     }
     float* o = p.dst + (size_t)y * p.dst_pitch + x0 + cx;
     if (full4) {

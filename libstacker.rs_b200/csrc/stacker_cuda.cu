@@ -260,7 +260,13 @@ int launch_prep(stk_ecc_ctx* c, const uint8_t* d_src, size_t pitch, float* dst, 
   p.dst = dst;
   const size_t smem = stk::prep_smem_bytes(p.radius);
   dim3 grid((c->cfg.width + stk::kPrepTW - 1) / stk::kPrepTW, (c->cfg.height + stk::kPrepTH - 1) / stk::kPrepTH);
-  stk::prep_grey_blur_kernel<<<grid, stk::kPrepThreads, smem, s>>>(p);
+  switch (p.radius) {   // radii 1..4 (gauss_filt_size 3..9) get unrolled instantiations
+    case 1: stk::prep_grey_blur_kernel<1><<<grid, stk::kPrepThreads, smem, s>>>(p); break;
+    case 2: stk::prep_grey_blur_kernel<2><<<grid, stk::kPrepThreads, smem, s>>>(p); break;
+    case 3: stk::prep_grey_blur_kernel<3><<<grid, stk::kPrepThreads, smem, s>>>(p); break;
+    case 4: stk::prep_grey_blur_kernel<4><<<grid, stk::kPrepThreads, smem, s>>>(p); break;
+    default: stk::prep_grey_blur_kernel<0><<<grid, stk::kPrepThreads, smem, s>>>(p); break;
+  }
   c->launches++;
   CU(cudaGetLastError());
   return STK_OK;
@@ -282,7 +288,7 @@ int launch_warp(stk_ecc_ctx* c, Lane& ln, const uint8_t* d_src, size_t pitch, bo
   for (int i = 0; i < 4; ++i) p.border[i] = border ? border[i] : 0.f;
   p.store = ln.acc_used ? 0 : 1;
   dim3 block(stk::kWarpBX, stk::kWarpBY);
-  dim3 grid((p.width + stk::kWarpBX - 1) / stk::kWarpBX, (p.height + stk::kWarpBY - 1) / stk::kWarpBY);
+  dim3 grid((p.width + stk::kWarpBX - 1) / stk::kWarpBX, (p.height + stk::kWarpTH - 1) / stk::kWarpTH);
   const int ch = c->cfg.channels;
   if (ch == 3) {
     if (persp) stk::warp_accumulate_kernel<3, true><<<grid, block, 0, ln.stream>>>(p);
@@ -516,7 +522,7 @@ int stk_ecc_create(const stk_ecc_config* cfg, stk_ecc_ctx** out) {
     gaussian_taps(cfg->gauss_filt_size, pp.taps);
     const size_t smem = stk::prep_smem_bytes(pp.radius);
     if (smem > 48 * 1024) {
-      if (cudaFuncSetAttribute(stk::prep_grey_blur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      if (cudaFuncSetAttribute(stk::prep_grey_blur_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return cleanup(fail(STK_ERR_CUDA, "cannot reserve %zu bytes of shared memory for the blur", smem));
     }
     if (cudaMalloc((void**)&c->img, (size_t)c->pitch_f * cfg->height * sizeof(float)) != cudaSuccess)

@@ -32,103 +32,136 @@ struct WarpAccParams {
   int store;              // 1: acc = v (first frame on this lane), 0: acc += v
 };
 
-constexpr int kWarpBX = 32, kWarpBY = 8;
+constexpr int kWarpBX = 32, kWarpBY = 8;   // thread block
+constexpr int kWarpRows = 4;               // destination rows per thread: the block tile is 32 x 32 pixels
+constexpr int kWarpTH = kWarpBY * kWarpRows;
 
-// One thread per destination pixel (32 x 8 tile per block).  The C interpolated values of the tile are
-// staged in shared memory and the accumulator read-modify-write is done as coalesced 128-bit accesses
-// (a tile row is 32*C contiguous floats), so the 24N bytes of accumulator traffic move at full line width.
+// 32 x 32 destination tile per 256-thread block, four rows per thread (so the per-thread column terms of the
+// coordinate transform, the parameter loads and the index math are paid once per four pixels).  The C
+// interpolated values of the tile are staged in shared memory and the accumulator read-modify-write is done
+// as coalesced 128-bit accesses (a tile row is 32*C contiguous floats).  ncu (profiles/) showed the first
+// versions to be issue-bound (390, then 234 instructions per pixel), so the per-pixel path is kept lean: the
+// inverse map is staged once per block, the 64-px column block start is a mask, the reciprocal replaces
+// the f64 divide (32/W == 32 * (1/W) exactly: a power-of-two scaling commutes with rounding),
+// __double2int_rn supplies the saturation, and pixels whose four taps are inside the source skip all
+// border selects.
 template <int C, bool PERSP>
 __global__ void __launch_bounds__(kWarpBX * kWarpBY) warp_accumulate_kernel(const WarpAccParams p) {
-  __shared__ __align__(16) float s_val[kWarpBY][kWarpBX * C];
+  __shared__ __align__(16) float s_val[kWarpTH][kWarpBX * C];
+  __shared__ double s_m[9];
   if (p.status_ptr && *p.status_ptr != 0) return;
+  const int tid = threadIdx.y * kWarpBX + threadIdx.x;
+  if (tid < 9) {
+    double mv = p.inv[0];
+#pragma unroll
+    for (int i = 1; i < 9; ++i) if (tid == i) mv = p.inv[i];
+    if (p.inv_ptr) mv = p.inv_ptr[tid];
+    s_m[tid] = mv;
+  }
+  __syncthreads();
   const int x = blockIdx.x * kWarpBX + threadIdx.x;
-  const int y = blockIdx.y * kWarpBY + threadIdx.y;
-  const bool inside = x < p.width && y < p.height;
-  float v[C];
-#pragma unroll
-  for (int c = 0; c < C; ++c) v[c] = 0.f;
-  if (inside) {
-    double m[9];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) m[i] = p.inv_ptr ? p.inv_ptr[i] : p.inv[i];
+  const int y_base = blockIdx.y * kWarpTH + threadIdx.y;
+  const float k255 = (float)(1.0 / 255.0);
+  const int sw = p.src_width, sh = p.src_height;
 
-    int xq, yq;
-    if (PERSP) {
-      // WarpPerspectiveInvoker: X0/Y0/W0 at the start of the 64-px column block, then + M*x1
-      const int bw = min(64, p.width);
-      const int xb = (x / bw) * bw;
-      const double xbd = (double)xb, x1 = (double)(x - xb), yd = (double)y;
-      const double X0 = __dadd_rn(__dadd_rn(__dmul_rn(m[0], xbd), __dmul_rn(m[1], yd)), m[2]);
-      const double Y0 = __dadd_rn(__dadd_rn(__dmul_rn(m[3], xbd), __dmul_rn(m[4], yd)), m[5]);
-      const double W0 = __dadd_rn(__dadd_rn(__dmul_rn(m[6], xbd), __dmul_rn(m[7], yd)), m[8]);
-      double W = __dadd_rn(W0, __dmul_rn(m[6], x1));
-      W = (W != 0.0) ? __ddiv_rn((double)kInterTab, W) : 0.0;
-      const double fX = fmax(-2147483648.0, fmin(2147483647.0, __dmul_rn(__dadd_rn(X0, __dmul_rn(m[0], x1)), W)));
-      const double fY = fmax(-2147483648.0, fmin(2147483647.0, __dmul_rn(__dadd_rn(Y0, __dmul_rn(m[3], x1)), W)));
-      xq = __double2int_rn(fX);
-      yq = __double2int_rn(fY);
-    } else {
-      const double xd = (double)x, yd = (double)y;
-      const int adelta = __double2int_rn(__dmul_rn(__dmul_rn(m[0], xd), kAbScale));
-      const int bdelta = __double2int_rn(__dmul_rn(__dmul_rn(m[3], xd), kAbScale));
-      const int X0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(m[1], yd), m[2]), kAbScale)) + 16;
-      const int Y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(m[4], yd), m[5]), kAbScale)) + 16;
-      xq = (int)((unsigned)X0 + (unsigned)adelta) >> (kAbBits - kInterBits);
-      yq = (int)((unsigned)Y0 + (unsigned)bdelta) >> (kAbBits - kInterBits);
-    }
-    // integer part is stored as short in OpenCV's map (saturate_cast<short>)
-    const int sx = max(-32768, min(32767, xq >> kInterBits));
-    const int sy = max(-32768, min(32767, yq >> kInterBits));
-    const float ax = (float)(xq & (kInterTab - 1)) * (1.f / kInterTab);
-    const float ay = (float)(yq & (kInterTab - 1)) * (1.f / kInterTab);
-    const float w00 = __fmul_rn(1.f - ay, 1.f - ax), w01 = __fmul_rn(1.f - ay, ax);
-    const float w10 = __fmul_rn(ay, 1.f - ax), w11 = __fmul_rn(ay, ax);
+  // per-thread (column) terms
+  double cx0 = 0, cx1 = 0, cy0 = 0, cy1 = 0, cw0 = 0, cw1 = 0;
+  int adelta = 0, bdelta = 0;
+  if (PERSP) {
+    // WarpPerspectiveInvoker: X0/Y0/W0 at the start of the 64-px column block, then + M*x1
+    const int xb = p.width >= 64 ? (x & ~63) : 0;
+    const double xbd = (double)xb, x1 = (double)(x - xb);
+    cx0 = __dmul_rn(s_m[0], xbd); cx1 = __dmul_rn(s_m[0], x1);
+    cy0 = __dmul_rn(s_m[3], xbd); cy1 = __dmul_rn(s_m[3], x1);
+    cw0 = __dmul_rn(s_m[6], xbd); cw1 = __dmul_rn(s_m[6], x1);
+  } else {
+    const double xd = (double)x;
+    adelta = __double2int_rn(__dmul_rn(__dmul_rn(s_m[0], xd), kAbScale));
+    bdelta = __double2int_rn(__dmul_rn(__dmul_rn(s_m[3], xd), kAbScale));
+  }
 
-    const int sw = p.src_width, sh = p.src_height;
-    if (sx >= sw || sx + 1 < 0 || sy >= sh || sy + 1 < 0) {
 #pragma unroll
-      for (int c = 0; c < C; ++c) v[c] = p.border[c];
-    } else {
-      const bool x0in = (unsigned)sx < (unsigned)sw, x1in = (unsigned)(sx + 1) < (unsigned)sw;
-      const bool y0in = (unsigned)sy < (unsigned)sh, y1in = (unsigned)(sy + 1) < (unsigned)sh;
+  for (int rr = 0; rr < kWarpRows; ++rr) {
+    const int y = y_base + rr * kWarpBY;
+    float v[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) v[c] = 0.f;
+    if (x < p.width && y < p.height) {
+      const double yd = (double)y;
+      int xq, yq;
+      if (PERSP) {
+        const double X0 = __dadd_rn(__dadd_rn(cx0, __dmul_rn(s_m[1], yd)), s_m[2]);
+        const double Y0 = __dadd_rn(__dadd_rn(cy0, __dmul_rn(s_m[4], yd)), s_m[5]);
+        const double W0 = __dadd_rn(__dadd_rn(cw0, __dmul_rn(s_m[7], yd)), s_m[8]);
+        const double W = __dadd_rn(W0, cw1);
+        const double W32 = (W != 0.0) ? __dmul_rn(__drcp_rn(W), (double)kInterTab) : 0.0;      // == INTER_TAB_SIZE / W
+        // cvRound with saturation == clamp to [INT_MIN, INT_MAX] then round half to even
+        xq = __double2int_rn(__dmul_rn(__dadd_rn(X0, cx1), W32));
+        yq = __double2int_rn(__dmul_rn(__dadd_rn(Y0, cy1), W32));
+      } else {
+        const int X0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(s_m[1], yd), s_m[2]), kAbScale)) + 16;
+        const int Y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(s_m[4], yd), s_m[5]), kAbScale)) + 16;
+        xq = (int)((unsigned)X0 + (unsigned)adelta) >> (kAbBits - kInterBits);
+        yq = (int)((unsigned)Y0 + (unsigned)bdelta) >> (kAbBits - kInterBits);
+      }
+      // integer part is stored as short in OpenCV's map (saturate_cast<short>)
+      const int sx = max(-32768, min(32767, xq >> kInterBits));
+      const int sy = max(-32768, min(32767, yq >> kInterBits));
+      const float ax = (float)(xq & (kInterTab - 1)) * (1.f / kInterTab);
+      const float ay = (float)(yq & (kInterTab - 1)) * (1.f / kInterTab);
+      const float w00 = __fmul_rn(1.f - ay, 1.f - ax), w01 = __fmul_rn(1.f - ay, ax);
+      const float w10 = __fmul_rn(ay, 1.f - ax), w11 = __fmul_rn(ay, ax);
       const uint8_t* r0 = p.src + (ptrdiff_t)sy * (ptrdiff_t)p.src_pitch + (ptrdiff_t)sx * C;
       const uint8_t* r1 = r0 + p.src_pitch;
-      const float k255 = (float)(1.0 / 255.0);
-      // issue all tap loads first (independent), then convert and blend
-      unsigned t00[C], t01[C], t10[C], t11[C];
+      if ((unsigned)sx < (unsigned)(sw - 1) && (unsigned)sy < (unsigned)(sh - 1)) {
+        // all four taps inside the source: the common case, no border logic
+        unsigned t00[C], t01[C], t10[C], t11[C];
 #pragma unroll
-      for (int c = 0; c < C; ++c) {
-        t00[c] = (y0in && x0in) ? __ldg(r0 + c) : 0u;
-        t01[c] = (y0in && x1in) ? __ldg(r0 + C + c) : 0u;
-        t10[c] = (y1in && x0in) ? __ldg(r1 + c) : 0u;
-        t11[c] = (y1in && x1in) ? __ldg(r1 + C + c) : 0u;
-      }
+        for (int c = 0; c < C; ++c) { t00[c] = __ldg(r0 + c); t01[c] = __ldg(r0 + C + c); t10[c] = __ldg(r1 + c); t11[c] = __ldg(r1 + C + c); }
 #pragma unroll
-      for (int c = 0; c < C; ++c) {
-        const float s00 = (y0in && x0in) ? __fmul_rn((float)t00[c], k255) : p.border[c];
-        const float s01 = (y0in && x1in) ? __fmul_rn((float)t01[c], k255) : p.border[c];
-        const float s10 = (y1in && x0in) ? __fmul_rn((float)t10[c], k255) : p.border[c];
-        const float s11 = (y1in && x1in) ? __fmul_rn((float)t11[c], k255) : p.border[c];
-        v[c] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s00, w00), __fmul_rn(s01, w01)), __fmul_rn(s10, w10)),
-                         __fmul_rn(s11, w11));
+        for (int c = 0; c < C; ++c) {
+          const float s00 = __fmul_rn((float)t00[c], k255), s01 = __fmul_rn((float)t01[c], k255);
+          const float s10 = __fmul_rn((float)t10[c], k255), s11 = __fmul_rn((float)t11[c], k255);
+          v[c] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s00, w00), __fmul_rn(s01, w01)), __fmul_rn(s10, w10)),
+                           __fmul_rn(s11, w11));
+        }
+      } else if (sx >= sw || sx + 1 < 0 || sy >= sh || sy + 1 < 0) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) v[c] = p.border[c];
+      } else {
+        const bool x0in = (unsigned)sx < (unsigned)sw, x1in = (unsigned)(sx + 1) < (unsigned)sw;
+        const bool y0in = (unsigned)sy < (unsigned)sh, y1in = (unsigned)(sy + 1) < (unsigned)sh;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const float s00 = (y0in && x0in) ? __fmul_rn((float)__ldg(r0 + c), k255) : p.border[c];
+          const float s01 = (y0in && x1in) ? __fmul_rn((float)__ldg(r0 + C + c), k255) : p.border[c];
+          const float s10 = (y1in && x0in) ? __fmul_rn((float)__ldg(r1 + c), k255) : p.border[c];
+          const float s11 = (y1in && x1in) ? __fmul_rn((float)__ldg(r1 + C + c), k255) : p.border[c];
+          v[c] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s00, w00), __fmul_rn(s01, w01)), __fmul_rn(s10, w10)),
+                           __fmul_rn(s11, w11));
+        }
       }
     }
-  }
 #pragma unroll
-  for (int c = 0; c < C; ++c) s_val[threadIdx.y][threadIdx.x * C + c] = v[c];
+    for (int c = 0; c < C; ++c) s_val[threadIdx.y + rr * kWarpBY][threadIdx.x * C + c] = v[c];
+  }
   __syncthreads();
 
-  // coalesced accumulate: the tile row y holds floats [x_tile0*C, x_tile0*C + 32*C) of accumulator row y
+  // coalesced accumulate: tile row r holds floats [x_tile0*C, x_tile0*C + 32*C) of accumulator row y0 + r
   const int tx0 = blockIdx.x * kWarpBX;
+  const int ty0 = blockIdx.y * kWarpTH;
   const int row_elems = min(kWarpBX, p.width - tx0) * C;        // valid floats in this tile row
   const size_t row_base = (size_t)tx0 * C;                       // float offset of the tile inside a row
   const bool vec_ok = (((size_t)p.width * C) % 4 == 0) && (row_base % 4 == 0);
-  const int tid = threadIdx.y * kWarpBX + threadIdx.x;
   if (vec_ok) {
     constexpr int kVecPerRow = kWarpBX * C / 4;
-    for (int i = tid; i < kWarpBY * kVecPerRow; i += kWarpBX * kWarpBY) {
+    constexpr int kVecs = kWarpTH * kVecPerRow;
+#pragma unroll
+    for (int i0 = 0; i0 < kVecs; i0 += kWarpBX * kWarpBY) {
+      const int i = i0 + tid;
+      if (i >= kVecs) break;
       const int r = i / kVecPerRow, q = i - r * kVecPerRow;
-      const int yy = blockIdx.y * kWarpBY + r;
+      const int yy = ty0 + r;
       if (yy >= p.height || q * 4 >= row_elems) continue;
       float* a = p.acc + (size_t)yy * p.width * C + row_base + q * 4;
       const float4 nv = *reinterpret_cast<const float4*>(&s_val[r][q * 4]);
@@ -145,9 +178,9 @@ __global__ void __launch_bounds__(kWarpBX * kWarpBY) warp_accumulate_kernel(cons
       }
     }
   } else {
-    for (int i = tid; i < kWarpBY * kWarpBX * C; i += kWarpBX * kWarpBY) {
+    for (int i = tid; i < kWarpTH * kWarpBX * C; i += kWarpBX * kWarpBY) {
       const int r = i / (kWarpBX * C), q = i - r * (kWarpBX * C);
-      const int yy = blockIdx.y * kWarpBY + r;
+      const int yy = ty0 + r;
       if (yy >= p.height || q >= row_elems) continue;
       float* a = p.acc + (size_t)yy * p.width * C + row_base + q;
       *a = p.store ? s_val[r][q] : __fadd_rn(*a, s_val[r][q]);

@@ -1,6 +1,7 @@
 #include <array>
 #include "libstacker.hpp"
 
+#include <algorithm>
 #include <cstring>
 #include <fstream>
 #include <future>
@@ -114,10 +115,13 @@ ImageF32 ecc_match(const std::vector<std::filesystem::path>& files, const EccMat
     details->clear();
     for (int i = 0; i < count; ++i) {
       FrameAlignment a;
+      a.frame = res[i].tag;
       std::memcpy(a.warp, res[i].warp, sizeof a.warp);
       a.rho = res[i].rho; a.iterations = res[i].iterations;
       details->push_back(a);
     }
+    // submissions race on the decode pool: report in file order
+    std::sort(details->begin(), details->end(), [](const FrameAlignment& x, const FrameAlignment& y) { return x.frame < y.frame; });
   }
   return out;
 }

@@ -66,7 +66,7 @@ struct ImageF32 {                    // the stacked result: CV_32FC3 in [0,1]
 using Decoder = std::function<ImageU8(const std::filesystem::path&)>;
 ImageU8 read_pnm(const std::filesystem::path& path);          // P6 (RGB -> stored as BGR) and P5
 
-struct FrameAlignment { float warp[9]; double rho; int iterations; };
+struct FrameAlignment { int64_t frame; float warp[9]; double rho; int iterations; };   // frame = index into `files`
 
 // ---- the API ---------------------------------------------------------------------------------------
 // scale_down_width: Some(width) is SURVEY §8(f) row N1 — not built yet -> NotImplemented.

@@ -50,8 +50,9 @@ def test_cpp_host_gpu_stack_matches_oracle(selftest, tmp_path):
     want_stack, want_warps, _ = R.ecc_match(frames, 0, 200, 1e-6, 5)
     assert len(warps) == 3
     for (tx, ty), m in zip(warps, want_warps[1:]):
-        assert abs(tx - m[0, 2]) < 0.05 and abs(ty - m[1, 2]) < 0.05
+        assert abs(tx - m[0, 2]) < 0.05 and abs(ty - m[1, 2]) < 0.05, (tx, ty, m)
     stack_sum = float(next(ln for ln in lines if ln.startswith("stack_sum")).split()[1])
-    assert abs(stack_sum - float(want_stack.astype(np.float64).sum())) < 1e-3 * want_stack.size / 255
+    want_sum = float(want_stack.astype(np.float64).sum())
+    assert abs(stack_sum - want_sum) < 2e-4 * want_sum, (stack_sum, want_sum)
     teng = float(next(ln for ln in lines if ln.startswith("tenengrad")).split()[1])
     assert teng == R.sharpness_tenengrad(grey, 3)
