@@ -65,7 +65,9 @@ def make_stack(a):
 
 # ---- clocks -----------------------------------------------------------------------------------------------
 class ClockSampler:
-    """Samples SM clock and throttle reasons of one GPU while the timed region runs (NVML, 20 ms period)."""
+    """Samples SM clock and throttle reasons of one GPU while the timed region runs (NVML: one sample at the
+    start, one every 100 ms, one at the end).  NVML queries take a driver lock, so the period is kept long and
+    only rank 0 samples: at 8 ranks x 50 Hz the polling itself produced multi-millisecond stragglers."""
 
     def __init__(self, device_index: int):
         self.samples, self.reasons = [], set()
@@ -107,17 +109,25 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.02)
+            self._stop.wait(0.1)
 
     def start(self):
         if self._h is not None:
             self._thr = threading.Thread(target=self._loop, daemon=True)
             self._thr.start()
 
+    def _sample_once(self):
+        try:
+            self.samples.append(self._nv.nvmlDeviceGetClockInfo(self._h, self._nv.NVML_CLOCK_SM))
+        except Exception:
+            pass
+
     def stop(self):
         self._stop.set()
         if self._thr:
             self._thr.join()
+        if self._h is not None:
+            self._sample_once()
         return {
             "sm_mhz": statistics.median(self.samples) if self.samples else None,
             "sm_max_mhz": self.max_mhz,
@@ -214,18 +224,29 @@ def run_b200(a, rank, local_rank, world):
             dist.barrier()
             torch.cuda.synchronize()
 
+    trace = os.environ.get("STK_BENCH_TRACE") == "1"
+
     def step_resident():
+        t = [time.perf_counter()]
         st.reset()
         st.set_reference(dev_frames[0])
+        t.append(time.perf_counter())
         for i in mine:
             st.submit(dev_frames[i], tag=i)
+        t.append(time.perf_counter())
         ptr, nfl = st.partial()
+        t.append(time.perf_counter())
         if world > 1:
             part = torch.as_tensor(D.DevicePtrArray(ptr, nfl), device=dev)
             D.reduce_partial_stack(part, 0)
             torch.cuda.synchronize()
+        t.append(time.perf_counter())
         if rank == 0:
             st.finish_device(ptr, n, out_dev.data_ptr())
+        t.append(time.perf_counter())
+        if trace:
+            names = ["reset+set_reference", "submit", "partial(sync+lane sum)", "reduce", "finish"]
+            print(f"TRACE rank{rank} " + " ".join(f"{k}={1e3 * (b - a):.3f}ms" for k, a, b in zip(names, t, t[1:])), file=sys.stderr)
 
     def step_e2e():
         st.reset()
@@ -241,11 +262,22 @@ def run_b200(a, rank, local_rank, world):
             st.finish_device(ptr, n, out_dev.data_ptr())
             out_host.copy_(out_dev, non_blocking=False)
 
+    if world > 1:
+        # NCCL sets up channels lazily over its first collectives on a buffer (measured: one 13 ms reduce among
+        # the first five); do that outside the timed region, on the very buffer the steps reduce
+        step_resident()
+        ptr0, nfl0 = st.partial()
+        warm = torch.as_tensor(D.DevicePtrArray(ptr0, nfl0), device=dev)
+        for _ in range(10):
+            D.reduce_partial_stack(warm, 0)
+        torch.cuda.synchronize()
+        dist.barrier()
+
     def timed(fn, steps, warmup, sample_clocks):
         for _ in range(warmup):
             fn()
         barrier()
-        sampler = ClockSampler(local_rank) if sample_clocks else None
+        sampler = ClockSampler(local_rank) if (sample_clocks and rank == 0) else None
         if sampler:
             sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -125,6 +125,7 @@ struct Lane {
   cudaGraphExec_t exec = nullptr;
   cudaGraphConditionalHandle handle = 0;
   CUtensorMap tm_tmpl;
+  CUtensorMap tm_tmpl_p2;
 };
 
 struct ResultSlot {
@@ -152,7 +153,10 @@ struct stk_ecc_ctx {
   int max_iter = 0;
   double eps = 0;
   CUtensorMap tm_img;
+  CUtensorMap tm_img_p2;
   bool exact_coords = false;
+  bool pack2 = false;          // Homography with FastPersp coordinates runs the packed-pair kernel
+  int iter_threads = 0, iter_smem = 0;
   bool host_loop = false;
   bool have_ref = false;
   stk::PrepParams prep_proto;
@@ -170,7 +174,8 @@ struct stk_ecc_ctx {
 namespace {
 
 // homography has two instantiations: FastPersp coordinates (default) and exact f64 (STK_ECC_EXACT_COORDS=1)
-void* iter_kernel_for(int motion, bool exact) {
+void* iter_kernel_for(int motion, bool exact, bool pack2 = false) {
+  if (pack2) return (void*)stk::ecc_iter_pack2_kernel;
   switch (motion) {
     case STK_MOTION_TRANSLATION: return (void*)stk::ecc_iter_kernel<stk::kTranslation, true>;
     case STK_MOTION_EUCLIDEAN: return (void*)stk::ecc_iter_kernel<stk::kEuclidean, true>;
@@ -194,6 +199,8 @@ stk::EccIterParams iter_params(stk_ecc_ctx* c, Lane& ln, bool use_handle) {
   memset(&p, 0, sizeof p);
   p.tm_img = c->tm_img;
   p.tm_tmpl = ln.tm_tmpl;
+  p.tm_img_p2 = c->tm_img_p2;
+  p.tm_tmpl_p2 = ln.tm_tmpl_p2;
   p.img = c->img;
   p.tmpl = ln.tmpl;
   p.pitch = c->pitch_f;
@@ -242,10 +249,10 @@ int build_lane_graph(stk_ecc_ctx* c, Lane& ln) {
     stk::EccIterParams ip = iter_params(c, ln, true);
     void* args[] = {&ip};
     cudaKernelNodeParams kp = {};
-    kp.func = iter_kernel_for(c->cfg.motion_type, c->exact_coords);
+    kp.func = iter_kernel_for(c->cfg.motion_type, c->exact_coords, c->pack2);
     kp.gridDim = dim3(c->n_tiles);
-    kp.blockDim = dim3(stk::kEccThreads);
-    kp.sharedMemBytes = stk::kEccDynSmem;
+    kp.blockDim = dim3(c->iter_threads);
+    kp.sharedMemBytes = c->iter_smem;
     kp.kernelParams = args;
     CU(cudaGraphAddKernelNode(&iter_node, body, nullptr, 0, &kp));
   }
@@ -375,7 +382,7 @@ int enqueue_align(stk_ecc_ctx* c, Lane& ln, const uint8_t* d_src, size_t pitch, 
     while (*h_cont && done_iters < c->max_iter) {
       const int chunk = std::min(4, c->max_iter - done_iters);
       for (int i = 0; i < chunk; ++i)
-        CU(cudaLaunchKernel(iter_kernel_for(c->cfg.motion_type, c->exact_coords), dim3(c->n_tiles), dim3(stk::kEccThreads), args, stk::kEccDynSmem, ln.stream));
+        CU(cudaLaunchKernel(iter_kernel_for(c->cfg.motion_type, c->exact_coords, c->pack2), dim3(c->n_tiles), dim3(c->iter_threads), args, c->iter_smem, ln.stream));
       done_iters += chunk;
       CU(cudaMemcpyAsync(h_cont, &ln.st->cont, sizeof(int), cudaMemcpyDeviceToHost, ln.stream));
       CU(cudaStreamSynchronize(ln.stream));
@@ -498,17 +505,23 @@ int stk_ecc_create(const stk_ecc_config* cfg, stk_ecc_ctx** out) {
   auto cleanup = [&](int code) { stk_ecc_destroy(c); return code; };
 
   if (cfg->align) {
-    // work split: 128-column strips x 16-row chunks, dealt evenly to one persistent block per resident slot
-    if (cudaFuncSetAttribute((const void*)iter_kernel_for(cfg->motion_type, c->exact_coords), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             stk::kEccDynSmem) != cudaSuccess)
-      return cleanup(fail(STK_ERR_CUDA, "cannot reserve %d bytes of dynamic shared memory for the ECC kernel", stk::kEccDynSmem));
+    // work split: 128-column strips x row chunks, dealt evenly to one persistent block per resident slot
+    const char* p2 = getenv("STK_ECC_PACK2");
+    // the packed-pair kernel is opt-in (STK_ECC_PACK2=1): measured 26 % fewer instructions but IPC 0.50 vs
+    // 0.71 at 168 registers / 3 warps per scheduler, i.e. no faster than the scalar kernel
+    c->pack2 = cfg->motion_type == STK_MOTION_HOMOGRAPHY && !c->exact_coords && p2 && strcmp(p2, "1") == 0;
+    c->iter_threads = c->pack2 ? stk::kP2Threads : stk::kEccThreads;
+    c->iter_smem = c->pack2 ? stk::kP2DynSmem : stk::kEccDynSmem;
+    const void* kfn = (const void*)iter_kernel_for(cfg->motion_type, c->exact_coords, c->pack2);
+    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, c->iter_smem) != cudaSuccess)
+      return cleanup(fail(STK_ERR_CUDA, "cannot reserve %d bytes of dynamic shared memory for the ECC kernel", c->iter_smem));
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)iter_kernel_for(cfg->motion_type, c->exact_coords), stk::kEccThreads,
-                                                      stk::kEccDynSmem) != cudaSuccess || occ < 1) occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, c->iter_threads, c->iter_smem) != cudaSuccess || occ < 1) occ = 1;
     const int slots = c->sm_count * occ;
     c->n_strips = (cfg->width + stk::kEccStripW - 1) / stk::kEccStripW;
     c->chunks_per_strip = (cfg->height + stk::kChunkH - 1) / stk::kChunkH;
-    const long long total_chunks = (long long)c->n_strips * c->chunks_per_strip;
+    const int chunk_h = c->pack2 ? stk::kP2ChunkH : stk::kChunkH;
+    const long long total_chunks = (long long)c->n_strips * ((cfg->height + chunk_h - 1) / chunk_h);
     // at least two chunks per block so the per-run fold/reduction stays amortised on small frames
     c->n_tiles = (int)std::max(1LL, std::min<long long>(slots, total_chunks / 2));
     c->nv = model_nv(cfg->motion_type);
@@ -529,6 +542,8 @@ int stk_ecc_create(const stk_ecc_config* cfg, stk_ecc_ctx** out) {
       return cleanup(fail(STK_ERR_NOMEM, "cudaMalloc(I plane) failed"));
     rc = make_plane_tensor_map(&c->tm_img, c->img, cfg->width, cfg->height, c->pitch_f, stk::kBoxW, stk::kBoxH);
     if (rc) return cleanup(rc);
+    rc = make_plane_tensor_map(&c->tm_img_p2, c->img, cfg->width, cfg->height, c->pitch_f, stk::kBoxW, stk::kP2BoxH);
+    if (rc) return cleanup(rc);
 
   }
   c->lanes.resize(c->n_lanes);
@@ -539,6 +554,8 @@ int stk_ecc_create(const stk_ecc_config* cfg, stk_ecc_ctx** out) {
     if (cfg->align) {
       if (cudaMalloc((void**)&ln.tmpl, (size_t)c->pitch_f * cfg->height * sizeof(float)) != cudaSuccess) return cleanup(fail(STK_ERR_NOMEM, "cudaMalloc(T plane) failed"));
       rc = make_plane_tensor_map(&ln.tm_tmpl, ln.tmpl, cfg->width, cfg->height, c->pitch_f, stk::kEccStripW, stk::kChunkH);
+      if (rc) return cleanup(rc);
+      rc = make_plane_tensor_map(&ln.tm_tmpl_p2, ln.tmpl, cfg->width, cfg->height, c->pitch_f, stk::kEccStripW, stk::kP2ChunkH);
       if (rc) return cleanup(rc);
       if (cudaMalloc((void**)&ln.st, sizeof(stk::EccState)) != cudaSuccess) return cleanup(fail(STK_ERR_NOMEM, "cudaMalloc(state) failed"));
       if (cudaMemsetAsync(ln.st, 0, sizeof(stk::EccState), ln.stream) != cudaSuccess ||
@@ -587,8 +604,10 @@ static int set_reference_impl(stk_ecc_ctx* c, const uint8_t* d_bgr, size_t pitch
   }
   if (c->cfg.seed_reference) {
     const int row = c->cfg.width * c->cfg.channels;
-    dim3 grid((row + 255) / 256, c->cfg.height);
-    stk::seed_accumulator_kernel<<<grid, 256, 0, l0.stream>>>(d_bgr, pitch, l0.acc, row, c->cfg.height);
+    dim3 grid((row + 1023) / 1024, c->cfg.height);
+    // 4-byte loads / 16-byte stores need the rows of both buffers to start on those boundaries
+    const int vec_ok = (row % 4 == 0) && (pitch % 4 == 0) && (((uintptr_t)d_bgr) % 4 == 0);
+    stk::seed_accumulator_kernel<<<grid, 256, 0, l0.stream>>>(d_bgr, pitch, l0.acc, row, c->cfg.height, vec_ok);
     c->launches++;
     CU(cudaGetLastError());
     l0.acc_used = true;
@@ -893,7 +912,7 @@ int stk_ecc_debug_iteration(stk_ecc_ctx* c, const uint8_t* bgr, size_t pitch, co
   stk::EccIterParams ip = iter_params(c, ln, false);
   ip.totals_out = d_tot;
   void* args[] = {&ip};
-  cudaError_t e = cudaLaunchKernel(iter_kernel_for(c->cfg.motion_type, c->exact_coords), dim3(c->n_tiles), dim3(stk::kEccThreads), args, stk::kEccDynSmem, ln.stream);
+  cudaError_t e = cudaLaunchKernel(iter_kernel_for(c->cfg.motion_type, c->exact_coords, c->pack2), dim3(c->n_tiles), dim3(c->iter_threads), args, c->iter_smem, ln.stream);
   stk::EccState hs;
   if (e == cudaSuccess) e = cudaMemcpyAsync(totals, d_tot, sizeof(double) * c->nv, cudaMemcpyDeviceToHost, ln.stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(&hs, ln.st, sizeof hs, cudaMemcpyDeviceToHost, ln.stream);
@@ -936,7 +955,7 @@ int stk_ecc_debug_timing(stk_ecc_ctx* c, const uint8_t* bgr, size_t pitch, const
   void* args[] = {&ip};
   cudaError_t e = cudaSuccess;
   for (int i = 0; i < std::max(1, iters) && e == cudaSuccess; ++i)
-    e = cudaLaunchKernel(iter_kernel_for(c->cfg.motion_type, c->exact_coords), dim3(c->n_tiles), dim3(stk::kEccThreads), args, stk::kEccDynSmem, ln.stream);
+    e = cudaLaunchKernel(iter_kernel_for(c->cfg.motion_type, c->exact_coords, c->pack2), dim3(c->n_tiles), dim3(c->iter_threads), args, c->iter_smem, ln.stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(stamps, d_t, sizeof(unsigned long long) * need, cudaMemcpyDeviceToHost, ln.stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ln.stream);
   cudaFree(d_t);

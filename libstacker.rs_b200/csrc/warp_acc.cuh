@@ -189,12 +189,28 @@ __global__ void __launch_bounds__(kWarpBX * kWarpBY) warp_accumulate_kernel(cons
 }
 
 // frame 0 enters the stack unwarped: acc = u8 * (1/255)        (/root/reference/src/lib.rs:752-754)
+// four bytes in, one 128-bit store out per thread when the row layout allows it
 __global__ void seed_accumulator_kernel(const uint8_t* src, size_t src_pitch, float* acc, int row_elems,
-                                        int height) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+                                        int height, int vec_ok) {
   const int y = blockIdx.y;
-  if (i >= row_elems || y >= height) return;
-  acc[(size_t)y * row_elems + i] = __fmul_rn((float)__ldg(src + (size_t)y * src_pitch + i), (float)(1.0 / 255.0));
+  if (y >= height) return;
+  const float k255 = (float)(1.0 / 255.0);
+  const uint8_t* row = src + (size_t)y * src_pitch;
+  float* out = acc + (size_t)y * row_elems;
+  if (vec_ok) {
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= row_elems) return;
+    const uchar4 b = *reinterpret_cast<const uchar4*>(row + i);
+    float4 o;
+    o.x = __fmul_rn((float)b.x, k255); o.y = __fmul_rn((float)b.y, k255);
+    o.z = __fmul_rn((float)b.z, k255); o.w = __fmul_rn((float)b.w, k255);
+    *reinterpret_cast<float4*>(out + i) = o;
+  } else {
+    for (int k = 0; k < 4; ++k) {
+      const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4 + k;
+      if (i < row_elems) out[i] = __fmul_rn((float)__ldg(row + i), k255);
+    }
+  }
 }
 
 struct LaneSumParams {

@@ -12,8 +12,10 @@ from typing import List
 
 def shard_frames(n_frames: int, rank: int, world: int) -> List[int]:
     """Indices (into the stack, frame 0 = reference excluded) this rank aligns: interleaved, so that every
-    rank gets the same number of frames +-1 regardless of how the caller ordered them."""
-    return [i for i in range(1, n_frames) if (i - 1) % world == rank]
+    rank gets the same number of frames +-1 regardless of how the caller ordered them.  Frame i goes to rank
+    i % world, so when the count does not divide evenly the short shard is rank 0's — the rank that also
+    seeds the stack with frame 0 and does the final scale."""
+    return [i for i in range(1, n_frames) if i % world == rank]
 
 
 class DevicePtrArray:

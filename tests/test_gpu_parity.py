@@ -287,6 +287,24 @@ def test_lanes_and_device_resident_input(pkg):
         assert np.abs(o - outs[0]).max() <= 1e-6
 
 
+def test_kernel_variants_agree(pkg, monkeypatch):
+    """The homography iteration kernel has three instantiations: FastPersp coordinates (default), exact f64
+    coordinates (STK_ECC_EXACT_COORDS=1) and packed pixel pairs (STK_ECC_PACK2=1).  Same stack, same bars."""
+    w, h = 400, 300
+    frames = synth.Stack(w, h, 4, 3, seed=50).frames()
+    want, warps, _ = R.ecc_match(frames, 3, 5000, 1e-5, 5)
+    params = pkg.EccMatchParameters(pkg.MotionType.Homography, 5000, 1e-5, 5)
+    for env in ({}, {"STK_ECC_EXACT_COORDS": "1"}, {"STK_ECC_PACK2": "1"}, {"STK_LOOP_MODE": "host"}):
+        for k in ("STK_ECC_EXACT_COORDS", "STK_ECC_PACK2", "STK_LOOP_MODE"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        got, res = pkg.ecc_match(frames, params, None, device=0, return_details=True)
+        for r, wm in zip(res, warps[1:]):
+            assert synth.corner_displacement(r["warp"], wm, w, h) <= 0.05, env
+        assert_stack_parity(got, want, warps, 3, 4)
+
+
 # ---- K6: Tenengrad, bit-identical ------------------------------------------------------------------------
 @pytest.mark.parametrize("k", [1, 3, 5, 7])
 @pytest.mark.parametrize("size", [(320, 240), (65, 33), (1000, 701)])
