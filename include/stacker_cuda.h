@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define STK_ABI_VERSION 1
+#define STK_ABI_VERSION 2
 
 /* ---- status codes ------------------------------------------------------------------------- */
 enum {
@@ -72,6 +72,12 @@ typedef struct stk_ecc_config {
                                  (src/lib.rs:752-754); 0 on the non-root shards of a multi-GPU stack */
   int32_t align;              /* 1: ECC alignment (ecc_match); 0: warp-only context (keypoint_match
                                  tail, src/lib.rs:289-350) — no reference planes are built          */
+  int32_t ecc_width, ecc_height; /* 0,0: ECC runs on the full-size grey planes (ecc_match_no_scaling,
+                                 src/lib.rs:719-847).  Otherwise ecc_match_scaling_down (src/lib.rs:849-1028):
+                                 the grey planes are INTER_AREA-resized to this size (utils::scale_image,
+                                 src/utils.rs:186-214 — use stk_scaled_size), ECC runs there, and the
+                                 matrix is taken back to full resolution (src/lib.rs:941-958,
+                                 src/utils.rs:218-248) before the full-size warp                     */
 } stk_ecc_config;
 
 /* per-frame outcome of findTransformECC                          (src/lib.rs:769-777) */
@@ -87,6 +93,12 @@ typedef struct stk_frame_result {
 int         stk_abi_version(void);
 const char* stk_last_error(void);
 int         stk_device_count(int* count);
+
+/* utils::scale_image's size rule (src/utils.rs:186-200): the SMALLER dimension becomes `scale_down`, both
+   new sizes are truncated (`as i32`).  Also applies ecc_match_scaling_down's validation
+   (src/lib.rs:876-888): scale_down >= width or scale_down <= 10 -> STK_ERR_BAD_ARG.  A rule that would
+   ENLARGE the planes (landscape frame, height < scale_down < width) is STK_ERR_UNSUPPORTED. */
+int stk_scaled_size(int width, int height, float scale_down, int* scaled_width, int* scaled_height);
 
 /* pinned host memory for decode targets: "JPEG decode stays on the host and feeds pinned,
    asynchronous uploads".  Replaces the Mat allocation inside imgcodecs::imread (src/utils.rs:132). */
@@ -157,6 +169,10 @@ int stk_ecc_stage_times(stk_ecc_ctx* ctx, double ms[3], int64_t* frames, int64_t
    (out_pitch bytes per row, width floats). */
 int stk_prep_grey_blur(const uint8_t* bgr, size_t pitch, int width, int height, int channels, int ksize,
                        int device, float* out, size_t out_pitch);
+/* cvt_color(BGR2GRAY) (skipped for channels == 1) + resize(INTER_AREA) to out_width x out_height: the plane
+   utils::scale_image builds from the grey frame (src/utils.rs:186-214).  Host in, host out, 8-bit. */
+int stk_grey_resize_area(const uint8_t* img, size_t pitch, int width, int height, int channels, int out_width,
+                         int out_height, int device, uint8_t* out, size_t out_pitch);
 /* ONE ECC iteration of `frame` (host, 8-bit) against the context's reference, starting from `warp_in`
    (row-major 3x3 f32): returns the kernel's reduced sums (layout documented in csrc/ecc_iter.cuh,
    *nv values written, capacity `cap`), the updated warp, rho and the loop status.  Does not touch the
@@ -182,6 +198,19 @@ int stk_tenengrad_device(const uint8_t* d_img, size_t pitch, int width, int heig
 /* n same-sized frames resident on the device, frame i at d_imgs + i*frame_stride; out[n] */
 int stk_tenengrad_batch_device(const uint8_t* d_imgs, size_t frame_stride, size_t pitch, int width,
                                int height, int channels, int ksize, int n, int device, double* out);
+
+/* ---- the crate's other sharpness metrics, fused with Tenengrad(3) into ONE pass over the plane ---------
+   out[4] = { LAPM  sharpness_modified_laplacian              src/lib.rs:1032-1068,
+              LAPV  sharpness_variance_of_laplacian           src/lib.rs:1070-1090,
+              TENG  sharpness_tenengrad(k_size = 3)           src/lib.rs:1101-1147,
+              GLVN  sharpness_normalized_gray_level_variance  src/lib.rs:1151-1166 }
+   — the order examples/main.rs:43-46 evaluates them in.  Same input rules as stk_tenengrad; every value is
+   bit-identical to the CV_64F OpenCV pipeline on 8-bit input. */
+int stk_sharpness_all(const uint8_t* img, size_t pitch, int width, int height, int channels, int device,
+                      double out[4]);
+/* n same-sized frames resident on the device, frame i at d_imgs + i*frame_stride; out[n*4] */
+int stk_sharpness_all_batch_device(const uint8_t* d_imgs, size_t frame_stride, size_t pitch, int width, int height,
+                                   int channels, int n, int device, double* out);
 
 #ifdef __cplusplus
 }

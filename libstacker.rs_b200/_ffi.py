@@ -14,7 +14,7 @@ STK_OK, STK_ERR_BAD_ARG, STK_ERR_CUDA, STK_ERR_NOT_ENOUGH, STK_ERR_ECC_NOCONV, S
     STK_ERR_CRITERIA, STK_ERR_STATE, STK_ERR_UNSUPPORTED, STK_ERR_NOMEM = range(10)
 STK_TERM_COUNT, STK_TERM_EPS = 1, 2
 STK_BORDER_CONSTANT = 0
-STK_ABI_VERSION = 1
+STK_ABI_VERSION = 2
 
 
 class EccConfig(C.Structure):
@@ -23,6 +23,7 @@ class EccConfig(C.Structure):
         ("motion_type", C.c_int32), ("criteria_type", C.c_int32), ("max_count", C.c_int32),
         ("epsilon", C.c_double), ("gauss_filt_size", C.c_int32), ("device", C.c_int32),
         ("lanes", C.c_int32), ("seed_reference", C.c_int32), ("align", C.c_int32),
+        ("ecc_width", C.c_int32), ("ecc_height", C.c_int32),
     ]
 
 
@@ -39,6 +40,7 @@ SYMBOLS = {
     "stk_abi_version": (C.c_int, []),
     "stk_last_error": (C.c_char_p, []),
     "stk_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "stk_scaled_size": (C.c_int, [C.c_int, C.c_int, C.c_float, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "stk_pinned_alloc": (C.c_int, [C.POINTER(_P), C.c_size_t]),
     "stk_pinned_free": (C.c_int, [_P]),
     "stk_ecc_create": (C.c_int, [C.POINTER(EccConfig), C.POINTER(_P)]),
@@ -61,12 +63,15 @@ SYMBOLS = {
     "stk_ecc_set_profiling": (C.c_int, [_P, C.c_int]),
     "stk_ecc_stage_times": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "stk_prep_grey_blur": (C.c_int, [_P, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_size_t]),
+    "stk_grey_resize_area": (C.c_int, [_P, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_size_t]),
     "stk_ecc_debug_iteration": (C.c_int, [_P, _P, C.c_size_t, C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_int,
                                           C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "stk_ecc_debug_timing": (C.c_int, [_P, _P, C.c_size_t, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_uint64), C.c_int, C.POINTER(C.c_int)]),
     "stk_tenengrad": (C.c_int, [_P, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "stk_tenengrad_device": (C.c_int, [_P, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "stk_tenengrad_batch_device": (C.c_int, [_P, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
+    "stk_sharpness_all": (C.c_int, [_P, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
+    "stk_sharpness_all_batch_device": (C.c_int, [_P, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
 }
 
 

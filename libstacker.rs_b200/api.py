@@ -136,8 +136,12 @@ class EccStack:
     (keypoint_match tail)."""
 
     def __init__(self, width: int, height: int, channels: int = 3, params: Optional[EccMatchParameters] = None,
-                 device: int = -1, lanes: int = 0, seed_reference: bool = True):
+                 device: int = -1, lanes: int = 0, seed_reference: bool = True, ecc_size=None):
+        """`ecc_size=(w, h)`: ecc_match_scaling_down — ECC runs on greys INTER_AREA-resized to that size
+        (see scaled_size) and the matrix is rescaled to full resolution on the device."""
         cfg = _ffi.EccConfig()
+        if ecc_size is not None:
+            cfg.ecc_width, cfg.ecc_height = int(ecc_size[0]), int(ecc_size[1])
         cfg.width, cfg.height, cfg.channels = int(width), int(height), int(channels)
         cfg.device, cfg.lanes = int(device), int(lanes)
         cfg.seed_reference = 1 if seed_reference else 0
@@ -299,6 +303,26 @@ class EccStack:
         return n.value
 
 
+def scaled_size(width: int, height: int, scale_down: float):
+    """utils::scale_image's size rule (src/utils.rs:186-200) + ecc_match_scaling_down's validation
+    (src/lib.rs:876-888), evaluated by the library: (small_width, small_height) or InvalidParams."""
+    sw, sh = C.c_int(), C.c_int()
+    _check(lib.stk_scaled_size(int(width), int(height), C.c_float(scale_down), C.byref(sw), C.byref(sh)))
+    return sw.value, sh.value
+
+
+def grey_resize_area(frame: np.ndarray, out_width: int, out_height: int, device: int = -1) -> np.ndarray:
+    """cvtColor(BGR2GRAY) (skipped for 2-D input) + cv::resize(INTER_AREA): utils::scale_image on the grey
+    frame (src/utils.rs:186-214)."""
+    frame = np.ascontiguousarray(frame)
+    h, w = frame.shape[:2]
+    ch = 1 if frame.ndim == 2 else frame.shape[2]
+    out = np.empty((out_height, out_width), np.uint8)
+    _check(lib.stk_grey_resize_area(frame.ctypes.data, frame.strides[0], w, h, ch, int(out_width), int(out_height),
+                                    device, out.ctypes.data, out.strides[0]))
+    return out
+
+
 def prep_grey_blur(frame: np.ndarray, ksize: int, device: int = -1) -> np.ndarray:
     """The f32 plane findTransformECC builds from an 8-bit BGR frame: grey -> f32 -> GaussianBlur(k)."""
     frame = np.ascontiguousarray(frame)
@@ -347,16 +371,17 @@ def ecc_match(files: Iterable, params: EccMatchParameters, scale_down_width: Opt
     items = list(files)
     if not items:
         raise NotEnoughFiles()
-    if scale_down_width is not None:
-        # ecc_match_scaling_down (src/lib.rs:849-1028) is row N1 of SURVEY.md §8(f): next, not yet built
-        raise NotImplementedError_("ecc_match with scale_down_width is not implemented yet")
     typ, _, _ = term_criteria(params)
     first = _load(items[0])
     _check_colour_frame(first)
+    h, w, ch = first.shape
+    ecc_size = None
+    if scale_down_width is not None:
+        # ecc_match_scaling_down (src/lib.rs:849-1028): width validation (:876-888) comes before any ECC call
+        ecc_size = scaled_size(w, h, float(np.float32(scale_down_width)))
     if not typ:
         raise OpenCvError("findTransformECC: criteria.type must have COUNT or EPS set")
-    h, w, ch = first.shape
-    with EccStack(w, h, ch, params, device=device) as st:
+    with EccStack(w, h, ch, params, device=device, ecc_size=ecc_size) as st:
         st.set_reference(first)
         n_workers = workers or min(8, os.cpu_count() or 1)
         rest = items[1:]
@@ -470,3 +495,54 @@ def sharpness_tenengrad(src_grey_mat, k_size: int, *, device: int = -1) -> float
         a = np.ascontiguousarray(a)
     _check(lib.stk_tenengrad(a.ctypes.data, a.strides[0], a.shape[1], a.shape[0], 1, k_size, device, C.byref(out)))
     return out.value
+
+
+# ---- the other sharpness metrics: src/lib.rs:1032-1090, :1151-1166 ---------------------------------------
+def sharpness_all(src_mat, *, device: int = -1):
+    """(LAPM, LAPV, TENG(3), GLVN) of one 8-bit grey image (host array, or anything with
+    __cuda_array_interface__) in ONE pass over the plane — what examples/main.rs:43-46 computes per file."""
+    out = (C.c_double * 4)()
+    dv = _device_view(src_mat)
+    if dv is not None:
+        shape = src_mat.__cuda_array_interface__["shape"]
+        ch = 1 if len(shape) == 2 else shape[2]
+        _check(lib.stk_sharpness_all_batch_device(dv[0], 0, dv[1], shape[1], shape[0], ch, 1, device, out))
+        return tuple(out)
+    a = np.asarray(src_mat)
+    if a.dtype != np.uint8:
+        raise NotImplementedError_("sharpness metrics: only 8-bit input is implemented on the GPU path")
+    if a.ndim != 2:
+        raise OpenCvError("the sharpness metrics expect a single-channel image")
+    if a.strides[1] != 1:
+        a = np.ascontiguousarray(a)
+    _check(lib.stk_sharpness_all(a.ctypes.data, a.strides[0], a.shape[1], a.shape[0], 1, device, out))
+    return tuple(out)
+
+
+def sharpness_batch(frames, *, device: int = -1):
+    """n same-sized frames resident on the device as one (n, H, W[, C]) uint8 array (e.g. a torch CUDA
+    tensor; C = 3/4 fuses cvtColor(BGR2GRAY)): an (n, 4) array of (LAPM, LAPV, TENG(3), GLVN)."""
+    iface = frames.__cuda_array_interface__
+    shape = iface["shape"]
+    if iface.get("strides"):
+        raise InvalidParams("sharpness_batch needs a contiguous (n, H, W[, C]) array")
+    n, h, w = shape[0], shape[1], shape[2]
+    ch = 1 if len(shape) == 3 else shape[3]
+    out = (C.c_double * (4 * n))()
+    _check(lib.stk_sharpness_all_batch_device(int(iface["data"][0]), h * w * ch, w * ch, w, h, ch, n, device, out))
+    return np.array(out[:], np.float64).reshape(n, 4)
+
+
+def sharpness_modified_laplacian(src_mat, *, device: int = -1) -> float:
+    """LAPM (Nayar89), src/lib.rs:1032-1068."""
+    return sharpness_all(src_mat, device=device)[0]
+
+
+def sharpness_variance_of_laplacian(src_mat, *, device: int = -1) -> float:
+    """LAPV (Pech2000), src/lib.rs:1070-1090."""
+    return sharpness_all(src_mat, device=device)[1]
+
+
+def sharpness_normalized_gray_level_variance(src_mat, *, device: int = -1) -> float:
+    """GLVN (Santos97), src/lib.rs:1151-1166."""
+    return sharpness_all(src_mat, device=device)[3]

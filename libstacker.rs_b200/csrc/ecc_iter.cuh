@@ -63,6 +63,9 @@ struct EccState {
   int cont;                 // 1 while the loop should run another iteration
   unsigned int tile_counter;
   int pad;
+  // ecc_match_scaling_down: factors that take the matrix estimated on the downscaled planes to full
+  // resolution once the loop has ended (0 = no rescale).  Set once per context, never by the init kernel.
+  float rescale_x, rescale_y;
 };
 
 struct alignas(64) EccIterParams {
@@ -510,6 +513,20 @@ __device__ inline void compute_inverse(EccState* st, bool persp) {
   }
 }
 
+// Full-resolution matrix from the one estimated on the downscaled greys, in the reference's f32 arithmetic:
+// the 2x3 models scale only the translation column (/root/reference/src/lib.rs:941-951), the homography
+// goes through adjust_homography_for_scale_f32 (/root/reference/src/utils.rs:218-248).
+__device__ inline void rescale_to_full(EccState* st, bool persp) {
+  const float sx = st->rescale_x, sy = st->rescale_y;
+  if (sx == 0.f) return;
+  st->m[2] = __fmul_rn(st->m[2], sx);
+  st->m[5] = __fmul_rn(st->m[5], sy);
+  if (persp) {
+    st->m[6] = __fdiv_rn(st->m[6], sx);
+    st->m[7] = __fdiv_rn(st->m[7], sy);
+  }
+}
+
 // One warp: lane r < P owns row r of the augmented system [H | ip | tp] in registers; Gauss-Jordan in
 // f64 (H is symmetric positive definite: no pivoting), then lambda, delta-p, the f32 matrix update and the
 // convergence test.  `tot` is the f64 totals vector in shared memory.
@@ -713,7 +730,7 @@ __device__ __forceinline__ void finish_iteration(const EccIterParams& p, EccStat
     if (tail && lane == 0) tail[1] = global_ns();     // solve + update done
     if (lane == 0) {
       st->tile_counter = 0;
-      if (st->cont == 0) compute_inverse(st, Model<MOTION>::persp);
+      if (st->cont == 0) { rescale_to_full(st, Model<MOTION>::persp); compute_inverse(st, Model<MOTION>::persp); }
       if (p.use_handle) cudaGraphSetConditional(p.handle, (unsigned)st->cont);
       if (tail) { tail[2] = global_ns(); tail[3] = (unsigned long long)blockIdx.x; }
     }

@@ -1,4 +1,5 @@
-// K1 — frame preparation: 8-bit BGR(A) -> grey (cvtColor BGR2GRAY, exact 15-bit fixed point) -> f32
+// K1 — frame preparation: 8-bit BGR(A) (or an already-grey plane, channels == 1: the downscaled grey of
+// ecc_match_scaling_down) -> grey (cvtColor BGR2GRAY, exact 15-bit fixed point) -> f32
 // -> separable Gaussian blur (BORDER_REFLECT_101) -> f32 plane.
 //
 // Replaces, per frame, utils::read_grey_and_f32's cvt_color (/root/reference/src/utils.rs:136-142) and
@@ -64,12 +65,16 @@ __global__ void __launch_bounds__(kPrepThreads) prep_grey_blur_kernel(const Prep
 #pragma unroll
       for (int q = 0; q < kCols; ++q) {
         const int tx = lane + 32 * q;
-        if (tx < gw) { const uint8_t* px = row + tx * ch; b[q] = __ldg(px); g[q] = __ldg(px + 1); rch[q] = __ldg(px + 2); }
+        if (tx < gw) {
+          const uint8_t* px = row + tx * ch;
+          b[q] = __ldg(px);
+          if (ch != 1) { g[q] = __ldg(px + 1); rch[q] = __ldg(px + 2); }
+        }
       }
 #pragma unroll
       for (int q = 0; q < kCols; ++q) {
         const int tx = lane + 32 * q;
-        if (tx < gw) grey[ty * gp + tx] = (float)bgr2gray(b[q], g[q], rch[q]);
+        if (tx < gw) grey[ty * gp + tx] = ch == 1 ? (float)b[q] : (float)bgr2gray(b[q], g[q], rch[q]);
       }
     }
   } else {
@@ -79,7 +84,7 @@ __global__ void __launch_bounds__(kPrepThreads) prep_grey_blur_kernel(const Prep
       for (int tx = lane; tx < gw; tx += 32) {
         const int sx = reflect101(x0 + tx - r, p.width);
         const uint8_t* px = row + (size_t)sx * ch;
-        grey[ty * gp + tx] = (float)bgr2gray(__ldg(px), __ldg(px + 1), __ldg(px + 2));
+        grey[ty * gp + tx] = ch == 1 ? (float)__ldg(px) : (float)bgr2gray(__ldg(px), __ldg(px + 1), __ldg(px + 2));
       }
     }
   }

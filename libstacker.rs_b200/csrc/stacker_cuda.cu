@@ -22,6 +22,7 @@
 #include "common.cuh"
 #include "ecc_iter.cuh"
 #include "prep.cuh"
+#include "resize_area.cuh"
 #include "tenengrad.cuh"
 #include "warp_acc.cuh"
 
@@ -111,10 +112,95 @@ int make_plane_tensor_map(CUtensorMap* tm, const float* base, int width, int hei
   return STK_OK;
 }
 
+// computeResizeAreaTab (OpenCV imgproc/resize.cpp), as restated in oracle/restate.py::_area_tab: per
+// destination index the contiguous run of source indices and their f32 weights, built in f64.
+struct AreaTab {
+  std::vector<int> first, count;
+  std::vector<float> w;     // [dsize][k], zero padded
+  int k = 0;
+};
+
+void build_area_tab(int ssize, int dsize, double scale, AreaTab& t) {
+  std::vector<std::vector<float>> wts(dsize);
+  t.first.assign(dsize, 0);
+  t.count.assign(dsize, 0);
+  t.k = 1;
+  for (int dx = 0; dx < dsize; ++dx) {
+    const double fsx1 = dx * scale, fsx2 = fsx1 + scale;
+    const double cell = std::min(scale, ssize - fsx1);
+    int sx1 = (int)std::ceil(fsx1), sx2 = (int)std::floor(fsx2);
+    sx2 = std::min(sx2, ssize - 1);
+    sx1 = std::min(sx1, sx2);
+    int first = sx1;
+    if (sx1 - fsx1 > 1e-3) { first = sx1 - 1; wts[dx].push_back((float)((sx1 - fsx1) / cell)); }
+    for (int sx = sx1; sx < sx2; ++sx) wts[dx].push_back((float)(1.0 / cell));
+    if (fsx2 - sx2 > 1e-3) wts[dx].push_back((float)(std::min(std::min(fsx2 - sx2, 1.0), cell) / cell));
+    t.first[dx] = std::max(first, 0);
+    t.count[dx] = (int)wts[dx].size();
+    t.k = std::max(t.k, t.count[dx]);
+  }
+  t.w.assign((size_t)dsize * t.k, 0.f);
+  for (int dx = 0; dx < dsize; ++dx)
+    for (size_t j = 0; j < wts[dx].size(); ++j) t.w[(size_t)dx * t.k + j] = wts[dx][j];
+}
+
+// device-side description of one INTER_AREA downscale (sw x sh -> dw x dh)
+struct AreaPlan {
+  int sw = 0, sh = 0, dw = 0, dh = 0;
+  int ix = 0, iy = 0;              // integer-scale fast path when > 0
+  int kx = 0, ky = 0;
+  int *xfirst = nullptr, *xcount = nullptr, *yfirst = nullptr, *ycount = nullptr;
+  float *xw = nullptr, *yw = nullptr;
+};
+
+void free_area_plan(AreaPlan& a) {
+  cudaFree(a.xfirst); cudaFree(a.xcount); cudaFree(a.yfirst); cudaFree(a.ycount); cudaFree(a.xw); cudaFree(a.yw);
+  a = AreaPlan();
+}
+
+int make_area_plan(int sw, int sh, int dw, int dh, AreaPlan& a) {
+  a.sw = sw; a.sh = sh; a.dw = dw; a.dh = dh;
+  // cv::resize: inv_scale = dsize / ssize ; scale = 1 / inv_scale ; is_area_fast when both are integers
+  const double scale_x = 1.0 / ((double)dw / sw), scale_y = 1.0 / ((double)dh / sh);
+  const int ix = (int)std::nearbyint(scale_x), iy = (int)std::nearbyint(scale_y);
+  if (std::fabs(scale_x - ix) < 2.220446049250313e-16 && std::fabs(scale_y - iy) < 2.220446049250313e-16) {
+    a.ix = ix; a.iy = iy;
+    return STK_OK;
+  }
+  AreaTab tx, ty;
+  build_area_tab(sw, dw, scale_x, tx);
+  build_area_tab(sh, dh, scale_y, ty);
+  a.kx = tx.k; a.ky = ty.k;
+  auto up = [](const void* h, size_t bytes, void** d) -> bool {
+    return cudaMalloc(d, bytes) == cudaSuccess && cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
+  };
+  const bool ok = up(tx.first.data(), sizeof(int) * dw, (void**)&a.xfirst) && up(tx.count.data(), sizeof(int) * dw, (void**)&a.xcount) &&
+                  up(tx.w.data(), sizeof(float) * tx.w.size(), (void**)&a.xw) && up(ty.first.data(), sizeof(int) * dh, (void**)&a.yfirst) &&
+                  up(ty.count.data(), sizeof(int) * dh, (void**)&a.ycount) && up(ty.w.data(), sizeof(float) * ty.w.size(), (void**)&a.yw);
+  if (!ok) { free_area_plan(a); return fail(STK_ERR_NOMEM, "cannot upload the INTER_AREA tables"); }
+  return STK_OK;
+}
+
+int launch_resize(const AreaPlan& a, const uint8_t* d_src, size_t pitch, int channels, uint8_t* d_dst, int dst_pitch,
+                  cudaStream_t s) {
+  stk::ResizeAreaParams p = {};
+  p.src = d_src; p.src_pitch = pitch; p.dst = d_dst; p.dst_pitch = dst_pitch;
+  p.sw = a.sw; p.sh = a.sh; p.dw = a.dw; p.dh = a.dh; p.channels = channels;
+  p.ix = a.ix; p.iy = a.iy;
+  p.xfirst = a.xfirst; p.xcount = a.xcount; p.xw = a.xw; p.kx = a.kx;
+  p.yfirst = a.yfirst; p.ycount = a.ycount; p.yw = a.yw; p.ky = a.ky;
+  dim3 block(stk::kResizeBX, stk::kResizeBY);
+  dim3 grid((a.dw + stk::kResizeBX - 1) / stk::kResizeBX, (a.dh + stk::kResizeBY - 1) / stk::kResizeBY);
+  stk::resize_area_grey_kernel<<<grid, block, 0, s>>>(p);
+  CU(cudaGetLastError());
+  return STK_OK;
+}
+
 struct Lane {
   cudaStream_t stream = nullptr;
   float* tmpl = nullptr;            // T plane
   uint8_t* d_frame = nullptr;       // device staging for host-submitted frames
+  uint8_t* small = nullptr;         // downscaled grey (ecc_match_scaling_down), ew x eh, small_pitch bytes per row
   uint8_t* h_stage = nullptr;       // pinned staging for pageable host buffers
   cudaEvent_t stage_free = nullptr; // H2D out of h_stage finished
   stk::EccState* st = nullptr;
@@ -145,6 +231,10 @@ struct stk_ecc_ctx {
   float* img = nullptr;             // I plane (blurred reference grey)
   uint8_t* d_ref = nullptr;         // device copy of the reference frame when it came from the host
   float* d_out = nullptr;           // scaled result before D2H
+  int ew = 0, eh = 0;               // size of the planes ECC runs on (== frame size unless scaling down)
+  bool scaled = false;
+  AreaPlan area;
+  int small_pitch = 0;
   int pitch_f = 0;                  // floats per row of I / T
   size_t frame_bytes = 0;           // width*channels*height (dense staging)
   size_t acc_floats = 0;
@@ -204,8 +294,8 @@ stk::EccIterParams iter_params(stk_ecc_ctx* c, Lane& ln, bool use_handle) {
   p.img = c->img;
   p.tmpl = ln.tmpl;
   p.pitch = c->pitch_f;
-  p.width = c->cfg.width;
-  p.height = c->cfg.height;
+  p.width = c->ew;
+  p.height = c->eh;
   p.n_strips = c->n_strips;
   p.chunks_per_strip = c->chunks_per_strip;
   p.partials = ln.partials;
@@ -260,13 +350,23 @@ int build_lane_graph(stk_ecc_ctx* c, Lane& ln) {
   return STK_OK;
 }
 
-int launch_prep(stk_ecc_ctx* c, const uint8_t* d_src, size_t pitch, float* dst, cudaStream_t s) {
+// frame (full size, BGR(A)) -> blurred f32 plane at the ECC working size; `small` = the lane's downscaled
+// grey buffer when the context scales down
+int launch_prep(stk_ecc_ctx* c, const uint8_t* d_src, size_t pitch, uint8_t* small, float* dst, cudaStream_t s) {
   stk::PrepParams p = c->prep_proto;
   p.src = d_src;
   p.src_pitch = pitch;
   p.dst = dst;
+  if (c->scaled) {
+    int rc = launch_resize(c->area, d_src, pitch, c->cfg.channels, small, c->small_pitch, s);
+    if (rc) return rc;
+    c->launches++;
+    p.src = small;
+    p.src_pitch = (size_t)c->small_pitch;
+    p.channels = 1;
+  }
   const size_t smem = stk::prep_smem_bytes(p.radius);
-  dim3 grid((c->cfg.width + stk::kPrepTW - 1) / stk::kPrepTW, (c->cfg.height + stk::kPrepTH - 1) / stk::kPrepTH);
+  dim3 grid((c->ew + stk::kPrepTW - 1) / stk::kPrepTW, (c->eh + stk::kPrepTH - 1) / stk::kPrepTH);
   switch (p.radius) {   // radii 1..4 (gauss_filt_size 3..9) get unrolled instantiations
     case 1: stk::prep_grey_blur_kernel<1><<<grid, stk::kPrepThreads, smem, s>>>(p); break;
     case 2: stk::prep_grey_blur_kernel<2><<<grid, stk::kPrepThreads, smem, s>>>(p); break;
@@ -361,7 +461,7 @@ int enqueue_align(stk_ecc_ctx* c, Lane& ln, const uint8_t* d_src, size_t pitch, 
   };
   int rc = mark(0);
   if (rc) return rc;
-  rc = launch_prep(c, d_src, pitch, ln.tmpl, ln.stream);
+  rc = launch_prep(c, d_src, pitch, ln.small, ln.tmpl, ln.stream);
   if (rc) return rc;
   if ((rc = mark(1))) return rc;
   const bool persp = c->cfg.motion_type == STK_MOTION_HOMOGRAPHY;
@@ -454,6 +554,50 @@ int stk_device_count(int* count) {
   return STK_OK;
 }
 
+int stk_scaled_size(int width, int height, float scale_down, int* sw, int* sh) {
+  if (!sw || !sh) return fail(STK_ERR_BAD_ARG, "null argument");
+  if (width <= 0 || height <= 0) return fail(STK_ERR_BAD_ARG, "bad frame size %dx%d", width, height);
+  if (scale_down >= (float)width)
+    return fail(STK_ERR_BAD_ARG, "scale_down_to was larger (or equal) to the full image width: full_size:%d, scale_down_to:%g",
+                width, (double)scale_down);
+  if (scale_down <= 10.0f) return fail(STK_ERR_BAD_ARG, "scale_down_to was too small scale_down_to:%g", (double)scale_down);
+  const double factor = (double)scale_down / (double)(width < height ? width : height);
+  const int nw = (int)((double)width * factor), nh = (int)((double)height * factor);
+  if (nw > width || nh > height)
+    return fail(STK_ERR_UNSUPPORTED, "scale_down_to %g enlarges a %dx%d frame (%dx%d): only INTER_AREA down-scaling is implemented",
+                (double)scale_down, width, height, nw, nh);
+  if (nw < 1 || nh < 1) return fail(STK_ERR_BAD_ARG, "scaled size %dx%d is empty", nw, nh);
+  *sw = nw; *sh = nh;
+  return STK_OK;
+}
+
+int stk_grey_resize_area(const uint8_t* img, size_t pitch, int width, int height, int channels, int out_width,
+                         int out_height, int device, uint8_t* out, size_t out_pitch) {
+  if (!img || !out) return fail(STK_ERR_BAD_ARG, "null argument");
+  if (width <= 0 || height <= 0 || out_width <= 0 || out_height <= 0) return fail(STK_ERR_BAD_ARG, "bad size");
+  if (out_width > width || out_height > height) return fail(STK_ERR_UNSUPPORTED, "only INTER_AREA down-scaling is implemented");
+  if (channels != 1 && channels != 3 && channels != 4) return fail(STK_ERR_UNSUPPORTED, "channels must be 1, 3 or 4");
+  const size_t row = (size_t)width * channels;
+  if (pitch < row || out_pitch < (size_t)out_width) return fail(STK_ERR_BAD_ARG, "pitch too small");
+  if (device >= 0) CU(cudaSetDevice(device));
+  AreaPlan plan;
+  int rc = make_area_plan(width, height, out_width, out_height, plan);
+  if (rc) return rc;
+  uint8_t *d_src = nullptr, *d_dst = nullptr;
+  cudaError_t e = cudaMalloc((void**)&d_src, row * height);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_dst, (size_t)out_width * out_height);
+  if (e == cudaSuccess) e = cudaMemcpy2D(d_src, row, img, pitch, row, height, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    rc = launch_resize(plan, d_src, row, channels, d_dst, out_width, 0);
+    if (rc == STK_OK) e = cudaMemcpy2D(out, out_pitch, d_dst, out_width, out_width, out_height, cudaMemcpyDeviceToHost);
+  }
+  cudaFree(d_src); cudaFree(d_dst);
+  free_area_plan(plan);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(STK_ERR_CUDA, "grey_resize_area: %s", cudaGetErrorString(e));
+  return STK_OK;
+}
+
 int stk_pinned_alloc(void** ptr, size_t bytes) {
   if (!ptr) return fail(STK_ERR_BAD_ARG, "null ptr");
   CU(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
@@ -476,6 +620,11 @@ int stk_ecc_create(const stk_ecc_config* cfg, stk_ecc_ctx** out) {
       return fail(STK_ERR_CRITERIA, "TermCriteria needs COUNT or EPS (findTransformECC asserts)");
     if (cfg->gauss_filt_size < 1 || cfg->gauss_filt_size % 2 == 0 || cfg->gauss_filt_size / 2 > stk::kMaxGaussRadius)
       return fail(STK_ERR_BAD_ARG, "gauss_filt_size must be odd, in [1, %d]", 2 * stk::kMaxGaussRadius + 1);
+    if ((cfg->ecc_width != 0) != (cfg->ecc_height != 0) || cfg->ecc_width < 0 || cfg->ecc_height < 0)
+      return fail(STK_ERR_BAD_ARG, "ecc_width/ecc_height must both be 0 or both be positive");
+    if (cfg->ecc_width > cfg->width || cfg->ecc_height > cfg->height)
+      return fail(STK_ERR_UNSUPPORTED, "ecc size %dx%d enlarges the %dx%d frame: only INTER_AREA down-scaling is implemented",
+                  cfg->ecc_width, cfg->ecc_height, cfg->width, cfg->height);
   }
   int dev = cfg->device;
   if (dev < 0) CU(cudaGetDevice(&dev));
@@ -491,7 +640,11 @@ int stk_ecc_create(const stk_ecc_config* cfg, stk_ecc_ctx** out) {
   c->device = dev;
   c->sm_count = prop.multiProcessorCount;
   c->n_lanes = cfg->lanes > 0 ? std::min(cfg->lanes, 16) : 4;
-  c->pitch_f = (cfg->width + 31) / 32 * 32;
+  c->scaled = cfg->align && cfg->ecc_width > 0;
+  c->ew = c->scaled ? cfg->ecc_width : cfg->width;
+  c->eh = c->scaled ? cfg->ecc_height : cfg->height;
+  c->small_pitch = (c->ew + 15) / 16 * 16;
+  c->pitch_f = (c->ew + 31) / 32 * 32;
   c->frame_bytes = (size_t)cfg->width * cfg->channels * cfg->height;
   c->acc_floats = (size_t)cfg->width * cfg->channels * cfg->height;
   c->max_iter = (cfg->criteria_type & STK_TERM_COUNT) ? cfg->max_count : 200;
@@ -518,18 +671,18 @@ int stk_ecc_create(const stk_ecc_config* cfg, stk_ecc_ctx** out) {
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, c->iter_threads, c->iter_smem) != cudaSuccess || occ < 1) occ = 1;
     const int slots = c->sm_count * occ;
-    c->n_strips = (cfg->width + stk::kEccStripW - 1) / stk::kEccStripW;
-    c->chunks_per_strip = (cfg->height + stk::kChunkH - 1) / stk::kChunkH;
+    c->n_strips = (c->ew + stk::kEccStripW - 1) / stk::kEccStripW;
+    c->chunks_per_strip = (c->eh + stk::kChunkH - 1) / stk::kChunkH;
     const int chunk_h = c->pack2 ? stk::kP2ChunkH : stk::kChunkH;
-    const long long total_chunks = (long long)c->n_strips * ((cfg->height + chunk_h - 1) / chunk_h);
+    const long long total_chunks = (long long)c->n_strips * ((c->eh + chunk_h - 1) / chunk_h);
     // at least two chunks per block so the per-run fold/reduction stays amortised on small frames
     c->n_tiles = (int)std::max(1LL, std::min<long long>(slots, total_chunks / 2));
     c->nv = model_nv(cfg->motion_type);
     stk::PrepParams& pp = c->prep_proto;
     memset(&pp, 0, sizeof pp);
     pp.dst_pitch = c->pitch_f;
-    pp.width = cfg->width;
-    pp.height = cfg->height;
+    pp.width = c->ew;
+    pp.height = c->eh;
     pp.channels = cfg->channels;
     pp.radius = cfg->gauss_filt_size / 2;
     gaussian_taps(cfg->gauss_filt_size, pp.taps);
@@ -538,12 +691,16 @@ int stk_ecc_create(const stk_ecc_config* cfg, stk_ecc_ctx** out) {
       if (cudaFuncSetAttribute(stk::prep_grey_blur_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return cleanup(fail(STK_ERR_CUDA, "cannot reserve %zu bytes of shared memory for the blur", smem));
     }
-    if (cudaMalloc((void**)&c->img, (size_t)c->pitch_f * cfg->height * sizeof(float)) != cudaSuccess)
+    if (cudaMalloc((void**)&c->img, (size_t)c->pitch_f * c->eh * sizeof(float)) != cudaSuccess)
       return cleanup(fail(STK_ERR_NOMEM, "cudaMalloc(I plane) failed"));
-    rc = make_plane_tensor_map(&c->tm_img, c->img, cfg->width, cfg->height, c->pitch_f, stk::kBoxW, stk::kBoxH);
+    rc = make_plane_tensor_map(&c->tm_img, c->img, c->ew, c->eh, c->pitch_f, stk::kBoxW, stk::kBoxH);
     if (rc) return cleanup(rc);
-    rc = make_plane_tensor_map(&c->tm_img_p2, c->img, cfg->width, cfg->height, c->pitch_f, stk::kBoxW, stk::kP2BoxH);
+    rc = make_plane_tensor_map(&c->tm_img_p2, c->img, c->ew, c->eh, c->pitch_f, stk::kBoxW, stk::kP2BoxH);
     if (rc) return cleanup(rc);
+    if (c->scaled) {
+      rc = make_area_plan(cfg->width, cfg->height, c->ew, c->eh, c->area);
+      if (rc) return cleanup(rc);
+    }
 
   }
   c->lanes.resize(c->n_lanes);
@@ -552,14 +709,29 @@ int stk_ecc_create(const stk_ecc_config* cfg, stk_ecc_ctx** out) {
     if (cudaEventCreateWithFlags(&ln.stage_free, cudaEventDisableTiming) != cudaSuccess) return cleanup(fail(STK_ERR_CUDA, "cudaEventCreate failed"));
     if (cudaMalloc((void**)&ln.acc, c->acc_floats * sizeof(float)) != cudaSuccess) return cleanup(fail(STK_ERR_NOMEM, "cudaMalloc(accumulator) failed"));
     if (cfg->align) {
-      if (cudaMalloc((void**)&ln.tmpl, (size_t)c->pitch_f * cfg->height * sizeof(float)) != cudaSuccess) return cleanup(fail(STK_ERR_NOMEM, "cudaMalloc(T plane) failed"));
-      rc = make_plane_tensor_map(&ln.tm_tmpl, ln.tmpl, cfg->width, cfg->height, c->pitch_f, stk::kEccStripW, stk::kChunkH);
+      if (cudaMalloc((void**)&ln.tmpl, (size_t)c->pitch_f * c->eh * sizeof(float)) != cudaSuccess) return cleanup(fail(STK_ERR_NOMEM, "cudaMalloc(T plane) failed"));
+      rc = make_plane_tensor_map(&ln.tm_tmpl, ln.tmpl, c->ew, c->eh, c->pitch_f, stk::kEccStripW, stk::kChunkH);
       if (rc) return cleanup(rc);
-      rc = make_plane_tensor_map(&ln.tm_tmpl_p2, ln.tmpl, cfg->width, cfg->height, c->pitch_f, stk::kEccStripW, stk::kP2ChunkH);
+      rc = make_plane_tensor_map(&ln.tm_tmpl_p2, ln.tmpl, c->ew, c->eh, c->pitch_f, stk::kEccStripW, stk::kP2ChunkH);
       if (rc) return cleanup(rc);
+      if (c->scaled && cudaMalloc((void**)&ln.small, (size_t)c->small_pitch * c->eh) != cudaSuccess) return cleanup(fail(STK_ERR_NOMEM, "cudaMalloc(downscaled grey) failed"));
       if (cudaMalloc((void**)&ln.st, sizeof(stk::EccState)) != cudaSuccess) return cleanup(fail(STK_ERR_NOMEM, "cudaMalloc(state) failed"));
-      if (cudaMemsetAsync(ln.st, 0, sizeof(stk::EccState), ln.stream) != cudaSuccess ||
-          cudaStreamSynchronize(ln.stream) != cudaSuccess) return cleanup(fail(STK_ERR_CUDA, "cudaMemset failed"));
+      {
+        // the rescale factors are the only fields the init kernel leaves alone
+        stk::EccState zero;
+        memset(&zero, 0, sizeof zero);
+        if (c->scaled) {
+          if (cfg->motion_type == STK_MOTION_HOMOGRAPHY) {     // src/utils.rs:228-241: f64 ratio, then `as f32`
+            zero.rescale_x = (float)((double)cfg->width / (double)c->ew);
+            zero.rescale_y = (float)((double)cfg->height / (double)c->eh);
+          } else {                                             // src/lib.rs:946-949: f32 / f32
+            zero.rescale_x = (float)cfg->width / (float)c->ew;
+            zero.rescale_y = (float)cfg->height / (float)c->eh;
+          }
+        }
+        if (cudaMemcpyAsync(ln.st, &zero, sizeof zero, cudaMemcpyHostToDevice, ln.stream) != cudaSuccess ||
+            cudaStreamSynchronize(ln.stream) != cudaSuccess) return cleanup(fail(STK_ERR_CUDA, "state upload failed"));
+      }
       if (cudaMalloc((void**)&ln.partials, (size_t)((c->n_tiles + 31) / 32 * 32) * c->nv * sizeof(double)) != cudaSuccess) return cleanup(fail(STK_ERR_NOMEM, "cudaMalloc(partials) failed"));
       if (!c->host_loop) {
         rc = build_lane_graph(c, ln);
@@ -578,13 +750,14 @@ int stk_ecc_destroy(stk_ecc_ctx* c) {
     if (ln.stream) cudaStreamSynchronize(ln.stream);
     if (ln.exec) cudaGraphExecDestroy(ln.exec);
     if (ln.graph) cudaGraphDestroy(ln.graph);
-    cudaFree(ln.tmpl); cudaFree(ln.d_frame); cudaFree(ln.st); cudaFree(ln.partials); cudaFree(ln.acc);
+    cudaFree(ln.tmpl); cudaFree(ln.d_frame); cudaFree(ln.small); cudaFree(ln.st); cudaFree(ln.partials); cudaFree(ln.acc);
     if (ln.h_stage) cudaFreeHost(ln.h_stage);
     if (ln.stage_free) cudaEventDestroy(ln.stage_free);
     if (ln.stream) cudaStreamDestroy(ln.stream);
   }
   for (auto& r : c->results) for (auto& e : r.ev) if (e) cudaEventDestroy(e);
   cudaFree(c->img); cudaFree(c->d_ref); cudaFree(c->d_out);
+  free_area_plan(c->area);
   for (auto* p : c->state_chunks) cudaFreeHost(p);
   delete c;
   return STK_OK;
@@ -599,7 +772,7 @@ static int ensure_host_staging(stk_ecc_ctx* c, Lane& ln, bool need_pinned_stage)
 static int set_reference_impl(stk_ecc_ctx* c, const uint8_t* d_bgr, size_t pitch) {
   Lane& l0 = c->lanes[0];
   if (c->cfg.align) {
-    int rc = launch_prep(c, d_bgr, pitch, c->img, l0.stream);
+    int rc = launch_prep(c, d_bgr, pitch, l0.small, c->img, l0.stream);
     if (rc) return rc;
   }
   if (c->cfg.seed_reference) {
@@ -901,7 +1074,7 @@ int stk_ecc_debug_iteration(stk_ecc_ctx* c, const uint8_t* bgr, size_t pitch, co
   rc = upload_frame(c, ln, bgr, pitch, false);
   if (rc) return rc;
   const size_t row = (size_t)c->cfg.width * c->cfg.channels;
-  rc = launch_prep(c, ln.d_frame, row, ln.tmpl, ln.stream);
+  rc = launch_prep(c, ln.d_frame, row, ln.small, ln.tmpl, ln.stream);
   if (rc) return rc;
   const bool persp = c->cfg.motion_type == STK_MOTION_HOMOGRAPHY;
   stk::ecc_init_kernel<<<1, 32, 0, ln.stream>>>(ln.st, persp ? 1 : 0, 1 << 30, -1.0, 0, 0);
@@ -942,7 +1115,7 @@ int stk_ecc_debug_timing(stk_ecc_ctx* c, const uint8_t* bgr, size_t pitch, const
   rc = upload_frame(c, ln, bgr, pitch, false);
   if (rc) return rc;
   const size_t row = (size_t)c->cfg.width * c->cfg.channels;
-  rc = launch_prep(c, ln.d_frame, row, ln.tmpl, ln.stream);
+  rc = launch_prep(c, ln.d_frame, row, ln.small, ln.tmpl, ln.stream);
   if (rc) return rc;
   const bool persp = c->cfg.motion_type == STK_MOTION_HOMOGRAPHY;
   stk::ecc_init_kernel<<<1, 32, 0, ln.stream>>>(ln.st, persp ? 1 : 0, 1 << 30, -1.0, 0, 0);
@@ -1033,6 +1206,71 @@ int stk_tenengrad(const uint8_t* img, size_t pitch, int width, int height, int c
   cudaError_t e = cudaMemcpy2D(d, row, img, pitch, row, height, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) { cudaFree(d); return fail(STK_ERR_CUDA, "tenengrad upload: %s", cudaGetErrorString(e)); }
   rc = stk_tenengrad_batch_device(d, 0, row, width, height, channels, ksize, 1, -1, out);
+  cudaFree(d);
+  return rc;
+}
+
+/* ---- LAPM / LAPV / TENG(3) / GLVN in one pass ----------------------------------------------------------- */
+// scalar tails in cv::mean / cv::meanStdDev's order (oracle/restate.py::_mean_std_from_sums); host code is
+// compiled for baseline x86-64, so nothing here is contracted into an FMA
+static void sharpness_from_sums(const unsigned long long* v, double n_px, double* out) {
+  const double scale = 1.0 / n_px;
+  auto mean_sigma = [&](double s, double sq, double& mean, double& sigma) {
+    mean = s * scale;
+    const double var = sq * scale - mean * mean;
+    sigma = std::sqrt(var > 0.0 ? var : 0.0);
+  };
+  out[0] = ((double)v[1] / 4.0) * scale;                                  // LAPM: mean(|lx| + |ly|)
+  double mean, sigma;
+  mean_sigma((double)(long long)v[2], (double)v[3], mean, sigma);
+  out[1] = sigma * sigma;                                                 // LAPV
+  out[2] = (double)v[0] * scale;                                          // TENG
+  mean_sigma((double)v[4], (double)v[5], mean, sigma);
+  const double eps = 2.220446049250313e-16;
+  out[3] = (sigma * sigma) / (mean > eps ? mean : eps);                   // GLVN
+}
+
+int stk_sharpness_all_batch_device(const uint8_t* d_imgs, size_t frame_stride, size_t pitch, int width, int height,
+                                   int channels, int n, int device, double* out) {
+  if (!d_imgs || !out || n <= 0) return fail(STK_ERR_BAD_ARG, "null/empty argument");
+  if (width <= 0 || height <= 0) return fail(STK_ERR_BAD_ARG, "bad size");
+  if (channels != 1 && channels != 3 && channels != 4) return fail(STK_ERR_UNSUPPORTED, "channels must be 1, 3 or 4");
+  if (pitch < (size_t)width * channels) return fail(STK_ERR_BAD_ARG, "pitch too small");
+  if (device >= 0) CU(cudaSetDevice(device));
+  const size_t bytes = sizeof(unsigned long long) * stk::kSharpSums * (size_t)n;
+  unsigned long long* d_sums = nullptr;
+  CU(cudaMalloc((void**)&d_sums, bytes));
+  cudaError_t e = cudaMemset(d_sums, 0, bytes);
+  std::vector<unsigned long long> h((size_t)n * stk::kSharpSums);
+  for (int z0 = 0; z0 < n && e == cudaSuccess; z0 += 32768) {
+    stk::SharpnessParams p = {};
+    p.src = d_imgs + (size_t)z0 * frame_stride;
+    p.frame_stride = frame_stride; p.pitch = pitch;
+    p.width = width; p.height = height; p.channels = channels;
+    p.sums = d_sums + (size_t)z0 * stk::kSharpSums;
+    dim3 grid((width + stk::kTenTW - 1) / stk::kTenTW, (height + stk::kTenTH - 1) / stk::kTenTH, std::min(32768, n - z0));
+    stk::sharpness_all_kernel<<<grid, stk::kTenThreads>>>(p);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(h.data(), d_sums, bytes, cudaMemcpyDeviceToHost);
+  cudaFree(d_sums);
+  if (e != cudaSuccess) return fail(STK_ERR_CUDA, "sharpness: %s", cudaGetErrorString(e));
+  for (int i = 0; i < n; ++i) sharpness_from_sums(h.data() + (size_t)i * stk::kSharpSums, (double)width * (double)height, out + 4 * (size_t)i);
+  return STK_OK;
+}
+
+int stk_sharpness_all(const uint8_t* img, size_t pitch, int width, int height, int channels, int device, double out[4]) {
+  if (!img || !out) return fail(STK_ERR_BAD_ARG, "null argument");
+  if (width <= 0 || height <= 0) return fail(STK_ERR_BAD_ARG, "bad size");
+  if (channels != 1 && channels != 3 && channels != 4) return fail(STK_ERR_UNSUPPORTED, "channels must be 1, 3 or 4");
+  const size_t row = (size_t)width * channels;
+  if (pitch < row) return fail(STK_ERR_BAD_ARG, "pitch too small");
+  if (device >= 0) CU(cudaSetDevice(device));
+  uint8_t* d = nullptr;
+  CU(cudaMalloc((void**)&d, row * height));
+  cudaError_t e = cudaMemcpy2D(d, row, img, pitch, row, height, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(d); return fail(STK_ERR_CUDA, "sharpness upload: %s", cudaGetErrorString(e)); }
+  const int rc = stk_sharpness_all_batch_device(d, 0, row, width, height, channels, 1, -1, out);
   cudaFree(d);
   return rc;
 }

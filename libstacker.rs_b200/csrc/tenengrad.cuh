@@ -73,4 +73,87 @@ __global__ void __launch_bounds__(kTenThreads) tenengrad_kernel(const TenengradP
   }
 }
 
+// ---- all four sharpness metrics of the crate in one pass -----------------------------------------------
+// LAPM  sharpness_modified_laplacian            /root/reference/src/lib.rs:1032-1068
+// LAPV  sharpness_variance_of_laplacian         /root/reference/src/lib.rs:1070-1090
+// TENG  sharpness_tenengrad(k = 3)              /root/reference/src/lib.rs:1101-1147
+// GLVN  sharpness_normalized_gray_level_variance /root/reference/src/lib.rs:1151-1166
+// which examples/main.rs:37-50 evaluates per file with ~14 OpenCV passes over CV_64F planes.  All four are
+// 3x3 stencils (or none) over the 8-bit grey plane, so one read of the plane (N bytes; 3N with the grey
+// conversion fused in) yields six exact integer sums per frame:
+//   [0] sum(gx^2 + gy^2)            Sobel 3x3, BORDER_REFLECT_101
+//   [1] sum(|4 lx| + |4 ly|)        [-1 2 -1] x [1 2 1] and transposed, BORDER_REFLECT_101 (lx, ly in 1/4 units)
+//   [2] sum(lap)  [3] sum(lap^2)    [[2 0 2],[0 -8 0],[2 0 2]], BORDER_REPLICATE  ([2] two's complement)
+//   [4] sum(g)    [5] sum(g^2)
+// The host finishes each metric with the same few f64 operations cv::mean / cv::meanStdDev use
+// (oracle/restate.py, pinned bit-exact against cv2).
+constexpr int kSharpSums = 6;
+
+struct SharpnessParams {
+  const uint8_t* src;
+  size_t frame_stride, pitch;
+  int width, height, channels;
+  unsigned long long* sums;     // [n_frames][kSharpSums]
+};
+
+__global__ void __launch_bounds__(kTenThreads) sharpness_all_kernel(const SharpnessParams p) {
+  constexpr int GW = kTenTW + 2, GH = kTenTH + 2;
+  __shared__ short s_g[GH][GW];
+  __shared__ unsigned long long s_part[kTenThreads / 32][kSharpSums];
+  const int x0 = blockIdx.x * kTenTW, y0 = blockIdx.y * kTenTH;
+  const uint8_t* src = p.src + (size_t)blockIdx.z * p.frame_stride;
+  const int tid = threadIdx.x;
+  const int w = p.width, h = p.height;
+
+  for (int i = tid; i < GW * GH; i += kTenThreads) {
+    const int ty = i / GW, tx = i - ty * GW;
+    const int sx = reflect101(x0 + tx - 1, w);
+    const int sy = reflect101(y0 + ty - 1, h);
+    const uint8_t* px = src + (size_t)sy * p.pitch + (size_t)sx * p.channels;
+    s_g[ty][tx] = (short)(p.channels == 1 ? (int)px[0] : bgr2gray(px[0], px[1], px[2]));
+  }
+  __syncthreads();
+
+  unsigned long long teng = 0, lapm = 0, lapsq = 0;
+  long long lapsum = 0;
+  unsigned int gsum = 0, gsq = 0;
+  for (int i = tid; i < kTenTH * kTenTW; i += kTenThreads) {
+    const int ty = i / kTenTW, tx = i - ty * kTenTW;
+    const int x = x0 + tx, y = y0 + ty;
+    if (x >= w || y >= h) continue;
+    const int cy = ty + 1, cx = tx + 1;
+    // REFLECT_101 neighbourhood
+    const int a00 = s_g[cy - 1][cx - 1], a01 = s_g[cy - 1][cx], a02 = s_g[cy - 1][cx + 1];
+    const int a10 = s_g[cy][cx - 1], a11 = s_g[cy][cx], a12 = s_g[cy][cx + 1];
+    const int a20 = s_g[cy + 1][cx - 1], a21 = s_g[cy + 1][cx], a22 = s_g[cy + 1][cx + 1];
+    const int gx = (a02 - a00) + 2 * (a12 - a10) + (a22 - a20);
+    const int gy = (a20 - a00) + 2 * (a21 - a01) + (a22 - a02);
+    teng += (unsigned long long)(gx * gx) + (unsigned long long)(gy * gy);
+    // 4*lx: [-1 2 -1] along x, [1 2 1] along y ; 4*ly transposed
+    const int r0 = 2 * a01 - a00 - a02, r1 = 2 * a11 - a10 - a12, r2 = 2 * a21 - a20 - a22;
+    const int c0 = 2 * a10 - a00 - a20, c1 = 2 * a11 - a01 - a21, c2 = 2 * a12 - a02 - a22;
+    lapm += (unsigned)(abs(r0 + 2 * r1 + r2) + abs(c0 + 2 * c1 + c2));
+    // BORDER_REPLICATE corners (the clamped positions are always inside the tile)
+    const int xl = cx - (x > 0 ? 1 : 0), xr = cx + (x < w - 1 ? 1 : 0);
+    const int yu = cy - (y > 0 ? 1 : 0), yd = cy + (y < h - 1 ? 1 : 0);
+    const int lap = 2 * (s_g[yu][xl] + s_g[yu][xr] + s_g[yd][xl] + s_g[yd][xr]) - 8 * a11;
+    lapsum += lap;
+    lapsq += (unsigned long long)(lap * lap);
+    gsum += (unsigned)a11;
+    gsq += (unsigned)(a11 * a11);
+  }
+  unsigned long long v[kSharpSums] = {teng, lapm, (unsigned long long)lapsum, lapsq, gsum, gsq};
+#pragma unroll
+  for (int k = 0; k < kSharpSums; ++k) {
+    v[k] = warp_sum(v[k]);
+    if ((tid & 31) == 0) s_part[tid >> 5][k] = v[k];
+  }
+  __syncthreads();
+  if (tid < kSharpSums) {
+    unsigned long long t = 0;
+    for (int wp = 0; wp < kTenThreads / 32; ++wp) t += s_part[wp][tid];
+    atomicAdd(p.sums + (size_t)blockIdx.z * kSharpSums + tid, t);     // integer: order-independent
+  }
+}
+
 }  // namespace stk

@@ -74,13 +74,18 @@ ImageF32 ecc_match(const std::vector<std::filesystem::path>& files, const EccMat
                    std::optional<float> scale_down_width, const Decoder& decode, int device,
                    std::vector<FrameAlignment>* details) {
   if (files.empty()) throw NotEnoughFiles();                                            // src/lib.rs:725
-  if (scale_down_width) throw NotImplemented("ecc_match with scale_down_width is not implemented yet");
   const TermCriteria crit = term_criteria(params);
   ImageU8 first = decode(files[0]);
   check_colour(first);
-  if (!crit.typ) throw OpenCvError("findTransformECC: criteria.type must have COUNT or EPS set");
   stk_ecc_config cfg{};
   cfg.width = first.width; cfg.height = first.height; cfg.channels = first.channels;
+  if (scale_down_width) {
+    // ecc_match_scaling_down (src/lib.rs:849-1028): validation (:876-888) and utils::scale_image's size rule
+    int sw = 0, sh = 0;
+    check(stk_scaled_size(first.width, first.height, *scale_down_width, &sw, &sh));
+    cfg.ecc_width = sw; cfg.ecc_height = sh;
+  }
+  if (!crit.typ) throw OpenCvError("findTransformECC: criteria.type must have COUNT or EPS set");
   cfg.motion_type = (int)params.motion_type;
   cfg.criteria_type = crit.typ; cfg.max_count = crit.max_count; cfg.epsilon = crit.epsilon;
   cfg.gauss_filt_size = params.gauss_filt_size;
@@ -157,5 +162,15 @@ double sharpness_tenengrad(const ImageU8& grey, int k_size, int device) {
   check(stk_tenengrad(grey.data.data(), (size_t)grey.width, grey.width, grey.height, 1, k_size, device, &out));
   return out;
 }
+
+std::array<double, 4> sharpness_all(const ImageU8& grey, int device) {
+  if (grey.channels != 1) throw OpenCvError("the sharpness metrics expect a single-channel image");
+  std::array<double, 4> out{};
+  check(stk_sharpness_all(grey.data.data(), (size_t)grey.width, grey.width, grey.height, 1, device, out.data()));
+  return out;
+}
+double sharpness_modified_laplacian(const ImageU8& grey, int device) { return sharpness_all(grey, device)[0]; }
+double sharpness_variance_of_laplacian(const ImageU8& grey, int device) { return sharpness_all(grey, device)[1]; }
+double sharpness_normalized_gray_level_variance(const ImageU8& grey, int device) { return sharpness_all(grey, device)[3]; }
 
 }  // namespace libstacker

@@ -69,7 +69,8 @@ ImageU8 read_pnm(const std::filesystem::path& path);          // P6 (RGB -> stor
 struct FrameAlignment { int64_t frame; float warp[9]; double rho; int iterations; };   // frame = index into `files`
 
 // ---- the API ---------------------------------------------------------------------------------------
-// scale_down_width: Some(width) is SURVEY §8(f) row N1 — not built yet -> NotImplemented.
+// scale_down_width: Some(width) = ecc_match_scaling_down (src/lib.rs:849-1028): ECC on INTER_AREA-downscaled
+// greys, matrix rescaled to full resolution, full-size warp.
 ImageF32 ecc_match(const std::vector<std::filesystem::path>& files, const EccMatchParameters& params,
                    std::optional<float> scale_down_width = std::nullopt, const Decoder& decode = read_pnm,
                    int device = -1, std::vector<FrameAlignment>* details = nullptr);
@@ -80,5 +81,11 @@ ImageF32 stack_with_homographies(const std::vector<ImageU8>& frames, const std::
                                  const KeyPointMatchParameters& params = {}, int device = -1);
 
 double sharpness_tenengrad(const ImageU8& grey, int k_size, int device = -1);
+// {LAPM, LAPV, TENG(3), GLVN} in one pass (examples/main.rs:43-46), and the crate's three single-metric entry
+// points (src/lib.rs:1032-1090, :1151-1166) on top of it
+std::array<double, 4> sharpness_all(const ImageU8& grey, int device = -1);
+double sharpness_modified_laplacian(const ImageU8& grey, int device = -1);
+double sharpness_variance_of_laplacian(const ImageU8& grey, int device = -1);
+double sharpness_normalized_gray_level_variance(const ImageU8& grey, int device = -1);
 
 }  // namespace libstacker

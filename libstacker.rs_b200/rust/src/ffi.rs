@@ -1,4 +1,4 @@
-//! Thin `extern "C"` layer over include/stacker_cuda.h (ABI version 1).  One declaration per entry point the
+//! Thin `extern "C"` layer over include/stacker_cuda.h (ABI version 2).  One declaration per entry point the
 //! Rust wrappers use; see the header for ownership and threading rules.
 #![allow(non_camel_case_types)]
 use std::os::raw::{c_char, c_int, c_void};
@@ -34,6 +34,8 @@ pub struct stk_ecc_config {
     pub lanes: i32,
     pub seed_reference: i32,
     pub align: i32,
+    pub ecc_width: i32,
+    pub ecc_height: i32,
 }
 
 #[repr(C)]
@@ -50,6 +52,7 @@ unsafe extern "C" {
     pub fn stk_abi_version() -> c_int;
     pub fn stk_last_error() -> *const c_char;
     pub fn stk_device_count(count: *mut c_int) -> c_int;
+    pub fn stk_scaled_size(width: c_int, height: c_int, scale_down: f32, sw: *mut c_int, sh: *mut c_int) -> c_int;
     pub fn stk_pinned_alloc(ptr: *mut *mut c_void, bytes: usize) -> c_int;
     pub fn stk_pinned_free(ptr: *mut c_void) -> c_int;
 
@@ -72,6 +75,9 @@ unsafe extern "C" {
     pub fn stk_tenengrad(
         img: *const u8, pitch: usize, width: c_int, height: c_int, channels: c_int, ksize: c_int,
         device: c_int, out: *mut f64,
+    ) -> c_int;
+    pub fn stk_sharpness_all(
+        img: *const u8, pitch: usize, width: c_int, height: c_int, channels: c_int, device: c_int, out: *mut f64,
     ) -> c_int;
 }
 

@@ -75,11 +75,15 @@ pub struct EccMatchParameters {
     pub gauss_filt_size: i32,
 }
 
-fn new_ctx(first: &Mat, ecc: Option<(EccMatchParameters, core::TermCriteria)>) -> Result<ffi::Ctx, StackerError> {
+fn new_ctx(first: &Mat, ecc: Option<(EccMatchParameters, core::TermCriteria)>, ecc_size: Option<(i32, i32)>) -> Result<ffi::Ctx, StackerError> {
     let mut cfg = ffi::stk_ecc_config {
         width: first.cols(), height: first.rows(), channels: first.channels(),
         device: -1, lanes: 0, seed_reference: 1, ..Default::default()
     };
+    if let Some((w, h)) = ecc_size {
+        cfg.ecc_width = w;
+        cfg.ecc_height = h;
+    }
     if let Some((p, c)) = ecc {
         cfg.align = 1;
         cfg.motion_type = p.motion_type as i32;
@@ -109,15 +113,23 @@ where
     P: AsRef<std::path::Path>,
 {
     let files: Vec<PathBuf> = files.into_iter().map(|p| p.as_ref().to_path_buf()).collect();
-    if scale_down_width.is_some() {
-        return Err(StackerError::NotImplemented); // next
-    }
     if files.is_empty() {
         return Err(StackerError::NotEnoughFiles);
     }
     let criteria = Result::<core::TermCriteria, StackerError>::from(params)?;
     let first = utils::read_frame(&files[0])?;
-    let ctx = new_ctx(&first, Some((params, criteria)))?;
+    // ecc_match_scaling_down (reference src/lib.rs:849-1028): the library validates the width
+    // (:876-888), applies utils::scale_image's size rule, resizes the greys with INTER_AREA on the GPU,
+    // runs ECC there and takes the matrix back to full resolution before the full-size warp.
+    let ecc_size = match scale_down_width {
+        Some(sd) => {
+            let (mut sw, mut sh) = (0, 0);
+            check(unsafe { ffi::stk_scaled_size(first.cols(), first.rows(), sd, &mut sw, &mut sh) })?;
+            Some((sw, sh))
+        }
+        None => None,
+    };
+    let ctx = new_ctx(&first, Some((params, criteria)), ecc_size)?;
     check(unsafe { ffi::stk_ecc_set_reference(ctx.0, first.data(), first.mat_step().get(0)) })?;
     // decode on the Rayon pool, one task per frame (reference: src/lib.rs:746-749); submission is thread-safe,
     // asynchronous, and copies the frame into pinned staging before returning
@@ -158,7 +170,7 @@ where
         Ok((kp, des))
     };
     let (kp0, des0) = orb(&grey(&first)?)?;
-    let ctx = new_ctx(&first, None)?;
+    let ctx = new_ctx(&first, None, None)?;
     check(unsafe { ffi::stk_ecc_set_reference(ctx.0, first.data(), first.mat_step().get(0)) })?;
     let border = [params.border_value[0], params.border_value[1], params.border_value[2], params.border_value[3]];
     let dropped: i32 = (1..files.len()).into_par_iter().with_min_len(1).map(|i| -> Result<i32, StackerError> {
@@ -216,6 +228,34 @@ pub fn sharpness_tenengrad(src_grey_mat: &Mat, k_size: i32) -> Result<f64, Stack
         ffi::stk_tenengrad(src_grey_mat.data(), src_grey_mat.mat_step().get(0), src_grey_mat.cols(), src_grey_mat.rows(), 1, k_size, -1, &mut out)
     })?;
     Ok(out)
+}
+
+/// LAPM, LAPV, TENG(3) and GLVN of an 8-bit single-channel image in one pass over the plane
+/// (`examples/main.rs:43-46` computes exactly these four per file).
+pub fn sharpness_all(src_grey_mat: &Mat) -> Result<[f64; 4], StackerError> {
+    if src_grey_mat.depth() != core::CV_8U || src_grey_mat.channels() != 1 {
+        return Err(StackerError::NotImplemented);
+    }
+    let mut out = [0f64; 4];
+    check(unsafe {
+        ffi::stk_sharpness_all(src_grey_mat.data(), src_grey_mat.mat_step().get(0), src_grey_mat.cols(), src_grey_mat.rows(), 1, -1, out.as_mut_ptr())
+    })?;
+    Ok(out)
+}
+
+/// 'LAPM' (Nayar89) — same contract as the reference (`src/lib.rs:1032-1068`).
+pub fn sharpness_modified_laplacian(src_mat: &Mat) -> Result<f64, StackerError> {
+    Ok(sharpness_all(src_mat)?[0])
+}
+
+/// 'LAPV' (Pech2000) — same contract as the reference (`src/lib.rs:1070-1090`).
+pub fn sharpness_variance_of_laplacian(src_mat: &Mat) -> Result<f64, StackerError> {
+    Ok(sharpness_all(src_mat)?[1])
+}
+
+/// 'GLVN' (Santos97) — same contract as the reference (`src/lib.rs:1151-1166`).
+pub fn sharpness_normalized_gray_level_variance(src_mat: &Mat) -> Result<f64, StackerError> {
+    Ok(sharpness_all(src_mat)?[3])
 }
 
 pub mod prelude {

@@ -91,6 +91,58 @@ def ecc_match(frames_u8, motion, max_count, epsilon, gauss_filt_size, workers=No
     return stack, [r[1] for r in results], [r[2] for r in results]
 
 
+def scale_image(img, scale_down):
+    """src/utils.rs:186-214: smaller dimension -> scale_down, sizes truncated, INTER_AREA."""
+    h, w = img.shape[:2]
+    factor = float(scale_down) / float(w if w < h else h)
+    return cv2.resize(img, (int(w * factor), int(h * factor)), interpolation=cv2.INTER_AREA)
+
+
+def ecc_match_scaling_down(frames_u8, motion, max_count, epsilon, gauss_filt_size, scale_down, workers=1):
+    """ecc_match_scaling_down (src/lib.rs:849-1028) over in-memory frames.
+    Returns (stack f32, full-resolution warps, rhos)."""
+    if len(frames_u8) == 0:
+        raise ValueError("NotEnoughFiles")
+    criteria = term_criteria(max_count, epsilon)
+    grey0, f32_0 = read_grey_and_f32(frames_u8[0])
+    h, w = grey0.shape
+    if scale_down >= w:
+        raise ValueError("InvalidParams: scale_down_to was larger (or equal) to the full image width")
+    if scale_down <= 10.0:
+        raise ValueError("InvalidParams: scale_down_to was too small")
+    grey0_small = scale_image(grey0, scale_down)
+    sh, sw = grey0_small.shape
+
+    def task(i):
+        if i == 0:
+            return f32_0.copy(), None, None
+        grey, f32 = read_grey_and_f32(frames_u8[i])
+        grey_small = scale_image(grey, scale_down)
+        rho, m = align_frame(grey_small, grey0_small, motion, criteria, gauss_filt_size)
+        if motion != MOTION_HOMOGRAPHY:
+            m = m.copy()
+            m[0, 2] *= np.float32(w) / np.float32(sw)          # src/lib.rs:946-949
+            m[1, 2] *= np.float32(h) / np.float32(sh)
+        else:
+            sx, sy = np.float32(w / sw), np.float32(h / sh)    # src/utils.rs:228-241 (f32 variant)
+            m = m.copy()
+            m[0, 2] *= sx
+            m[1, 2] *= sy
+            m[2, 0] /= sx
+            m[2, 1] /= sy
+        return warp_frame(f32, m, motion), m, rho
+
+    if workers == 1:
+        results = [task(i) for i in range(len(frames_u8))]
+    else:
+        with ThreadPoolExecutor(max_workers=workers) as ex:
+            results = list(ex.map(task, range(len(frames_u8))))
+    acc = None
+    for warped, _, _ in results:
+        acc = warped if acc is None else acc + warped
+    return acc * np.float32(1.0 / len(frames_u8)), [r[1] for r in results], [r[2] for r in results]
+
+
 def sharpness_tenengrad(grey_u8, ksize):
     """src/lib.rs:1101-1147."""
     if ksize not in (1, 3, 5, 7):
@@ -99,6 +151,28 @@ def sharpness_tenengrad(grey_u8, ksize):
     gy = cv2.Sobel(grey_u8, cv2.CV_64F, 0, 1, ksize=ksize, scale=1.0, delta=0.0, borderType=cv2.BORDER_DEFAULT)
     s = cv2.add(cv2.multiply(gx, gx), cv2.multiply(gy, gy))
     return cv2.mean(s)[0]
+
+
+def sharpness_modified_laplacian(grey_u8):
+    """src/lib.rs:1032-1068."""
+    m = np.array([[-1.0, 2.0, -1.0]], np.float64)
+    g = cv2.getGaussianKernel(3, -1.0, cv2.CV_64F)
+    lx = cv2.sepFilter2D(grey_u8, cv2.CV_64F, m, g, anchor=(-1, -1), delta=0.0, borderType=cv2.BORDER_DEFAULT)
+    ly = cv2.sepFilter2D(grey_u8, cv2.CV_64F, g, m, anchor=(-1, -1), delta=0.0, borderType=cv2.BORDER_DEFAULT)
+    return cv2.mean(np.abs(lx) + np.abs(ly))[0]
+
+
+def sharpness_variance_of_laplacian(grey_u8):
+    """src/lib.rs:1070-1090."""
+    lap = cv2.Laplacian(grey_u8, cv2.CV_64F, ksize=3, scale=1.0, delta=0.0, borderType=cv2.BORDER_REPLICATE)
+    _, sigma = cv2.meanStdDev(lap)
+    return float(sigma[0, 0]) * float(sigma[0, 0])
+
+
+def sharpness_normalized_gray_level_variance(grey_u8):
+    """src/lib.rs:1151-1166."""
+    mu, sigma = cv2.meanStdDev(grey_u8.astype(np.float64))
+    return float(sigma[0, 0]) ** 2 / max(float(mu[0, 0]), float(np.finfo(np.float64).eps))
 
 
 def keypoint_homography(grey0_kp_des, grey_i, method, reproj, match_ratio, keep_ratio):

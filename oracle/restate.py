@@ -439,6 +439,116 @@ def ecc_match(frames_u8, motion: int, max_count, epsilon, gauss_filt_size: int):
 
 
 # --------------------------------------------------------------------------------------------
+# ecc_match_scaling_down                             /root/reference/src/lib.rs:849-1028
+#                                                    /root/reference/src/utils.rs:186-248
+# --------------------------------------------------------------------------------------------
+def scaled_size(width: int, height: int, scale_down: float):
+    """utils::scale_image: the SMALLER dimension becomes `scale_down`; both new sizes are truncated."""
+    factor = float(scale_down) / float(width if width < height else height)
+    return int(width * factor), int(height * factor)
+
+
+def _area_tab(ssize: int, dsize: int, scale: float):
+    """computeResizeAreaTab [OpenCV imgproc/resize.cpp]: per destination index the list of
+    (source index, f32 weight), built in f64."""
+    tab = [[] for _ in range(dsize)]
+    for dx in range(dsize):
+        fsx1 = dx * scale
+        fsx2 = fsx1 + scale
+        cell = min(scale, ssize - fsx1)
+        sx1, sx2 = int(math.ceil(fsx1)), int(math.floor(fsx2))
+        sx2 = min(sx2, ssize - 1)
+        sx1 = min(sx1, sx2)
+        if sx1 - fsx1 > 1e-3:
+            tab[dx].append((sx1 - 1, np.float32((sx1 - fsx1) / cell)))
+        for sx in range(sx1, sx2):
+            tab[dx].append((sx, np.float32(1.0 / cell)))
+        if fsx2 - sx2 > 1e-3:
+            tab[dx].append((sx2, np.float32(min(min(fsx2 - sx2, 1.0), cell) / cell)))
+    return tab
+
+
+def resize_area_u8(src: np.ndarray, dw: int, dh: int) -> np.ndarray:
+    """cv2.resize(src, (dw, dh), interpolation=INTER_AREA) for single-channel 8-bit DOWNSCALING.
+    Integer scale factors take OpenCV's fast path (2x2: (sum + 2) >> 2, otherwise rint(sum * f32(1/area)));
+    everything else the generic f32 path: per source row buf += S*alpha in table order, then
+    sum = beta*buf for the first row of a destination row and sum += beta*buf after, saturate_cast<uchar>."""
+    sh, sw = src.shape
+    scale_x, scale_y = 1.0 / (dw / sw), 1.0 / (dh / sh)     # cv::resize: inv_scale = dsize/ssize; scale = 1/inv_scale
+    ix, iy = int(round(scale_x)), int(round(scale_y))
+    if abs(scale_x - ix) < np.finfo(np.float64).eps and abs(scale_y - iy) < np.finfo(np.float64).eps:
+        s = src[:dh * iy, :dw * ix].reshape(dh, iy, dw, ix).astype(np.int64).sum(axis=(1, 3))
+        if ix == 2 and iy == 2:
+            return ((s + 2) >> 2).astype(np.uint8)
+        return np.clip(np.rint(s.astype(np.float32) * np.float32(1.0 / (ix * iy))), 0, 255).astype(np.uint8)
+    xt, yt = _area_tab(sw, dw, scale_x), _area_tab(sh, dh, scale_y)
+
+    def dense(tab):
+        k = max(len(t) for t in tab)
+        idx = np.zeros((len(tab), k), np.int64)
+        wgt = np.zeros((len(tab), k), np.float32)
+        for d, t in enumerate(tab):
+            for j, (si, a) in enumerate(t):
+                idx[d, j], wgt[d, j] = si, a
+        return idx, wgt
+
+    xi, xw = dense(xt)
+    yi, yw = dense(yt)
+    s32 = src.astype(np.float32)
+    # horizontal pass for every source row: buf[sy][dx] (adding S*0 for padded entries changes nothing)
+    buf = np.zeros((sh, dw), np.float32)
+    for j in range(xi.shape[1]):
+        buf = buf + s32[:, xi[:, j]] * xw[None, :, j]
+    out = np.zeros((dh, dw), np.float32)
+    for j in range(yi.shape[1]):
+        out = out + yw[:, j, None] * buf[yi[:, j], :]
+    return np.clip(np.rint(out), 0, 255).astype(np.uint8)
+
+
+def rescale_warp(m_small: np.ndarray, motion: int, full_size, small_size) -> np.ndarray:
+    """Full-resolution matrix from the one estimated on the downscaled greys, with the reference's f32
+    arithmetic: non-homography scales ONLY the translation column (src/lib.rs:941-951); homography goes
+    through adjust_homography_for_scale_f32 (src/utils.rs:218-248)."""
+    fw, fh = full_size
+    sw, sh = small_size
+    m = np.array(m_small, np.float32, copy=True)
+    if motion != MOTION_HOMOGRAPHY:
+        m[0, 2] *= np.float32(fw) / np.float32(sw)
+        m[1, 2] *= np.float32(fh) / np.float32(sh)
+        return m
+    sx, sy = np.float32(fw / sw), np.float32(fh / sh)
+    m[0, 2] *= sx
+    m[1, 2] *= sy
+    m[2, 0] /= sx
+    m[2, 1] /= sy
+    return m
+
+
+def ecc_match_scaling_down(frames_u8, motion: int, max_count, epsilon, gauss_filt_size: int, scale_down: float):
+    """Returns (stack f32, [full-resolution warp per frame], [iterations per frame])."""
+    if len(frames_u8) == 0:
+        raise ValueError("NotEnoughFiles")
+    h, w = frames_u8[0].shape[:2]
+    if scale_down >= w:
+        raise ValueError("InvalidParams: scale_down_to was larger (or equal) to the full image width")
+    if scale_down <= 10.0:
+        raise ValueError("InvalidParams: scale_down_to was too small")
+    crit = term_criteria(max_count, epsilon)
+    sw, sh = scaled_size(w, h, scale_down)
+    grey0 = resize_area_u8(bgr2gray_u8(frames_u8[0]), sw, sh)
+    acc = to_f32_unit(frames_u8[0])
+    warps, iters = [None], [0]
+    for fr in frames_u8[1:]:
+        small = resize_area_u8(bgr2gray_u8(fr), sw, sh)
+        _, m, it = find_transform_ecc(small, grey0, motion, crit, gauss_filt_size)
+        mf = rescale_warp(m, motion, (w, h), (sw, sh))
+        warps.append(mf)
+        iters.append(it)
+        acc = acc + final_warp(fr, mf, motion)
+    return acc * np.float32(1.0 / len(frames_u8)), warps, iters
+
+
+# --------------------------------------------------------------------------------------------
 # sharpness_tenengrad                                /root/reference/src/lib.rs:1101-1147
 # --------------------------------------------------------------------------------------------
 SOBEL_KERNELS = {            # getDerivKernels(dx=1, dy=0, ksize): (derivative taps, smoothing taps)
@@ -476,6 +586,55 @@ def sharpness_tenengrad(grey_u8: np.ndarray, ksize: int) -> float:
     gy = _sep_corr_int(g, s, d)
     total = int((gx * gx + gy * gy).sum())
     return float(total) * (1.0 / float(grey_u8.size))
+
+
+# --------------------------------------------------------------------------------------------
+# the other three sharpness metrics                  /root/reference/src/lib.rs:1032-1090, :1151-1166
+# (SURVEY §8(f) N3).  On 8-bit input every intermediate is an integer (or a multiple of 1/4), so the
+# sums are exact in f64 and only the last few scalar operations round — restated in cv2's order.
+# --------------------------------------------------------------------------------------------
+def _replicate(idx: np.ndarray, n: int) -> np.ndarray:
+    return np.clip(idx, 0, n - 1)
+
+
+def _mean_std_from_sums(s: int, sq: int, n: int):
+    """cv::meanStdDev's scalar tail: scale = 1/N; mean = s*scale; sigma = sqrt(max(sq*scale - mean^2, 0))."""
+    scale = 1.0 / float(n)
+    mean = float(s) * scale
+    var = max(float(sq) * scale - mean * mean, 0.0)
+    return mean, math.sqrt(var)
+
+
+def sharpness_modified_laplacian(grey_u8: np.ndarray) -> float:
+    """LAPM (src/lib.rs:1032-1068): sepFilter2D with [-1 2 -1] along one axis and getGaussianKernel(3,-1) =
+    [1 2 1]/4 along the other, BORDER_REFLECT_101, CV_64F; mean(|lx| + |ly|).  4*lx, 4*ly are integers."""
+    g = grey_u8.astype(np.int64)
+    lx4 = _sep_corr_int(g, [-1, 2, -1], [1, 2, 1])
+    ly4 = _sep_corr_int(g, [1, 2, 1], [-1, 2, -1])
+    total4 = int((np.abs(lx4) + np.abs(ly4)).sum())
+    return (float(total4) / 4.0) * (1.0 / float(grey_u8.size))
+
+
+def laplacian3_int(grey_u8: np.ndarray) -> np.ndarray:
+    """cv::Laplacian(ksize=3, scale 1, BORDER_REPLICATE): kernel [[2 0 2], [0 -8 0], [2 0 2]]."""
+    h, w = grey_u8.shape
+    g = grey_u8.astype(np.int64)
+    pad = g[_replicate(np.arange(-1, h + 1), h)][:, _replicate(np.arange(-1, w + 1), w)]
+    return 2 * (pad[:-2, :-2] + pad[:-2, 2:] + pad[2:, :-2] + pad[2:, 2:]) - 8 * pad[1:-1, 1:-1]
+
+
+def sharpness_variance_of_laplacian(grey_u8: np.ndarray) -> float:
+    """LAPV (src/lib.rs:1070-1090): meanStdDev of the CV_64F Laplacian, sigma^2."""
+    lap = laplacian3_int(grey_u8)
+    _, sigma = _mean_std_from_sums(int(lap.sum()), int((lap * lap).sum()), lap.size)
+    return sigma * sigma
+
+
+def sharpness_normalized_gray_level_variance(grey_u8: np.ndarray) -> float:
+    """GLVN (src/lib.rs:1151-1166): sigma^2 / max(mu, f64::EPSILON) of the image itself."""
+    g = grey_u8.astype(np.int64)
+    mu, sigma = _mean_std_from_sums(int(g.sum()), int((g * g).sum()), g.size)
+    return (sigma ** 2) / max(mu, float(np.finfo(np.float64).eps))
 
 
 def rank_by_sharpness(values):

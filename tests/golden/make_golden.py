@@ -49,7 +49,44 @@ def primitive_cases():
     return out
 
 
+RESIZE_CASES = [  # (width, height, scale_down): generic table path, 2x2, 3x3 and 4x4 integer fast paths, portrait
+    (200, 150, 64.0), (256, 192, 96.0), (300, 240, 80.0), (640, 480, 120.0), (301, 201, 67.0), (150, 200, 70.0),
+]
+SCALE_DOWN_CASES = [  # (motion, width, height, scale_down, seed)
+    (0, 480, 360, 240.0, 61), (1, 480, 360, 240.0, 62), (2, 640, 480, 320.0, 63), (3, 800, 600, 400.0, 65),
+]
+
+
+def scale_down_cases():
+    """ecc_match_scaling_down (src/lib.rs:849-1028): INTER_AREA resize of the greys and the whole scaled path."""
+    out = {}
+    for w, h, sd in RESIZE_CASES:
+        rng = np.random.default_rng(w * 7 + h)
+        grey = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        out[f"resize_{w}x{h}_{int(sd)}"] = cvref.scale_image(grey, sd)
+    for motion, w, h, sd, seed in SCALE_DOWN_CASES:
+        frames = synth.Stack(w, h, 4, motion, seed=seed).frames()
+        stack, warps, _ = cvref.ecc_match_scaling_down(frames, motion, 60, 1e-5, 5, sd)
+        out[f"sd_m{motion}_warps"] = np.stack([np.vstack([m, [0, 0, 1]]) if m.shape[0] == 2 else m for m in warps[1:]]).astype(np.float32)
+        out[f"sd_m{motion}_stack8"] = np.rint(stack * 255.0).astype(np.uint8)
+    return out
+
+
+def sharpness_cases():
+    """LAPM / LAPV / TENG(3) / GLVN (src/lib.rs:1032-1166) on a random and on a synthetic-scene grey plane."""
+    out = {}
+    rng = np.random.default_rng(21)
+    greys = {"rand": rng.integers(0, 256, (131, 257), dtype=np.uint8),
+             "scene": cv2.cvtColor(synth.Stack(320, 240, 1, 0, seed=22).frames()[0], cv2.COLOR_BGR2GRAY)}
+    for name, g in greys.items():
+        out[name] = np.array([cvref.sharpness_modified_laplacian(g), cvref.sharpness_variance_of_laplacian(g),
+                              cvref.sharpness_tenengrad(g, 3), cvref.sharpness_normalized_gray_level_variance(g)], np.float64)
+    return out
+
+
 if __name__ == "__main__":
+    np.savez_compressed(os.path.join(HERE, "scale_down.npz"), **scale_down_cases())
+    np.savez_compressed(os.path.join(HERE, "sharpness.npz"), **sharpness_cases())
     np.savez_compressed(os.path.join(HERE, "ecc_256x192.npz"), **ecc_cases())
     np.savez_compressed(os.path.join(HERE, "primitives_200x150.npz"), **primitive_cases())
     print("cv2", cv2.__version__, "golden vectors written")

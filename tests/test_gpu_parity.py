@@ -331,3 +331,117 @@ def test_tenengrad_vs_cv2_and_ordering(pkg, have_cv2):
 def test_tenengrad_invalid_k(pkg):
     with pytest.raises(pkg.InvalidParams):
         pkg.sharpness_tenengrad(np.zeros((8, 8), np.uint8), 4)
+
+
+# ---- N1: ecc_match_scaling_down (src/lib.rs:849-1028) ------------------------------------------------------
+@pytest.mark.parametrize("case", [(200, 150, 64.0), (256, 192, 96.0), (300, 240, 80.0), (640, 480, 120.0), (301, 201, 67.0),
+                                  (150, 200, 70.0), (1024, 768, 300.0), (333, 222, 221.5), (64, 48, 11.0)])
+def test_grey_resize_area_bit_exact(pkg, case):
+    """cvtColor(BGR2GRAY) + resize(INTER_AREA): generic table path, 2x2 / 3x3 / 4x4 fast paths, portrait."""
+    w, h, sd = case
+    rng = np.random.default_rng(w * 7 + h)
+    sw, sh = R.scaled_size(w, h, sd)
+    assert pkg.scaled_size(w, h, sd) == (sw, sh)
+    bgr = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    want = R.resize_area_u8(R.bgr2gray_u8(bgr), sw, sh)
+    assert np.array_equal(pkg.grey_resize_area(bgr, sw, sh, device=0), want)
+    grey = R.bgr2gray_u8(bgr)
+    assert np.array_equal(pkg.grey_resize_area(grey, sw, sh, device=0), want)
+
+
+def test_grey_resize_area_golden(pkg):
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "scale_down.npz"))
+    for w, h, sd in [(200, 150, 64.0), (256, 192, 96.0), (300, 240, 80.0), (640, 480, 120.0), (301, 201, 67.0), (150, 200, 70.0)]:
+        rng = np.random.default_rng(w * 7 + h)
+        grey = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        want = g[f"resize_{w}x{h}_{int(sd)}"]
+        assert np.array_equal(pkg.grey_resize_area(grey, want.shape[1], want.shape[0], device=0), want)
+
+
+SD_CASES = [(0, 480, 360, 240.0, 61), (1, 480, 360, 240.0, 62), (2, 640, 480, 320.0, 63), (3, 800, 600, 400.0, 65)]
+
+
+@pytest.mark.parametrize("case", SD_CASES)
+def test_ecc_match_scaling_down_vs_oracle_and_golden(pkg, case):
+    """ECC on the INTER_AREA-downscaled greys, matrix rescaled on the device with the reference's two f32
+    rules, full-size warp: against the restatement and against the committed cv2 vectors."""
+    import os
+    motion, w, h, sd, seed = case
+    frames = synth.Stack(w, h, 4, motion, seed=seed).frames()
+    params = pkg.EccMatchParameters(pkg.MotionType(motion), 60, 1e-5, 5)
+    got, res = pkg.ecc_match(frames, params, sd, device=0, return_details=True)
+    want, warps, iters = R.ecc_match_scaling_down(frames, motion, 60, 1e-5, 5, sd)
+    assert [r["status"] for r in res] == [0, 0, 0]
+    for r, wm in zip(res, warps[1:]):
+        mine = r["warp"] if motion == 3 else r["warp"][:2]
+        assert synth.corner_displacement(mine, wm, w, h) <= 0.05
+    assert_stack_parity(got, want, warps, motion, 4)
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "scale_down.npz"))
+    for r, ref in zip(res, g[f"sd_m{motion}_warps"]):
+        mine = r["warp"] if motion == 3 else r["warp"][:2]
+        assert synth.corner_displacement(mine, ref if motion == 3 else ref[:2], w, h) <= 0.05
+    assert_stack_parity(got, g[f"sd_m{motion}_stack8"].astype(np.float32) / np.float32(255.0), warps, motion, 4)
+
+
+def test_ecc_match_scaling_down_config1_vs_cv2(pkg, have_cv2):
+    """examples/main.rs:119-128 calls ecc_match with Some(width) on the config-1 stack."""
+    if not have_cv2:
+        pytest.skip("cv2 not installed")
+    from oracle import cvref
+    frames = synth.config_stack(1).frames()
+    params = pkg.EccMatchParameters(pkg.MotionType.Homography, 5000, 1e-5, 5)
+    got, res = pkg.ecc_match(frames, params, 400.0, device=0, return_details=True)
+    want, warps, _ = cvref.ecc_match_scaling_down(frames, 3, 5000, 1e-5, 5, 400.0)
+    for r, wm in zip(res, warps[1:]):
+        assert synth.corner_displacement(r["warp"], wm, 1024, 768) <= 0.05
+    g8, w8 = np.rint(got * 255.0), np.rint(want * 255.0)
+    assert np.abs(g8 - w8).max() <= 1
+    assert psnr8(g8, w8) >= 50.0
+
+
+def test_ecc_match_scaling_down_errors(pkg):
+    frames = synth.Stack(128, 96, 2, 0, seed=5).frames()
+    p = pkg.EccMatchParameters(pkg.MotionType.Translation, 20, 1e-4, 5)
+    with pytest.raises(pkg.InvalidParams):
+        pkg.ecc_match(frames, p, 128.0, device=0)          # >= full width (src/lib.rs:876-881)
+    with pytest.raises(pkg.InvalidParams):
+        pkg.ecc_match(frames, p, 10.0, device=0)           # too small (src/lib.rs:883-888)
+    with pytest.raises(pkg.NotEnoughFiles):
+        pkg.ecc_match([], p, 64.0, device=0)
+
+
+# ---- N3: the other sharpness metrics, bit-identical --------------------------------------------------------
+@pytest.mark.parametrize("size", [(320, 240), (65, 33), (1000, 701), (7, 5), (1, 9), (12, 1)])
+def test_sharpness_all_exact(pkg, size):
+    w, h = size
+    rng = np.random.default_rng(w * 3 + h)
+    grey = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    got = pkg.sharpness_all(grey, device=0)
+    want = (R.sharpness_modified_laplacian(grey), R.sharpness_variance_of_laplacian(grey),
+            R.sharpness_tenengrad(grey, 3), R.sharpness_normalized_gray_level_variance(grey))
+    assert got == want
+    assert pkg.sharpness_modified_laplacian(grey, device=0) == want[0]
+    assert pkg.sharpness_variance_of_laplacian(grey, device=0) == want[1]
+    assert pkg.sharpness_normalized_gray_level_variance(grey, device=0) == want[3]
+
+
+def test_sharpness_golden_and_batch(pkg):
+    import os
+    import torch
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sharpness.npz"))
+    rng = np.random.default_rng(21)
+    greys = {"rand": rng.integers(0, 256, (131, 257), dtype=np.uint8),
+             "scene": R.bgr2gray_u8(synth.Stack(320, 240, 1, 0, seed=22).frames()[0])}
+    for name, grey in greys.items():
+        assert list(pkg.sharpness_all(grey, device=0)) == list(g[name])
+    # batch entry point on device-resident BGR frames (grey conversion fused)
+    frames = synth.config_stack(3, n_frames=5, width=320, height=180).frames()
+    batch = torch.from_numpy(np.stack(frames)).cuda()
+    got = pkg.sharpness_batch(batch, device=0)
+    for row, f in zip(got, frames):
+        grey = R.bgr2gray_u8(f)
+        assert tuple(row) == (R.sharpness_modified_laplacian(grey), R.sharpness_variance_of_laplacian(grey),
+                              R.sharpness_tenengrad(grey, 3), R.sharpness_normalized_gray_level_variance(grey))
+    flat = np.full((30, 40), 9, np.uint8)
+    assert pkg.sharpness_all(flat, device=0) == (0.0, 0.0, 0.0, 0.0)

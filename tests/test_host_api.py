@@ -42,12 +42,13 @@ def test_abi_exports_every_declared_symbol(pkg):
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/stacker_cuda.h but not exported"
     assert declared == set(pkg._ffi.SYMBOLS), declared ^ set(pkg._ffi.SYMBOLS)
-    assert lib.stk_abi_version() == 1
+    assert lib.stk_abi_version() == 2
 
 
 def test_struct_layout_matches_header(pkg):
-    # stk_ecc_config: 6 int32, double, 5 int32 -> 8-byte aligned; stk_frame_result: i64, 9 f32, f64, 2 i32
-    assert ctypes.sizeof(pkg._ffi.EccConfig) == 56
+    # stk_ecc_config: 6 int32, double, 7 int32 -> 8-byte aligned; stk_frame_result: i64, 9 f32, f64, 2 i32
+    assert ctypes.sizeof(pkg._ffi.EccConfig) == 64
+    assert pkg._ffi.EccConfig.ecc_width.offset == 52
     assert pkg._ffi.EccConfig.epsilon.offset == 24
     assert ctypes.sizeof(pkg._ffi.FrameResult) == 64
     assert pkg._ffi.FrameResult.rho.offset == 48
@@ -64,6 +65,25 @@ def test_errors_before_any_gpu_work(pkg):
         pkg.ecc_match(["/nonexistent/a.jpg"], pkg.EccMatchParameters(pkg.MotionType.Homography, 10, 1e-3, 5))
 
 
+def test_scaled_size_rule_and_validation(pkg):
+    """utils::scale_image's size rule (src/utils.rs:186-200) and ecc_match_scaling_down's validation
+    (src/lib.rs:876-888) live in the library (no GPU needed); the oracle restates the same rule."""
+    from oracle import restate as R
+    for w, h, sd in [(1024, 768, 300.0), (3840, 2160, 540.0), (150, 200, 70.0), (301, 201, 67.0), (333, 222, 221.5),
+                     (6000, 4000, 1234.5)]:
+        assert pkg.scaled_size(w, h, sd) == R.scaled_size(w, h, sd)
+    with pytest.raises(pkg.InvalidParams, match="larger"):
+        pkg.scaled_size(1024, 768, 1024.0)
+    with pytest.raises(pkg.InvalidParams, match="too small"):
+        pkg.scaled_size(1024, 768, 10.0)
+    with pytest.raises(pkg.NotImplementedError_):      # landscape frame, height < scale_down < width: INTER_AREA up-scaling
+        pkg.scaled_size(1000, 500, 800.0)
+    # the validation runs before any device work
+    frames = [np.zeros((96, 128, 3), np.uint8)] * 2
+    with pytest.raises(pkg.InvalidParams):
+        pkg.ecc_match(frames, pkg.EccMatchParameters(pkg.MotionType.Affine, 5, 1e-3, 3), 500.0)
+
+
 def test_no_cpu_fallback_without_gpu(pkg):
     """On a box without a CUDA device the product path must fail loudly, not compute on the CPU."""
     import torch
@@ -71,6 +91,10 @@ def test_no_cpu_fallback_without_gpu(pkg):
         pytest.skip("GPU present")
     with pytest.raises(pkg.ProcessingError):
         pkg.sharpness_tenengrad(np.zeros((16, 16), np.uint8), 3)
+    with pytest.raises(pkg.ProcessingError):
+        pkg.sharpness_all(np.zeros((16, 16), np.uint8))
+    with pytest.raises(pkg.ProcessingError):
+        pkg.grey_resize_area(np.zeros((16, 16), np.uint8), 8, 8)
     frames = [np.zeros((32, 32, 3), np.uint8)] * 2
     with pytest.raises(pkg.ProcessingError):
         pkg.ecc_match(frames, pkg.EccMatchParameters(pkg.MotionType.Affine, 5, 1e-3, 3))

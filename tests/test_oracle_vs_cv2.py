@@ -136,3 +136,91 @@ def test_noconv_raises_like_opencv(cv2):
         cv2.findTransformECC(flat, a, np.eye(2, 3, dtype=np.float32), 0, (3, 20, 1e-4), None, 5)
     with pytest.raises(R.EccNoConvergence):
         R.find_transform_ecc(flat, a, 0, (3, 20, 1e-4), 5)
+
+
+# ---- ecc_match_scaling_down and the other sharpness metrics (N3) ------------------------------
+def _golden_module():
+    src = open(os.path.join(GOLD, "make_golden.py")).read()
+    # only the case tables are needed (the generator itself imports cv2)
+    ns = {}
+    start = src.index("RESIZE_CASES")
+    end = src.index("def scale_down_cases")
+    exec(src[start:end], ns)
+    return ns["RESIZE_CASES"], ns["SCALE_DOWN_CASES"]
+
+
+def test_golden_resize_area():
+    g = np.load(os.path.join(GOLD, "scale_down.npz"))
+    resize_cases, _ = _golden_module()
+    for w, h, sd in resize_cases:
+        rng = np.random.default_rng(w * 7 + h)
+        grey = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        want = g[f"resize_{w}x{h}_{int(sd)}"]
+        sw, sh = R.scaled_size(w, h, sd)
+        assert (sh, sw) == want.shape
+        assert np.array_equal(R.resize_area_u8(grey, sw, sh), want)
+
+
+@pytest.mark.parametrize("case", [0, 1, 2, 3])
+def test_golden_ecc_match_scaling_down(case):
+    g = np.load(os.path.join(GOLD, "scale_down.npz"))
+    _, sd_cases = _golden_module()
+    motion, w, h, sd, seed = sd_cases[case]
+    frames = synth.Stack(w, h, 4, motion, seed=seed).frames()
+    stack, warps, _ = R.ecc_match_scaling_down(frames, motion, 60, 1e-5, 5, sd)
+    for mine, ref in zip(warps[1:], g[f"sd_m{motion}_warps"]):
+        assert synth.corner_displacement(mine, ref if motion == 3 else ref[:2], w, h) <= 5e-3
+    assert_stack_parity(stack, g[f"sd_m{motion}_stack8"].astype(np.float32) / np.float32(255.0), warps, motion, 4)
+
+
+def test_golden_sharpness():
+    g = np.load(os.path.join(GOLD, "sharpness.npz"))
+    rng = np.random.default_rng(21)
+    greys = {"rand": rng.integers(0, 256, (131, 257), dtype=np.uint8),
+             "scene": R.bgr2gray_u8(synth.Stack(320, 240, 1, 0, seed=22).frames()[0])}
+    for name, grey in greys.items():
+        mine = [R.sharpness_modified_laplacian(grey), R.sharpness_variance_of_laplacian(grey),
+                R.sharpness_tenengrad(grey, 3), R.sharpness_normalized_gray_level_variance(grey)]
+        assert mine == list(g[name])
+
+
+def test_resize_area_exact(cv2):
+    """cv::resize(INTER_AREA) on 8-bit grey: the 2x2 / integer fast paths and the generic table path."""
+    from oracle import cvref
+    rng = np.random.default_rng(4)
+    for w, h, sd in [(200, 150, 64), (256, 192, 96), (300, 240, 80), (640, 480, 120), (1024, 768, 300), (301, 201, 67),
+                     (150, 200, 70), (1920, 1080, 540), (333, 222, 221.5), (64, 48, 11)]:
+        grey = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        sw, sh = R.scaled_size(w, h, sd)
+        want = cvref.scale_image(grey, sd)
+        assert want.shape == (sh, sw)
+        assert np.array_equal(R.resize_area_u8(grey, sw, sh), want)
+
+
+def test_ecc_match_scaling_down_vs_cv2(cv2):
+    """The whole scaled path against the reference's call sequence (src/lib.rs:849-1028), incl. the two
+    different matrix rescale rules (translation column only vs adjust_homography_for_scale_f32)."""
+    from oracle import cvref
+    for motion, w, h, sd, seed in [(2, 480, 360, 200.0, 71), (3, 640, 480, 360.0, 72)]:
+        frames = synth.Stack(w, h, 3, motion, seed=seed).frames()
+        a, wa, _ = R.ecc_match_scaling_down(frames, motion, 40, 1e-5, 5, sd)
+        b, wb, _ = cvref.ecc_match_scaling_down(frames, motion, 40, 1e-5, 5, sd)
+        for x, y in zip(wa[1:], wb[1:]):
+            assert synth.corner_displacement(x, y, w, h) <= 5e-3
+        assert_stack_parity(a, b, wa, motion, 3)
+    with pytest.raises(ValueError):
+        R.ecc_match_scaling_down(frames, 3, 40, 1e-5, 5, 640.0)     # >= full width
+    with pytest.raises(ValueError):
+        R.ecc_match_scaling_down(frames, 3, 40, 1e-5, 5, 10.0)      # too small
+
+
+def test_sharpness_metrics_exact(cv2):
+    from oracle import cvref
+    rng = np.random.default_rng(11)
+    greys = [rng.integers(0, 256, (h, w), dtype=np.uint8) for (w, h) in [(320, 240), (65, 33), (7, 5), (1, 9), (12, 1)]]
+    greys += [R.bgr2gray_u8(synth.Stack(400, 300, 1, 0, seed=3).frames()[0]), np.full((40, 50), 9, np.uint8),
+              np.zeros((16, 16), np.uint8)]
+    for g in greys:
+        assert R.sharpness_modified_laplacian(g) == cvref.sharpness_modified_laplacian(g)
+        assert R.sharpness_variance_of_laplacian(g) == cvref.sharpness_variance_of_laplacian(g)
+        assert R.sharpness_normalized_gray_level_variance(g) == cvref.sharpness_normalized_gray_level_variance(g)
