@@ -159,6 +159,17 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return r;
 }
 
+// packed FP32 pairs (Blackwell FFMA2 / FADD2 / FMUL2, PTX *.f32x2): one issue slot for two lanes of work.  The
+// SASS forms take a scalar register as a broadcast operand (R.F32) and negate packed sources, so
+// f2(s) operands and a - b cost nothing extra.
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }   // a - b
+__device__ __forceinline__ float2 lerp2(float2 a, float2 b, float2 t) { return fma2(t, sub2(b, a), a); }
+
 // fast path: 12 taps from the shared-memory box (row stride kBoxW), p = &box[sy][sx]
 __device__ __forceinline__ Sample sample_box(const float* p, float ax, float ay) {
   const float m0 = p[-kBoxW], m1 = p[-kBoxW + 1];
@@ -172,6 +183,22 @@ __device__ __forceinline__ Sample sample_box(const float* p, float ax, float ay)
   // GY taps (2*GY = I[r+1] - I[r-1])
   s.gy2 = lerp(lerp(b0 - m0, b1 - m1, ax), lerp(c0 - a0, c1 - a1, ax), ay);
   return s;
+}
+
+// Same values as sample_box with the arithmetic paired up: the two gradient planes share every step
+// (first/second horizontal tap, top/bottom row), so (gx2, gy2) comes out as one packed value in 10 packed
+// instructions instead of 20 scalar ones.  Operation order per lane is the one of sample_box.
+__device__ __forceinline__ void sample_box_packed(const float* p, float ax, float ay, float& w, float2& gxy2) {
+  const float m0 = p[-kBoxW], m1 = p[-kBoxW + 1];
+  const float a_1 = p[-1], a0 = p[0], a1 = p[1], a2 = p[2];
+  const float b_1 = p[kBoxW - 1], b0 = p[kBoxW], b1 = p[kBoxW + 1], b2 = p[kBoxW + 2];
+  const float c0 = p[2 * kBoxW], c1 = p[2 * kBoxW + 1];
+  w = lerp(lerp(a0, a1, ax), lerp(b0, b1, ax), ay);
+  // top row of the 2x2 gradient taps: (GX, GY) at (sy, sx) and (sy, sx+1); bottom row: at sy+1
+  const float2 t0 = sub2(f2(a1, b0), f2(a_1, m0)), t1 = sub2(f2(a2, b1), f2(a0, m1));
+  const float2 u0 = sub2(f2(b1, c0), f2(b_1, a0)), u1 = sub2(f2(b2, c1), f2(b0, a1));
+  const float2 ax2 = f2(ax);
+  gxy2 = lerp2(lerp2(t0, t1, ax2), lerp2(u0, u1, ax2), f2(ay));
 }
 
 // careful path: same 12 taps from the box, with the border rules of the gradient planes applied as 0/1
@@ -414,30 +441,147 @@ template <int MOTION> struct Accum {
     swt = fmaf(wm, t_, swt);
   }
 
-  // fold the per-thread column coordinate X into the moments and emit the NV values of this thread
+  // fold the per-thread column coordinate X into the moments and emit the NV values of this thread.
+  // TWICE_NEG (homography with FastPersp coordinates): the generators were accumulated as (2a, 2b, -2t) —
+  // the pixel loop skips the 0.5 and the negation — so products carry a factor 4 (and the sign of the t
+  // factors), the projections a factor 2; both are exact powers of two, undone here once per run.
+  template <bool TWICE_NEG = false>
   __device__ __forceinline__ void emit(float xf, float (&v)[L::NV]) const {
     v[0] = n; v[1] = sw; v[2] = sww; v[3] = st; v[4] = stt; v[5] = swt;
     const float xx = xf * xf;
+    int idx = 0;
 #pragma unroll
-    for (int i = 0; i < NP; ++i) {
-      if (kron) {
-        float* o = &v[L::kH + i * 6];
-        o[0] = p[i][0]; o[1] = xf * p[i][0]; o[2] = p[i][1];
-        o[3] = xx * p[i][0]; o[4] = xf * p[i][1]; o[5] = p[i][2];
-      } else {
-        v[L::kH + i] = p[i][0];
+    for (int gi = 0; gi < G; ++gi)
+#pragma unroll
+      for (int gj = gi; gj < G; ++gj) {
+        const float f = !TWICE_NEG ? 1.f : (((gi == G - 1) != (gj == G - 1)) ? -0.25f : 0.25f);
+        const float p0 = TWICE_NEG ? p[idx][0] * f : p[idx][0];
+        if (kron) {
+          const float p1 = TWICE_NEG ? p[idx][1] * f : p[idx][1];
+          const float p2 = TWICE_NEG ? p[idx][2] * f : p[idx][2];
+          float* o = &v[L::kH + idx * 6];
+          o[0] = p0; o[1] = xf * p0; o[2] = p1;
+          o[3] = xx * p0; o[4] = xf * p1; o[5] = p2;
+        } else {
+          v[L::kH + idx] = p0;
+        }
+        ++idx;
       }
-    }
 #pragma unroll
     for (int a = 0; a < 3; ++a)
 #pragma unroll
       for (int i = 0; i < G; ++i) {
+        const float f = !TWICE_NEG ? 1.f : (i == G - 1 ? -0.5f : 0.5f);
+        const float z0 = TWICE_NEG ? z[a][i][0] * f : z[a][i][0];
         if (kron) {
+          const float z1 = TWICE_NEG ? z[a][i][1] * f : z[a][i][1];
           float* o = &v[L::kZ + (a * G + i) * 3];
-          o[0] = z[a][i][0]; o[1] = xf * z[a][i][0]; o[2] = z[a][i][1];
+          o[0] = z0; o[1] = xf * z0; o[2] = z1;
         } else {
-          v[L::kZ + a * G + i] = z[a][i][0];
+          v[L::kZ + a * G + i] = z0;
         }
+      }
+  }
+};
+
+// Homography accumulator with the sums stored as register PAIRS so the interior path updates two of them
+// per instruction.  Same sums, same per-sum operation order as Accum<kHomography>; generators are
+// (g0, g1, g2) = (2a, 2b, -2t) (see Accum::emit<TWICE_NEG>).
+//   h[k]  = (p00, p01), (p02, p11), (p12, p22) for k = 0..2, each with moments {1, Y, Y^2}
+//   za/zm/zt[m] = (g0 z, g1 z) for z = w / 1 / t, moments {1, Y} ; zc[m] = (g2 w, g2 t) ; zm2[m] = g2
+//   s1 = (Sw, St), s2 = (Sww, Stt)
+struct AccumH2 {
+  using L = Layout<kHomography>;
+  static constexpr int G = 3;
+  float n, swt;
+  float2 s1, s2;
+  float2 h[3][3];
+  float2 za[2], zm[2], zt[2], zc[2];
+  float zm2[2];
+
+  __device__ __forceinline__ void clear() {
+    const float2 o = f2(0.f);
+    n = swt = 0.f; s1 = s2 = o;
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int m = 0; m < 3; ++m) h[k][m] = o;
+#pragma unroll
+    for (int m = 0; m < 2; ++m) { za[m] = zm[m] = zt[m] = zc[m] = o; zm2[m] = 0.f; }
+  }
+
+  // interior pixel (mask 1; the caller counts it): g01 = (g0, g1)
+  __device__ __forceinline__ void add_packed(float2 g01, float g2, float w_, float t_, float yf) {
+    const float2 y2 = f2(yf), yy2 = f2(yf * yf);
+    const float2 q0 = mul2(f2(g01.x), g01);                       // g0 g0, g0 g1
+    const float2 q1 = f2(g01.x * g2, g01.y * g01.y);              // g0 g2, g1 g1
+    const float2 q2 = mul2(f2(g2), f2(g01.y, g2));                // g1 g2, g2 g2
+    h[0][0] = add2(h[0][0], q0); h[0][1] = fma2(q0, y2, h[0][1]); h[0][2] = fma2(q0, yy2, h[0][2]);
+    h[1][0] = add2(h[1][0], q1); h[1][1] = fma2(q1, y2, h[1][1]); h[1][2] = fma2(q1, yy2, h[1][2]);
+    h[2][0] = add2(h[2][0], q2); h[2][1] = fma2(q2, y2, h[2][1]); h[2][2] = fma2(q2, yy2, h[2][2]);
+    const float2 wt = f2(w_, t_);
+    const float2 gw = mul2(g01, f2(w_)), gt = mul2(g01, f2(t_)), gc = mul2(f2(g2), wt);
+    za[0] = add2(za[0], gw);  za[1] = fma2(gw, y2, za[1]);
+    zm[0] = add2(zm[0], g01); zm[1] = fma2(g01, y2, zm[1]);
+    zt[0] = add2(zt[0], gt);  zt[1] = fma2(gt, y2, zt[1]);
+    zc[0] = add2(zc[0], gc);  zc[1] = fma2(gc, y2, zc[1]);
+    zm2[0] += g2; zm2[1] = fmaf(g2, yf, zm2[1]);
+    s1 = add2(s1, wt);
+    s2 = fma2(wt, wt, s2);
+    swt = fmaf(w_, t_, swt);
+  }
+
+  // general pixel (rim / careful / slow paths): scalar arithmetic on the same registers
+  template <bool INTERIOR>
+  __device__ __forceinline__ void add(const float (&g)[3], float w_, float t_, float mk, float yf) {
+    const float yy = yf * yf;
+    auto up = [&](float& a0, float& a1, float& a2, float pr) { a0 += pr; a1 = fmaf(pr, yf, a1); a2 = fmaf(pr, yy, a2); };
+    up(h[0][0].x, h[0][1].x, h[0][2].x, g[0] * g[0]);
+    up(h[0][0].y, h[0][1].y, h[0][2].y, g[0] * g[1]);
+    up(h[1][0].x, h[1][1].x, h[1][2].x, g[0] * g[2]);
+    up(h[1][0].y, h[1][1].y, h[1][2].y, g[1] * g[1]);
+    up(h[2][0].x, h[2][1].x, h[2][2].x, g[1] * g[2]);
+    up(h[2][0].y, h[2][1].y, h[2][2].y, g[2] * g[2]);
+    const float wm = INTERIOR ? w_ : w_ * mk;
+    const float tm = INTERIOR ? t_ : t_ * mk;
+    auto uz = [&](float& a0, float& a1, float v) { a0 += v; a1 = fmaf(v, yf, a1); };
+    uz(za[0].x, za[1].x, g[0] * w_); uz(za[0].y, za[1].y, g[1] * w_); uz(zc[0].x, zc[1].x, g[2] * w_);
+    uz(zm[0].x, zm[1].x, INTERIOR ? g[0] : g[0] * mk); uz(zm[0].y, zm[1].y, INTERIOR ? g[1] : g[1] * mk);
+    uz(zm2[0], zm2[1], INTERIOR ? g[2] : g[2] * mk);
+    uz(zt[0].x, zt[1].x, g[0] * tm); uz(zt[0].y, zt[1].y, g[1] * tm); uz(zc[0].y, zc[1].y, g[2] * tm);
+    if (!INTERIOR) n += mk;
+    s1.x += wm; s2.x = fmaf(wm, w_, s2.x);
+    s1.y += tm; s2.y = fmaf(tm, t_, s2.y);
+    swt = fmaf(wm, t_, swt);
+  }
+
+  template <bool TWICE_NEG>
+  __device__ __forceinline__ void emit(float xf, float (&v)[L::NV]) const {
+    static_assert(TWICE_NEG, "AccumH2 holds (2a, 2b, -2t) sums");
+    v[0] = n; v[1] = s1.x; v[2] = s2.x; v[3] = s1.y; v[4] = s2.y; v[5] = swt;
+    const float xx = xf * xf;
+    // product order of Layout<>: (0,0) (0,1) (0,2) (1,1) (1,2) (2,2); the sign flips where exactly one factor is g2
+    const float pf[6] = {0.25f, 0.25f, -0.25f, 0.25f, -0.25f, 0.25f};
+#pragma unroll
+    for (int idx = 0; idx < 6; ++idx) {
+      const float2 m0 = h[idx >> 1][0], m1 = h[idx >> 1][1], m2 = h[idx >> 1][2];
+      const float p0 = ((idx & 1) ? m0.y : m0.x) * pf[idx];
+      const float p1 = ((idx & 1) ? m1.y : m1.x) * pf[idx];
+      const float p2 = ((idx & 1) ? m2.y : m2.x) * pf[idx];
+      float* o = &v[L::kH + idx * 6];
+      o[0] = p0; o[1] = xf * p0; o[2] = p1; o[3] = xx * p0; o[4] = xf * p1; o[5] = p2;
+    }
+    // projections: z in {w, m, m t} x g_i, moments {1, X, Y}
+    const float z0[3][3] = {{za[0].x, za[0].y, zc[0].x}, {zm[0].x, zm[0].y, zm2[0]}, {zt[0].x, zt[0].y, zc[0].y}};
+    const float z1[3][3] = {{za[1].x, za[1].y, zc[1].x}, {zm[1].x, zm[1].y, zm2[1]}, {zt[1].x, zt[1].y, zc[1].y}};
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const float f = i == 2 ? -0.5f : 0.5f;
+        const float v0 = z0[a][i] * f, v1 = z1[a][i] * f;
+        float* o = &v[L::kZ + (a * 3 + i) * 3];
+        o[0] = v0; o[1] = xf * v0; o[2] = v1;
       }
   }
 };
@@ -737,6 +881,9 @@ __device__ __forceinline__ void finish_iteration(const EccIterParams& p, EccStat
   }
 }
 
+template <int MOTION, bool FAST> struct AccumFor { using type = Accum<MOTION>; };
+template <> struct AccumFor<kHomography, true> { using type = AccumH2; };
+
 // ---- the iteration kernel ----------------------------------------------------------------------------
 // EXACT = false (homography only): FastPersp coordinates for the boxed pixels; true: f64 everywhere.
 //
@@ -752,7 +899,7 @@ __global__ void __launch_bounds__(kEccThreads, 2) ecc_iter_kernel(const __grid_c
   constexpr int kWarps = kEccThreads / 32;
   extern __shared__ __align__(128) unsigned char dyn[];
   __shared__ float s_m[9];
-  __shared__ int s_box[kMaxChunks][2];          // xlo (multiple of 4, or INT_MIN = no box), ylo
+  __shared__ int s_box[kMaxChunks][3];          // xlo (multiple of 4, or INT_MIN = no box), ylo, interior flag
   __shared__ alignas(8) uint64_t s_full[kEccStages];
   __shared__ alignas(8) uint64_t s_empty[kEccStages];
   __shared__ float s_red[kWarps][NV];
@@ -814,6 +961,11 @@ __global__ void __launch_bounds__(kEccThreads, 2) ecc_iter_kernel(const __grid_c
       }
       s_box[tid][0] = ok ? xlo : INT_MIN;
       s_box[tid][1] = ylo;
+      // interior chunk: every sample of the chunk (quantised position within 1/64 px + f32 slack of the real
+      // one) has its four taps and their gradient stencils off the border rows/columns, so no border rule
+      // applies, the mask is 1 everywhere and the pixel loop needs no per-pixel test
+      s_box[tid][2] = (ok && floor(umin - 0.0625) >= 1.0 && floor(umax + 0.0625) <= (double)(p.width - 3) &&
+                       floor(vmin - 0.0625) >= 1.0 && floor(vmax + 0.0625) <= (double)(p.height - 3)) ? 1 : 0;
     }
     __syncthreads();
 
@@ -837,7 +989,7 @@ __global__ void __launch_bounds__(kEccThreads, 2) ecc_iter_kernel(const __grid_c
     const int x = x0 + col;
     const float xf = (float)x;
     const bool col_ok = x < p.width;
-    Accum<MOTION> acc;
+    typename AccumFor<MOTION, fast_coords>::type acc;
     acc.clear();
     int n_safe = 0;
     FastPersp fp;
@@ -866,6 +1018,7 @@ __global__ void __launch_bounds__(kEccThreads, 2) ecc_iter_kernel(const __grid_c
       float g[G];
       const float yf = (float)y;
       jac.eval(smp, yf, g);
+      if (fast_coords) { g[0] *= 2.f; g[1] *= 2.f; g[G - 1] *= -2.f; }     // the run accumulates (2a, 2b, -2t)
       acc.template add<false>(g, smp.w, t_, mk, yf);
     };
 
@@ -886,7 +1039,35 @@ __global__ void __launch_bounds__(kEccThreads, 2) ecc_iter_kernel(const __grid_c
       const unsigned wmask = __ballot_sync(0xffffffffu, col_ok && ya < yb);
       if (col_ok && ya < yb) {
         const float* trow = tbox + (ya - cy0) * kEccStripW + col;
-        if (boxed) {
+        if (fast_coords && boxed && s_box[c][2] != 0 && yb - ya == kChunkRowsPerThread) {
+          // lean path (interior chunk, full height): straight-line code for the thread's 8 rows — no border
+          // rule, no mask, no vote, no branch — so the rows interleave freely in the schedule
+          const float* bp0 = box + (ya - ylo) * kBoxW + (x - xlo);
+          const float yf0 = (float)ya;
+          if constexpr (fast_coords) {
+#pragma unroll
+            for (int r = 0; r < kChunkRowsPerThread; ++r) {
+              const float yf = yf0 + (float)r;
+              const float t_ = trow[r * kEccStripW];
+              // FastPersp::at with the two coordinates carried as a pair
+              const float rw = rcp_approx(fmaf(fp.m21, yf, fp.wc));
+              const float2 d = mul2(f2(fmaf(fp.beta, yf, fp.alpha), fmaf(fmaf(-fp.m21, yf, fp.delta), yf, fp.gamma)), f2(rw));
+              const float2 qf = fma2(d, f2(32.0f), f2(12582912.0f));
+              const int qx = __float_as_int(qf.x) - 0x4B400000, qy = __float_as_int(qf.y) - 0x4B400000;
+              const float* bp = bp0 + ((qy >> kInterBits) + r) * kBoxW + (qx >> kInterBits);
+              const float ax = (float)(qx & (kInterTab - 1)) * (1.f / kInterTab);
+              const float ay = (float)(qy & (kInterTab - 1)) * (1.f / kInterTab);
+              float w_;
+              float2 gxy2;
+              sample_box_packed(bp, ax, ay, w_, gxy2);
+              const float2 g01 = mul2(gxy2, f2(rw));                          // 2a, 2b
+              const float2 uv = add2(f2(xf, yf), d);                          // sample position (u, v)
+              const float g2 = fmaf(uv.x, g01.x, uv.y * g01.y);               // -2t  (t = hatX a + hatY b, hat = -(u, v))
+              acc.add_packed(g01, g2, w_, t_, yf);
+            }
+          }
+          n_safe += kChunkRowsPerThread;
+        } else if (boxed) {
           float yf = (float)ya;
           Coord<Md::persp> co;
           Jac<MOTION> jac;
@@ -929,10 +1110,10 @@ __global__ void __launch_bounds__(kEccThreads, 2) ecc_iter_kernel(const __grid_c
               mk = ((unsigned)xn < (unsigned)p.width && (unsigned)yn < (unsigned)p.height) ? 1.f : 0.f;
             }
             if (fast_coords) {
-              // a = gx / den, b = gy / den, t = hatX a + hatY b with hatX = -u, hatY = -v, den = w
-              const float hr = 0.5f * rw;
-              g[0] = smp.gx2 * hr; g[1] = smp.gy2 * hr;
-              g[G - 1] = -fmaf(xf + du, g[0], (yf + dv) * g[1]);
+              // a = gx / den, b = gy / den, t = hatX a + hatY b with hatX = -u, hatY = -v, den = w;
+              // accumulated as (2a, 2b, -2t), see Accum::emit
+              g[0] = smp.gx2 * rw; g[1] = smp.gy2 * rw;
+              g[G - 1] = fmaf(xf + du, g[0], (yf + dv) * g[1]);
             } else {
               jac.eval(smp, yf, g);
             }
@@ -951,7 +1132,7 @@ __global__ void __launch_bounds__(kEccThreads, 2) ecc_iter_kernel(const __grid_c
     // ---- segment end: registers -> warp transpose-reduce -> smem -> f64 block accumulator ----------
     {
       float v[NV];
-      acc.emit(xf, v);
+      acc.template emit<fast_coords>(xf, v);
       warp_reduce_vector<NV>(v, lane, s_red[wid]);
     }
     __syncthreads();
@@ -984,13 +1165,6 @@ constexpr int kP2TmplStageBytes = kEccStripW * kP2ChunkH * 4;    // 4096
 constexpr int kP2StageBytes = kP2ImgStageBytes + kP2TmplStageBytes;
 constexpr int kP2DynSmem = kP2Stages * kP2StageBytes;            // 71680
 
-__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
-__device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
-__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
-__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
-__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
-__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }   // a - b
-__device__ __forceinline__ float2 lerp2(float2 a, float2 b, float2 t) { return fma2(t, sub2(b, a), a); }
 
 struct Sample2 { float2 w, gx2, gy2; };
 

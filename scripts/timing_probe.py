@@ -25,3 +25,6 @@ with pkg.EccStack(w, h, 3, params, device=0, lanes=1) as st:
         print("  tail: cross-tile sum done %.1f, solve done %.1f, end %.1f  (last block %d)" % (tl[0], tl[1], tl[2], int(tail[3])))
         order = np.argsort(rel[:, 1])
         print("  slowest tiles:", [(int(i), round(float(rel[i, 1]), 1)) for i in order[-6:]])
+        if it == 4:
+            dur = rel[:, 1] - rel[:, 0]
+            print("  durations by block:", " ".join(str(int(round(float(d)))) for d in dur))
