@@ -32,6 +32,19 @@ struct WarpAccParams {
   int store;              // 1: acc = v (first frame on this lane), 0: acc += v
 };
 
+// Correctly rounded 1/w for w in the normal range (|w| in [2^-500, 2^500]): the instruction sequence of
+// __drcp_rn without its special-case branch.  scripts/rcp_check.cu compares it with IEEE division over 2^28
+// values on the GPU (0 mismatches).
+__device__ __forceinline__ double rcp_rn_normal(double w) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(w));
+  double t = __fma_rn(-w, r, 1.0);
+  t = __fma_rn(t, t, t);
+  r = __fma_rn(r, t, r);
+  const double e = __fma_rn(-w, r, 1.0);
+  return __fma_rn(r, e, r);
+}
+
 constexpr int kWarpBX = 32, kWarpBY = 8;   // thread block
 constexpr int kWarpRows = 4;               // destination rows per thread: the block tile is 32 x 32 pixels
 constexpr int kWarpTH = kWarpBY * kWarpRows;
@@ -46,7 +59,7 @@ constexpr int kWarpTH = kWarpBY * kWarpRows;
 // __double2int_rn supplies the saturation, and pixels whose four taps are inside the source skip all
 // border selects.
 template <int C, bool PERSP>
-__global__ void __launch_bounds__(kWarpBX * kWarpBY) warp_accumulate_kernel(const WarpAccParams p) {
+__global__ void __launch_bounds__(kWarpBX * kWarpBY, 8) warp_accumulate_kernel(const WarpAccParams p) {
   __shared__ __align__(16) float s_val[kWarpTH][kWarpBX * C];
   __shared__ double s_m[9];
   if (p.status_ptr && *p.status_ptr != 0) return;
@@ -80,6 +93,60 @@ __global__ void __launch_bounds__(kWarpBX * kWarpBY) warp_accumulate_kernel(cons
     bdelta = __double2int_rn(__dmul_rn(__dmul_rn(s_m[3], xd), kAbScale));
   }
 
+  // Interior tiles (the bulk of a frame): when the four corners of the tile land inside
+  // [1/16, sw-1-1/16] x [1/16, sh-1-1/16] with w in (1e-9, 1e9), every tap of every pixel of the tile is inside
+  // the source (a projective map with w > 0 sends the rectangle into the hull of its corner images; the slack
+  // covers the 1/32-px quantisation), so the pixel loop needs no bounds test, clamp or border select, the
+  // reciprocal no special cases and cvRound no saturation.  Decided per warp (lanes 0-3 take one corner each,
+  // inequalities multiplied through by w: no division), no extra barrier.
+  bool lean = blockIdx.x * kWarpBX + kWarpBX <= p.width && blockIdx.y * kWarpTH + kWarpTH <= p.height;
+  {
+    const int k = threadIdx.x & 3;
+    const double cxk = (double)(blockIdx.x * kWarpBX + ((k & 1) ? kWarpBX - 1 : 0));
+    const double cyk = (double)(blockIdx.y * kWarpTH + ((k & 2) ? kWarpTH - 1 : 0));
+    const double nu = s_m[0] * cxk + s_m[1] * cyk + s_m[2], nv = s_m[3] * cxk + s_m[4] * cyk + s_m[5];
+    const double ww = PERSP ? s_m[6] * cxk + s_m[7] * cyk + s_m[8] : 1.0;
+    const double lo = 0.0625 * ww, uhi = ((double)(sw - 1) - 0.0625) * ww, vhi = ((double)(sh - 1) - 0.0625) * ww;
+    lean = __all_sync(0xffffffffu, lean && ww > 1e-9 && ww < 1e9 && nu >= lo && nu < uhi && nv >= lo && nv < vhi);
+  }
+
+  if (lean) {
+#pragma unroll
+    for (int rr = 0; rr < kWarpRows; ++rr) {
+      const int ry = threadIdx.y + rr * kWarpBY;
+      const double yd = (double)(y_base + rr * kWarpBY);
+      int xq, yq;
+      if (PERSP) {
+        const double X0 = __dadd_rn(__dadd_rn(cx0, __dmul_rn(s_m[1], yd)), s_m[2]);
+        const double Y0 = __dadd_rn(__dadd_rn(cy0, __dmul_rn(s_m[4], yd)), s_m[5]);
+        const double W0 = __dadd_rn(__dadd_rn(cw0, __dmul_rn(s_m[7], yd)), s_m[8]);
+        const double W32 = __dmul_rn(rcp_rn_normal(__dadd_rn(W0, cw1)), (double)kInterTab);
+        xq = rint_magic(__dmul_rn(__dadd_rn(X0, cx1), W32));
+        yq = rint_magic(__dmul_rn(__dadd_rn(Y0, cy1), W32));
+      } else {
+        const int X0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(s_m[1], yd), s_m[2]), kAbScale)) + 16;
+        const int Y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(s_m[4], yd), s_m[5]), kAbScale)) + 16;
+        xq = (int)((unsigned)X0 + (unsigned)adelta) >> (kAbBits - kInterBits);
+        yq = (int)((unsigned)Y0 + (unsigned)bdelta) >> (kAbBits - kInterBits);
+      }
+      const float ax = (float)(xq & (kInterTab - 1)) * (1.f / kInterTab);
+      const float ay = (float)(yq & (kInterTab - 1)) * (1.f / kInterTab);
+      const float w00 = __fmul_rn(1.f - ay, 1.f - ax), w01 = __fmul_rn(1.f - ay, ax);
+      const float w10 = __fmul_rn(ay, 1.f - ax), w11 = __fmul_rn(ay, ax);
+      const uint8_t* r0 = p.src + (ptrdiff_t)(yq >> kInterBits) * (ptrdiff_t)p.src_pitch + (xq >> kInterBits) * C;
+      const uint8_t* r1 = r0 + p.src_pitch;
+      unsigned t00[C], t01[C], t10[C], t11[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) { t00[c] = __ldg(r0 + c); t01[c] = __ldg(r0 + C + c); t10[c] = __ldg(r1 + c); t11[c] = __ldg(r1 + C + c); }
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float s00 = __fmul_rn((float)t00[c], k255), s01 = __fmul_rn((float)t01[c], k255);
+        const float s10 = __fmul_rn((float)t10[c], k255), s11 = __fmul_rn((float)t11[c], k255);
+        s_val[ry][threadIdx.x * C + c] =
+            __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s00, w00), __fmul_rn(s01, w01)), __fmul_rn(s10, w10)), __fmul_rn(s11, w11));
+      }
+    }
+  } else {
 #pragma unroll
   for (int rr = 0; rr < kWarpRows; ++rr) {
     const int y = y_base + rr * kWarpBY;
@@ -144,6 +211,7 @@ __global__ void __launch_bounds__(kWarpBX * kWarpBY) warp_accumulate_kernel(cons
     }
 #pragma unroll
     for (int c = 0; c < C; ++c) s_val[threadIdx.y + rr * kWarpBY][threadIdx.x * C + c] = v[c];
+  }
   }
   __syncthreads();
 
