@@ -55,7 +55,46 @@ __global__ void __launch_bounds__(kPrepThreads) prep_grey_blur_kernel(const Prep
 
   // 1. grey tile with halo; tiles whose halo stays inside the image skip the BORDER_REFLECT_101 index math
   const bool interior = x0 - r >= 0 && x0 + kPrepTW + r <= p.width && y0 - r >= 0 && y0 + kPrepTH + r <= p.height;
-  if (interior) {
+  // raw-byte staging: 16-byte aligned rows of the source tile, aliased onto `tmp` (dead until pass 2)
+  const int raw_pitch = (gw * ch + 30) / 16 * 16;
+  if (interior && raw_pitch <= kPrepTW * (int)sizeof(float)) {
+    // The tile's source bytes come in as aligned 128-bit loads (an aligned chunk that holds one valid byte
+    // lies in a mapped page, so the slop before/after a row is harmless) and the grey conversion reads them
+    // from shared memory: ~1 global load per lane and row instead of 3 byte gathers per pixel.
+    unsigned char* raw = reinterpret_cast<unsigned char*>(tmp);
+    const uint8_t* base = p.src + (size_t)(y0 - r) * p.src_pitch + (size_t)(x0 - r) * ch;
+    const int row_bytes = gw * ch;
+    // every load of the warp's rows is in flight before the first store (one DRAM round trip, not one per row)
+    constexpr int kRowsPerWarp = (kPrepTH + 2 * (R > 0 ? R : kMaxGaussRadius) + kWarps - 1) / kWarps;
+    uint4 v[kRowsPerWarp];
+#pragma unroll
+    for (int i = 0; i < kRowsPerWarp; ++i) {
+      const int ty = wrp + i * kWarps;
+      const uint8_t* row = base + (size_t)ty * p.src_pitch;
+      const int off = (int)((uintptr_t)row & 15);
+      if (ty < gh && lane * 16 < off + row_bytes) v[i] = __ldg(reinterpret_cast<const uint4*>(row - off) + lane);
+    }
+#pragma unroll
+    for (int i = 0; i < kRowsPerWarp; ++i) {
+      const int ty = wrp + i * kWarps;
+      const int off = (int)((uintptr_t)(base + (size_t)ty * p.src_pitch) & 15);
+      if (ty < gh && lane * 16 < off + row_bytes) *reinterpret_cast<uint4*>(raw + ty * raw_pitch + lane * 16) = v[i];
+    }
+    __syncthreads();
+    constexpr int kCols = (kPrepTW + 2 * (R > 0 ? R : kMaxGaussRadius) + 31) / 32;
+    for (int ty = wrp; ty < gh; ty += kWarps) {
+      const int off = (int)((uintptr_t)(base + (size_t)ty * p.src_pitch) & 15);
+      const unsigned char* rrow = raw + ty * raw_pitch + off;
+#pragma unroll
+      for (int q = 0; q < kCols; ++q) {
+        const int tx = lane + 32 * q;
+        if (tx < gw) {
+          const unsigned char* px = rrow + tx * ch;
+          grey[ty * gp + tx] = ch == 1 ? (float)px[0] : (float)bgr2gray(px[0], px[1], px[2]);
+        }
+      }
+    }
+  } else if (interior) {
     const uint8_t* base = p.src + (size_t)(y0 - r) * p.src_pitch + (size_t)(x0 - r) * ch;
     // all byte loads of a row are issued before the first conversion (memory-level parallelism)
     constexpr int kCols = (kPrepTW + 2 * (R > 0 ? R : kMaxGaussRadius) + 31) / 32;
