@@ -407,10 +407,23 @@ def _orb(grey):
     return cv2.ORB_create().detectAndCompute(grey, None)      # utils::orb_detect_and_compute
 
 
-def _frame_homography(kp0, des0, img, params: KeyPointMatchParameters):
-    """Host stages of src/lib.rs:200-287; None == the reference drops the frame."""
+def _scale_image(img, scale_down: float):
+    """utils::scale_image (src/utils.rs:186-214) on the host, for the keypoint front end (which stays OpenCV)."""
+    import cv2
+    h, w = img.shape[:2]
+    factor = float(scale_down) / float(w if w < h else h)
+    return cv2.resize(img, (int(w * factor), int(h * factor)), interpolation=cv2.INTER_AREA)
+
+
+def _frame_homography(kp0, des0, img, params: KeyPointMatchParameters, scale_down: Optional[float] = None):
+    """Host stages of src/lib.rs:200-287 (scale_down: :424-547, features on the INTER_AREA-downscaled grey and
+    the homography taken back to full size with adjust_homography_for_scale_f64, src/utils.rs:218-248);
+    None == the reference drops the frame."""
     import cv2
     grey = cv2.cvtColor(img, cv2.COLOR_BGR2GRAY)
+    full_h, full_w = grey.shape
+    if scale_down is not None:
+        grey = _scale_image(grey, scale_down)
     kp, des = _orb(grey)
     if des is None or des0 is None:
         return None
@@ -430,6 +443,13 @@ def _frame_homography(kp0, des0, img, params: KeyPointMatchParameters):
         return None
     if hm is None or hm.shape != (3, 3) or abs(np.linalg.det(hm)) < 1e-6:
         return None
+    if scale_down is not None:
+        sx, sy = full_w / grey.shape[1], full_h / grey.shape[0]
+        hm = hm.copy()
+        hm[0, 2] *= sx
+        hm[1, 2] *= sy
+        hm[2, 0] /= sx
+        hm[2, 1] /= sy
     return hm
 
 
@@ -446,12 +466,18 @@ def keypoint_match(files: Iterable, params: KeyPointMatchParameters = KeyPointMa
     items = list(files)
     if not items:
         raise NotEnoughFiles()
-    if scale_down_width is not None:
-        raise NotImplementedError_("keypoint_match with scale_down_width is not implemented yet")
     first = _load(items[0])
     _check_colour_frame(first)
     h, w, ch = first.shape
-    kp0, des0 = _orb(cv2.cvtColor(first, cv2.COLOR_BGR2GRAY))
+    sd = None
+    if scale_down_width is not None:
+        # keypoint_match_scale_down (src/lib.rs:355-600): only the upper bound is validated (:378-383)
+        sd = float(np.float32(scale_down_width))
+        if sd >= float(w):
+            raise InvalidParams(f"scale_down_to was larger (or equal) to the full image width: full_size:{w}, "
+                                f"scale_down_to:{sd:g}")
+    grey0 = cv2.cvtColor(first, cv2.COLOR_BGR2GRAY)
+    kp0, des0 = _orb(grey0 if sd is None else _scale_image(grey0, sd))
     dropped = 0
     with EccStack(w, h, ch, None, device=device) as st:
         st.set_reference(first)
@@ -459,7 +485,7 @@ def keypoint_match(files: Iterable, params: KeyPointMatchParameters = KeyPointMa
         def work(item):
             img = _load(item)
             _check_colour_frame(img)
-            return img, _frame_homography(kp0, des0, img, params)
+            return img, _frame_homography(kp0, des0, img, params, sd)
 
         n_workers = workers or min(8, os.cpu_count() or 1)
         with ThreadPoolExecutor(max_workers=n_workers) as ex:

@@ -151,17 +151,25 @@ where
     P: AsRef<std::path::Path>,
 {
     let files: Vec<PathBuf> = files.into_iter().map(|p| p.as_ref().to_path_buf()).collect();
-    if scale_down_width.is_some() {
-        return Err(StackerError::NotImplemented);
-    }
     if files.is_empty() {
         return Err(StackerError::NotEnoughFiles);
     }
     let first = utils::read_frame(&files[0])?;
+    // keypoint_match_scale_down (reference src/lib.rs:355-600): only the upper bound is validated (:378-383)
+    if let Some(sd) = scale_down_width {
+        if sd >= first.cols() as f32 {
+            return Err(StackerError::InvalidParams(format!(
+                "scale_down_to was larger (or equal) to the full image width: full_size:{}, scale_down_to:{}", first.cols(), sd)));
+        }
+    }
+    // grey plane the features are detected on: full size, or utils::scale_image'd (INTER_AREA) like the reference
     let grey = |img: &Mat| -> Result<Mat, StackerError> {
         let mut g = Mat::default();
         imgproc::cvt_color(img, &mut g, imgproc::COLOR_BGR2GRAY, 0, core::AlgorithmHint::ALGO_HINT_DEFAULT)?;
-        Ok(g)
+        match scale_down_width {
+            Some(sd) => utils::scale_image(&g, sd),
+            None => Ok(g),
+        }
     };
     let orb = |g: &Mat| -> Result<(Vector<core::KeyPoint>, Mat), StackerError> {
         let mut orb = features2d::ORB::create_def()?;
@@ -175,7 +183,9 @@ where
     let border = [params.border_value[0], params.border_value[1], params.border_value[2], params.border_value[3]];
     let dropped: i32 = (1..files.len()).into_par_iter().with_min_len(1).map(|i| -> Result<i32, StackerError> {
         let img = utils::read_frame(&files[i])?;
-        let (kp, des) = orb(&grey(&img)?)?;
+        let g = grey(&img)?;
+        let small = g.size()?;
+        let (kp, des) = orb(&g)?;
         let mut matcher = features2d::BFMatcher::create(core::NORM_HAMMING, false)?;
         matcher.add(&des)?;
         let mut knn = Vector::<Vector<core::DMatch>>::new();
@@ -202,7 +212,15 @@ where
         if h.empty() || h.rows() != 3 || h.cols() != 3 || core::determinant(&h)?.abs() < 1e-6 {
             return Ok(1);
         }
-        let hv: Vec<f64> = h.data_typed::<f64>()?.to_vec();
+        let mut hv: Vec<f64> = h.data_typed::<f64>()?.to_vec();
+        if scale_down_width.is_some() {
+            // adjust_homography_for_scale_f64 (reference src/utils.rs:218-248)
+            let (sx, sy) = (img.cols() as f64 / small.width as f64, img.rows() as f64 / small.height as f64);
+            hv[2] *= sx;
+            hv[5] *= sy;
+            hv[6] /= sx;
+            hv[7] /= sy;
+        }
         check(unsafe {
             ffi::stk_ecc_submit_warp(ctx.0, img.data(), img.mat_step().get(0), hv.as_ptr(), params.border_mode, border.as_ptr(), i as i64)
         })?;

@@ -26,6 +26,20 @@ pub(crate) fn read_frame(path: &std::path::Path) -> Result<Mat, StackerError> {
     if img.is_continuous() { Ok(img) } else { Ok(img.try_clone()?) }
 }
 
+/// Aspect-preserving INTER_AREA downscale for the keypoint front end (reference: src/utils.rs:186-214): the
+/// SMALLER dimension becomes `scale_down`, both new sizes are truncated.  (The ECC path does this on the GPU.)
+pub(crate) fn scale_image(img: &Mat, scale_down: f32) -> Result<Mat, StackerError> {
+    let size = img.size()?;
+    let f = if size.width < size.height { scale_down as f64 / size.width as f64 } else { scale_down as f64 / size.height as f64 };
+    let mut resized = Mat::default();
+    opencv::imgproc::resize(
+        img, &mut resized,
+        opencv::core::Size::new((size.width as f64 * f) as i32, (size.height as f64 * f) as i32),
+        0.0, 0.0, opencv::imgproc::INTER_AREA,
+    )?;
+    Ok(resized)
+}
+
 impl From<EccMatchParameters> for Result<opencv::core::TermCriteria, StackerError> {
     /// ```
     /// # use libstacker::{prelude::*, opencv::core::TermCriteria_Type};

@@ -203,20 +203,35 @@ def keypoint_homography(grey0_kp_des, grey_i, method, reproj, match_ratio, keep_
 
 
 def keypoint_match(frames_u8, method=cv2.RANSAC, reproj=3.0, match_ratio=0.8, keep_ratio=0.75,
-                   border_mode=cv2.BORDER_CONSTANT, border_value=(0, 0, 0, 0)):
+                   border_mode=cv2.BORDER_CONSTANT, border_value=(0, 0, 0, 0), scale_down=None):
     """keypoint_match_no_scale, sequential fold (the reference's dropped-frame seeding quirk at
     src/lib.rs:307 depends on the Rayon split; with zero drops every order gives the same sum).
     Returns (dropped, stack f32, homographies)."""
     if len(frames_u8) == 0:
         raise ValueError("NotEnoughFiles")
     grey0, f32_0 = read_grey_and_f32(frames_u8[0])
+    h0, w0 = grey0.shape
+    if scale_down is not None:
+        # keypoint_match_scale_down (src/lib.rs:355-600): features on the downscaled greys, homography
+        # adjusted with adjust_homography_for_scale_f64 (src/utils.rs:218-248)
+        if scale_down >= w0:
+            raise ValueError("InvalidParams: scale_down_to was larger (or equal) to the full image width")
+        grey0 = scale_image(grey0, scale_down)
     orb = cv2.ORB_create()
     kp0, des0 = orb.detectAndCompute(grey0, None)
-    h0, w0 = grey0.shape
     acc, dropped, hs = f32_0.copy(), 0, [None]
     for fr in frames_u8[1:]:
         grey, f32 = read_grey_and_f32(fr)
+        if scale_down is not None:
+            grey = scale_image(grey, scale_down)
         h = keypoint_homography((kp0, des0), grey, method, reproj, match_ratio, keep_ratio)
+        if h is not None and scale_down is not None:
+            sx, sy = w0 / grey.shape[1], h0 / grey.shape[0]
+            h = h.copy()
+            h[0, 2] *= sx
+            h[1, 2] *= sy
+            h[2, 0] /= sx
+            h[2, 1] /= sy
         hs.append(h)
         if h is None:
             dropped += 1

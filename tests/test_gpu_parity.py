@@ -445,3 +445,25 @@ def test_sharpness_golden_and_batch(pkg):
                               R.sharpness_tenengrad(grey, 3), R.sharpness_normalized_gray_level_variance(grey))
     flat = np.full((30, 40), 9, np.uint8)
     assert pkg.sharpness_all(flat, device=0) == (0.0, 0.0, 0.0, 0.0)
+
+
+# ---- keypoint_match: host front end (OpenCV) + GPU tail, with and without scale_down_width ----------------
+@pytest.mark.parametrize("scale_down", [None, 300.0])
+def test_keypoint_match_vs_cv2(pkg, have_cv2, scale_down):
+    """src/lib.rs:129-353 and :355-600 against the same OpenCV calls made by the oracle: identical drops,
+    stack within the parity bar."""
+    if not have_cv2:
+        pytest.skip("cv2 not installed")
+    from oracle import cvref
+    w, h = 800, 600
+    frames = synth.Stack(w, h, 5, 3, seed=31).frames()
+    params = pkg.KeyPointMatchParameters(method=pkg.RANSAC, ransac_reproj_threshold=5.0, match_keep_ratio=0.8, match_ratio=0.9)
+    dropped, got = pkg.keypoint_match(frames, params, scale_down, device=0)
+    want_dropped, want, hs = cvref.keypoint_match(frames, reproj=5.0, match_ratio=0.9, keep_ratio=0.8, scale_down=scale_down)
+    assert dropped == want_dropped == 0
+    g8, w8 = np.rint(got * 255.0), np.rint(want * 255.0)
+    assert np.abs(g8 - w8).max() <= 1
+    assert psnr8(g8, w8) >= 50.0
+    if scale_down is not None:
+        with pytest.raises(pkg.InvalidParams):
+            pkg.keypoint_match(frames, params, float(w), device=0)
