@@ -84,7 +84,7 @@ struct alignas(64) EccIterParams {
   EccState* st;
   cudaGraphConditionalHandle handle;
   int use_handle;
-  int reserved0;
+  int rim_weight;           // cost of a chunk of the first/last strip in 1/8 of an interior chunk (8 = no bias)
   double* totals_out;       // optional: the NV reduced sums of this iteration (test hook), else null
   unsigned long long* timing_out;   // optional: %globaltimer stamps per tile [n_tiles][4] + tail [4] (profiling hook)
 };
@@ -881,6 +881,24 @@ __device__ __forceinline__ void finish_iteration(const EccIterParams& p, EccStat
   }
 }
 
+// Work split.  Chunks are dealt strip-major to the persistent blocks in contiguous runs of (nearly) equal
+// COST, where a chunk of the first or last strip counts rim_weight/8: those are the chunks whose samples can
+// leave the image, which sends the warp that owns the rim columns down the careful path (measured: blocks
+// working there took 45-47 us against 38 us elsewhere).  chunk_at() inverts the cumulative cost.
+__device__ __forceinline__ int chunk_at(long long t, int n_strips, int cps, int wr) {
+  const long long first = (long long)cps * wr;
+  if (n_strips == 1 || t < first) return (int)(t / wr);
+  const long long mid = (long long)(n_strips - 2) * cps * 8;
+  if (t < first + mid) return cps + (int)((t - first) / 8);
+  return cps * (n_strips - 1) + (int)((t - first - mid) / wr);
+}
+__device__ __forceinline__ void block_chunk_range(int n_strips, int cps, int wr, int& g0, int& g1) {
+  const long long total_w = (long long)cps * wr * (n_strips > 1 ? 2 : 1) + (long long)max(n_strips - 2, 0) * cps * 8;
+  g0 = chunk_at((long long)blockIdx.x * total_w / gridDim.x, n_strips, cps, wr);
+  g1 = blockIdx.x + 1 == gridDim.x ? n_strips * cps
+                                   : chunk_at((long long)(blockIdx.x + 1) * total_w / gridDim.x, n_strips, cps, wr);
+}
+
 template <int MOTION, bool FAST> struct AccumFor { using type = Accum<MOTION>; };
 template <> struct AccumFor<kHomography, true> { using type = AccumH2; };
 
@@ -892,7 +910,7 @@ template <> struct AccumFor<kHomography, true> { using type = AccumH2; };
 // or two "segments" (a run that crosses into the next strip).  Per segment the thread's column is fixed;
 // at a segment end the block folds its sums into an f64 shared accumulator.
 template <int MOTION, bool EXACT>
-__global__ void __launch_bounds__(kEccThreads, 2) ecc_iter_kernel(const __grid_constant__ EccIterParams p) {
+__global__ void __launch_bounds__(kEccThreads, 512 / kEccThreads) ecc_iter_kernel(const __grid_constant__ EccIterParams p) {
   using L = Layout<MOTION>;
   using Md = Model<MOTION>;
   constexpr int NV = L::NV, G = L::G;
@@ -908,7 +926,11 @@ __global__ void __launch_bounds__(kEccThreads, 2) ecc_iter_kernel(const __grid_c
   __shared__ double s_tot[NV];
 
   EccState* st = p.st;
-  // a frame whose loop already stopped (only reachable in the host-driven fallback loop)
+  // PDL: let the next kernel of the chain be launched now, and wait until the previous one (whose last block
+  // writes the state read below) has completed and flushed.  Both are no-ops without a programmatic edge.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  // a frame whose loop already stopped (a later kernel of the unrolled chain, or the host-driven loop)
   if (st->cont == 0) return;
 
   const int tid = threadIdx.x;
@@ -923,9 +945,8 @@ __global__ void __launch_bounds__(kEccThreads, 2) ecc_iter_kernel(const __grid_c
   }
 
   const int cps = p.chunks_per_strip;
-  const long long total = (long long)p.n_strips * cps;
-  int g0 = (int)((long long)blockIdx.x * total / gridDim.x);
-  const int g1 = (int)((long long)(blockIdx.x + 1) * total / gridDim.x);
+  int g0, g1;
+  block_chunk_range(p.n_strips, cps, p.rim_weight, g0, g1);
   int cc = 0;                       // chunks this block has consumed so far: drives stage and phase
 
   const int col = tid & (kEccStripW - 1);

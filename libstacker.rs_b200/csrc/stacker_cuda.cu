@@ -245,6 +245,9 @@ struct stk_ecc_ctx {
   CUtensorMap tm_img;
   CUtensorMap tm_img_p2;
   bool exact_coords = false;
+  bool pdl = false;            // programmatic dependent launch between the chained iteration kernels (opt-in STK_ECC_PDL=1: measured no gain on one lane and -5 % with four, the waiting blocks hold SM slots)
+  int loop_unroll = 4;         // iteration kernels per WHILE-body pass (STK_ECC_UNROLL)
+  int rim_weight = 10;         // cost of a rim-strip chunk in 1/8 of an interior one (STK_ECC_RIM_WEIGHT)
   bool pack2 = false;          // Homography with FastPersp coordinates runs the packed-pair kernel
   int iter_threads = 0, iter_smem = 0;
   bool host_loop = false;
@@ -303,6 +306,7 @@ stk::EccIterParams iter_params(stk_ecc_ctx* c, Lane& ln, bool use_handle) {
   p.st = ln.st;
   p.handle = ln.handle;
   p.use_handle = use_handle ? 1 : 0;
+  p.rim_weight = c->rim_weight;
   p.totals_out = nullptr;
   p.timing_out = nullptr;
   return p;
@@ -344,7 +348,27 @@ int build_lane_graph(stk_ecc_ctx* c, Lane& ln) {
     kp.blockDim = dim3(c->iter_threads);
     kp.sharedMemBytes = c->iter_smem;
     kp.kernelParams = args;
-    CU(cudaGraphAddKernelNode(&iter_node, body, nullptr, 0, &kp));
+    // The WHILE body holds `loop_unroll` copies of the iteration kernel in a chain: a kernel that finds the
+    // loop already finished (cont == 0) returns at once, so at most unroll-1 empty launches are spent per
+    // frame, while the condition round trip of the WHILE node (measured ~10 us against ~3 us for a
+    // kernel-to-kernel edge) is paid once per `loop_unroll` iterations.
+    // Inside the chain the edges are PROGRAMMATIC (PDL): kernel i+1 may be launched and have its blocks
+    // scheduled while kernel i is still in its serial tail; it waits at griddepcontrol.wait before reading
+    // the state kernel i writes.  This takes the launch latency off the iteration's critical path.
+    cudaGraphNode_t prev = nullptr;
+    for (int u = 0; u < c->loop_unroll; ++u) {
+      if (prev && c->pdl) {
+        CU(cudaGraphAddKernelNode(&iter_node, body, nullptr, 0, &kp));
+        cudaGraphEdgeData ed = {};
+        ed.from_port = cudaGraphKernelNodePortProgrammatic;
+        ed.to_port = cudaGraphKernelNodePortDefault;
+        ed.type = cudaGraphDependencyTypeProgrammatic;
+        CU(cudaGraphAddDependencies_v2(body, &prev, &iter_node, &ed, 1));
+      } else {
+        CU(cudaGraphAddKernelNode(&iter_node, body, prev ? &prev : nullptr, prev ? 1 : 0, &kp));
+      }
+      prev = iter_node;
+    }
   }
   CU(cudaGraphInstantiate(&ln.exec, ln.graph, 0));
   return STK_OK;
@@ -651,6 +675,9 @@ int stk_ecc_create(const stk_ecc_config* cfg, stk_ecc_ctx** out) {
   c->eps = (cfg->criteria_type & STK_TERM_EPS) ? cfg->epsilon : -1.0;
   const char* ec = getenv("STK_ECC_EXACT_COORDS");
   c->exact_coords = ec && strcmp(ec, "1") == 0;
+  if (const char* pd = getenv("STK_ECC_PDL")) c->pdl = strcmp(pd, "0") != 0;
+  if (const char* un = getenv("STK_ECC_UNROLL")) c->loop_unroll = std::max(1, std::min(16, atoi(un)));
+  if (const char* rw = getenv("STK_ECC_RIM_WEIGHT")) c->rim_weight = std::max(8, std::min(32, atoi(rw)));
   const char* lm = getenv("STK_LOOP_MODE");
   c->host_loop = lm && strcmp(lm, "host") == 0;
 
