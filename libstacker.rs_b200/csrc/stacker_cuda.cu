@@ -1165,6 +1165,34 @@ int stk_ecc_debug_timing(stk_ecc_ctx* c, const uint8_t* bgr, size_t pitch, const
 }
 
 /* ---- Tenengrad ------------------------------------------------------------------------------------ */
+}  // extern "C"  (reopened below)
+
+namespace {
+// Per-device scratch for the block sums of the sharpness kernels: cudaMalloc/cudaFree per call cost
+// milliseconds (measured 4-9 ms per call with a few hundred MB of frames resident), far more than the kernels.
+// Grow-only, one per device, calls serialised by the mutex for as long as they use it.
+struct SumScratch {
+  std::mutex mu;
+  unsigned long long* d[64] = {};
+  size_t cap[64] = {};
+};
+SumScratch g_scratch;
+
+int scratch_for(int dev, size_t bytes, unsigned long long** out) {
+  if (dev < 0 || dev >= 64) return fail(STK_ERR_BAD_ARG, "device ordinal %d out of range", dev);
+  if (g_scratch.cap[dev] < bytes) {
+    if (g_scratch.d[dev]) cudaFree(g_scratch.d[dev]);
+    g_scratch.d[dev] = nullptr; g_scratch.cap[dev] = 0;
+    const size_t want = std::max(bytes, (size_t)1 << 20);
+    if (cudaMalloc((void**)&g_scratch.d[dev], want) != cudaSuccess) return fail(STK_ERR_NOMEM, "cudaMalloc(sum scratch) failed");
+    g_scratch.cap[dev] = want;
+  }
+  *out = g_scratch.d[dev];
+  return STK_OK;
+}
+}  // namespace
+
+extern "C" {
 static int tenengrad_taps(int ksize, stk::TenengradParams& p) {
   memset(p.dtap, 0, sizeof p.dtap);
   memset(p.stap, 0, sizeof p.stap);
@@ -1189,26 +1217,34 @@ int stk_tenengrad_batch_device(const uint8_t* d_imgs, size_t frame_stride, size_
   if (pitch < (size_t)width * channels) return fail(STK_ERR_BAD_ARG, "pitch too small");
   if (device >= 0) CU(cudaSetDevice(device));
   unsigned long long* d_sums = nullptr;
-  CU(cudaMalloc((void**)&d_sums, sizeof(unsigned long long) * n));
-  cudaError_t e = cudaMemset(d_sums, 0, sizeof(unsigned long long) * n);
-  std::vector<unsigned long long> h(n);
+  const size_t sum_bytes = sizeof(unsigned long long) * stk::kSumSlots * (size_t)n;
+  int cur_dev = 0;
+  CU(cudaGetDevice(&cur_dev));
+  std::lock_guard<std::mutex> scratch_lock(g_scratch.mu);
+  rc = scratch_for(cur_dev, sum_bytes, &d_sums);
+  if (rc) return rc;
+  cudaError_t e = cudaMemsetAsync(d_sums, 0, sum_bytes, 0);
+  std::vector<unsigned long long> h((size_t)n * stk::kSumSlots);
   if (e == cudaSuccess) {
     p.src = d_imgs; p.frame_stride = frame_stride; p.pitch = pitch;
     p.width = width; p.height = height; p.channels = channels; p.sums = d_sums;
     for (int z0 = 0; z0 < n && e == cudaSuccess; z0 += 32768) {
       stk::TenengradParams q = p;
       q.src = d_imgs + (size_t)z0 * frame_stride;
-      q.sums = d_sums + z0;
+      q.sums = d_sums + (size_t)z0 * stk::kSumSlots;
       dim3 grid((width + stk::kTenTW - 1) / stk::kTenTW, (height + stk::kTenTH - 1) / stk::kTenTH, std::min(32768, n - z0));
       stk::tenengrad_kernel<<<grid, stk::kTenThreads>>>(q);
       e = cudaGetLastError();
     }
-    if (e == cudaSuccess) e = cudaMemcpy(h.data(), d_sums, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(h.data(), d_sums, sum_bytes, cudaMemcpyDeviceToHost);
   }
-  cudaFree(d_sums);
   if (e != cudaSuccess) return fail(STK_ERR_CUDA, "tenengrad: %s", cudaGetErrorString(e));
   const double scale = 1.0 / ((double)width * (double)height);
-  for (int i = 0; i < n; ++i) out[i] = (double)h[i] * scale;   // cv::mean: exact integer sum * (1.0 / N)
+  for (int i = 0; i < n; ++i) {
+    unsigned long long t = 0;
+    for (int k = 0; k < stk::kSumSlots; ++k) t += h[(size_t)i * stk::kSumSlots + k];
+    out[i] = (double)t * scale;   // cv::mean: exact integer sum * (1.0 / N)
+  }
   return STK_OK;
 }
 
@@ -1264,25 +1300,33 @@ int stk_sharpness_all_batch_device(const uint8_t* d_imgs, size_t frame_stride, s
   if (channels != 1 && channels != 3 && channels != 4) return fail(STK_ERR_UNSUPPORTED, "channels must be 1, 3 or 4");
   if (pitch < (size_t)width * channels) return fail(STK_ERR_BAD_ARG, "pitch too small");
   if (device >= 0) CU(cudaSetDevice(device));
-  const size_t bytes = sizeof(unsigned long long) * stk::kSharpSums * (size_t)n;
+  const size_t bytes = sizeof(unsigned long long) * stk::kSharpSums * stk::kSumSlots * (size_t)n;
   unsigned long long* d_sums = nullptr;
-  CU(cudaMalloc((void**)&d_sums, bytes));
-  cudaError_t e = cudaMemset(d_sums, 0, bytes);
-  std::vector<unsigned long long> h((size_t)n * stk::kSharpSums);
+  int cur_dev = 0;
+  CU(cudaGetDevice(&cur_dev));
+  std::lock_guard<std::mutex> scratch_lock(g_scratch.mu);
+  int rc = scratch_for(cur_dev, bytes, &d_sums);
+  if (rc) return rc;
+  cudaError_t e = cudaMemsetAsync(d_sums, 0, bytes, 0);
+  std::vector<unsigned long long> h((size_t)n * stk::kSharpSums * stk::kSumSlots);
   for (int z0 = 0; z0 < n && e == cudaSuccess; z0 += 32768) {
     stk::SharpnessParams p = {};
     p.src = d_imgs + (size_t)z0 * frame_stride;
     p.frame_stride = frame_stride; p.pitch = pitch;
     p.width = width; p.height = height; p.channels = channels;
-    p.sums = d_sums + (size_t)z0 * stk::kSharpSums;
+    p.sums = d_sums + (size_t)z0 * stk::kSharpSums * stk::kSumSlots;
     dim3 grid((width + stk::kTenTW - 1) / stk::kTenTW, (height + stk::kTenTH - 1) / stk::kTenTH, std::min(32768, n - z0));
     stk::sharpness_all_kernel<<<grid, stk::kTenThreads>>>(p);
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaMemcpy(h.data(), d_sums, bytes, cudaMemcpyDeviceToHost);
-  cudaFree(d_sums);
   if (e != cudaSuccess) return fail(STK_ERR_CUDA, "sharpness: %s", cudaGetErrorString(e));
-  for (int i = 0; i < n; ++i) sharpness_from_sums(h.data() + (size_t)i * stk::kSharpSums, (double)width * (double)height, out + 4 * (size_t)i);
+  for (int i = 0; i < n; ++i) {
+    unsigned long long v[stk::kSharpSums] = {};
+    for (int k = 0; k < stk::kSumSlots; ++k)
+      for (int j = 0; j < stk::kSharpSums; ++j) v[j] += h[((size_t)i * stk::kSumSlots + k) * stk::kSharpSums + j];   // two's complement for [2]
+    sharpness_from_sums(v, (double)width * (double)height, out + 4 * (size_t)i);
+  }
   return STK_OK;
 }
 
