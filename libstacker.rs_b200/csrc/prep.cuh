@@ -34,7 +34,8 @@ struct PrepParams {
   float taps[2 * kMaxGaussRadius + 1];
 };
 
-__host__ __device__ inline int prep_grey_pitch(int r) { return kPrepTW + 2 * r + 1; }   // odd: no bank conflicts on column walks
+// multiple of 4 floats: the horizontal pass reads its window as aligned 128-bit loads
+__host__ __device__ inline int prep_grey_pitch(int r) { return (kPrepTW + 2 * r + 3) / 4 * 4 + 4; }
 inline size_t prep_smem_bytes(int r) {
   return (size_t)((kPrepTH + 2 * r) * prep_grey_pitch(r) + (kPrepTH + 2 * r) * kPrepTW) * sizeof(float);
 }
@@ -134,7 +135,25 @@ __global__ void __launch_bounds__(kPrepThreads) prep_grey_blur_kernel(const Prep
 #pragma unroll
   for (int k = 0; k <= (R > 0 ? R : kMaxGaussRadius); ++k) tap[k] = (k <= r) ? p.taps[r + k] : 0.f;
 
-  // 2. horizontal pass
+  // 2. horizontal pass.  k = 5 (the reference's default): a thread produces 4 adjacent outputs from the 8 grey
+  // values they span — two aligned 128-bit loads and one 128-bit store instead of 20 + 4 scalar accesses (the
+  // kernel was bound by shared-memory wavefronts, profiles/r1_summary.md `pw_r1c`).
+  if constexpr (R == 2) {
+    for (int ty = wrp; ty < gh; ty += kWarps) {
+      const float4 lo = *reinterpret_cast<const float4*>(grey + ty * gp + lane * 4);
+      const float4 hi = *reinterpret_cast<const float4*>(grey + ty * gp + lane * 4 + 4);
+      const float g[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float s = tap[0] * g[j + 2];
+        s += tap[1] * (g[j + 1] + g[j + 3]);
+        s += tap[2] * (g[j] + g[j + 4]);
+        o[j] = s;
+      }
+      *reinterpret_cast<float4*>(tmp + ty * kPrepTW + lane * 4) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  } else
   for (int ty = wrp; ty < gh; ty += kWarps) {
 #pragma unroll
     for (int q = 0; q < kPrepTW / 32; ++q) {
@@ -155,6 +174,34 @@ __global__ void __launch_bounds__(kPrepThreads) prep_grey_blur_kernel(const Prep
   // 3. vertical pass: each thread 4 consecutive columns, 128-bit smem loads and global stores
   const int cx = lane * 4;                       // 32 lanes x 4 = 128 columns
   const bool full4 = x0 + cx + 3 < p.width;
+  if constexpr (R == 1 || R == 2) {
+    // a warp owns 4 consecutive output rows: the 4 + 2R rows of `tmp` they need are loaded once (2 loads per
+    // output row instead of 2R + 1)
+    constexpr int kRows = kPrepTH / kWarps;                 // 4
+    const int tyb = wrp * kRows;
+    float4 w[kRows + 2 * R];
+#pragma unroll
+    for (int i = 0; i < kRows + 2 * R; ++i) w[i] = *reinterpret_cast<const float4*>(tmp + (tyb + i) * kPrepTW + cx);
+#pragma unroll
+    for (int j = 0; j < kRows; ++j) {
+      const int y = y0 + tyb + j;
+      if (y >= p.height || x0 + cx >= p.width) continue;
+      const float4 c0 = w[j + R];
+      float4 s = make_float4(tap[0] * c0.x, tap[0] * c0.y, tap[0] * c0.z, tap[0] * c0.w);
+#pragma unroll
+      for (int k = 1; k <= R; ++k) {
+        const float4 a = w[j + R - k], b = w[j + R + k];
+        s.x += tap[k] * (a.x + b.x); s.y += tap[k] * (a.y + b.y); s.z += tap[k] * (a.z + b.z); s.w += tap[k] * (a.w + b.w);
+      }
+      float* o = p.dst + (size_t)y * p.dst_pitch + x0 + cx;
+      if (full4) {
+        *reinterpret_cast<float4*>(o) = s;
+      } else {
+        const float e[4] = {s.x, s.y, s.z, s.w};
+        for (int k = 0; k < 4 && x0 + cx + k < p.width; ++k) o[k] = e[k];
+      }
+    }
+  } else
   for (int ty = wrp; ty < kPrepTH; ty += kWarps) {
     const int y = y0 + ty;
     if (y >= p.height || x0 + cx >= p.width) continue;
