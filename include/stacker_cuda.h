@@ -124,6 +124,16 @@ int stk_ecc_submit_frame(stk_ecc_ctx* ctx, const uint8_t* bgr, size_t pitch, int
 int stk_ecc_submit_frame_pinned(stk_ecc_ctx* ctx, const uint8_t* pinned_bgr, size_t pitch, int64_t tag);
 int stk_ecc_submit_frame_device(stk_ecc_ctx* ctx, const uint8_t* d_bgr, size_t pitch, int64_t tag);
 
+/* Host feed for decode threads (replaces the Mat that imgcodecs::imread allocates, src/utils.rs:132, as the
+   decode target): the context owns a ring of pinned frame buffers (2 per lane, dense rows, *pitch =
+   width*channels).  acquire blocks until one is free; decode (imdecode_to / memcpy) into it from any thread
+   without holding any library lock; submit_acquired queues the asynchronous upload + alignment and recycles
+   the buffer when the upload has landed (do not touch it after the call); release gives an unused one back.
+   stk_ecc_submit_frame on a pageable buffer is exactly acquire + row copy + submit_acquired. */
+int stk_ecc_acquire_frame_buffer(stk_ecc_ctx* ctx, uint8_t** buf, size_t* pitch);
+int stk_ecc_submit_acquired(stk_ecc_ctx* ctx, uint8_t* buf, int64_t tag);
+int stk_ecc_release_frame_buffer(stk_ecc_ctx* ctx, uint8_t* buf);
+
 /* keypoint_match tail: warp_perspective(img_f32, H, size, INTER_LINEAR, border_mode, border_value)
    + accumulate                                           (src/lib.rs:289-316)
    h is the 3x3 f64 matrix from find_homography (forward map, inverted internally like OpenCV). */

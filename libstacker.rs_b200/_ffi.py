@@ -50,6 +50,9 @@ SYMBOLS = {
     "stk_ecc_submit_frame": (C.c_int, [_P, _P, C.c_size_t, C.c_int64]),
     "stk_ecc_submit_frame_pinned": (C.c_int, [_P, _P, C.c_size_t, C.c_int64]),
     "stk_ecc_submit_frame_device": (C.c_int, [_P, _P, C.c_size_t, C.c_int64]),
+    "stk_ecc_acquire_frame_buffer": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_size_t)]),
+    "stk_ecc_submit_acquired": (C.c_int, [_P, _P, C.c_int64]),
+    "stk_ecc_release_frame_buffer": (C.c_int, [_P, _P]),
     "stk_ecc_submit_warp": (C.c_int, [_P, _P, C.c_size_t, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.c_int64]),
     "stk_ecc_submit_warp_device": (C.c_int, [_P, _P, C.c_size_t, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.c_int64]),
     "stk_ecc_sync": (C.c_int, [_P]),

@@ -154,6 +154,7 @@ class EccStack:
         else:
             cfg.align = 0
         self.width, self.height, self.channels = cfg.width, cfg.height, cfg.channels
+        self.lanes = int(lanes) if lanes > 0 else 4        # the library's default
         self._ctx = C.c_void_p()
         self._keep = []          # host arrays that must outlive asynchronous copies
         _check(lib.stk_ecc_create(C.byref(cfg), C.byref(self._ctx)))
@@ -208,6 +209,22 @@ class EccStack:
             _check(lib.stk_ecc_submit_frame_pinned(self._ctx, ptr, pitch, int(tag)))
         else:
             _check(lib.stk_ecc_submit_frame(self._ctx, ptr, pitch, int(tag)))
+
+    # -- host feed: pinned ring buffers as decode targets
+    def acquire_buffer(self) -> np.ndarray:
+        """A free pinned frame buffer of the context's ring as an HxWxC uint8 array (blocks until one is free).
+        Fill it from any thread, then submit_acquired() it (or release_buffer())."""
+        ptr, pitch = C.c_void_p(), C.c_size_t()
+        _check(lib.stk_ecc_acquire_frame_buffer(self._ctx, C.byref(ptr), C.byref(pitch)))
+        n = self.height * self.width * self.channels
+        arr = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(n,))
+        return arr.reshape(self.height, self.width, self.channels)
+
+    def submit_acquired(self, buf: np.ndarray, tag: int = 0):
+        _check(lib.stk_ecc_submit_acquired(self._ctx, buf.ctypes.data, int(tag)))
+
+    def release_buffer(self, buf: np.ndarray):
+        _check(lib.stk_ecc_release_frame_buffer(self._ctx, buf.ctypes.data))
 
     def submit_warp(self, frame, h, border_mode: int = BORDER_CONSTANT, border_value=(0, 0, 0, 0), tag: int = 0):
         hm = (C.c_double * 9)(*np.asarray(h, np.float64).reshape(9))
@@ -391,10 +408,35 @@ def ecc_match(files: Iterable, params: EccMatchParameters, scale_down_width: Opt
                     _check_colour_frame(fr)
                     st.submit(fr, tag=k + 1)
             else:
-                with ThreadPoolExecutor(max_workers=n_workers) as ex:      # Rayon: one task per frame
-                    for k, fr in enumerate(ex.map(_load, rest)):
-                        _check_colour_frame(fr)
-                        st.submit(fr, tag=k + 1)
+                # Rayon: one task per frame (src/lib.rs:746-749).  Each task decodes and copies its frame into a
+                # pinned ring buffer (no library lock held); the main thread hands the buffers over in file order,
+                # so the summation order — and the result — does not depend on thread timing.  The window keeps at
+                # most one ring's worth of tasks alive, so a task can always get its buffer.
+                def load_into_ring(item):
+                    fr = _load(item)
+                    _check_colour_frame(fr)
+                    if fr.shape != (h, w, ch):
+                        raise OpenCvError(f"frame size {fr.shape[1]}x{fr.shape[0]} differs from the stack's {w}x{h}")
+                    buf = st.acquire_buffer()
+                    np.copyto(buf, fr)
+                    return buf
+
+                window = max(1, min(n_workers, 2 * st.lanes))
+                with ThreadPoolExecutor(max_workers=window) as ex:
+                    pending = []
+                    it = iter(enumerate(rest))
+                    done = False
+                    while pending or not done:
+                        while not done and len(pending) < window:
+                            try:
+                                k, item = next(it)
+                            except StopIteration:
+                                done = True
+                                break
+                            pending.append((k, ex.submit(load_into_ring, item)))
+                        if pending:
+                            k, fut = pending.pop(0)
+                            st.submit_acquired(fut.result(), tag=k + 1)
         out = st.finish(len(items))
         if return_details:
             return out, st.results()

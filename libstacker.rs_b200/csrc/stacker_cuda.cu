@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <condition_variable>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -214,6 +215,14 @@ struct Lane {
   CUtensorMap tm_tmpl_p2;
 };
 
+// Host feed: a ring of pinned frame buffers owned by the context.  Decode tasks fill a
+// buffer (straight from the decoder, or one memcpy from a pageable Mat) WITHOUT holding the context lock and
+// hand it over; the upload is asynchronous and the buffer returns to the ring guarded by its `uploaded` event.
+struct RingBuf {
+  uint8_t* host = nullptr;
+  cudaEvent_t uploaded = nullptr;
+};
+
 struct ResultSlot {
   int64_t tag;
   stk::EccState* host;      // pinned copy of the frame's final state (null for warp-only frames)
@@ -254,6 +263,10 @@ struct stk_ecc_ctx {
   bool have_ref = false;
   stk::PrepParams prep_proto;
   std::mutex mu;
+  std::vector<RingBuf> ring;        // lazily allocated: 2 buffers per lane
+  std::vector<int> ring_free;
+  std::mutex ring_mu;
+  std::condition_variable ring_cv;
   int next_lane = 0;
   std::vector<ResultSlot> results;
   std::vector<stk::EccState*> state_chunks;   // pinned, kChunk states each
@@ -470,6 +483,51 @@ Lane& pick_lane(stk_ecc_ctx* c) {
   Lane& ln = c->lanes[c->next_lane];
   c->next_lane = (c->next_lane + 1) % c->n_lanes;
   return ln;
+}
+
+int ring_acquire(stk_ecc_ctx* c, int* idx) {
+  std::unique_lock<std::mutex> lk(c->ring_mu);
+  if (c->ring.empty()) {
+    const int n = 2 * c->n_lanes;
+    std::vector<RingBuf> ring(n);
+    for (auto& b : ring) {
+      if (cudaHostAlloc((void**)&b.host, c->frame_bytes, cudaHostAllocDefault) != cudaSuccess ||
+          cudaEventCreateWithFlags(&b.uploaded, cudaEventDisableTiming) != cudaSuccess) {
+        for (auto& q : ring) { if (q.host) cudaFreeHost(q.host); if (q.uploaded) cudaEventDestroy(q.uploaded); }
+        return fail(STK_ERR_NOMEM, "cannot allocate the pinned frame ring (%d x %zu bytes)", n, c->frame_bytes);
+      }
+    }
+    c->ring.swap(ring);
+    for (int i = 0; i < n; ++i) c->ring_free.push_back(i);
+  }
+  c->ring_cv.wait(lk, [&] { return !c->ring_free.empty(); });
+  const int i = c->ring_free.back();
+  c->ring_free.pop_back();
+  lk.unlock();
+  // the upload that last used this buffer must have landed before the caller overwrites it
+  if (cudaEventSynchronize(c->ring[i].uploaded) != cudaSuccess) {
+    { std::lock_guard<std::mutex> g(c->ring_mu); c->ring_free.push_back(i); }
+    c->ring_cv.notify_one();
+    return fail(STK_ERR_CUDA, "cudaEventSynchronize(ring buffer) failed");
+  }
+  *idx = i;
+  return STK_OK;
+}
+
+void ring_release(stk_ecc_ctx* c, int idx) {
+  { std::lock_guard<std::mutex> g(c->ring_mu); c->ring_free.push_back(idx); }
+  c->ring_cv.notify_one();
+}
+
+int ring_index_of(stk_ecc_ctx* c, const uint8_t* buf) {
+  std::lock_guard<std::mutex> g(c->ring_mu);
+  for (size_t i = 0; i < c->ring.size(); ++i) if (c->ring[i].host == buf) return (int)i;
+  return -1;
+}
+
+void copy_rows(uint8_t* dst, const uint8_t* src, size_t pitch, size_t row, int height) {
+  if (pitch == row) { memcpy(dst, src, row * height); return; }
+  for (int y = 0; y < height; ++y) memcpy(dst + (size_t)y * row, src + (size_t)y * pitch, row);
 }
 
 // the ECC part of one frame on its lane: prep -> device loop -> warp+accumulate -> result record
@@ -783,6 +841,7 @@ int stk_ecc_destroy(stk_ecc_ctx* c) {
     if (ln.stream) cudaStreamDestroy(ln.stream);
   }
   for (auto& r : c->results) for (auto& e : r.ev) if (e) cudaEventDestroy(e);
+  for (auto& b : c->ring) { if (b.host) cudaFreeHost(b.host); if (b.uploaded) cudaEventDestroy(b.uploaded); }
   cudaFree(c->img); cudaFree(c->d_ref); cudaFree(c->d_out);
   free_area_plan(c->area);
   for (auto* p : c->state_chunks) cudaFreeHost(p);
@@ -840,6 +899,33 @@ int stk_ecc_set_reference_device(stk_ecc_ctx* c, const uint8_t* d_bgr, size_t pi
   return set_reference_impl(c, d_bgr, pitch);
 }
 
+// a filled ring buffer: asynchronous upload on the next lane, then align (inv == null) or warp-only; the
+// buffer goes back to the ring at once, guarded by its event
+static int submit_ring(stk_ecc_ctx* c, int idx, int64_t tag, const double* inv, const float* border) {
+  int rc = STK_OK;
+  {
+    std::lock_guard<std::mutex> g(c->mu);
+    Lane& ln = pick_lane(c);
+    RingBuf& rb = c->ring[idx];
+    const size_t row = (size_t)c->cfg.width * c->cfg.channels;
+    rc = ensure_host_staging(c, ln, false);
+    cudaError_t e = cudaSuccess;
+    if (rc == STK_OK) e = cudaMemcpyAsync(ln.d_frame, rb.host, c->frame_bytes, cudaMemcpyHostToDevice, ln.stream);
+    if (rc == STK_OK && e == cudaSuccess) e = cudaEventRecord(rb.uploaded, ln.stream);
+    if (rc == STK_OK && e != cudaSuccess) rc = fail(STK_ERR_CUDA, "frame upload: %s", cudaGetErrorString(e));
+    if (rc == STK_OK) {
+      if (inv) {
+        rc = launch_warp(c, ln, ln.d_frame, row, true, inv, border, false);
+        if (rc == STK_OK) { ResultSlot slot; slot.tag = tag; slot.host = nullptr; c->results.push_back(slot); }
+      } else {
+        rc = enqueue_align(c, ln, ln.d_frame, row, tag);
+      }
+    }
+  }
+  ring_release(c, idx);
+  return rc;
+}
+
 static int submit_align(stk_ecc_ctx* c, const uint8_t* buf, size_t pitch, int64_t tag, int kind) {
   int rc = check_ctx(c);
   if (rc) return rc;
@@ -847,13 +933,23 @@ static int submit_align(stk_ecc_ctx* c, const uint8_t* buf, size_t pitch, int64_
   if (!c->cfg.align) return fail(STK_ERR_STATE, "context was created with align = 0");
   const size_t row = (size_t)c->cfg.width * c->cfg.channels;
   if (pitch < row) return fail(STK_ERR_BAD_ARG, "pitch %zu < row bytes %zu", pitch, row);
+  if (kind == 0) {
+    // pageable buffer: one copy into a ring buffer, made without the context lock (decode threads copy in
+    // parallel), then the zero-copy path
+    { std::lock_guard<std::mutex> g(c->mu); if (!c->have_ref) return fail(STK_ERR_STATE, "stk_ecc_set_reference must come first"); }
+    int idx = -1;
+    rc = ring_acquire(c, &idx);
+    if (rc) return rc;
+    copy_rows(c->ring[idx].host, buf, pitch, row, c->cfg.height);
+    return submit_ring(c, idx, tag, nullptr, nullptr);
+  }
   std::lock_guard<std::mutex> g(c->mu);
   if (!c->have_ref) return fail(STK_ERR_STATE, "stk_ecc_set_reference must come first");
   Lane& ln = pick_lane(c);
   if (kind == 2) return enqueue_align(c, ln, buf, pitch, tag);
-  rc = ensure_host_staging(c, ln, kind == 0);
+  rc = ensure_host_staging(c, ln, false);
   if (rc) return rc;
-  rc = upload_frame(c, ln, buf, pitch, kind == 1);
+  rc = upload_frame(c, ln, buf, pitch, true);
   if (rc) return rc;
   return enqueue_align(c, ln, ln.d_frame, row, tag);
 }
@@ -861,6 +957,37 @@ static int submit_align(stk_ecc_ctx* c, const uint8_t* buf, size_t pitch, int64_
 int stk_ecc_submit_frame(stk_ecc_ctx* c, const uint8_t* bgr, size_t pitch, int64_t tag) { return submit_align(c, bgr, pitch, tag, 0); }
 int stk_ecc_submit_frame_pinned(stk_ecc_ctx* c, const uint8_t* bgr, size_t pitch, int64_t tag) { return submit_align(c, bgr, pitch, tag, 1); }
 int stk_ecc_submit_frame_device(stk_ecc_ctx* c, const uint8_t* d_bgr, size_t pitch, int64_t tag) { return submit_align(c, d_bgr, pitch, tag, 2); }
+
+int stk_ecc_acquire_frame_buffer(stk_ecc_ctx* c, uint8_t** buf, size_t* pitch) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  if (!buf) return fail(STK_ERR_BAD_ARG, "null argument");
+  int idx = -1;
+  rc = ring_acquire(c, &idx);
+  if (rc) return rc;
+  *buf = c->ring[idx].host;
+  if (pitch) *pitch = (size_t)c->cfg.width * c->cfg.channels;
+  return STK_OK;
+}
+
+int stk_ecc_release_frame_buffer(stk_ecc_ctx* c, uint8_t* buf) {
+  if (!c || !buf) return fail(STK_ERR_BAD_ARG, "null argument");
+  const int idx = ring_index_of(c, buf);
+  if (idx < 0) return fail(STK_ERR_BAD_ARG, "not a buffer of this context's frame ring");
+  ring_release(c, idx);
+  return STK_OK;
+}
+
+int stk_ecc_submit_acquired(stk_ecc_ctx* c, uint8_t* buf, int64_t tag) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  if (!buf) return fail(STK_ERR_BAD_ARG, "null frame");
+  if (!c->cfg.align) return fail(STK_ERR_STATE, "context was created with align = 0");
+  const int idx = ring_index_of(c, buf);
+  if (idx < 0) return fail(STK_ERR_BAD_ARG, "not a buffer of this context's frame ring");
+  { std::lock_guard<std::mutex> g(c->mu); if (!c->have_ref) { ring_release(c, idx); return fail(STK_ERR_STATE, "stk_ecc_set_reference must come first"); } }
+  return submit_ring(c, idx, tag, nullptr, nullptr);
+}
 
 static int submit_warp(stk_ecc_ctx* c, const uint8_t* buf, size_t pitch, const double* h, int border_mode,
                        const double* border_value, int64_t tag, bool device) {
@@ -874,18 +1001,17 @@ static int submit_warp(stk_ecc_ctx* c, const uint8_t* buf, size_t pitch, const d
   invert_perspective_host(h, inv);
   float border[4] = {0, 0, 0, 0};
   if (border_value) for (int i = 0; i < 4; ++i) border[i] = (float)border_value[i];
+  if (!device) {
+    int idx = -1;
+    rc = ring_acquire(c, &idx);
+    if (rc) return rc;
+    copy_rows(c->ring[idx].host, buf, pitch, row, c->cfg.height);
+    return submit_ring(c, idx, tag, inv, border);
+  }
   std::lock_guard<std::mutex> g(c->mu);
   Lane& ln = pick_lane(c);
   const uint8_t* d_src = buf;
   size_t d_pitch = pitch;
-  if (!device) {
-    rc = ensure_host_staging(c, ln, true);
-    if (rc) return rc;
-    rc = upload_frame(c, ln, buf, pitch, false);
-    if (rc) return rc;
-    d_src = ln.d_frame;
-    d_pitch = row;
-  }
   rc = launch_warp(c, ln, d_src, d_pitch, true, inv, border, false);
   if (rc) return rc;
   { ResultSlot slot; slot.tag = tag; slot.host = nullptr; c->results.push_back(slot); }

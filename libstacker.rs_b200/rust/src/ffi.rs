@@ -61,6 +61,9 @@ unsafe extern "C" {
     pub fn stk_ecc_set_reference(ctx: *mut stk_ecc_ctx, bgr: *const u8, pitch: usize) -> c_int;
     pub fn stk_ecc_submit_frame(ctx: *mut stk_ecc_ctx, bgr: *const u8, pitch: usize, tag: i64) -> c_int;
     pub fn stk_ecc_submit_frame_pinned(ctx: *mut stk_ecc_ctx, bgr: *const u8, pitch: usize, tag: i64) -> c_int;
+    pub fn stk_ecc_acquire_frame_buffer(ctx: *mut stk_ecc_ctx, buf: *mut *mut u8, pitch: *mut usize) -> c_int;
+    pub fn stk_ecc_submit_acquired(ctx: *mut stk_ecc_ctx, buf: *mut u8, tag: i64) -> c_int;
+    pub fn stk_ecc_release_frame_buffer(ctx: *mut stk_ecc_ctx, buf: *mut u8) -> c_int;
     pub fn stk_ecc_submit_warp(
         ctx: *mut stk_ecc_ctx, bgr: *const u8, pitch: usize, h: *const f64, border_mode: c_int,
         border_value: *const f64, tag: i64,

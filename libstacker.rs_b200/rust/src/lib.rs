@@ -131,14 +131,23 @@ where
     };
     let ctx = new_ctx(&first, Some((params, criteria)), ecc_size)?;
     check(unsafe { ffi::stk_ecc_set_reference(ctx.0, first.data(), first.mat_step().get(0)) })?;
-    // decode on the Rayon pool, one task per frame (reference: src/lib.rs:746-749); submission is thread-safe,
-    // asynchronous, and copies the frame into pinned staging before returning
+    // decode on the Rayon pool, one task per frame (reference: src/lib.rs:746-749); submission is thread-safe
+    // and asynchronous
     (1..files.len()).into_par_iter().with_min_len(1).try_for_each(|i| -> Result<(), StackerError> {
         let img = utils::read_frame(&files[i])?;
         if img.size()? != first.size()? || img.channels() != first.channels() {
             return Err(StackerError::InvalidParams(format!("{:?}: size differs from the first frame", files[i])));
         }
-        check(unsafe { ffi::stk_ecc_submit_frame(ctx.0, img.data(), img.mat_step().get(0), i as i64) })
+        // host feed: copy the decoded rows into a pinned ring buffer of the context (no library lock is held
+        // while this task copies) and hand it over; the upload is asynchronous and the buffer is recycled by
+        // the library.  (`imgcodecs::imdecode_to` on a Mat wrapped around `buf` would save this copy too.)
+        let (mut buf, mut pitch) = (std::ptr::null_mut::<u8>(), 0usize);
+        check(unsafe { ffi::stk_ecc_acquire_frame_buffer(ctx.0, &mut buf, &mut pitch) })?;
+        let step = img.mat_step().get(0);
+        for y in 0..img.rows() as usize {
+            unsafe { std::ptr::copy_nonoverlapping(img.data().add(y * step), buf.add(y * pitch), pitch) };
+        }
+        check(unsafe { ffi::stk_ecc_submit_acquired(ctx.0, buf, i as i64) })
     })?;
     finish(&ctx, &first, files.len())
 }

@@ -1,6 +1,7 @@
 #!/bin/bash
 # quick GPU iteration loop: stage times (prep / ecc / warp per frame) and frames/s on 16 frames of the 4K stack
-python bench.py --frames 16 --steps 3 --warmup 2 --skip-cpu --skip-e2e 2>/dev/null | python -c "
+# usage: scripts/quick_bench.sh [extra bench.py args, e.g. --motion 2]
+python bench.py --frames 16 --steps 3 --warmup 2 --skip-cpu --skip-e2e "$@" 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read())
 print('frames/s %.0f  K2 us/launch %.1f  prep %.1f us  warp %.1f us  ecc loop %.1f us/frame (%.2f it)  err %.3f px' % (

@@ -467,3 +467,47 @@ def test_keypoint_match_vs_cv2(pkg, have_cv2, scale_down):
     if scale_down is not None:
         with pytest.raises(pkg.InvalidParams):
             pkg.keypoint_match(frames, params, float(w), device=0)
+
+
+# ---- N2: host feed through the pinned frame ring ------------------------------------------------------------
+def test_frame_ring_threads_and_files(pkg, tmp_path):
+    """Decode threads fill ring buffers concurrently (more tasks than buffers, so acquire must block and
+    recycle), files go through ecc_match's windowed feed: same warps, same stack as in-memory submission."""
+    import threading
+    import cv2
+    w, h, n = 320, 240, 12
+    frames = synth.Stack(w, h, n, 2, seed=93).frames()
+    params = pkg.EccMatchParameters(pkg.MotionType.Affine, 200, 1e-5, 5)
+    want, res_want = pkg.ecc_match(frames, params, None, device=0, return_details=True)
+    with pkg.EccStack(w, h, 3, params, device=0, lanes=2) as st:         # ring of 4 buffers, 11 frames, 6 threads
+        st.set_reference(frames[0])
+        errs = []
+
+        def worker(ids):
+            try:
+                for i in ids:
+                    buf = st.acquire_buffer()
+                    np.copyto(buf, frames[i])
+                    st.submit_acquired(buf, tag=i)
+            except Exception as e:          # pragma: no cover
+                errs.append(e)
+        ths = [threading.Thread(target=worker, args=(list(range(1 + t, n, 6)),)) for t in range(6)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        assert not errs
+        b = st.acquire_buffer()             # an unused buffer can be handed back
+        st.release_buffer(b)
+        got = st.finish(n)
+        res = sorted(st.results(), key=lambda r: r["tag"])
+    for a, b in zip(res, sorted(res_want, key=lambda r: r["tag"])):
+        assert np.array_equal(a["warp"], b["warp"])
+    assert np.abs(got - want).max() <= 1e-6                      # f32 summation order only
+    paths = []
+    for i, f in enumerate(frames):
+        p = str(tmp_path / f"f{i:02d}.png")
+        cv2.imwrite(p, f)
+        paths.append(p)
+    from_files = pkg.ecc_match(paths, params, None, device=0, workers=5)
+    assert np.array_equal(from_files, want)                      # same order of submission -> bit-identical
