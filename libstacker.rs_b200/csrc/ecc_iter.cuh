@@ -1060,7 +1060,7 @@ __global__ void __launch_bounds__(kEccThreads, 512 / kEccThreads) ecc_iter_kerne
       const unsigned wmask = __ballot_sync(0xffffffffu, col_ok && ya < yb);
       if (col_ok && ya < yb) {
         const float* trow = tbox + (ya - cy0) * kEccStripW + col;
-        if (fast_coords && boxed && s_box[c][2] != 0 && yb - ya == kChunkRowsPerThread) {
+        if (boxed && s_box[c][2] != 0 && yb - ya == kChunkRowsPerThread) {
           // lean path (interior chunk, full height): straight-line code for the thread's 8 rows — no border
           // rule, no mask, no vote, no branch — so the rows interleave freely in the schedule
           const float* bp0 = box + (ya - ylo) * kBoxW + (x - xlo);
@@ -1085,6 +1085,27 @@ __global__ void __launch_bounds__(kEccThreads, 512 / kEccThreads) ecc_iter_kerne
               const float2 uv = add2(f2(xf, yf), d);                          // sample position (u, v)
               const float g2 = fmaf(uv.x, g01.x, uv.y * g01.y);               // -2t  (t = hatX a + hatY b, hat = -(u, v))
               acc.add_packed(g01, g2, w_, t_, yf);
+            }
+          } else {
+            // the other instantiations (2x3 models with OpenCV's exact 10-bit fixed point, homography with exact
+            // f64 coordinates): same straight-line shape, exact coordinates, scalar sums
+            Coord<Md::persp> co;
+            Jac<MOTION> jac;
+            co.init(s_m, x);
+            jac.init(s_m, xf);
+#pragma unroll
+            for (int r = 0; r < kChunkRowsPerThread; ++r) {
+              const float yf = yf0 + (float)r;
+              const float t_ = trow[r * kEccStripW];
+              int xq, yq;
+              co.at(ya + r, xq, yq);
+              const float* bp = box + ((yq >> kInterBits) - ylo) * kBoxW + ((xq >> kInterBits) - xlo);
+              const float ax = (float)(xq & (kInterTab - 1)) * (1.f / kInterTab);
+              const float ay = (float)(yq & (kInterTab - 1)) * (1.f / kInterTab);
+              const Sample smp = sample_box(bp, ax, ay);
+              float g[G];
+              jac.eval(smp, yf, g);
+              acc.template add<true>(g, smp.w, t_, 1.f, yf);
             }
           }
           n_safe += kChunkRowsPerThread;
