@@ -1342,6 +1342,15 @@ int stk_tenengrad_batch_device(const uint8_t* d_imgs, size_t frame_stride, size_
   if (channels != 1 && channels != 3 && channels != 4) return fail(STK_ERR_UNSUPPORTED, "channels must be 1, 3 or 4");
   if (pitch < (size_t)width * channels) return fail(STK_ERR_BAD_ARG, "pitch too small");
   if (device >= 0) CU(cudaSetDevice(device));
+  if (ksize == 3 && channels == 1 && width % 4 == 0 && width >= 8 && height >= 2 && pitch % 4 == 0 && frame_stride % 4 == 0 &&
+      ((uintptr_t)d_imgs) % 4 == 0) {
+    // k = 3 on grey planes: the streaming kernel (same exact integer sum, ~4x faster than the tiled one)
+    std::vector<double> all((size_t)n * 4);
+    rc = stk_sharpness_all_batch_device(d_imgs, frame_stride, pitch, width, height, channels, n, -1, all.data());
+    if (rc) return rc;
+    for (int i = 0; i < n; ++i) out[i] = all[(size_t)i * 4 + 2];
+    return STK_OK;
+  }
   unsigned long long* d_sums = nullptr;
   const size_t sum_bytes = sizeof(unsigned long long) * stk::kSumSlots * (size_t)n;
   int cur_dev = 0;
@@ -1441,8 +1450,16 @@ int stk_sharpness_all_batch_device(const uint8_t* d_imgs, size_t frame_stride, s
     p.frame_stride = frame_stride; p.pitch = pitch;
     p.width = width; p.height = height; p.channels = channels;
     p.sums = d_sums + (size_t)z0 * stk::kSharpSums * stk::kSumSlots;
-    dim3 grid((width + stk::kTenTW - 1) / stk::kTenTW, (height + stk::kTenTH - 1) / stk::kTenTH, std::min(32768, n - z0));
-    stk::sharpness_all_kernel<<<grid, stk::kTenThreads>>>(p);
+    const bool stream_ok = channels == 1 && width % 4 == 0 && width >= 8 && height >= 2 && pitch % 4 == 0 &&
+                           frame_stride % 4 == 0 && ((uintptr_t)d_imgs) % 4 == 0;
+    if (stream_ok) {
+      const int cols_per_block = stk::kStreamThreads * stk::kStreamCols;
+      dim3 grid((width + cols_per_block - 1) / cols_per_block, (height + stk::kStreamBand - 1) / stk::kStreamBand, std::min(32768, n - z0));
+      stk::sharpness_stream_kernel<<<grid, stk::kStreamThreads>>>(p);
+    } else {
+      dim3 grid((width + stk::kTenTW - 1) / stk::kTenTW, (height + stk::kTenTH - 1) / stk::kTenTH, std::min(32768, n - z0));
+      stk::sharpness_all_kernel<<<grid, stk::kTenThreads>>>(p);
+    }
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaMemcpy(h.data(), d_sums, bytes, cudaMemcpyDeviceToHost);
