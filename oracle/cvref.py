@@ -12,6 +12,10 @@ arguments the Rust code makes, on frames shared in memory (decode stays outside)
   ecc_match           /root/reference/src/lib.rs:719-847   (ecc_match_no_scaling)
   keypoint_match      /root/reference/src/lib.rs:146-353   (keypoint_match_no_scale)
   sharpness_tenengrad /root/reference/src/lib.rs:1101-1147
+  ecc_match_scaling_down  /root/reference/src/lib.rs:849-1028, scale_image /root/reference/src/utils.rs:186-214
+  keypoint_match(scale_down=...)  /root/reference/src/lib.rs:355-600 (adjust_homography_for_scale_f64, utils.rs:218-248)
+  sharpness_modified_laplacian / _variance_of_laplacian / _normalized_gray_level_variance
+                      /root/reference/src/lib.rs:1032-1090, :1151-1166
 """
 from __future__ import annotations
 
