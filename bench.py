@@ -226,6 +226,18 @@ def run_b200(a, rank, local_rank, world):
 
     trace = os.environ.get("STK_BENCH_TRACE") == "1"
 
+    # the exchange step: the library's fused reduce-scatter + divide over NVLink peer memory (default), or the
+    # NCCL reduce + scale kernel it replaces (STK_REDUCE=nccl, and the fallback when peers cannot be mapped)
+    use_peers = False
+    if world > 1 and os.environ.get("STK_REDUCE", "peer") != "nccl":
+        use_peers = D.connect_peers(st)
+        if not use_peers and rank == 0:
+            print(f"peer exchange unavailable, using NCCL: {D.connect_peers.last_failure}", file=sys.stderr)
+    peer_out = {}
+
+    def peer_result():
+        return torch.as_tensor(D.DevicePtrArray(peer_out["ptr"], h * w * 3), device=dev).view(h, w, 3)
+
     def step_resident():
         t = [time.perf_counter()]
         st.reset()
@@ -234,6 +246,14 @@ def run_b200(a, rank, local_rank, world):
         for i in mine:
             st.submit(dev_frames[i], tag=i)
         t.append(time.perf_counter())
+        if use_peers:
+            peer_out["ptr"] = st.peer_reduce(n)       # asynchronous; the next step's reset() joins the lanes
+            if trace:
+                torch.cuda.synchronize()
+                t.append(time.perf_counter())
+                print(f"TRACE rank{rank} " + " ".join(f"{k}={1e3 * (b - a):.3f}ms" for k, a, b in
+                                                      zip(["reset+set_reference", "submit", "peer exchange"], t, t[1:])), file=sys.stderr)
+            return
         ptr, nfl = st.partial()
         t.append(time.perf_counter())
         if world > 1:
@@ -253,6 +273,12 @@ def run_b200(a, rank, local_rank, world):
         st.set_reference(pinned_np[0])
         for i in mine:
             st.submit(pinned_np[i], tag=i, pinned=True)
+        if use_peers:
+            peer_out["ptr"] = st.peer_reduce(n)
+            st.sync()
+            if rank == 0:
+                out_host.copy_(peer_result(), non_blocking=False)
+            return
         ptr, nfl = st.partial()
         if world > 1:
             part = torch.as_tensor(D.DevicePtrArray(ptr, nfl), device=dev)
@@ -262,7 +288,7 @@ def run_b200(a, rank, local_rank, world):
             st.finish_device(ptr, n, out_dev.data_ptr())
             out_host.copy_(out_dev, non_blocking=False)
 
-    if world > 1:
+    if world > 1 and not use_peers:
         # NCCL sets up channels lazily over its first collectives on a buffer (measured: one 13 ms reduce among
         # the first five); do that outside the timed region, on the very buffer the steps reduce
         step_resident()
@@ -276,8 +302,10 @@ def run_b200(a, rank, local_rank, world):
     def timed(fn, steps, warmup, sample_clocks):
         for _ in range(warmup):
             fn()
-        barrier()
+        # NVML set-up takes milliseconds: do it BEFORE the barrier, or rank 0 enters the timed region late and
+        # every other rank's first exchange waits for it (measured: +1 ms per step on the max-over-ranks time)
         sampler = ClockSampler(local_rank) if (sample_clocks and rank == 0) else None
+        barrier()
         if sampler:
             sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -292,6 +320,11 @@ def run_b200(a, rank, local_rank, world):
         e1.record()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
+        if use_peers:
+            # the peer path never synchronises inside a step, so the device-launched iteration kernels of a step
+            # are only accounted once its results are in: every step does the same work
+            st.sync()
+            launches = steps * st.launch_count()
         clocks = sampler.stop() if sampler else None
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -321,6 +354,11 @@ def run_b200(a, rank, local_rank, world):
             dist.all_reduce(tot)
             e2e["h2d_bytes_per_step"] = int(tot.item())
 
+    stack_mean = float((peer_result() if use_peers else out_dev).mean().item()) if rank == 0 else None
+    if use_peers:
+        barrier()                 # nobody unmaps while a peer may still be inside an exchange
+        st.peer_disconnect()
+        barrier()
     # ---- roofline of the dominant kernel (ecc_iter_kernel), measured alone: 1 lane, CUDA events per stage ----
     st.close()
     roof = stages = None
@@ -394,14 +432,15 @@ def run_b200(a, rank, local_rank, world):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(a), "lanes": a.lanes,
                        "l2": "inputs larger than L2: every step reads all frames (%.2f GB u8) from HBM" % (n * n_px * 3 / 1e9),
-                       "parallelism": f"frames sharded over {world} GPU(s), one NCCL reduce" if world > 1 else "1 GPU",
+                       "parallelism": (f"frames sharded over {world} GPU(s), " + ("one fused reduce-scatter+divide kernel per rank over NVLink peer memory"
+                                                                                   if use_peers else "one NCCL reduce")) if world > 1 else "1 GPU",
                        "ecc_iterations_per_step": total_iters, "wall_ms_per_step": wall_ms / a.steps},
             "whole_step": {"algorithmic_GBps_per_gpu": alg_bytes / (ms / a.steps * 1e-3) / 1e9 / world,
                            "frac_of_hbm_peak": alg_bytes / (ms / a.steps * 1e-3) / 1e9 / world / peak},
             "roofline": roof, "stages": stages, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": launches, "clocks": clocks,
             "check": {"max_corner_error_vs_ground_truth_px": truth_err, "ecc_status_codes": statuses,
-                      "stack_mean": float(out_dev.mean().item())},
+                      "stack_mean": stack_mean},
         }
         print(json.dumps(line))
     if world > 1:

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define STK_ABI_VERSION 2
+#define STK_ABI_VERSION 3
 
 /* ---- status codes ------------------------------------------------------------------------- */
 enum {
@@ -161,6 +161,29 @@ int stk_ecc_partial(stk_ecc_ctx* ctx, float** d_partial, size_t* n_floats);
 int stk_ecc_finish_from(stk_ecc_ctx* ctx, const float* d_sum, int divisor, float* out, size_t out_pitch);
 /* same, result left on the device (d_out: height*width*channels floats) */
 int stk_ecc_finish_device(stk_ecc_ctx* ctx, const float* d_sum, int divisor, float* d_out);
+
+/* ---- multi-GPU: the ONE exchange step, fused with the divide, over NVLink peer memory -----------------------
+   Replaces Rayon's try_reduce of the partial sums + MatExpr `/ n` (src/lib.rs:819-839, :319-346) when the
+   frames of a stack were sharded over several devices (one context per device, rank 0 = the context created with
+   seed_reference = 1).  Reduce-scatter style: rank r sums slice r of EVERY rank's partial stack with peer loads
+   over NVLink/NVSwitch (rank order, deterministic), scales by 1/divisor and stores the finished pixels straight
+   into rank 0's output buffer; no library collective, no separate scale pass (csrc/peer_reduce.cuh).
+
+   One process per GPU:  every rank calls stk_ecc_peer_export, the caller's plumbing all-gathers the handles
+   (plain bytes: torch.distributed / MPI / a pipe), every rank calls stk_ecc_peer_connect with all of them.
+   One process, several GPUs (the Rust crate): stk_ecc_peer_connect_local with the contexts in rank order.
+   Then, per stack, EVERY rank calls stk_ecc_peer_reduce after submitting its frames (collective: same number of
+   calls on every rank).  It is asynchronous and needs no host synchronisation: the lanes are joined on the device,
+   summed, exchanged.  On rank 0 *d_out receives the device pointer of the finished stack (height*width*channels
+   floats, library-owned, valid after stk_ecc_sync until the next peer_reduce); elsewhere NULL.  stk_ecc_sync
+   afterwards returns per-frame ECC errors, and STK_ERR_CUDA if a rank did not show up within
+   STK_PEER_TIMEOUT_MS (default 10000) — the kernels never spin forever. */
+typedef struct stk_peer_handle { unsigned char bytes[256]; } stk_peer_handle;
+int stk_ecc_peer_export(stk_ecc_ctx* ctx, stk_peer_handle* out);
+int stk_ecc_peer_connect(stk_ecc_ctx* ctx, int rank, int world, const stk_peer_handle* handles /* [world] */);
+int stk_ecc_peer_connect_local(stk_ecc_ctx* const* ctxs /* [world], rank order */, int world);
+int stk_ecc_peer_reduce(stk_ecc_ctx* ctx, int divisor, const float** d_out);
+int stk_ecc_peer_disconnect(stk_ecc_ctx* ctx);
 
 /* start a new stack on the same context (same geometry/parameters): clears accumulators/results */
 int stk_ecc_reset(stk_ecc_ctx* ctx);

@@ -14,7 +14,7 @@ STK_OK, STK_ERR_BAD_ARG, STK_ERR_CUDA, STK_ERR_NOT_ENOUGH, STK_ERR_ECC_NOCONV, S
     STK_ERR_CRITERIA, STK_ERR_STATE, STK_ERR_UNSUPPORTED, STK_ERR_NOMEM = range(10)
 STK_TERM_COUNT, STK_TERM_EPS = 1, 2
 STK_BORDER_CONSTANT = 0
-STK_ABI_VERSION = 2
+STK_ABI_VERSION = 3
 
 
 class EccConfig(C.Structure):
@@ -32,6 +32,12 @@ class FrameResult(C.Structure):
         ("tag", C.c_int64), ("warp", C.c_float * 9), ("rho", C.c_double),
         ("iterations", C.c_int32), ("status", C.c_int32),
     ]
+
+
+class PeerHandle(C.Structure):
+    """stk_peer_handle: opaque bytes a rank publishes so that the other ranks can map its partial stack,
+    its flag block and (rank 0) its output buffer."""
+    _fields_ = [("bytes", C.c_ubyte * 256)]
 
 
 # every symbol include/stacker_cuda.h declares: name -> (restype, argtypes)
@@ -61,6 +67,11 @@ SYMBOLS = {
     "stk_ecc_partial": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_size_t)]),
     "stk_ecc_finish_from": (C.c_int, [_P, _P, C.c_int, _P, C.c_size_t]),
     "stk_ecc_finish_device": (C.c_int, [_P, _P, C.c_int, _P]),
+    "stk_ecc_peer_export": (C.c_int, [_P, C.POINTER(PeerHandle)]),
+    "stk_ecc_peer_connect": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(PeerHandle)]),
+    "stk_ecc_peer_connect_local": (C.c_int, [C.POINTER(_P), C.c_int]),
+    "stk_ecc_peer_reduce": (C.c_int, [_P, C.c_int, C.POINTER(_P)]),
+    "stk_ecc_peer_disconnect": (C.c_int, [_P]),
     "stk_ecc_reset": (C.c_int, [_P]),
     "stk_ecc_launch_count": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "stk_ecc_set_profiling": (C.c_int, [_P, C.c_int]),

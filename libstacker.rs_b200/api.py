@@ -276,6 +276,40 @@ class EccStack:
     def finish_device(self, d_sum_ptr: Optional[int], divisor: int, d_out_ptr: int):
         _check(lib.stk_ecc_finish_device(self._ctx, d_sum_ptr, int(divisor), d_out_ptr))
 
+    # -- multi-GPU exchange over peer memory (stk_ecc_peer_*; csrc/peer_reduce.cuh)
+    def peer_export(self) -> bytes:
+        """This rank's stk_peer_handle as bytes: all-gather them and give the list to peer_connect."""
+        h = _ffi.PeerHandle()
+        _check(lib.stk_ecc_peer_export(self._ctx, C.byref(h)))
+        return bytes(h.bytes)
+
+    def peer_connect(self, rank: int, world: int, handles):
+        """`handles[r]` = rank r's peer_export() bytes (one process per GPU; CUDA IPC mappings)."""
+        if len(handles) != world:
+            raise InvalidParams(f"{len(handles)} peer handles for world size {world}")
+        arr = (_ffi.PeerHandle * world)()
+        for r, b in enumerate(handles):
+            if len(b) != C.sizeof(_ffi.PeerHandle):
+                raise InvalidParams(f"peer handle {r} has {len(b)} bytes")
+            C.memmove(C.byref(arr[r]), bytes(b), len(b))
+        _check(lib.stk_ecc_peer_connect(self._ctx, int(rank), int(world), arr))
+
+    @staticmethod
+    def peer_connect_local(stacks):
+        """All ranks' contexts live in THIS process (one per device, rank order): peer access, no IPC."""
+        arr = (C.c_void_p * len(stacks))(*[s._ctx.value for s in stacks])
+        _check(lib.stk_ecc_peer_connect_local(arr, len(stacks)))
+
+    def peer_reduce(self, divisor: int) -> Optional[int]:
+        """The exchange step + divide (collective, asynchronous).  Rank 0: device pointer of the finished
+        stack (valid after sync()); other ranks: None."""
+        out = C.c_void_p()
+        _check(lib.stk_ecc_peer_reduce(self._ctx, int(divisor), C.byref(out)))
+        return out.value
+
+    def peer_disconnect(self):
+        _check(lib.stk_ecc_peer_disconnect(self._ctx))
+
     def set_profiling(self, enabled: bool):
         _check(lib.stk_ecc_set_profiling(self._ctx, 1 if enabled else 0))
 

@@ -26,6 +26,7 @@
 #include "resize_area.cuh"
 #include "tenengrad.cuh"
 #include "warp_acc.cuh"
+#include "peer_reduce.cuh"
 
 namespace {
 
@@ -204,6 +205,7 @@ struct Lane {
   uint8_t* small = nullptr;         // downscaled grey (ecc_match_scaling_down), ew x eh, small_pitch bytes per row
   uint8_t* h_stage = nullptr;       // pinned staging for pageable host buffers
   cudaEvent_t stage_free = nullptr; // H2D out of h_stage finished
+  cudaEvent_t drained = nullptr;    // lane's queued work finished (peer exchange joins the lanes on the device)
   stk::EccState* st = nullptr;
   double* partials = nullptr;
   float* acc = nullptr;
@@ -221,6 +223,19 @@ struct Lane {
 struct RingBuf {
   uint8_t* host = nullptr;
   cudaEvent_t uploaded = nullptr;
+};
+
+// Multi-GPU exchange (csrc/peer_reduce.cuh): this context's view of every rank's partial stack / flag block and of
+// the root's output buffer, mapped through CUDA IPC (one process per GPU) or peer access (one process).
+struct PeerLink {
+  bool connected = false;
+  int rank = 0, world = 0;
+  uint32_t step = 0;
+  uint32_t* flags = nullptr;                  // local flag block (cudaMalloc, exported)
+  const float* partial[stk::kMaxPeers] = {};
+  uint32_t* pflags[stk::kMaxPeers] = {};
+  float* root_out = nullptr;
+  std::vector<void*> opened;                  // IPC mappings to close on disconnect
 };
 
 struct ResultSlot {
@@ -274,6 +289,7 @@ struct stk_ecc_ctx {
   std::atomic<int64_t> launches{0};
   int64_t iter_launches_counted = 0;
   bool profiling = false;
+  PeerLink peer;
   static constexpr size_t kChunk = 256;
 };
 
@@ -594,6 +610,14 @@ int sync_all(stk_ecc_ctx* c) {
   }
   c->launches += iters - c->iter_launches_counted;
   c->iter_launches_counted = iters;
+  if (c->peer.connected) {
+    uint32_t perr = 0;
+    CU(cudaMemcpy(&perr, c->peer.flags + stk::kPeerError, sizeof perr, cudaMemcpyDeviceToHost));
+    if (perr) {
+      cudaMemset(c->peer.flags + stk::kPeerError, 0, sizeof perr);
+      return fail(STK_ERR_CUDA, "peer exchange step %u timed out waiting for another rank", perr);
+    }
+  }
   if (first_err == STK_ERR_ECC_NOCONV)
     return fail(first_err, "findTransformECC: the algorithm stopped before its convergence (lambda denominator <= 0)");
   if (first_err == STK_ERR_ECC_NAN) return fail(first_err, "findTransformECC: NaN encountered");
@@ -838,10 +862,13 @@ int stk_ecc_destroy(stk_ecc_ctx* c) {
     cudaFree(ln.tmpl); cudaFree(ln.d_frame); cudaFree(ln.small); cudaFree(ln.st); cudaFree(ln.partials); cudaFree(ln.acc);
     if (ln.h_stage) cudaFreeHost(ln.h_stage);
     if (ln.stage_free) cudaEventDestroy(ln.stage_free);
+    if (ln.drained) cudaEventDestroy(ln.drained);
     if (ln.stream) cudaStreamDestroy(ln.stream);
   }
   for (auto& r : c->results) for (auto& e : r.ev) if (e) cudaEventDestroy(e);
   for (auto& b : c->ring) { if (b.host) cudaFreeHost(b.host); if (b.uploaded) cudaEventDestroy(b.uploaded); }
+  for (void* m : c->peer.opened) cudaIpcCloseMemHandle(m);
+  cudaFree(c->peer.flags);
   cudaFree(c->img); cudaFree(c->d_ref); cudaFree(c->d_out);
   free_area_plan(c->area);
   for (auto* p : c->state_chunks) cudaFreeHost(p);
@@ -1136,6 +1163,205 @@ int stk_ecc_finish(stk_ecc_ctx* c, int divisor, float* out, size_t out_pitch) {
     CU(cudaStreamSynchronize(c->lanes[0].stream));
   }
   CU(cudaMemcpy2D(out, out_pitch, c->d_out, row, row, c->cfg.height, cudaMemcpyDeviceToHost));
+  return STK_OK;
+}
+
+
+/* ---- multi-GPU exchange over peer memory (csrc/peer_reduce.cuh) ------------------------------------------- */
+}  // extern "C"
+namespace {
+
+int peer_prepare(stk_ecc_ctx* c) {
+  if (!c->peer.flags) {
+    CU(cudaMalloc((void**)&c->peer.flags, stk::kPeerFlagWords * sizeof(uint32_t)));
+    CU(cudaMemset(c->peer.flags, 0, stk::kPeerFlagWords * sizeof(uint32_t)));
+  }
+  if (!c->d_out) CU(cudaMalloc((void**)&c->d_out, c->acc_floats * sizeof(float)));
+  return STK_OK;
+}
+
+void peer_clear(stk_ecc_ctx* c) {
+  for (void* m : c->peer.opened) cudaIpcCloseMemHandle(m);
+  c->peer.opened.clear();
+  c->peer.connected = false;
+  c->peer.world = 0;
+}
+
+struct PeerHandleWire {          // what stk_peer_handle carries
+  cudaIpcMemHandle_t partial, out, flags;
+  uint64_t n_floats;
+  int32_t device;
+  int32_t abi;
+};
+static_assert(sizeof(PeerHandleWire) <= sizeof(stk_peer_handle), "stk_peer_handle too small");
+
+template <int W>
+void launch_peer_reduce(const stk::PeerReduceParams& p, int blocks, cudaStream_t s) {
+  stk::peer_reduce_scale_kernel<W><<<blocks, 256, 0, s>>>(p);
+}
+
+}  // namespace
+extern "C" {
+
+int stk_ecc_peer_export(stk_ecc_ctx* c, stk_peer_handle* out) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  if (!out) return fail(STK_ERR_BAD_ARG, "null handle");
+  std::lock_guard<std::mutex> g(c->mu);
+  if ((rc = peer_prepare(c))) return rc;
+  PeerHandleWire w;
+  memset(&w, 0, sizeof w);
+  CU(cudaIpcGetMemHandle(&w.partial, c->lanes[0].acc));
+  CU(cudaIpcGetMemHandle(&w.out, c->d_out));
+  CU(cudaIpcGetMemHandle(&w.flags, c->peer.flags));
+  w.n_floats = c->acc_floats;
+  w.device = c->device;
+  w.abi = STK_ABI_VERSION;
+  memset(out, 0, sizeof *out);
+  memcpy(out, &w, sizeof w);
+  return STK_OK;
+}
+
+int stk_ecc_peer_connect(stk_ecc_ctx* c, int rank, int world, const stk_peer_handle* handles) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  if (!handles) return fail(STK_ERR_BAD_ARG, "null handles");
+  if (world < 1 || world > stk::kMaxPeers || rank < 0 || rank >= world)
+    return fail(STK_ERR_BAD_ARG, "rank %d / world %d out of range (at most %d ranks)", rank, world, stk::kMaxPeers);
+  std::lock_guard<std::mutex> g(c->mu);
+  if ((rc = peer_prepare(c))) return rc;
+  peer_clear(c);
+  PeerLink& pl = c->peer;
+  for (int r = 0; r < world; ++r) {
+    PeerHandleWire w;
+    memcpy(&w, &handles[r], sizeof w);
+    if (w.abi != STK_ABI_VERSION || w.n_floats != c->acc_floats) {
+      peer_clear(c);
+      return fail(STK_ERR_BAD_ARG, "peer %d exported a different stack geometry or ABI", r);
+    }
+    if (r == rank) {
+      pl.partial[r] = c->lanes[0].acc;
+      pl.pflags[r] = pl.flags;
+      if (r == 0) pl.root_out = c->d_out;
+      continue;
+    }
+    void *mp = nullptr, *mf = nullptr, *mo = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&mp, w.partial, cudaIpcMemLazyEnablePeerAccess);
+    if (e == cudaSuccess) { pl.opened.push_back(mp); e = cudaIpcOpenMemHandle(&mf, w.flags, cudaIpcMemLazyEnablePeerAccess); }
+    if (e == cudaSuccess) { pl.opened.push_back(mf); if (r == 0) { e = cudaIpcOpenMemHandle(&mo, w.out, cudaIpcMemLazyEnablePeerAccess); if (e == cudaSuccess) pl.opened.push_back(mo); } }
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      peer_clear(c);
+      return fail(STK_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d, device %d) failed: %s", r, w.device, cudaGetErrorString(e));
+    }
+    pl.partial[r] = (const float*)mp;
+    pl.pflags[r] = (uint32_t*)mf;
+    if (r == 0) pl.root_out = (float*)mo;
+  }
+  pl.rank = rank;
+  pl.world = world;
+  pl.connected = true;
+  return STK_OK;
+}
+
+int stk_ecc_peer_connect_local(stk_ecc_ctx* const* ctxs, int world) {
+  if (!ctxs) return fail(STK_ERR_BAD_ARG, "null contexts");
+  if (world < 1 || world > stk::kMaxPeers) return fail(STK_ERR_BAD_ARG, "world %d out of range (at most %d ranks)", world, stk::kMaxPeers);
+  for (int r = 0; r < world; ++r) {
+    if (!ctxs[r]) return fail(STK_ERR_BAD_ARG, "null context %d", r);
+    if (ctxs[r]->acc_floats != ctxs[0]->acc_floats) return fail(STK_ERR_BAD_ARG, "context %d has a different stack geometry", r);
+    for (int q = 0; q < r; ++q)
+      if (ctxs[q]->device == ctxs[r]->device) return fail(STK_ERR_BAD_ARG, "contexts %d and %d share device %d", q, r, ctxs[r]->device);
+  }
+  for (int r = 0; r < world; ++r) {
+    stk_ecc_ctx* c = ctxs[r];
+    CU(cudaSetDevice(c->device));
+    std::lock_guard<std::mutex> g(c->mu);
+    int rc = peer_prepare(c);
+    if (rc) return rc;
+    peer_clear(c);
+    for (int q = 0; q < world; ++q) {
+      if (q == r) continue;
+      int can = 0;
+      CU(cudaDeviceCanAccessPeer(&can, c->device, ctxs[q]->device));
+      if (!can) return fail(STK_ERR_UNSUPPORTED, "device %d cannot access device %d's memory", c->device, ctxs[q]->device);
+      cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[q]->device, 0);
+      if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+      else if (e != cudaSuccess) return fail(STK_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", c->device, ctxs[q]->device, cudaGetErrorString(e));
+    }
+  }
+  for (int r = 0; r < world; ++r) {
+    PeerLink& pl = ctxs[r]->peer;
+    for (int q = 0; q < world; ++q) { pl.partial[q] = ctxs[q]->lanes[0].acc; pl.pflags[q] = ctxs[q]->peer.flags; }
+    pl.root_out = ctxs[0]->d_out;
+    pl.rank = r;
+    pl.world = world;
+    pl.connected = true;
+  }
+  return STK_OK;
+}
+
+int stk_ecc_peer_disconnect(stk_ecc_ctx* c) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> g(c->mu);
+  for (auto& ln : c->lanes) CU(cudaStreamSynchronize(ln.stream));
+  peer_clear(c);
+  return STK_OK;
+}
+
+int stk_ecc_peer_reduce(stk_ecc_ctx* c, int divisor, const float** d_out) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  if (divisor <= 0) return fail(STK_ERR_BAD_ARG, "divisor must be positive (got %d)", divisor);
+  std::lock_guard<std::mutex> g(c->mu);
+  PeerLink& pl = c->peer;
+  if (!pl.connected) return fail(STK_ERR_STATE, "stk_ecc_peer_reduce before stk_ecc_peer_connect");
+  Lane& l0 = c->lanes[0];
+  // join the lanes on the device (no host synchronisation), then sum them into lane 0's accumulator
+  const float* ordered[16];
+  int m = 0;
+  if (l0.acc_used) ordered[m++] = l0.acc;
+  for (auto& ln : c->lanes) {
+    if (&ln == &l0) continue;
+    if (!ln.drained) CU(cudaEventCreateWithFlags(&ln.drained, cudaEventDisableTiming));
+    CU(cudaEventRecord(ln.drained, ln.stream));
+    CU(cudaStreamWaitEvent(l0.stream, ln.drained, 0));
+    if (ln.acc_used) ordered[m++] = ln.acc;
+  }
+  if (!(m == 1 && ordered[0] == l0.acc)) {
+    rc = lane_sum(c, l0.acc, ordered, m, false, 1, l0.stream);
+    if (rc) return rc;
+  }
+  for (auto& ln : c->lanes) ln.acc_used = false;
+  l0.acc_used = true;
+
+  stk::PeerReduceParams p;
+  memset(&p, 0, sizeof p);
+  for (int r = 0; r < pl.world; ++r) { p.partial[r] = pl.partial[r]; p.flags[r] = pl.pflags[r]; }
+  p.out = pl.root_out;
+  // equal slices in units of 4 floats; the last rank also takes the remainder
+  const size_t n4 = c->acc_floats / 4, per = n4 / pl.world;
+  p.begin = (size_t)pl.rank * per * 4;
+  p.end = pl.rank == pl.world - 1 ? c->acc_floats : (size_t)(pl.rank + 1) * per * 4;
+  p.rank = pl.rank;
+  p.world = pl.world;
+  p.step = ++pl.step;
+  p.scale = (float)(1.0 / (double)divisor);
+  static const unsigned long long timeout_ms = [] { const char* e = getenv("STK_PEER_TIMEOUT_MS"); return e ? strtoull(e, nullptr, 10) : 10000ull; }();
+  p.timeout_ns = timeout_ms * 1000000ull;
+  const int blocks = c->sm_count * 4;
+  switch (pl.world) {
+    case 2: launch_peer_reduce<2>(p, blocks, l0.stream); break;
+    case 4: launch_peer_reduce<4>(p, blocks, l0.stream); break;
+    case 8: launch_peer_reduce<8>(p, blocks, l0.stream); break;
+    default: launch_peer_reduce<0>(p, blocks, l0.stream); break;
+  }
+  CU(cudaGetLastError());
+  stk::peer_wait_done_kernel<<<1, 32, 0, l0.stream>>>(pl.flags, pl.world, p.step, p.timeout_ns);
+  CU(cudaGetLastError());
+  c->launches += 2;
+  if (d_out) *d_out = pl.rank == 0 ? c->d_out : nullptr;
   return STK_OK;
 }
 

@@ -1,5 +1,9 @@
 """Multi-GPU plumbing for one stack: one process per GPU (torch.distributed, NCCL over NVLink), frames
-sharded across ranks, ONE sum-reduce of the partial stacks to rank 0, then the divide.
+sharded across ranks, ONE exchange step of the partial stacks to rank 0 fused with the divide.
+
+The exchange is the library's own reduce-scatter kernel over NVLink peer memory (csrc/peer_reduce.cuh,
+`connect_peers` + `EccStack.peer_reduce`): torch.distributed only carries the 256-byte handles once.  The
+NCCL form (`reduce_partial_stack` + `finish_device`) stays as the baseline it is measured against.
 
 This is the B200 form of the reference's Rayon map-reduce (/root/reference/src/lib.rs:746-751, :819-839):
 `try_fold` = each rank aligning + accumulating its own frames, `try_reduce` = the reduce, `/ n` = the final
@@ -35,13 +39,65 @@ def reduce_partial_stack(tensor, dst: int = 0, group=None):
     return tensor
 
 
-def stack_on_ranks(stack, frames_by_index, n_frames: int, rank: int, world: int, device=None):
+def slice_bounds(n_floats: int, rank: int, world: int):
+    """[begin, end) of the stack (in floats) that `rank` reduces in the peer exchange: equal slices in units
+    of 4 floats, the last rank also takes the remainder — the rule stk_ecc_peer_reduce applies."""
+    per = (n_floats // 4) // world
+    begin = rank * per * 4
+    end = n_floats if rank == world - 1 else (rank + 1) * per * 4
+    return begin, end
+
+
+def gather_handles(handle: bytes, group=None):
+    """All ranks' peer handles, rank order (plain bytes through all_gather_object; works under gloo and nccl)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    out = [None] * world
+    dist.all_gather_object(out, bytes(handle), group=group)
+    return out
+
+
+def connect_peers(stack, group=None) -> bool:
+    """Map every rank's partial stack into this rank's context (CUDA IPC).  Collective.  Returns False —
+    on EVERY rank — if any rank could not map its peers (no NVLink/P2P between the devices, IPC forbidden by
+    the container), so that all ranks take the same path afterwards."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    handles = gather_handles(stack.peer_export(), group)
+    ok, why = True, ""
+    try:
+        stack.peer_connect(rank, world, handles)
+    except Exception as e:  # the outcome is agreed on below; nothing is swallowed silently
+        ok, why = False, str(e)
+    votes = [None] * world
+    dist.all_gather_object(votes, (ok, why), group=group)
+    if all(v[0] for v in votes):
+        return True
+    if ok:
+        stack.peer_disconnect()
+    connect_peers.last_failure = "; ".join(f"rank {r}: {v[1]}" for r, v in enumerate(votes) if not v[0])
+    return False
+
+
+connect_peers.last_failure = ""
+
+
+def stack_on_ranks(stack, frames_by_index, n_frames: int, rank: int, world: int, device=None, peers: bool = False):
     """Run this rank's shard through `stack` (an EccStack whose reference is already set; rank 0's was
     created with seed_reference=True, the others with False), reduce, and return the final HxWxC f32 torch
-    tensor on rank 0 (None elsewhere).  `frames_by_index[i]` is frame i as a host array or CUDA tensor."""
+    tensor on rank 0 (None elsewhere).  `frames_by_index[i]` is frame i as a host array or CUDA tensor.
+    `peers=True` (after connect_peers succeeded) uses the fused peer-memory exchange; the returned tensor then
+    views the library's output buffer (valid until the next exchange)."""
     import torch
     for i in shard_frames(n_frames, rank, world):
         stack.submit(frames_by_index[i], tag=i)
+    if peers:
+        d_out = stack.peer_reduce(n_frames)
+        stack.sync()
+        if rank != 0:
+            return None
+        n = stack.height * stack.width * stack.channels
+        return torch.as_tensor(DevicePtrArray(d_out, n), device=device).view(stack.height, stack.width, stack.channels)
     ptr, n = stack.partial()
     part = torch.as_tensor(DevicePtrArray(ptr, n), device=device)
     reduce_partial_stack(part, 0)

@@ -80,3 +80,45 @@ def test_shard_frames_partition(pkg):
             assert got == list(range(1, n))
             sizes = [len(D.shard_frames(n, r, world)) for r in range(world)]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_peer_slices_cover_the_stack(pkg):
+    """stk_ecc_peer_reduce's slice rule (distributed.slice_bounds mirrors it): contiguous, 4-float aligned
+    starts, every float exactly once, the tail on the last rank."""
+    D = pkg.distributed
+    for n in (0, 3, 4, 17, 96 * 64 * 3, 3840 * 2160 * 3, 1001 * 3):
+        for world in (1, 2, 3, 4, 8, 16):
+            edges = [D.slice_bounds(n, r, world) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == n
+            for (b0, e0), (b1, e1) in zip(edges, edges[1:]):
+                assert e0 == b1 and b1 % 4 == 0 and b0 <= e0
+
+
+def _handle_worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as ge
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    D = ge.load_package().distributed
+    mine = bytes([rank]) * 256                       # stands in for EccStack.peer_export()
+    q.put((rank, D.gather_handles(mine)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_peer_handles_are_gathered_in_rank_order():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_handle_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, handles in results:
+        assert handles == [bytes([0]) * 256, bytes([1]) * 256]

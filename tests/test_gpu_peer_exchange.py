@@ -1,0 +1,115 @@
+"""The multi-GPU exchange step (stk_ecc_peer_*, csrc/peer_reduce.cuh) against the single-context result.
+
+The fused reduce-scatter + divide must give exactly what the reference's try_reduce + `/ n`
+(/root/reference/src/lib.rs:819-839) gives for the same partial sums: the kernel adds the ranks' partial stacks in
+rank order and multiplies by float(1/n), which is what `finish` does on one device with the lanes in place of the
+ranks.  World size 1 runs on any GPU box; the 2-rank cases need two devices."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+def _n_gpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+def _stack(pkg, n=5, w=320, h=240, motion=2, seed=31):
+    from oracle import synth
+    frames = synth.Stack(w, h, n, motion, seed=seed).frames()
+    params = pkg.EccMatchParameters(pkg.MotionType(motion), 50, 1e-4, 5)
+    return frames, params
+
+
+def _device_array(ptr, shape):
+    import torch
+    from_ptr = type("P", (), {})()
+    n = int(np.prod(shape))
+    from_ptr.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (int(ptr), False), "version": 3,
+                                         "strides": None}
+    return torch.as_tensor(from_ptr, device="cuda").view(*shape).cpu().numpy()
+
+
+def test_world_of_one_equals_finish(pkg):
+    frames, params = _stack(pkg)
+    h, w = frames[0].shape[:2]
+    with pkg.EccStack(w, h, 3, params, device=0, lanes=3) as st:
+        st.set_reference(frames[0])
+        for i, f in enumerate(frames[1:], 1):
+            st.submit(f, tag=i)
+        want = st.finish(len(frames))
+        # same stack again through the exchange path, twice (step counter, reset in between)
+        st.peer_connect(0, 1, [st.peer_export()])
+        for _ in range(2):
+            st.reset()
+            st.set_reference(frames[0])
+            for i, f in enumerate(frames[1:], 1):
+                st.submit(f, tag=i)
+            ptr = st.peer_reduce(len(frames))
+            st.sync()
+            got = _device_array(ptr, (h, w, 3))
+            assert np.array_equal(got, want)
+        st.peer_disconnect()
+
+
+def test_peer_reduce_needs_connect(pkg):
+    frames, params = _stack(pkg, n=2)
+    h, w = frames[0].shape[:2]
+    with pkg.EccStack(w, h, 3, params, device=0) as st:
+        st.set_reference(frames[0])
+        with pytest.raises(pkg.StackerError):
+            st.peer_reduce(2)
+        with pytest.raises(pkg.StackerError):
+            st.peer_connect(0, 2, [st.peer_export()])          # one handle for a world of two
+
+
+def test_two_devices_one_process(pkg):
+    if _n_gpus() < 2:
+        pytest.skip("needs two GPUs")
+    D = pkg.distributed
+    frames, params = _stack(pkg, n=6)
+    n = len(frames)
+    h, w = frames[0].shape[:2]
+    with pkg.EccStack(w, h, 3, params, device=0, lanes=1) as one:
+        one.set_reference(frames[0])
+        for i in range(1, n):
+            one.submit(frames[i], tag=i)
+        one.sync()
+        single = one.finish(n)
+    stacks = [pkg.EccStack(w, h, 3, params, device=r, lanes=2, seed_reference=(r == 0)) for r in range(2)]
+    try:
+        pkg.EccStack.peer_connect_local(stacks)
+        for rep in range(2):
+            for r, st in enumerate(stacks):
+                st.reset()
+                st.set_reference(frames[0])
+                for i in D.shard_frames(n, r, 2):
+                    st.submit(frames[i], tag=i)
+            ptrs = [st.peer_reduce(n) for st in stacks]
+            for st in stacks:
+                st.sync()
+            assert ptrs[1] is None
+            import torch
+            with torch.cuda.device(0):
+                got = _device_array(ptrs[0], (h, w, 3))
+            # same frames, same warps; only the f32 summation order differs from the single-device stack
+            assert np.abs(got - single).max() <= 1e-6
+    finally:
+        for st in stacks:
+            st.close()
+
+
+def test_two_processes_ipc_equals_nccl():
+    if _n_gpus() < 2:
+        pytest.skip("needs two GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29731", os.path.join(ROOT, "scripts", "peer_check.py")]
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "peer exchange ok" in r.stdout
