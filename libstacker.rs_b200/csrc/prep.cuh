@@ -229,4 +229,211 @@ __global__ void __launch_bounds__(kPrepThreads) prep_grey_blur_kernel(const Prep
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Streaming variant for gauss_filt_size 3 and 5 (the reference's default, examples/main.rs:122): no shared memory.
+//
+// With 8-bit input and the dyadic taps [1 2 1]/4, [1 4 6 4 1]/16 the blurred value is v / 16 resp. v / 256 with v
+// an INTEGER below 2^16 (A3.1 of SURVEY §8), so the whole filter runs in exact integer arithmetic — two pixels per
+// 32-bit register (16-bit halves never carry into each other: 256 * 255 < 2^16) — and the result is bit-identical to
+// cv2.GaussianBlur on the f32 plane (every f32 intermediate of OpenCV's pipeline is exactly representable, so its
+// summation order cannot matter).
+//
+// A warp owns a band of 120 output columns (lanes 1..30 store 4 columns each, lanes 0 and 31 only supply the
+// horizontal halo) and streams down a strip of rows: per row a lane loads its 4 pixels (12 contiguous bytes for
+// BGR: the warp reads 384 contiguous bytes), converts them to grey, exchanges two packed registers with its
+// neighbours (the +-2 column halo), does the horizontal pass, pushes the row into a 2R+1-row register window and
+// emits one finished row: 128-bit coalesced stores.  Loads of the next four rows are issued before the current four
+// are processed.  The u16 -> f32 conversion is an exponent splice (0x47000000 | v is 32768 + v/256) and one FADD,
+// not a conversion-unit I2F.
+constexpr int kPrepBandCols = 120;
+constexpr int kPrepStreamThreads = 128;
+
+struct PrepStreamParams {
+  const uint8_t* src;
+  size_t src_pitch;
+  float* dst;
+  int dst_pitch;        // floats
+  int width, height;
+  int strip_rows;       // output rows per warp
+  int n_bands, n_strips;
+};
+
+template <bool V>
+struct PrepTag { static constexpr bool value = V; };
+
+template <int C>
+struct RawRow { uint32_t w[C == 3 ? 3 : (C == 4 ? 4 : 1)]; };
+
+template <int C>
+__device__ __forceinline__ void load_raw(RawRow<C>& r, const uint8_t* px) {
+  if constexpr (C == 3) {
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(px);
+    r.w[0] = __ldg(q); r.w[1] = __ldg(q + 1); r.w[2] = __ldg(q + 2);
+  } else if constexpr (C == 4) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(px));
+    r.w[0] = v.x; r.w[1] = v.y; r.w[2] = v.z; r.w[3] = v.w;
+  } else {
+    r.w[0] = __ldg(reinterpret_cast<const uint32_t*>(px));
+  }
+}
+
+// four greys of a lane as two packed pairs: lo = g0 | g1 << 16, hi = g2 | g3 << 16.
+// cvtColor's 15-bit weights (3735, 19235, 9798) are split into bytes so that one pixel costs two 4-way byte dot
+// products on the raw (B, G, R, x) word instead of three extractions and three multiply-adds:
+//   3735 = 14*256 + 151,  19235 = 75*256 + 35,  9798 = 38*256 + 70;  the 4th weight is 0 (next pixel's B / alpha).
+template <int C>
+__device__ __forceinline__ void grey_pairs(const RawRow<C>& r, uint32_t& lo, uint32_t& hi) {
+  if constexpr (C == 1) {
+    lo = __byte_perm(r.w[0], 0, 0x4140);     // bytes (b0, 0, b1, 0)
+    hi = __byte_perm(r.w[0], 0, 0x4342);
+  } else {
+    uint32_t px[4];
+    if constexpr (C == 3) {
+      // 12 bytes: B0 G0 R0 B1 | G1 R1 B2 G2 | R2 B3 G3 R3
+      px[0] = r.w[0];
+      px[1] = __funnelshift_r(r.w[0], r.w[1], 24);
+      px[2] = __funnelshift_r(r.w[1], r.w[2], 16);
+      px[3] = r.w[2] >> 8;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) px[i] = r.w[i];
+    }
+    constexpr uint32_t kWLo = 151u | (35u << 8) | (70u << 16);
+    constexpr uint32_t kWHi = 14u | (75u << 8) | (38u << 16);
+    uint32_t y[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) y[i] = (__dp4a(px[i], kWLo, 16384u) + (__dp4a(px[i], kWHi, 0u) << 8)) >> 15;
+    lo = y[0] | (y[1] << 16);
+    hi = y[2] | (y[3] << 16);
+  }
+}
+
+template <int C, int R>   // C channels in {1, 3, 4}; R = 1 (k = 3) or 2 (k = 5)
+__global__ void __launch_bounds__(kPrepStreamThreads) prep_stream_kernel(const PrepStreamParams p) {
+  const int warp = (blockIdx.x * kPrepStreamThreads + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= p.n_bands * p.n_strips) return;
+  // consecutive warps walk along a strip of bands: neighbouring warps read neighbouring bytes of the same rows
+  const int band = warp % p.n_bands, strip = warp / p.n_bands;
+  const int x = band * kPrepBandCols + 4 * (lane - 1);       // first of this lane's 4 columns
+  const int y0 = strip * p.strip_rows;
+  const int y1 = min(y0 + p.strip_rows, p.height);
+  const bool stores = x >= 0 && x < p.width && lane >= 1 && lane <= 30;   // width % 4 == 0: a lane is all in or all out
+  const bool left_edge = x == 0, right_edge = x + 4 == p.width;
+  const int n_in = (y1 - y0) + 2 * R;                        // input rows y0-R .. y1+R-1 (reflected at the border)
+  // halo lanes outside the image read a clamped (valid) address; what they produce is never used: the lane next
+  // to them applies the mirror rule instead
+  const int xc = min(max(x, 0), p.width - 4);
+  const uint8_t* src_lane = p.src + (size_t)xc * C;
+  const uint32_t pitch = (uint32_t)p.src_pitch;              // host guarantees pitch * height < 2^32
+  const int h = p.height;
+
+  // magic exponent: LSB of the spliced mantissa weighs 1/256 (k = 5) resp. 1/16 (k = 3)
+  constexpr uint32_t kSplice = R == 2 ? 0x47000000u : 0x49000000u;
+  constexpr float kBias = R == 2 ? 32768.f : 524288.f;
+
+  uint32_t wa[2 * R + 1], wb[2 * R + 1];     // window of horizontally filtered rows: pairs (h0,h1) and (h2,h3)
+#pragma unroll
+  for (int i = 0; i < 2 * R + 1; ++i) wa[i] = wb[i] = 0;
+  const uint32_t m_left = left_edge ? 0xffffffffu : 0u, m_right = right_edge ? 0xffffffffu : 0u;
+  float* out_lane = p.dst + x;               // only dereferenced when `stores`
+
+  constexpr int U = R == 2 ? 5 : 6;          // rows per group: a multiple of the window length (no register moves)
+  auto row_ptr = [&](int i) {                // input row i of the strip = image row y0 - R + i, BORDER_REFLECT_101
+    int sy = y0 - R + i;                     // one reflection is enough (height > 2R)
+    sy = sy < 0 ? -sy : sy;
+    sy = sy >= h ? 2 * h - 2 - sy : sy;
+    return src_lane + (uint32_t)sy * pitch;
+  };
+  // one input row: grey, halo exchange, horizontal pass, push into the window; kStore: emit output row `yo`
+  auto row = [&](const RawRow<C>& raw, auto store_tag, int yo) {
+    uint32_t lo, hi;
+    grey_pairs<C>(raw, lo, hi);
+    uint32_t lm = __shfl_up_sync(0xffffffffu, hi, 1);      // left neighbour's (g2, g3) = (g[-2], g[-1])
+    uint32_t rp = __shfl_down_sync(0xffffffffu, lo, 1);    // right neighbour's (g0, g1) = (g[4], g[5])
+    // BORDER_REFLECT_101: (g[-2], g[-1]) = (g2, g1) and (g[W], g[W+1]) = (g[W-2], g[W-3]) = (g2, g1) too
+    const uint32_t mirror = __byte_perm(lo, hi, 0x3254);
+    lm = (mirror & m_left) | (lm & ~m_left);
+    rp = (mirror & m_right) | (rp & ~m_right);
+    const uint32_t s1 = __byte_perm(lm, lo, 0x5432);       // (g[-1], g0)
+    const uint32_t s2 = __byte_perm(lo, hi, 0x5432);       // (g1, g2)
+    const uint32_t s3 = __byte_perm(hi, rp, 0x5432);       // (g3, g4)
+    uint32_t ha, hb;
+    if constexpr (R == 2) {
+      ha = (lm + hi) + 4u * (s1 + s2) + 6u * lo;           // (h0, h1)
+      hb = (lo + rp) + 4u * (s2 + s3) + 6u * hi;           // (h2, h3)
+    } else {
+      ha = s1 + 2u * lo + s2;                              // h0 = g[-1] + 2 g0 + g1 ; h1 = g0 + 2 g1 + g2
+      hb = s2 + 2u * hi + s3;
+    }
+#pragma unroll
+    for (int k = 0; k < 2 * R; ++k) { wa[k] = wa[k + 1]; wb[k] = wb[k + 1]; }
+    wa[2 * R] = ha; wb[2 * R] = hb;
+    if constexpr (decltype(store_tag)::value) {
+      uint32_t va, vb;
+      if constexpr (R == 2) {
+        va = (wa[0] + wa[4]) + 4u * (wa[1] + wa[3]) + 6u * wa[2];
+        vb = (wb[0] + wb[4]) + 4u * (wb[1] + wb[3]) + 6u * wb[2];
+      } else {
+        va = wa[0] + 2u * wa[1] + wa[2];
+        vb = wb[0] + 2u * wb[1] + wb[2];
+      }
+      float4 o;
+      o.x = __uint_as_float(__byte_perm(va, kSplice, 0x7410)) - kBias;
+      o.y = __uint_as_float(__byte_perm(va, kSplice, 0x7432)) - kBias;
+      o.z = __uint_as_float(__byte_perm(vb, kSplice, 0x7410)) - kBias;
+      o.w = __uint_as_float(__byte_perm(vb, kSplice, 0x7432)) - kBias;
+      if (stores) *reinterpret_cast<float4*>(out_lane + (size_t)yo * p.dst_pitch) = o;
+    }
+  };
+  using Yes = PrepTag<true>;
+  using No = PrepTag<false>;
+  // a group of U input rows starting at input row `base`; whole groups carry no per-row tests
+  auto fetch = [&](RawRow<C>* dst, int base) {
+    if (base + U <= n_in) {
+#pragma unroll
+      for (int j = 0; j < U; ++j) load_raw<C>(dst[j], row_ptr(base + j));
+    } else {
+#pragma unroll
+      for (int j = 0; j < U; ++j)
+        if (base + j < n_in) load_raw<C>(dst[j], row_ptr(base + j));
+    }
+  };
+  auto process = [&](const RawRow<C>* rows, int base) {
+    if (base + U <= n_in) {
+#pragma unroll
+      for (int j = 0; j < U; ++j) row(rows[j], Yes(), y0 + base + j - 2 * R);
+    } else {
+#pragma unroll
+      for (int j = 0; j < U; ++j)
+        if (base + j < n_in) row(rows[j], Yes(), y0 + base + j - 2 * R);
+    }
+  };
+
+  // the first 2R input rows only fill the window; then two groups of rows ping-pong: the loads of one are in
+  // flight while the other is filtered
+  RawRow<C> pro[2 * R], ga[U], gb[U];
+#pragma unroll
+  for (int j = 0; j < 2 * R; ++j) load_raw<C>(pro[j], row_ptr(j));
+  fetch(ga, 2 * R);
+#pragma unroll
+  for (int j = 0; j < 2 * R; ++j) row(pro[j], No(), 0);
+  for (int base = 2 * R; base < n_in; base += 2 * U) {
+    fetch(gb, base + U);
+    process(ga, base);
+    fetch(ga, base + 2 * U);
+    process(gb, base + U);
+  }
+}
+
+// the streaming kernel's preconditions (everything else takes the tiled kernel)
+inline bool prep_stream_ok(const void* src, size_t pitch, int width, int height, int channels, int radius) {
+  if (radius != 1 && radius != 2) return false;
+  if (channels != 1 && channels != 3 && channels != 4) return false;
+  if (width % 4 != 0 || width < 8 || height < 2 * radius + 1) return false;
+  if ((unsigned long long)pitch * (unsigned long long)height >= (1ull << 32)) return false;   // 32-bit row offsets
+  const size_t align = channels == 4 ? 16 : 4;
+  return ((uintptr_t)src % align) == 0 && pitch % align == 0;
+}
+
 }  // namespace stk

@@ -418,6 +418,38 @@ int launch_prep(stk_ecc_ctx* c, const uint8_t* d_src, size_t pitch, uint8_t* sma
     p.src_pitch = (size_t)c->small_pitch;
     p.channels = 1;
   }
+  // gauss_filt_size 3 / 5 on 4-byte aligned rows: the shared-memory-free streaming kernel (exact integers)
+  static const bool stream_on = [] { const char* e = getenv("STK_PREP_STREAM"); return !(e && e[0] == '0'); }();
+  static const int strip_env = [] { const char* e = getenv("STK_PREP_STRIP"); return e ? atoi(e) : 0; }();
+  if (stream_on && stk::prep_stream_ok(p.src, p.src_pitch, c->ew, c->eh, p.channels, p.radius)) {
+    stk::PrepStreamParams q;
+    q.src = p.src; q.src_pitch = p.src_pitch; q.dst = p.dst; q.dst_pitch = p.dst_pitch;
+    q.width = c->ew; q.height = c->eh;
+    q.n_bands = (c->ew + stk::kPrepBandCols - 1) / stk::kPrepBandCols;
+    const int key = p.channels * 10 + p.radius;
+    void (*kern)(const stk::PrepStreamParams) =
+        key == 11 ? stk::prep_stream_kernel<1, 1> : key == 12 ? stk::prep_stream_kernel<1, 2>
+      : key == 31 ? stk::prep_stream_kernel<3, 1> : key == 32 ? stk::prep_stream_kernel<3, 2>
+      : key == 41 ? stk::prep_stream_kernel<4, 1> : stk::prep_stream_kernel<4, 2>;
+    // ONE resident wave: strips sized from the kernel's real occupancy (2R halo rows are re-read per strip, so
+    // strips are as tall as one wave allows, at least 8 rows)
+    static std::atomic<int> occ_cache[64];
+    int per_sm = occ_cache[key].load();
+    if (per_sm <= 0) {
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, stk::kPrepStreamThreads, 0));
+      occ_cache[key].store(per_sm);
+    }
+    const int warp_slots = std::max(1, c->sm_count * per_sm * (stk::kPrepStreamThreads / 32));
+    const int strips_wanted = std::max(1, warp_slots / q.n_bands);
+    q.strip_rows = strip_env > 0 ? strip_env : std::max(8, (c->eh + strips_wanted - 1) / strips_wanted);
+    q.n_strips = (c->eh + q.strip_rows - 1) / q.strip_rows;
+    const int warps = q.n_bands * q.n_strips;
+    const int blocks = (warps * 32 + stk::kPrepStreamThreads - 1) / stk::kPrepStreamThreads;
+    kern<<<blocks, stk::kPrepStreamThreads, 0, s>>>(q);
+    c->launches++;
+    CU(cudaGetLastError());
+    return STK_OK;
+  }
   const size_t smem = stk::prep_smem_bytes(p.radius);
   dim3 grid((c->ew + stk::kPrepTW - 1) / stk::kPrepTW, (c->eh + stk::kPrepTH - 1) / stk::kPrepTH);
   switch (p.radius) {   // radii 1..4 (gauss_filt_size 3..9) get unrolled instantiations

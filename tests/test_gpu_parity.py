@@ -18,7 +18,10 @@ MOTIONS = [0, 1, 2, 3]
 
 
 # ---- K1: grey + blur, bit-exact ------------------------------------------------------------------------
-@pytest.mark.parametrize("size", [(320, 240), (257, 131), (64, 40), (1000, 37)])
+# widths that are multiples of 4 take the streaming kernel for k = 3 / 5 (bands of 120 columns, strips of rows):
+# several bands, a last band that ends mid-warp, a single partial band, the smallest legal plane, 3-row planes
+@pytest.mark.parametrize("size", [(320, 240), (257, 131), (64, 40), (1000, 37), (3840, 40), (244, 20), (124, 33),
+                                  (120, 9), (8, 5), (480, 3)])
 @pytest.mark.parametrize("k", [1, 3, 5, 7, 9])
 def test_prep_bit_exact(pkg, size, k):
     w, h = size
@@ -38,12 +41,26 @@ def test_prep_large_kernel_close(pkg):
         assert np.abs(got - want).max() <= 1e-4
 
 
-def test_prep_bgra(pkg):
-    rng = np.random.default_rng(6)
-    frame = rng.integers(0, 256, (50, 70, 4), dtype=np.uint8)
-    got = pkg.prep_grey_blur(frame, 5, device=0)
-    want = R.gaussian_blur_f32(R.bgr2gray_u8(frame[..., :3]).astype(np.float32), 5)
+@pytest.mark.parametrize("size", [(70, 50), (72, 50), (368, 31)])
+@pytest.mark.parametrize("k", [3, 5])
+def test_prep_bgra(pkg, size, k):
+    w, h = size
+    rng = np.random.default_rng(6 + w)
+    frame = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+    got = pkg.prep_grey_blur(frame, k, device=0)
+    want = R.gaussian_blur_f32(R.bgr2gray_u8(frame[..., :3]).astype(np.float32), k)
     assert np.array_equal(got, want)
+
+
+def test_prep_extreme_values(pkg):
+    """all-255 and checkerboard planes: the packed 16-bit halves of the streaming kernel reach their maximum
+    (256 * 255) without carrying into each other"""
+    for k in (3, 5):
+        for frame in (np.full((24, 256, 3), 255, np.uint8),
+                      np.tile(np.array([[0, 255], [255, 0]], np.uint8), (12, 128))[..., None].repeat(3, axis=2)):
+            got = pkg.prep_grey_blur(np.ascontiguousarray(frame), k, device=0)
+            want = R.gaussian_blur_f32(R.bgr2gray_u8(frame).astype(np.float32), k)
+            assert np.array_equal(got, want)
 
 
 # ---- K4: final warp + accumulate, bit-exact ------------------------------------------------------------
