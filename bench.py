@@ -404,11 +404,16 @@ def run_b200(a, rank, local_rank, world):
         it_t = torch.tensor([float(sum(iters))], dtype=torch.float64, device=dev)
         dist.all_reduce(it_t)
         total_iters = int(it_t.item())
+        per_rank = torch.zeros(world, dtype=torch.float64, device=dev)
+        per_rank[rank] = float(sum(iters))
+        dist.all_reduce(per_rank)
+        iters_per_rank = [int(v) for v in per_rank.tolist()]
         l_t = torch.tensor([float(launches)], dtype=torch.float64, device=dev)
         dist.all_reduce(l_t)
         launches = int(l_t.item())
     else:
         total_iters = sum(iters)
+        iters_per_rank = [total_iters]
 
     cpu = None
     if rank == 0 and world == 1 and not a.skip_cpu:
@@ -434,7 +439,7 @@ def run_b200(a, rank, local_rank, world):
                        "l2": "inputs larger than L2: every step reads all frames (%.2f GB u8) from HBM" % (n * n_px * 3 / 1e9),
                        "parallelism": (f"frames sharded over {world} GPU(s), " + ("one fused reduce-scatter+divide kernel per rank over NVLink peer memory"
                                                                                    if use_peers else "one NCCL reduce")) if world > 1 else "1 GPU",
-                       "ecc_iterations_per_step": total_iters, "wall_ms_per_step": wall_ms / a.steps},
+                       "ecc_iterations_per_step": total_iters, "ecc_iterations_per_rank": iters_per_rank, "wall_ms_per_step": wall_ms / a.steps},
             "whole_step": {"algorithmic_GBps_per_gpu": alg_bytes / (ms / a.steps * 1e-3) / 1e9 / world,
                            "frac_of_hbm_peak": alg_bytes / (ms / a.steps * 1e-3) / 1e9 / world / peak},
             "roofline": roof, "stages": stages, "cpu_baseline": cpu, "e2e": e2e,

@@ -12,9 +12,13 @@
 //   them in rank order (deterministic, independent of which rank does it), multiplies by 1/n and (4) stores the
 //   finished pixels straight into the ROOT's output buffer (peer stores), then (5) announces "slice r done".
 //
-// Traffic per rank: (world-1)/world of a stack in over NVLink, 1/world out — all ranks in parallel — versus a
-// whole stack through a ring/tree plus a separate 24N-byte scale pass on the root.  `peer_wait_done_kernel`
-// closes the step on every rank: the root's output is complete and nobody still reads this rank's partial.
+// Traffic: a worker's inbound side carries the remote partials of its slice, the root's inbound side carries the
+// finished stack (S bytes, irreducible when the result must end on the root).  With more than two ranks the root
+// therefore takes NO slice (host side, stk_ecc_peer_reduce): a root slice would add (world-1) remote reads per
+// pixel on the links that already carry the result — measured at world 4 with equal slices: 260 us, the root's
+// inbound side carrying 1.5 S.  Without it every rank's inbound traffic is S, all ranks in parallel, and there is
+// no separate 24N-byte scale pass on the root.  `peer_wait_done_kernel` closes the step on every rank: the root's
+// output is complete and nobody still reads this rank's partial.
 //
 // Flags are 32-bit step counters (monotonic, wrap-safe compare) in a small cudaMalloc'ed block per context that
 // peers map (CUDA IPC between processes, peer access inside one process).  Spins are bounded by %globaltimer:

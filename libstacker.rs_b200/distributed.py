@@ -40,11 +40,17 @@ def reduce_partial_stack(tensor, dst: int = 0, group=None):
 
 
 def slice_bounds(n_floats: int, rank: int, world: int):
-    """[begin, end) of the stack (in floats) that `rank` reduces in the peer exchange: equal slices in units
-    of 4 floats, the last rank also takes the remainder — the rule stk_ecc_peer_reduce applies."""
-    per = (n_floats // 4) // world
-    begin = rank * per * 4
-    end = n_floats if rank == world - 1 else (rank + 1) * per * 4
+    """[begin, end) of the stack (in floats) that `rank` reduces in the peer exchange — the rule
+    stk_ecc_peer_reduce applies: slices in units of 4 floats, the last worker also takes the remainder; with
+    more than two ranks the root (rank 0) takes no slice, because every finished pixel already has to enter
+    the root over its inbound NVLink side."""
+    workers = world - 1 if world > 2 else world
+    w = rank - 1 if world > 2 else rank
+    if w < 0:
+        return 0, 0
+    per = (n_floats // 4) // workers
+    begin = w * per * 4
+    end = n_floats if w == workers - 1 else (w + 1) * per * 4
     return begin, end
 
 

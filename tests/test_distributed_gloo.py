@@ -84,11 +84,14 @@ def test_shard_frames_partition(pkg):
 
 def test_peer_slices_cover_the_stack(pkg):
     """stk_ecc_peer_reduce's slice rule (distributed.slice_bounds mirrors it): contiguous, 4-float aligned
-    starts, every float exactly once, the tail on the last rank."""
+    starts, every float exactly once, the tail on the last rank, no slice for the root of a world > 2."""
     D = pkg.distributed
     for n in (0, 3, 4, 17, 96 * 64 * 3, 3840 * 2160 * 3, 1001 * 3):
         for world in (1, 2, 3, 4, 8, 16):
             edges = [D.slice_bounds(n, r, world) for r in range(world)]
+            if world > 2:
+                assert edges[0] == (0, 0)
+                edges = edges[1:]
             assert edges[0][0] == 0 and edges[-1][1] == n
             for (b0, e0), (b1, e1) in zip(edges, edges[1:]):
                 assert e0 == b1 and b1 % 4 == 0 and b0 <= e0
