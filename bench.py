@@ -234,6 +234,7 @@ def run_b200(a, rank, local_rank, world):
         if not use_peers and rank == 0:
             print(f"peer exchange unavailable, using NCCL: {D.connect_peers.last_failure}", file=sys.stderr)
     peer_out = {}
+    shared_host = D.SharedHostStack((h, w, 3)) if use_peers else None
 
     def peer_result():
         return torch.as_tensor(D.DevicePtrArray(peer_out["ptr"], h * w * 3), device=dev).view(h, w, 3)
@@ -274,10 +275,12 @@ def run_b200(a, rank, local_rank, world):
         for i in mine:
             st.submit(pinned_np[i], tag=i, pinned=True)
         if use_peers:
-            peer_out["ptr"] = st.peer_reduce(n)
+            # every rank keeps its slice of the finished stack and copies it out over its OWN PCIe link into the
+            # host stack all ranks map; rank 0 owns the result once every rank's copy has landed
+            st.peer_reduce_scatter(n)
+            st.peer_slice_to_host(shared_host.ptr)
             st.sync()
-            if rank == 0:
-                out_host.copy_(peer_result(), non_blocking=False)
+            dist.barrier()
             return
         ptr, nfl = st.partial()
         if world > 1:
@@ -348,15 +351,21 @@ def run_b200(a, rank, local_rank, world):
         h2d = sum(pinned_np[i].nbytes for i in [0] + mine)
         e2e = {"value": n * a.steps / (ems / 1e3), "unit": UNIT, "ms_per_step": ems / a.steps,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(out_host.numel() * 4) if rank == 0 else 0,
-               "api": "EccStack.set_reference/submit(pinned host frames)/partial/finish_device + D2H of the stack"}
+               "api": ("EccStack.set_reference/submit(pinned host frames)/peer_reduce_scatter/peer_slice_to_host: every rank "
+                       "copies its slice of the stack into the shared pinned host stack" if use_peers else
+                       "EccStack.set_reference/submit(pinned host frames)/partial/finish_device + D2H of the stack")}
         if world > 1:
             tot = torch.tensor([float(h2d)], dtype=torch.float64, device=dev)
             dist.all_reduce(tot)
             e2e["h2d_bytes_per_step"] = int(tot.item())
 
     stack_mean = float((peer_result() if use_peers else out_dev).mean().item()) if rank == 0 else None
+    e2e_mean = None
     if use_peers:
         barrier()                 # nobody unmaps while a peer may still be inside an exchange
+        if rank == 0 and not a.skip_e2e:
+            e2e_mean = float(shared_host.array.mean(dtype=np.float64))
+        shared_host.close()
         st.peer_disconnect()
         barrier()
     # ---- roofline of the dominant kernel (ecc_iter_kernel), measured alone: 1 lane, CUDA events per stage ----
@@ -445,7 +454,7 @@ def run_b200(a, rank, local_rank, world):
             "roofline": roof, "stages": stages, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": launches, "clocks": clocks,
             "check": {"max_corner_error_vs_ground_truth_px": truth_err, "ecc_status_codes": statuses,
-                      "stack_mean": stack_mean},
+                      "stack_mean": stack_mean, "e2e_stack_mean": e2e_mean},
         }
         print(json.dumps(line))
     if world > 1:

@@ -71,6 +71,8 @@ SYMBOLS = {
     "stk_ecc_peer_connect": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(PeerHandle)]),
     "stk_ecc_peer_connect_local": (C.c_int, [C.POINTER(_P), C.c_int]),
     "stk_ecc_peer_reduce": (C.c_int, [_P, C.c_int, C.POINTER(_P)]),
+    "stk_ecc_peer_reduce_scatter": (C.c_int, [_P, C.c_int, C.POINTER(_P), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "stk_ecc_peer_slice_to_host": (C.c_int, [_P, _P]),
     "stk_ecc_peer_disconnect": (C.c_int, [_P]),
     "stk_ecc_reset": (C.c_int, [_P]),
     "stk_ecc_launch_count": (C.c_int, [_P, C.POINTER(C.c_int64)]),

@@ -307,6 +307,18 @@ class EccStack:
         _check(lib.stk_ecc_peer_reduce(self._ctx, int(divisor), C.byref(out)))
         return out.value
 
+    def peer_reduce_scatter(self, divisor: int):
+        """The exchange step + divide with every rank keeping the finished pixels of its own slice:
+        (device pointer of the slice, begin, count) in floats of the flat H*W*C stack."""
+        ptr, b, n = C.c_void_p(), C.c_size_t(), C.c_size_t()
+        _check(lib.stk_ecc_peer_reduce_scatter(self._ctx, int(divisor), C.byref(ptr), C.byref(b), C.byref(n)))
+        return ptr.value, b.value, n.value
+
+    def peer_slice_to_host(self, host_ptr: int):
+        """Queue the device-to-host copy of this rank's slice into the dense host stack at `host_ptr` (done
+        after sync())."""
+        _check(lib.stk_ecc_peer_slice_to_host(self._ctx, C.c_void_p(int(host_ptr))))
+
     def peer_disconnect(self):
         _check(lib.stk_ecc_peer_disconnect(self._ctx))
 

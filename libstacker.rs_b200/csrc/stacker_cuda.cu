@@ -235,6 +235,8 @@ struct PeerLink {
   const float* partial[stk::kMaxPeers] = {};
   uint32_t* pflags[stk::kMaxPeers] = {};
   float* root_out = nullptr;
+  size_t slice_begin = 0, slice_end = 0;      // this rank's slice of the last exchange
+  bool scattered = false;                     // last exchange was a reduce-scatter (result slice in d_out)
   std::vector<void*> opened;                  // IPC mappings to close on disconnect
 };
 
@@ -1342,7 +1344,11 @@ int stk_ecc_peer_disconnect(stk_ecc_ctx* c) {
   return STK_OK;
 }
 
-int stk_ecc_peer_reduce(stk_ecc_ctx* c, int divisor, const float** d_out) {
+}  // extern "C"
+namespace {
+// scatter == false: finished pixels go to the root's output buffer (reduce);  true: every rank keeps the finished
+// pixels of its own slice in its own output buffer (reduce-scatter), to be copied out by stk_ecc_peer_slice_to_host
+int peer_exchange(stk_ecc_ctx* c, int divisor, bool scatter) {
   int rc = check_ctx(c);
   if (rc) return rc;
   if (divisor <= 0) return fail(STK_ERR_BAD_ARG, "divisor must be positive (got %d)", divisor);
@@ -1371,14 +1377,16 @@ int stk_ecc_peer_reduce(stk_ecc_ctx* c, int divisor, const float** d_out) {
   stk::PeerReduceParams p;
   memset(&p, 0, sizeof p);
   for (int r = 0; r < pl.world; ++r) { p.partial[r] = pl.partial[r]; p.flags[r] = pl.pflags[r]; }
-  p.out = pl.root_out;
+  p.out = scatter ? c->d_out : pl.root_out;
   // Slices in units of 4 floats, the last worker also takes the remainder.  With more than two ranks the ROOT
   // takes no slice: every finished pixel has to enter the root over its inbound links anyway (S bytes), and a
   // root slice would add (world-1) remote reads per pixel on those same links (measured at world 4: 260 us with
   // equal slices, the root's inbound side carrying 1.5 S).  Without it every rank's inbound traffic is S.
   {
-    const int workers = pl.world > 2 ? pl.world - 1 : pl.world;
-    const int w = pl.world > 2 ? pl.rank - 1 : pl.rank;          // -1: the root of a world > 2
+    // (reduce-scatter: nothing converges on the root, every rank takes an equal slice)
+    const bool rootless = pl.world > 2 && !scatter;
+    const int workers = rootless ? pl.world - 1 : pl.world;
+    const int w = rootless ? pl.rank - 1 : pl.rank;              // -1: the root of a world > 2
     const size_t n4 = c->acc_floats / 4, per = n4 / workers;
     if (w < 0) { p.begin = p.end = 0; }
     else {
@@ -1403,7 +1411,39 @@ int stk_ecc_peer_reduce(stk_ecc_ctx* c, int divisor, const float** d_out) {
   stk::peer_wait_done_kernel<<<1, 32, 0, l0.stream>>>(pl.flags, pl.world, p.step, p.timeout_ns);
   CU(cudaGetLastError());
   c->launches += 2;
-  if (d_out) *d_out = pl.rank == 0 ? c->d_out : nullptr;
+  pl.slice_begin = p.begin;
+  pl.slice_end = p.end;
+  pl.scattered = scatter;
+  return STK_OK;
+}
+}  // namespace
+extern "C" {
+
+int stk_ecc_peer_reduce(stk_ecc_ctx* c, int divisor, const float** d_out) {
+  int rc = peer_exchange(c, divisor, false);
+  if (rc) return rc;
+  if (d_out) *d_out = c->peer.rank == 0 ? c->d_out : nullptr;
+  return STK_OK;
+}
+
+int stk_ecc_peer_reduce_scatter(stk_ecc_ctx* c, int divisor, const float** d_slice, size_t* begin, size_t* count) {
+  int rc = peer_exchange(c, divisor, true);
+  if (rc) return rc;
+  if (d_slice) *d_slice = c->d_out + c->peer.slice_begin;
+  if (begin) *begin = c->peer.slice_begin;
+  if (count) *count = c->peer.slice_end - c->peer.slice_begin;
+  return STK_OK;
+}
+
+int stk_ecc_peer_slice_to_host(stk_ecc_ctx* c, float* out) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  if (!out) return fail(STK_ERR_BAD_ARG, "null output");
+  std::lock_guard<std::mutex> g(c->mu);
+  PeerLink& pl = c->peer;
+  if (!pl.connected || !pl.scattered) return fail(STK_ERR_STATE, "stk_ecc_peer_slice_to_host needs a preceding stk_ecc_peer_reduce_scatter");
+  const size_t n = pl.slice_end - pl.slice_begin;
+  if (n) CU(cudaMemcpyAsync(out + pl.slice_begin, c->d_out + pl.slice_begin, n * sizeof(float), cudaMemcpyDeviceToHost, c->lanes[0].stream));
   return STK_OK;
 }
 

@@ -54,6 +54,15 @@ def slice_bounds(n_floats: int, rank: int, world: int):
     return begin, end
 
 
+def scatter_bounds(n_floats: int, rank: int, world: int):
+    """[begin, end) of the slice `rank` keeps after stk_ecc_peer_reduce_scatter: equal slices in units of 4 floats
+    for every rank (nothing converges on the root), the last rank also takes the remainder."""
+    per = (n_floats // 4) // world
+    begin = rank * per * 4
+    end = n_floats if rank == world - 1 else (rank + 1) * per * 4
+    return begin, end
+
+
 def gather_handles(handle: bytes, group=None):
     """All ranks' peer handles, rank order (plain bytes through all_gather_object; works under gloo and nccl)."""
     import torch.distributed as dist
@@ -86,6 +95,63 @@ def connect_peers(stack, group=None) -> bool:
 
 
 connect_peers.last_failure = ""
+
+
+class SharedHostStack:
+    """The finished stack in HOST memory that every rank of the node maps (POSIX shared memory, page-locked in
+    each process): after `EccStack.peer_reduce_scatter` every rank copies its own slice out over its own PCIe
+    link (`EccStack.peer_slice_to_host(shared.ptr)`), so the device-to-host copy of the result is spread over
+    all GPUs instead of serialised on the root's link.  Collective constructor; `array` is the H x W x C f32
+    view (read it on any rank after every rank's sync() + a barrier)."""
+
+    def __init__(self, shape, group=None, register: bool = True):
+        import numpy as np
+        import torch.distributed as dist
+        from multiprocessing import resource_tracker, shared_memory
+        self.group = group
+        self.rank = dist.get_rank(group)
+        nbytes = 4
+        for d in shape:
+            nbytes *= int(d)
+        name = [None]
+        if self.rank == 0:
+            self.shm = shared_memory.SharedMemory(create=True, size=nbytes)
+            name[0] = self.shm.name
+        dist.broadcast_object_list(name, src=0, group=group)
+        if self.rank != 0:
+            self.shm = shared_memory.SharedMemory(name=name[0])
+            # only the creator owns the segment: keep this process's resource tracker from unlinking it at exit
+            try:
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:
+                pass
+        self.nbytes = nbytes
+        self.array = np.ndarray(tuple(int(d) for d in shape), np.float32, buffer=self.shm.buf)
+        self.ptr = self.array.ctypes.data
+        self.registered = False
+        if register:
+            import torch
+            if torch.cuda.is_available():
+                rc = torch.cuda.cudart().cudaHostRegister(self.ptr, nbytes, 0)
+                if int(rc) != 0:
+                    raise RuntimeError(f"cudaHostRegister(shared stack) failed: {rc}")
+                self.registered = True
+        dist.barrier(group)
+
+    def close(self):
+        import torch.distributed as dist
+        if getattr(self, "shm", None) is None:
+            return
+        if self.registered:
+            import torch
+            torch.cuda.cudart().cudaHostUnregister(self.ptr)
+            self.registered = False
+        self.array = None
+        dist.barrier(self.group)
+        self.shm.close()
+        if self.rank == 0:
+            self.shm.unlink()
+        self.shm = None
 
 
 def stack_on_ranks(stack, frames_by_index, n_frames: int, rank: int, world: int, device=None, peers: bool = False):

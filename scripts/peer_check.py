@@ -57,6 +57,20 @@ def main():
             assert err <= 1e-6, err
         else:
             assert d_out is None
+    # reduce-scatter + every rank copying its slice into the host stack all ranks map
+    shared = D.SharedHostStack((h, w, 3))
+    for rep in range(2):
+        fill()
+        d_slice, begin, count = st.peer_reduce_scatter(n)
+        assert (begin, begin + count) == tuple(D.scatter_bounds(h * w * 3, rank, world))
+        st.peer_slice_to_host(shared.ptr)
+        st.sync()
+        dist.barrier()
+        if rank == 0:
+            err = float(np.abs(shared.array - want).max())
+            assert err <= 1e-6, err
+        dist.barrier()
+    shared.close()
     # timing of the exchange alone (partials in place)
     for name in ("peer", "nccl"):
         dist.barrier()

@@ -125,3 +125,48 @@ def test_peer_handles_are_gathered_in_rank_order():
         assert p.exitcode == 0
     for _, handles in results:
         assert handles == [bytes([0]) * 256, bytes([1]) * 256]
+
+
+def _shared_worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as ge
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    D = ge.load_package().distributed
+    shape = (7, 5, 3)
+    shared = D.SharedHostStack(shape, register=False)        # no CUDA here: the mapping itself is under test
+    n = 7 * 5 * 3
+    b, e = D.scatter_bounds(n, rank, world)
+    shared.array.reshape(-1)[b:e] = np.arange(b, e, dtype=np.float32) + 1000 * rank    # "this rank's slice"
+    dist.barrier()
+    if rank == 0:
+        q.put(shared.array.reshape(-1).copy())
+    dist.barrier()
+    shared.close()
+    dist.destroy_process_group()
+
+
+def test_shared_host_stack_collects_every_ranks_slice(pkg):
+    import torch.multiprocessing as mp
+    D = pkg.distributed
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_shared_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    n = 7 * 5 * 3
+    want = np.empty(n, np.float32)
+    for r in range(2):
+        b, e = D.scatter_bounds(n, r, 2)
+        want[b:e] = np.arange(b, e, dtype=np.float32) + 1000 * r
+    assert np.array_equal(got, want)
+    for world in (1, 2, 3, 8):
+        edges = [D.scatter_bounds(n, r, world) for r in range(world)]
+        assert edges[0][0] == 0 and edges[-1][1] == n and all(a[1] == b[0] for a, b in zip(edges, edges[1:]))

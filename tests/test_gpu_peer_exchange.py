@@ -55,7 +55,20 @@ def test_world_of_one_equals_finish(pkg):
             st.sync()
             got = _device_array(ptr, (h, w, 3))
             assert np.array_equal(got, want)
+        # reduce-scatter form: the (only) rank keeps the whole stack as its slice and copies it to the host
+        st.reset()
+        st.set_reference(frames[0])
+        for i, f in enumerate(frames[1:], 1):
+            st.submit(f, tag=i)
+        d_slice, begin, count = st.peer_reduce_scatter(len(frames))
+        assert (begin, count) == (0, h * w * 3)
+        host = np.zeros((h, w, 3), np.float32)
+        st.peer_slice_to_host(host.ctypes.data)
+        st.sync()
+        assert np.array_equal(host, want)
         st.peer_disconnect()
+        with pytest.raises(pkg.StackerError):
+            st.peer_slice_to_host(host.ctypes.data)
 
 
 def test_peer_reduce_needs_connect(pkg):
