@@ -202,6 +202,8 @@ def run_b200(a, rank, local_rank, world):
         dist.init_process_group("nccl", device_id=dev)
     pkg = ge.load_package()
     D = pkg.distributed
+    # one process per GPU: allocate this rank's pinned frame buffers on the GPU's own NUMA node
+    numa_bound = D.bind_to_gpu_numa_node(local_rank) if (world > 1 and os.environ.get("STK_NUMA_BIND", "1") != "0") else False
 
     n, w, h = a.frames, a.width, a.height
     n_px = w * h
@@ -448,7 +450,7 @@ def run_b200(a, rank, local_rank, world):
                        "l2": "inputs larger than L2: every step reads all frames (%.2f GB u8) from HBM" % (n * n_px * 3 / 1e9),
                        "parallelism": (f"frames sharded over {world} GPU(s), " + ("one fused reduce-scatter+divide kernel per rank over NVLink peer memory"
                                                                                    if use_peers else "one NCCL reduce")) if world > 1 else "1 GPU",
-                       "ecc_iterations_per_step": total_iters, "ecc_iterations_per_rank": iters_per_rank, "wall_ms_per_step": wall_ms / a.steps},
+                       "numa_bound": bool(numa_bound), "ecc_iterations_per_step": total_iters, "ecc_iterations_per_rank": iters_per_rank, "wall_ms_per_step": wall_ms / a.steps},
             "whole_step": {"algorithmic_GBps_per_gpu": alg_bytes / (ms / a.steps * 1e-3) / 1e9 / world,
                            "frac_of_hbm_peak": alg_bytes / (ms / a.steps * 1e-3) / 1e9 / world / peak},
             "roofline": roof, "stages": stages, "cpu_baseline": cpu, "e2e": e2e,
