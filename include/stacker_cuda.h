@@ -188,7 +188,9 @@ int stk_ecc_peer_reduce(stk_ecc_ctx* ctx, int divisor, const float** d_out);
    that want the stack in HOST memory: stk_ecc_peer_slice_to_host then queues the device-to-host copy of the slice
    into `out + begin` (`out` = the dense host stack, ideally pinned and, with one process per GPU, a shared
    mapping), so the result leaves over EVERY GPU's PCIe link at once instead of the root's alone (the copy of a
-   4K stack is 2 ms over one link — at 8 GPUs as long as the alignment itself).  Complete after stk_ecc_sync. */
+   4K stack is 2 ms over one link — at 8 GPUs as long as the alignment itself).  Complete after stk_ecc_sync.  With several contexts in ONE process, queue the
+   reduce_scatter on every context before the first slice_to_host: an exchange waits for all ranks, and a copy into
+   pageable host memory blocks the calling thread until its device's exchange is done. */
 int stk_ecc_peer_reduce_scatter(stk_ecc_ctx* ctx, int divisor, const float** d_slice, size_t* begin, size_t* count);
 int stk_ecc_peer_slice_to_host(stk_ecc_ctx* ctx, float* out);
 int stk_ecc_peer_disconnect(stk_ecc_ctx* ctx);

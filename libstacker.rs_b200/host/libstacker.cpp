@@ -5,6 +5,7 @@
 #include <cstring>
 #include <fstream>
 #include <future>
+#include <memory>
 #include <thread>
 
 #include "../../include/stacker_cuda.h"
@@ -73,7 +74,26 @@ ImageU8 read_pnm(const std::filesystem::path& path) {
 ImageF32 ecc_match(const std::vector<std::filesystem::path>& files, const EccMatchParameters& params,
                    std::optional<float> scale_down_width, const Decoder& decode, int device,
                    std::vector<FrameAlignment>* details) {
+  return ecc_match_on_devices(files, params, {device}, scale_down_width, decode, details);
+}
+
+std::vector<int> all_devices() {
+  int n = 0;
+  check(stk_device_count(&n));
+  std::vector<int> d(n);
+  for (int i = 0; i < n; ++i) d[i] = i;
+  return d;
+}
+
+// One context per device.  Frame 0 goes to every device (each builds its own reference planes; only the first
+// seeds its accumulator with it, src/lib.rs:752-754), the other frames are dealt round-robin, and the partial stacks
+// meet in ONE exchange step fused with the `/ n` (src/lib.rs:819-839): stk_ecc_peer_reduce_scatter over NVLink
+// peer memory, every device then copying its slice of the result into `out` over its own PCIe link.
+ImageF32 ecc_match_on_devices(const std::vector<std::filesystem::path>& files, const EccMatchParameters& params,
+                              const std::vector<int>& devices, std::optional<float> scale_down_width,
+                              const Decoder& decode, std::vector<FrameAlignment>* details) {
   if (files.empty()) throw NotEnoughFiles();                                            // src/lib.rs:725
+  if (devices.empty()) throw InvalidParams("no CUDA device given");
   const TermCriteria crit = term_criteria(params);
   ImageU8 first = decode(files[0]);
   check_colour(first);
@@ -89,9 +109,20 @@ ImageF32 ecc_match(const std::vector<std::filesystem::path>& files, const EccMat
   cfg.motion_type = (int)params.motion_type;
   cfg.criteria_type = crit.typ; cfg.max_count = crit.max_count; cfg.epsilon = crit.epsilon;
   cfg.gauss_filt_size = params.gauss_filt_size;
-  cfg.device = device; cfg.lanes = 0; cfg.seed_reference = 1; cfg.align = 1;
-  Ctx ctx(cfg);
-  check(stk_ecc_set_reference(ctx.c, first.data.data(), (size_t)first.width * first.channels));
+  cfg.lanes = 0; cfg.align = 1;
+  const size_t ndev = devices.size();
+  std::vector<std::unique_ptr<Ctx>> ctxs;
+  for (size_t d = 0; d < ndev; ++d) {
+    cfg.device = devices[d];
+    cfg.seed_reference = d == 0 ? 1 : 0;
+    ctxs.push_back(std::make_unique<Ctx>(cfg));
+    check(stk_ecc_set_reference(ctxs[d]->c, first.data.data(), (size_t)first.width * first.channels));
+  }
+  if (ndev > 1) {
+    std::vector<stk_ecc_ctx*> raw;
+    for (auto& c : ctxs) raw.push_back(c->c);
+    check(stk_ecc_peer_connect_local(raw.data(), (int)ndev));
+  }
   // one decode task per frame (Rayon's into_par_iter, src/lib.rs:746-749); submission is thread-safe
   const size_t n = files.size();
   const unsigned workers = std::max(1u, std::min<unsigned>(8, std::thread::hardware_concurrency()));
@@ -104,7 +135,7 @@ ImageF32 ecc_match(const std::vector<std::filesystem::path>& files, const EccMat
         check_colour(f);
         if (f.width != first.width || f.height != first.height || f.channels != first.channels)
           throw OpenCvError("frame size differs from the first frame");
-        check(stk_ecc_submit_frame(ctx.c, f.data.data(), (size_t)f.width * f.channels, (int64_t)i));
+        check(stk_ecc_submit_frame(ctxs[i % ndev]->c, f.data.data(), (size_t)f.width * f.channels, (int64_t)i));
       }
     }));
   }
@@ -112,18 +143,28 @@ ImageF32 ecc_match(const std::vector<std::filesystem::path>& files, const EccMat
   ImageF32 out;
   out.width = first.width; out.height = first.height; out.channels = first.channels;
   out.data.resize((size_t)out.width * out.height * out.channels);
-  check(stk_ecc_finish(ctx.c, (int)n, out.data.data(), (size_t)out.width * out.channels * sizeof(float)));
+  if (ndev == 1) {
+    check(stk_ecc_finish(ctxs[0]->c, (int)n, out.data.data(), (size_t)out.width * out.channels * sizeof(float)));
+  } else {
+    // queue the exchange on EVERY device first: a device's exchange kernel waits for all the others, and a copy
+    // into pageable host memory blocks this thread until that device's exchange is done
+    for (auto& c : ctxs) check(stk_ecc_peer_reduce_scatter(c->c, (int)n, nullptr, nullptr, nullptr));
+    for (auto& c : ctxs) check(stk_ecc_peer_slice_to_host(c->c, out.data.data()));
+    for (auto& c : ctxs) check(stk_ecc_sync(c->c));      // also surfaces per-frame ECC failures (src/lib.rs:777)
+  }
   if (details) {
-    std::vector<stk_frame_result> res(n);
-    int count = 0;
-    check(stk_ecc_results(ctx.c, res.data(), (int)n, &count));
     details->clear();
-    for (int i = 0; i < count; ++i) {
-      FrameAlignment a;
-      a.frame = res[i].tag;
-      std::memcpy(a.warp, res[i].warp, sizeof a.warp);
-      a.rho = res[i].rho; a.iterations = res[i].iterations;
-      details->push_back(a);
+    for (auto& c : ctxs) {
+      std::vector<stk_frame_result> res(n);
+      int count = 0;
+      check(stk_ecc_results(c->c, res.data(), (int)n, &count));
+      for (int i = 0; i < count; ++i) {
+        FrameAlignment a;
+        a.frame = res[i].tag;
+        std::memcpy(a.warp, res[i].warp, sizeof a.warp);
+        a.rho = res[i].rho; a.iterations = res[i].iterations;
+        details->push_back(a);
+      }
     }
     // submissions race on the decode pool: report in file order
     std::sort(details->begin(), details->end(), [](const FrameAlignment& x, const FrameAlignment& y) { return x.frame < y.frame; });

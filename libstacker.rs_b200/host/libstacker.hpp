@@ -75,6 +75,14 @@ ImageF32 ecc_match(const std::vector<std::filesystem::path>& files, const EccMat
                    std::optional<float> scale_down_width = std::nullopt, const Decoder& decode = read_pnm,
                    int device = -1, std::vector<FrameAlignment>* details = nullptr);
 
+// The same stack sharded over several GPUs of one box from ONE process (what the Rust crate does with its Rayon
+// pool): one context per device, frames dealt round-robin, one fused exchange + divide over NVLink peer memory
+// (stk_ecc_peer_connect_local / stk_ecc_peer_reduce_scatter), every device copying its slice of the result out.
+std::vector<int> all_devices();
+ImageF32 ecc_match_on_devices(const std::vector<std::filesystem::path>& files, const EccMatchParameters& params,
+                              const std::vector<int>& devices, std::optional<float> scale_down_width = std::nullopt,
+                              const Decoder& decode = read_pnm, std::vector<FrameAlignment>* details = nullptr);
+
 // The GPU tail of keypoint_match (src/lib.rs:289-350): frames[0] unwarped + warp_perspective(frames[i],
 // homographies[i-1]) accumulated, divided by the frame count.  The feature stages stay OpenCV on the host.
 ImageF32 stack_with_homographies(const std::vector<ImageU8>& frames, const std::vector<std::array<double, 9>>& homographies,

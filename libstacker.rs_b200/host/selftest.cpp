@@ -2,6 +2,8 @@
 // error behaviour); `selftest gpu <dir>` stacks PNM frames written by tests/test_cpp_host.py and prints the
 // recovered translations, the Tenengrad value and a checksum of the stack for the Python side to compare.
 #include <array>
+#include <cmath>
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <iostream>
@@ -44,6 +46,18 @@ int main(int argc, char** argv) {
   double sum = 0;
   for (float v : out.data) sum += v;
   std::printf("stack_sum %.6f\n", sum);
+  // the same stack over every GPU of the box from this one process (skipped on a single-GPU box)
+  const std::vector<int> devs = all_devices();
+  if (devs.size() >= 2) {
+    std::vector<FrameAlignment> det2;
+    ImageF32 out2 = ecc_match_on_devices(files, {MotionType::Translation, 200, 1e-6, 5}, devs, std::nullopt, read_pnm, &det2);
+    EXPECT(det2.size() == det.size());
+    for (size_t i = 0; i < det.size(); ++i) EXPECT(std::memcmp(det[i].warp, det2[i].warp, sizeof det[i].warp) == 0);
+    double worst = 0;
+    for (size_t i = 0; i < out.data.size(); ++i) worst = std::max(worst, (double)std::fabs(out.data[i] - out2.data[i]));
+    EXPECT(worst <= 1e-6);                                  // f32 summation order only
+    std::printf("multi_gpu devices %zu max_abs_diff %.3g\n", devs.size(), worst);
+  }
   ImageU8 grey = read_pnm(dir / "grey.pgm");
   std::printf("tenengrad %.17g\n", sharpness_tenengrad(grey, 3, 0));
   // neither COUNT nor EPS: CV_Assert inside findTransformECC -> OpenCvError

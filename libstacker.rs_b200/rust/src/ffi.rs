@@ -1,4 +1,4 @@
-//! Thin `extern "C"` layer over include/stacker_cuda.h (ABI version 2).  One declaration per entry point the
+//! Thin `extern "C"` layer over include/stacker_cuda.h (ABI version 3).  One declaration per entry point the
 //! Rust wrappers use; see the header for ownership and threading rules.
 #![allow(non_camel_case_types)]
 use std::os::raw::{c_char, c_int, c_void};
@@ -74,6 +74,15 @@ unsafe extern "C" {
     pub fn stk_ecc_partial(ctx: *mut stk_ecc_ctx, d_partial: *mut *mut f32, n_floats: *mut usize) -> c_int;
     pub fn stk_ecc_finish_from(ctx: *mut stk_ecc_ctx, d_sum: *const f32, divisor: c_int, out: *mut f32, out_pitch: usize) -> c_int;
     pub fn stk_ecc_reset(ctx: *mut stk_ecc_ctx) -> c_int;
+
+    // multi-GPU exchange over NVLink peer memory, all contexts in this process (include/stacker_cuda.h)
+    pub fn stk_ecc_peer_connect_local(ctxs: *const *mut stk_ecc_ctx, world: c_int) -> c_int;
+    pub fn stk_ecc_peer_reduce(ctx: *mut stk_ecc_ctx, divisor: c_int, d_out: *mut *const f32) -> c_int;
+    pub fn stk_ecc_peer_reduce_scatter(
+        ctx: *mut stk_ecc_ctx, divisor: c_int, d_slice: *mut *const f32, begin: *mut usize, count: *mut usize,
+    ) -> c_int;
+    pub fn stk_ecc_peer_slice_to_host(ctx: *mut stk_ecc_ctx, out: *mut f32) -> c_int;
+    pub fn stk_ecc_peer_disconnect(ctx: *mut stk_ecc_ctx) -> c_int;
 
     pub fn stk_tenengrad(
         img: *const u8, pitch: usize, width: c_int, height: c_int, channels: c_int, ksize: c_int,

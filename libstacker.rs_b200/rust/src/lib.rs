@@ -75,10 +75,23 @@ pub struct EccMatchParameters {
     pub gauss_filt_size: i32,
 }
 
+/// CUDA devices a stack is sharded over: all of the box, or the first `STACKER_GPUS` of them.
+fn devices() -> Result<Vec<i32>, StackerError> {
+    let mut n = 0;
+    check(unsafe { ffi::stk_device_count(&mut n) })?;
+    let want = std::env::var("STACKER_GPUS").ok().and_then(|v| v.parse::<i32>().ok()).unwrap_or(n);
+    Ok((0..n.min(want).max(1)).collect())
+}
+
 fn new_ctx(first: &Mat, ecc: Option<(EccMatchParameters, core::TermCriteria)>, ecc_size: Option<(i32, i32)>) -> Result<ffi::Ctx, StackerError> {
+    new_ctx_on(first, ecc, ecc_size, -1, true)
+}
+
+fn new_ctx_on(first: &Mat, ecc: Option<(EccMatchParameters, core::TermCriteria)>, ecc_size: Option<(i32, i32)>,
+              device: i32, seed_reference: bool) -> Result<ffi::Ctx, StackerError> {
     let mut cfg = ffi::stk_ecc_config {
         width: first.cols(), height: first.rows(), channels: first.channels(),
-        device: -1, lanes: 0, seed_reference: 1, ..Default::default()
+        device, lanes: 0, seed_reference: seed_reference as i32, ..Default::default()
     };
     if let Some((w, h)) = ecc_size {
         cfg.ecc_width = w;
@@ -129,8 +142,20 @@ where
         }
         None => None,
     };
-    let ctx = new_ctx(&first, Some((params, criteria)), ecc_size)?;
-    check(unsafe { ffi::stk_ecc_set_reference(ctx.0, first.data(), first.mat_step().get(0)) })?;
+    // one context per GPU of the box: every device gets frame 0 (only the first seeds its accumulator with it,
+    // reference src/lib.rs:752-754), the other frames are dealt round-robin
+    let devs = devices()?;
+    let mut ctxs = Vec::with_capacity(devs.len());
+    for (k, d) in devs.iter().enumerate() {
+        let c = new_ctx_on(&first, Some((params, criteria)), ecc_size, *d, k == 0)?;
+        check(unsafe { ffi::stk_ecc_set_reference(c.0, first.data(), first.mat_step().get(0)) })?;
+        ctxs.push(c);
+    }
+    if ctxs.len() > 1 {
+        let raw: Vec<*mut ffi::stk_ecc_ctx> = ctxs.iter().map(|c| c.0).collect();
+        check(unsafe { ffi::stk_ecc_peer_connect_local(raw.as_ptr(), raw.len() as i32) })?;
+    }
+    let ctxs = &ctxs;
     // decode on the Rayon pool, one task per frame (reference: src/lib.rs:746-749); submission is thread-safe
     // and asynchronous
     (1..files.len()).into_par_iter().with_min_len(1).try_for_each(|i| -> Result<(), StackerError> {
@@ -142,6 +167,7 @@ where
         // while this task copies) and hand it over; the upload is asynchronous and the buffer is recycled by
         // the library.  (`imgcodecs::imdecode_to` on a Mat wrapped around `buf` would save this copy too.)
         let (mut buf, mut pitch) = (std::ptr::null_mut::<u8>(), 0usize);
+        let ctx = &ctxs[i % ctxs.len()];
         check(unsafe { ffi::stk_ecc_acquire_frame_buffer(ctx.0, &mut buf, &mut pitch) })?;
         let step = img.mat_step().get(0);
         for y in 0..img.rows() as usize {
@@ -149,7 +175,24 @@ where
         }
         check(unsafe { ffi::stk_ecc_submit_acquired(ctx.0, buf, i as i64) })
     })?;
-    finish(&ctx, &first, files.len())
+    if ctxs.len() == 1 {
+        return finish(&ctxs[0], &first, files.len());
+    }
+    // Rayon's try_reduce + `/ n` (reference src/lib.rs:819-839) as ONE exchange step over NVLink peer memory: every
+    // device reduces and scales its slice of the stack and copies it into the result Mat over its own PCIe link.
+    // All exchanges are queued before the first copy-out (a copy into pageable memory blocks this thread).
+    let typ = core::CV_MAKETYPE(core::CV_32F, first.channels());
+    let mut out = unsafe { Mat::new_rows_cols(first.rows(), first.cols(), typ)? };
+    for c in ctxs.iter() {
+        check(unsafe { ffi::stk_ecc_peer_reduce_scatter(c.0, files.len() as i32, std::ptr::null_mut(), std::ptr::null_mut(), std::ptr::null_mut()) })?;
+    }
+    for c in ctxs.iter() {
+        check(unsafe { ffi::stk_ecc_peer_slice_to_host(c.0, out.data_mut() as *mut f32) })?;
+    }
+    for c in ctxs.iter() {
+        check(unsafe { ffi::stk_ecc_sync(c.0) })?;      // also surfaces a frame's ECC failure (reference :777)
+    }
+    Ok(out)
 }
 
 /// Feature-based alignment: ORB / BFMatcher / findHomography on the host exactly as the reference
