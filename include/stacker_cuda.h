@@ -52,8 +52,10 @@ enum { STK_MOTION_TRANSLATION = 0, STK_MOTION_EUCLIDEAN = 1, STK_MOTION_AFFINE =
 /* TermCriteria_Type bits                                          (src/utils.rs:159-170) */
 enum { STK_TERM_COUNT = 1, STK_TERM_EPS = 2 };
 
-/* cv::BorderTypes accepted by the warp-only path                  (src/lib.rs:297-298) */
-enum { STK_BORDER_CONSTANT = 0 };
+/* cv::BorderTypes accepted by the warp-only path (KeyPointMatchParameters::border_mode, src/lib.rs:66-68, :297-298).
+   BORDER_TRANSPARENT (5) is STK_ERR_UNSUPPORTED: the reference warps into a fresh Mat, so "transparent" pixels would
+   add uninitialised memory to the stack. */
+enum { STK_BORDER_CONSTANT = 0, STK_BORDER_REPLICATE = 1, STK_BORDER_REFLECT = 2, STK_BORDER_WRAP = 3, STK_BORDER_REFLECT_101 = 4 };
 
 typedef struct stk_ecc_ctx stk_ecc_ctx;
 
@@ -96,8 +98,9 @@ int         stk_device_count(int* count);
 
 /* utils::scale_image's size rule (src/utils.rs:186-200): the SMALLER dimension becomes `scale_down`, both
    new sizes are truncated (`as i32`).  Also applies ecc_match_scaling_down's validation
-   (src/lib.rs:876-888): scale_down >= width or scale_down <= 10 -> STK_ERR_BAD_ARG.  A rule that would
-   ENLARGE the planes (landscape frame, height < scale_down < width) is STK_ERR_UNSUPPORTED. */
+   (src/lib.rs:876-888): scale_down >= width or scale_down <= 10 -> STK_ERR_BAD_ARG.  On a landscape frame with
+   height < scale_down < width the rule ENLARGES the planes, exactly as in the reference (cv::resize INTER_AREA then
+   runs its 8-bit bilinear kernels in "area mode"; restated bit-exactly). */
 int stk_scaled_size(int width, int height, float scale_down, int* scaled_width, int* scaled_height);
 
 /* pinned host memory for decode targets: "JPEG decode stays on the host and feeds pinned,

@@ -22,6 +22,7 @@ from . import _ffi
 from ._ffi import lib
 
 BORDER_CONSTANT = 0          # opencv::core::BORDER_CONSTANT
+BORDER_REPLICATE, BORDER_REFLECT, BORDER_WRAP, BORDER_REFLECT_101 = 1, 2, 3, 4      # the other cv::BorderTypes the warp path implements
 RANSAC = 8                   # opencv::calib3d::RANSAC
 LMEDS = 4
 

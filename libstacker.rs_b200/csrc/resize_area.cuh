@@ -7,6 +7,9 @@
 // traffic is 3N bytes in + n bytes out (n = small size).  The colour resize the reference also computes
 // (lib.rs:919-920) is only ever asked for its size, so it is not computed at all.
 //
+// An enlarging axis (landscape frame with height < scale_down_width < width) sends the call through OpenCV's 8-bit
+// bilinear kernels in "area mode" (oracle/restate.py::resize_area_up_u8): integer arithmetic, bit-exact.
+//
 // Bit-exact restatement of OpenCV's two INTER_AREA down-scaling paths for 8-bit single-channel input
 // (oracle/restate.py::resize_area_u8, pinned against cv2.resize):
 //   * integer scale in both directions (resizeAreaFast_Invoker): integer block sum; 2x2 -> (s + 2) >> 2,
@@ -30,6 +33,9 @@ struct ResizeAreaParams {
   // kx / ky weights (dense, zero padded)
   const int* xfirst; const int* xcount; const float* xw; int kx;
   const int* yfirst; const int* ycount; const float* yw; int ky;
+  // an axis enlarges (landscape frame, height < scale_down_width < width): OpenCV emulates INTER_AREA with its
+  // 8-bit bilinear kernels ("area mode"): xfirst / yfirst = first source index, xcoef / ycoef = the two 11-bit weights
+  int up; const int* xcoef; const int* ycoef;
 };
 
 __device__ __forceinline__ int grey_at(const uint8_t* row, int x, int ch) {
@@ -45,7 +51,17 @@ __global__ void __launch_bounds__(kResizeBX * kResizeBY) resize_area_grey_kernel
   if (dx >= p.dw || dy >= p.dh) return;
   const int ch = p.channels;
   int out;
-  if (p.ix > 0) {
+  if (p.up) {
+    // HResizeLinear<uchar,int,short> then VResizeLinear<uchar,int,short>:
+    //   S = g[x0]*a0 + g[x1]*a1 ;  out = (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2
+    const int x0 = p.xfirst[dx], x1 = min(x0 + 1, p.sw - 1), a0 = p.xcoef[2 * dx], a1 = p.xcoef[2 * dx + 1];
+    const int y0 = p.yfirst[dy], y1 = min(y0 + 1, p.sh - 1), b0 = p.ycoef[2 * dy], b1 = p.ycoef[2 * dy + 1];
+    const uint8_t* r0 = p.src + (size_t)y0 * p.src_pitch;
+    const uint8_t* r1 = p.src + (size_t)y1 * p.src_pitch;
+    const int s0 = grey_at(r0, x0, ch) * a0 + grey_at(r0, x1, ch) * a1;
+    const int s1 = grey_at(r1, x0, ch) * a0 + grey_at(r1, x1, ch) * a1;
+    out = (((b0 * (s0 >> 4)) >> 16) + ((b1 * (s1 >> 4)) >> 16) + 2) >> 2;
+  } else if (p.ix > 0) {
     int s = 0;
     for (int ky = 0; ky < p.iy; ++ky) {
       const uint8_t* row = p.src + (size_t)(dy * p.iy + ky) * p.src_pitch;

@@ -153,15 +153,51 @@ struct AreaPlan {
   int kx = 0, ky = 0;
   int *xfirst = nullptr, *xcount = nullptr, *yfirst = nullptr, *ycount = nullptr;
   float *xw = nullptr, *yw = nullptr;
+  bool up = false;                 // an axis enlarges: OpenCV's 8-bit bilinear "area mode" (xfirst/yfirst + coefficients)
+  int *xcoef = nullptr, *ycoef = nullptr;   // [2 * dsize] 11-bit fixed-point weights
 };
 
 void free_area_plan(AreaPlan& a) {
   cudaFree(a.xfirst); cudaFree(a.xcount); cudaFree(a.yfirst); cudaFree(a.ycount); cudaFree(a.xw); cudaFree(a.yw);
+  cudaFree(a.xcoef); cudaFree(a.ycoef);
   a = AreaPlan();
+}
+
+// cv::resize's coefficient table when INTER_AREA is not a pure down-scale ("area mode" of the bilinear path,
+// imgproc/resize.cpp), as restated in oracle/restate.py::_linear_area_tab: first source index and the two weights
+// saturate_cast<short>(w * INTER_RESIZE_COEF_SCALE) per destination index.
+void build_linear_area_tab(int ssize, int dsize, std::vector<int>& ofs, std::vector<int>& coef) {
+  const double inv = (double)dsize / ssize, scale = 1.0 / inv;
+  ofs.assign(dsize, 0);
+  coef.assign((size_t)dsize * 2, 0);
+  for (int d = 0; d < dsize; ++d) {
+    int s = (int)std::floor(d * scale);
+    float f = (float)((d + 1) - (s + 1) * inv);
+    f = f <= 0 ? 0.f : f - (float)(int)std::floor(f);
+    if (s < 0) { f = 0.f; s = 0; }
+    if (s >= ssize - 1) { f = 0.f; s = ssize - 1; }
+    ofs[d] = s;
+    auto to_short = [](float v) { const long r = std::lrintf(v); return (int)std::max(-32768l, std::min(32767l, r)); };
+    coef[2 * d] = to_short((1.f - f) * 2048.f);
+    coef[2 * d + 1] = to_short(f * 2048.f);
+  }
 }
 
 int make_area_plan(int sw, int sh, int dw, int dh, AreaPlan& a) {
   a.sw = sw; a.sh = sh; a.dw = dw; a.dh = dh;
+  if (dw > sw || dh > sh) {
+    std::vector<int> xo, xc, yo, yc;
+    build_linear_area_tab(sw, dw, xo, xc);
+    build_linear_area_tab(sh, dh, yo, yc);
+    auto up = [](const void* h, size_t bytes, void** d) -> bool {
+      return cudaMalloc(d, bytes) == cudaSuccess && cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
+    };
+    const bool ok = up(xo.data(), sizeof(int) * dw, (void**)&a.xfirst) && up(xc.data(), sizeof(int) * 2 * dw, (void**)&a.xcoef) &&
+                    up(yo.data(), sizeof(int) * dh, (void**)&a.yfirst) && up(yc.data(), sizeof(int) * 2 * dh, (void**)&a.ycoef);
+    if (!ok) { free_area_plan(a); return fail(STK_ERR_NOMEM, "cannot upload the resize tables"); }
+    a.up = true;
+    return STK_OK;
+  }
   // cv::resize: inv_scale = dsize / ssize ; scale = 1 / inv_scale ; is_area_fast when both are integers
   const double scale_x = 1.0 / ((double)dw / sw), scale_y = 1.0 / ((double)dh / sh);
   const int ix = (int)std::nearbyint(scale_x), iy = (int)std::nearbyint(scale_y);
@@ -189,6 +225,7 @@ int launch_resize(const AreaPlan& a, const uint8_t* d_src, size_t pitch, int cha
   p.src = d_src; p.src_pitch = pitch; p.dst = d_dst; p.dst_pitch = dst_pitch;
   p.sw = a.sw; p.sh = a.sh; p.dw = a.dw; p.dh = a.dh; p.channels = channels;
   p.ix = a.ix; p.iy = a.iy;
+  p.up = a.up ? 1 : 0; p.xcoef = a.xcoef; p.ycoef = a.ycoef;
   p.xfirst = a.xfirst; p.xcount = a.xcount; p.xw = a.xw; p.kx = a.kx;
   p.yfirst = a.yfirst; p.ycount = a.ycount; p.yw = a.yw; p.ky = a.ky;
   dim3 block(stk::kResizeBX, stk::kResizeBY);
@@ -480,6 +517,7 @@ int launch_warp(stk_ecc_ctx* c, Lane& ln, const uint8_t* d_src, size_t pitch, bo
   p.status_ptr = from_state ? &ln.st->status : nullptr;
   if (inv_host) for (int i = 0; i < 9; ++i) p.inv[i] = inv_host[i];
   for (int i = 0; i < 4; ++i) p.border[i] = border ? border[i] : 0.f;
+  p.border_mode = border ? (int)border[4] : STK_BORDER_CONSTANT;      // border[4]: the cv::BorderTypes value
   p.store = ln.acc_used ? 0 : 1;
   dim3 block(stk::kWarpBX, stk::kWarpBY);
   dim3 grid((p.width + stk::kWarpBX - 1) / stk::kWarpBX, (p.height + stk::kWarpTH - 1) / stk::kWarpTH);
@@ -703,9 +741,6 @@ int stk_scaled_size(int width, int height, float scale_down, int* sw, int* sh) {
   if (scale_down <= 10.0f) return fail(STK_ERR_BAD_ARG, "scale_down_to was too small scale_down_to:%g", (double)scale_down);
   const double factor = (double)scale_down / (double)(width < height ? width : height);
   const int nw = (int)((double)width * factor), nh = (int)((double)height * factor);
-  if (nw > width || nh > height)
-    return fail(STK_ERR_UNSUPPORTED, "scale_down_to %g enlarges a %dx%d frame (%dx%d): only INTER_AREA down-scaling is implemented",
-                (double)scale_down, width, height, nw, nh);
   if (nw < 1 || nh < 1) return fail(STK_ERR_BAD_ARG, "scaled size %dx%d is empty", nw, nh);
   *sw = nw; *sh = nh;
   return STK_OK;
@@ -715,7 +750,6 @@ int stk_grey_resize_area(const uint8_t* img, size_t pitch, int width, int height
                          int out_height, int device, uint8_t* out, size_t out_pitch) {
   if (!img || !out) return fail(STK_ERR_BAD_ARG, "null argument");
   if (width <= 0 || height <= 0 || out_width <= 0 || out_height <= 0) return fail(STK_ERR_BAD_ARG, "bad size");
-  if (out_width > width || out_height > height) return fail(STK_ERR_UNSUPPORTED, "only INTER_AREA down-scaling is implemented");
   if (channels != 1 && channels != 3 && channels != 4) return fail(STK_ERR_UNSUPPORTED, "channels must be 1, 3 or 4");
   const size_t row = (size_t)width * channels;
   if (pitch < row || out_pitch < (size_t)out_width) return fail(STK_ERR_BAD_ARG, "pitch too small");
@@ -762,9 +796,8 @@ int stk_ecc_create(const stk_ecc_config* cfg, stk_ecc_ctx** out) {
       return fail(STK_ERR_BAD_ARG, "gauss_filt_size must be odd, in [1, %d]", 2 * stk::kMaxGaussRadius + 1);
     if ((cfg->ecc_width != 0) != (cfg->ecc_height != 0) || cfg->ecc_width < 0 || cfg->ecc_height < 0)
       return fail(STK_ERR_BAD_ARG, "ecc_width/ecc_height must both be 0 or both be positive");
-    if (cfg->ecc_width > cfg->width || cfg->ecc_height > cfg->height)
-      return fail(STK_ERR_UNSUPPORTED, "ecc size %dx%d enlarges the %dx%d frame: only INTER_AREA down-scaling is implemented",
-                  cfg->ecc_width, cfg->ecc_height, cfg->width, cfg->height);
+    // (an ECC size larger than the frame is legal: utils::scale_image enlarges a landscape frame when
+    //  height < scale_down_width < width — the INTER_AREA resize then runs OpenCV's bilinear "area mode")
   }
   int dev = cfg->device;
   if (dev < 0) CU(cudaGetDevice(&dev));
@@ -1055,12 +1088,15 @@ static int submit_warp(stk_ecc_ctx* c, const uint8_t* buf, size_t pitch, const d
   int rc = check_ctx(c);
   if (rc) return rc;
   if (!buf || !h) return fail(STK_ERR_BAD_ARG, "null argument");
-  if (border_mode != STK_BORDER_CONSTANT) return fail(STK_ERR_UNSUPPORTED, "border mode %d: only BORDER_CONSTANT is implemented", border_mode);
+  if (border_mode != STK_BORDER_CONSTANT && border_mode != STK_BORDER_REPLICATE && border_mode != STK_BORDER_REFLECT &&
+      border_mode != STK_BORDER_WRAP && border_mode != STK_BORDER_REFLECT_101)
+    return fail(STK_ERR_UNSUPPORTED, "border mode %d: CONSTANT, REPLICATE, REFLECT, WRAP and REFLECT_101 are implemented "
+                "(BORDER_TRANSPARENT would add uninitialised memory to the stack in the reference)", border_mode);
   const size_t row = (size_t)c->cfg.width * c->cfg.channels;
   if (pitch < row) return fail(STK_ERR_BAD_ARG, "pitch %zu < row bytes %zu", pitch, row);
   double inv[9];
   invert_perspective_host(h, inv);
-  float border[4] = {0, 0, 0, 0};
+  float border[5] = {0, 0, 0, 0, (float)border_mode};
   if (border_value) for (int i = 0; i < 4; ++i) border[i] = (float)border_value[i];
   if (!device) {
     int idx = -1;

@@ -29,6 +29,7 @@ struct WarpAccParams {
   const int* status_ptr;  // device pointer to the frame's ECC status (skip when != 0), or null
   double inv[9];
   float border[4];
+  int border_mode;        // cv::BorderTypes: 0 CONSTANT, 1 REPLICATE, 2 REFLECT, 3 WRAP, 4 REFLECT_101
   int store;              // 1: acc = v (first frame on this lane), 0: acc += v
 };
 
@@ -43,6 +44,21 @@ __device__ __forceinline__ double rcp_rn_normal(double w) {
   r = __fma_rn(r, t, r);
   const double e = __fma_rn(-w, r, 1.0);
   return __fma_rn(r, e, r);
+}
+
+// cv::borderInterpolate for the modes that always yield a source index (REPLICATE 1, REFLECT 2, WRAP 3,
+// REFLECT_101 4), restated in oracle/restate.py::border_interpolate and pinned against cv2 there
+__device__ __forceinline__ int border_index(int p, int len, int mode) {
+  if ((unsigned)p < (unsigned)len) return p;
+  if (mode == 1) return p < 0 ? 0 : len - 1;
+  if (mode == 3) { const int r = p % len; return r < 0 ? r + len : r; }
+  if (len == 1) return 0;
+  const int delta = mode == 4 ? 1 : 0;
+  do {
+    if (p < 0) p = -p - 1 + delta;
+    else p = len - 1 - (p - len) - delta;
+  } while ((unsigned)p >= (unsigned)len);
+  return p;
 }
 
 constexpr int kWarpBX = 32, kWarpBY = 8;   // thread block
@@ -189,6 +205,19 @@ __global__ void __launch_bounds__(kWarpBX * kWarpBY, 8) warp_accumulate_kernel(c
         for (int c = 0; c < C; ++c) {
           const float s00 = __fmul_rn((float)t00[c], k255), s01 = __fmul_rn((float)t01[c], k255);
           const float s10 = __fmul_rn((float)t10[c], k255), s11 = __fmul_rn((float)t11[c], k255);
+          v[c] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s00, w00), __fmul_rn(s01, w01)), __fmul_rn(s10, w10)),
+                           __fmul_rn(s11, w11));
+        }
+      } else if (p.border_mode != 0) {
+        // REPLICATE / REFLECT / WRAP / REFLECT_101: each tap's coordinates go through borderInterpolate on their own
+        const int x0 = border_index(sx, sw, p.border_mode), x1 = border_index(sx + 1, sw, p.border_mode);
+        const int y0 = border_index(sy, sh, p.border_mode), y1 = border_index(sy + 1, sh, p.border_mode);
+        const uint8_t* q0 = p.src + (size_t)y0 * p.src_pitch;
+        const uint8_t* q1 = p.src + (size_t)y1 * p.src_pitch;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const float s00 = __fmul_rn((float)__ldg(q0 + x0 * C + c), k255), s01 = __fmul_rn((float)__ldg(q0 + x1 * C + c), k255);
+          const float s10 = __fmul_rn((float)__ldg(q1 + x0 * C + c), k255), s11 = __fmul_rn((float)__ldg(q1 + x1 * C + c), k255);
           v[c] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s00, w00), __fmul_rn(s01, w01)), __fmul_rn(s10, w10)),
                            __fmul_rn(s11, w11));
         }

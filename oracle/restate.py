@@ -222,10 +222,38 @@ def affine_fixed_coords(im: np.ndarray, width: int, height: int, nearest: bool =
     return xx, yy
 
 
-def sample_bilinear_fixed(src: np.ndarray, xq: np.ndarray, yq: np.ndarray, border_value=0.0):
-    """remapBilinear<float> with BORDER_CONSTANT: integer part = q >> 5 (saturated to short),
-    weights from the 5-bit fraction, value = s00*w00 + s01*w01 + s10*w10 + s11*w11 summed left to
-    right in f32, taps outside the source replaced by the border value."""
+BORDER_CONSTANT, BORDER_REPLICATE, BORDER_REFLECT, BORDER_WRAP, BORDER_REFLECT_101 = 0, 1, 2, 3, 4
+
+
+def border_interpolate(p: np.ndarray, length: int, border_mode: int) -> np.ndarray:
+    """cv::borderInterpolate for the modes that always yield a valid index (REPLICATE, REFLECT, WRAP,
+    REFLECT_101) — what KeyPointMatchParameters::border_mode (/root/reference/src/lib.rs:66-68, used at
+    :297) may select besides BORDER_CONSTANT."""
+    p = np.asarray(p, np.int64).copy()
+    if border_mode == BORDER_REPLICATE:
+        return np.clip(p, 0, length - 1)
+    if border_mode in (BORDER_REFLECT, BORDER_REFLECT_101):
+        if length == 1:
+            return np.zeros_like(p)
+        delta = 1 if border_mode == BORDER_REFLECT_101 else 0
+        while True:
+            neg, big = p < 0, p >= length
+            if not (neg.any() or big.any()):
+                return p
+            p = np.where(neg, -p - 1 + delta, p)
+            big = p >= length
+            p = np.where(big, length - 1 - (p - length) - delta, p)
+    if border_mode == BORDER_WRAP:
+        return np.mod(p, length)
+    raise ValueError(f"unsupported border mode {border_mode}")
+
+
+def sample_bilinear_fixed(src: np.ndarray, xq: np.ndarray, yq: np.ndarray, border_value=0.0,
+                          border_mode: int = BORDER_CONSTANT):
+    """remapBilinear<float>: integer part = q >> 5 (saturated to short), weights from the 5-bit fraction,
+    value = s00*w00 + s01*w01 + s10*w10 + s11*w11 summed left to right in f32.  BORDER_CONSTANT: taps outside
+    the source are the border value; REPLICATE / REFLECT / WRAP / REFLECT_101: every tap's coordinates go
+    through borderInterpolate on their own."""
     h, w = src.shape[:2]
     chan = 1 if src.ndim == 2 else src.shape[2]
     s = src.reshape(h, w, chan).astype(np.float32)
@@ -240,6 +268,15 @@ def sample_bilinear_fixed(src: np.ndarray, xq: np.ndarray, yq: np.ndarray, borde
     w11 = (ay * ax)[..., None]
     bv = np.broadcast_to(np.asarray(border_value, np.float32).reshape(-1)[:chan] if np.ndim(border_value)
                          else np.full(chan, border_value, np.float32), (chan,))
+
+    if border_mode != BORDER_CONSTANT:
+        x0, x1 = border_interpolate(sx, w, border_mode), border_interpolate(sx + 1, w, border_mode)
+        y0, y1 = border_interpolate(sy, h, border_mode), border_interpolate(sy + 1, h, border_mode)
+        out = s[y0, x0] * w00
+        out = out + s[y0, x1] * w01
+        out = out + s[y1, x0] * w10
+        out = out + s[y1, x1] * w11
+        return out.reshape(xq.shape + ((chan,) if src.ndim == 3 else ()))
 
     def tap(yy, xx):
         ok = (xx >= 0) & (xx < w) & (yy >= 0) & (yy < h)
@@ -257,8 +294,9 @@ def sample_bilinear_fixed(src: np.ndarray, xq: np.ndarray, yq: np.ndarray, borde
 
 
 def warp_linear(src: np.ndarray, m: np.ndarray, width: int, height: int, perspective: bool,
-                inverse_map: bool, border_value=0.0) -> np.ndarray:
-    """warpPerspective / warpAffine, INTER_LINEAR, BORDER_CONSTANT
+                inverse_map: bool, border_value=0.0, border_mode: int = BORDER_CONSTANT) -> np.ndarray:
+    """warpPerspective / warpAffine, INTER_LINEAR, border mode CONSTANT (default) / REPLICATE / REFLECT / WRAP /
+    REFLECT_101
     (/root/reference/src/lib.rs:780-803 forward map; ECC-internal warps use WARP_INVERSE_MAP)."""
     if perspective:
         im = np.asarray(m, np.float64).reshape(3, 3)
@@ -270,7 +308,7 @@ def warp_linear(src: np.ndarray, m: np.ndarray, width: int, height: int, perspec
         if not inverse_map:
             im = invert_affine(im)
         xq, yq = affine_fixed_coords(im, width, height)
-    return sample_bilinear_fixed(src, xq, yq, border_value)
+    return sample_bilinear_fixed(src, xq, yq, border_value, border_mode)
 
 
 def warp_mask_nearest(m: np.ndarray, width: int, height: int, src_w: int, src_h: int,
@@ -414,12 +452,12 @@ def find_transform_ecc(tmpl_u8: np.ndarray, img_u8: np.ndarray, motion: int, cri
 # --------------------------------------------------------------------------------------------
 # ecc_match_no_scaling                               /root/reference/src/lib.rs:719-847
 # --------------------------------------------------------------------------------------------
-def final_warp(frame_u8: np.ndarray, m, motion: int, border_value=0.0) -> np.ndarray:
+def final_warp(frame_u8: np.ndarray, m, motion: int, border_value=0.0, border_mode: int = BORDER_CONSTANT) -> np.ndarray:
     """convert_to(CV_32F, 1/255) then warp_affine | warp_perspective forward map
     (/root/reference/src/lib.rs:780-803)."""
     h, w = frame_u8.shape[:2]
     return warp_linear(to_f32_unit(frame_u8), m, w, h, perspective=(motion == MOTION_HOMOGRAPHY),
-                       inverse_map=False, border_value=border_value)
+                       inverse_map=False, border_value=border_value, border_mode=border_mode)
 
 
 def ecc_match(frames_u8, motion: int, max_count, epsilon, gauss_filt_size: int):
@@ -468,12 +506,53 @@ def _area_tab(ssize: int, dsize: int, scale: float):
     return tab
 
 
-def resize_area_u8(src: np.ndarray, dw: int, dh: int) -> np.ndarray:
-    """cv2.resize(src, (dw, dh), interpolation=INTER_AREA) for single-channel 8-bit DOWNSCALING.
-    Integer scale factors take OpenCV's fast path (2x2: (sum + 2) >> 2, otherwise rint(sum * f32(1/area)));
-    everything else the generic f32 path: per source row buf += S*alpha in table order, then
-    sum = beta*buf for the first row of a destination row and sum += beta*buf after, saturate_cast<uchar>."""
+def _linear_area_tab(ssize: int, dsize: int):
+    """cv::resize's coefficient table for INTER_AREA when it is NOT a pure down-scale ("area mode" of the bilinear
+    path, imgproc/resize.cpp): per destination index the first source index and the two 11-bit fixed-point
+    weights saturate_cast<short>(w * 2048)."""
+    inv = dsize / ssize
+    scale = 1.0 / inv
+    ofs = np.zeros(dsize, np.int64)
+    coef = np.zeros((dsize, 2), np.int64)
+    for d in range(dsize):
+        s = int(np.floor(d * scale))
+        f = np.float32((d + 1) - (s + 1) * inv)
+        f = np.float32(0.0) if f <= 0 else np.float32(f - np.floor(f))
+        if s < 0:
+            f, s = np.float32(0.0), 0
+        if s >= ssize - 1:
+            f, s = np.float32(0.0), ssize - 1
+        ofs[d] = s
+        coef[d, 0] = int(np.clip(np.rint(np.float32((np.float32(1.0) - f) * np.float32(2048.0))), -32768, 32767))
+        coef[d, 1] = int(np.clip(np.rint(np.float32(f * np.float32(2048.0))), -32768, 32767))
+    return ofs, coef
+
+
+def resize_area_up_u8(src: np.ndarray, dw: int, dh: int) -> np.ndarray:
+    """cv2.resize(src, (dw, dh), interpolation=INTER_AREA) when at least one axis ENLARGES (utils::scale_image on
+    a landscape frame with height < scale_down_width < width, /root/reference/src/utils.rs:186-214): OpenCV
+    emulates "area" with its 8-bit bilinear kernels — horizontal pass in 11-bit fixed point, vertical pass
+    ((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2."""
     sh, sw = src.shape
+    xo, xa = _linear_area_tab(sw, dw)
+    yo, ya = _linear_area_tab(sh, dh)
+    s = src.astype(np.int64)
+    rows = s[:, xo] * xa[None, :, 0] + s[:, np.minimum(xo + 1, sw - 1)] * xa[None, :, 1]
+    s0, s1 = rows[yo, :], rows[np.minimum(yo + 1, sh - 1), :]
+    b0, b1 = ya[:, 0][:, None], ya[:, 1][:, None]
+    out = (((b0 * (s0 >> 4)) >> 16) + ((b1 * (s1 >> 4)) >> 16) + 2) >> 2
+    return np.clip(out, 0, 255).astype(np.uint8)
+
+
+def resize_area_u8(src: np.ndarray, dw: int, dh: int) -> np.ndarray:
+    """cv2.resize(src, (dw, dh), interpolation=INTER_AREA) for single-channel 8-bit planes.
+    Down-scaling: integer scale factors take OpenCV's fast path (2x2: (sum + 2) >> 2, otherwise
+    rint(sum * f32(1/area))); everything else the generic f32 path: per source row buf += S*alpha in table order,
+    then sum = beta*buf for the first row of a destination row and sum += beta*buf after, saturate_cast<uchar>.
+    An enlarging axis sends the whole call through resize_area_up_u8."""
+    sh, sw = src.shape
+    if dw > sw or dh > sh:
+        return resize_area_up_u8(src, dw, dh)
     scale_x, scale_y = 1.0 / (dw / sw), 1.0 / (dh / sh)     # cv::resize: inv_scale = dsize/ssize; scale = 1/inv_scale
     ix, iy = int(round(scale_x)), int(round(scale_y))
     if abs(scale_x - ix) < np.finfo(np.float64).eps and abs(scale_y - iy) < np.finfo(np.float64).eps:

@@ -72,6 +72,28 @@ def scale_down_cases():
     return out
 
 
+RESIZE_UP_CASES = [  # landscape frames with height < scale_down < width: utils::scale_image ENLARGES (cv::resize INTER_AREA
+    # falls back to its 8-bit bilinear kernels in "area mode"); the last one enlarges x only (new height == height)
+    (320, 240, 250.0), (512, 384, 400.0), (200, 100, 199.0), (301, 201, 260.0), (333, 250, 250.9),
+]
+SCALE_UP_CASES = [(2, 480, 360, 400.0, 66), (3, 400, 300, 330.0, 67)]   # (motion, width, height, scale_down, seed)
+
+
+def scale_up_cases():
+    """ecc_match_scaling_down when utils::scale_image enlarges the greys (src/utils.rs:186-214)."""
+    out = {}
+    for w, h, sd in RESIZE_UP_CASES:
+        rng = np.random.default_rng(w * 7 + h)
+        grey = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        out[f"resize_{w}x{h}_{int(sd)}"] = cvref.scale_image(grey, sd)
+    for motion, w, h, sd, seed in SCALE_UP_CASES:
+        frames = synth.Stack(w, h, 4, motion, seed=seed).frames()
+        stack, warps, _ = cvref.ecc_match_scaling_down(frames, motion, 60, 1e-5, 5, sd)
+        out[f"sd_m{motion}_warps"] = np.stack([np.vstack([m, [0, 0, 1]]) if m.shape[0] == 2 else m for m in warps[1:]]).astype(np.float32)
+        out[f"sd_m{motion}_stack8"] = np.rint(stack * 255.0).astype(np.uint8)
+    return out
+
+
 def sharpness_cases():
     """LAPM / LAPV / TENG(3) / GLVN (src/lib.rs:1032-1166) on a random and on a synthetic-scene grey plane."""
     out = {}
@@ -86,6 +108,7 @@ def sharpness_cases():
 
 if __name__ == "__main__":
     np.savez_compressed(os.path.join(HERE, "scale_down.npz"), **scale_down_cases())
+    np.savez_compressed(os.path.join(HERE, "scale_up.npz"), **scale_up_cases())
     np.savez_compressed(os.path.join(HERE, "sharpness.npz"), **sharpness_cases())
     np.savez_compressed(os.path.join(HERE, "ecc_256x192.npz"), **ecc_cases())
     np.savez_compressed(os.path.join(HERE, "primitives_200x150.npz"), **primitive_cases())

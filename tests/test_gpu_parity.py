@@ -107,6 +107,35 @@ def test_warp_only_border_value_and_bgra(pkg):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("mode", [1, 2, 3, 4])
+@pytest.mark.parametrize("chan", [3, 4])
+def test_warp_only_border_modes_bit_exact(pkg, mode, chan):
+    """keypoint_match's border_mode (src/lib.rs:297): REPLICATE / REFLECT / WRAP / REFLECT_101 against the oracle
+    (itself pinned bit-exact to cv2.warpPerspective in tests/test_oracle_vs_cv2.py)."""
+    w, h = 200, 130
+    rng = np.random.default_rng(70 + mode)
+    frames = [rng.integers(0, 256, (h, w, chan), dtype=np.uint8) for _ in range(4)]
+    hs = [_rand_h(rng, w, h, True) for _ in range(3)]
+    hs[2][:2, 2] += np.array([2.5 * w, -1.7 * h])            # far outside: the reflect loop runs more than once
+    with pkg.EccStack(w, h, chan, None, device=0, lanes=1) as st:
+        st.set_reference(frames[0])
+        for f, hm in zip(frames[1:], hs):
+            st.submit_warp(f, hm, mode)
+        got = st.finish(4)
+    acc = R.to_f32_unit(frames[0])
+    for f, hm in zip(frames[1:], hs):
+        acc = acc + R.warp_linear(R.to_f32_unit(f), hm, w, h, True, False, border_mode=mode)
+    assert np.array_equal(got, acc * np.float32(0.25))
+
+
+def test_warp_only_transparent_border_unsupported(pkg):
+    frame = np.zeros((16, 16, 3), np.uint8)
+    with pkg.EccStack(16, 16, 3, None, device=0, lanes=1) as st:
+        st.set_reference(frame)
+        with pytest.raises(pkg.StackerError):
+            st.submit_warp(frame, np.eye(3), 5)
+
+
 def test_warp_only_vs_cv2(pkg, have_cv2):
     if not have_cv2:
         pytest.skip("cv2 not installed")
@@ -364,6 +393,47 @@ def test_grey_resize_area_bit_exact(pkg, case):
     assert np.array_equal(pkg.grey_resize_area(bgr, sw, sh, device=0), want)
     grey = R.bgr2gray_u8(bgr)
     assert np.array_equal(pkg.grey_resize_area(grey, sw, sh, device=0), want)
+
+
+@pytest.mark.parametrize("case", [(320, 240, 250.0), (512, 384, 400.0), (200, 100, 199.0), (301, 201, 260.0), (333, 250, 250.9),
+                                  (1024, 768, 800.0), (64, 48, 50.0)])
+def test_grey_resize_area_enlarging_bit_exact(pkg, case):
+    """landscape frame, height < scale_down < width: utils::scale_image ENLARGES and cv::resize(INTER_AREA) runs its
+    8-bit bilinear kernels in "area mode" (K0's `up` branch) — against the restatement and the cv2 golden vectors."""
+    import os
+    w, h, sd = case
+    rng = np.random.default_rng(w * 7 + h)
+    sw, sh = R.scaled_size(w, h, sd)
+    assert pkg.scaled_size(w, h, sd) == (sw, sh) and (sw > w or sh > h)
+    grey = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    want = R.resize_area_u8(grey, sw, sh)
+    assert np.array_equal(pkg.grey_resize_area(grey, sw, sh, device=0), want)
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "scale_up.npz"))
+    key = f"resize_{w}x{h}_{int(sd)}"
+    if key in g:
+        assert np.array_equal(want, g[key])
+    bgr = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    assert np.array_equal(pkg.grey_resize_area(bgr, sw, sh, device=0), R.resize_area_u8(R.bgr2gray_u8(bgr), sw, sh))
+
+
+@pytest.mark.parametrize("case", [(2, 480, 360, 400.0, 66), (3, 400, 300, 330.0, 67)])
+def test_ecc_match_scaling_down_enlarging_vs_oracle_and_golden(pkg, case):
+    import os
+    motion, w, h, sd, seed = case
+    frames = synth.Stack(w, h, 4, motion, seed=seed).frames()
+    params = pkg.EccMatchParameters(pkg.MotionType(motion), 60, 1e-5, 5)
+    got, res = pkg.ecc_match(frames, params, sd, device=0, return_details=True)
+    want, warps, _ = R.ecc_match_scaling_down(frames, motion, 60, 1e-5, 5, sd)
+    assert [r["status"] for r in res] == [0, 0, 0]
+    for r, wm in zip(res, warps[1:]):
+        mine = r["warp"] if motion == 3 else r["warp"][:2]
+        assert synth.corner_displacement(mine, wm, w, h) <= 0.05
+    assert_stack_parity(got, want, warps, motion, 4)
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "scale_up.npz"))
+    for r, ref in zip(res, g[f"sd_m{motion}_warps"]):
+        mine = r["warp"] if motion == 3 else r["warp"][:2]
+        assert synth.corner_displacement(mine, ref if motion == 3 else ref[:2], w, h) <= 0.05
+    assert_stack_parity(got, g[f"sd_m{motion}_stack8"].astype(np.float32) / np.float32(255.0), warps, motion, 4)
 
 
 def test_grey_resize_area_golden(pkg):

@@ -76,8 +76,9 @@ def test_scaled_size_rule_and_validation(pkg):
         pkg.scaled_size(1024, 768, 1024.0)
     with pytest.raises(pkg.InvalidParams, match="too small"):
         pkg.scaled_size(1024, 768, 10.0)
-    with pytest.raises(pkg.NotImplementedError_):      # landscape frame, height < scale_down < width: INTER_AREA up-scaling
-        pkg.scaled_size(1000, 500, 800.0)
+    # landscape frame, height < scale_down < width: the rule ENLARGES (cv::resize INTER_AREA then runs its bilinear
+    # "area mode"); legal in the reference, so legal here
+    assert pkg.scaled_size(1000, 500, 800.0) == R.scaled_size(1000, 500, 800.0) == (1600, 800)
     # the validation runs before any device work
     frames = [np.zeros((96, 128, 3), np.uint8)] * 2
     with pytest.raises(pkg.InvalidParams):

@@ -173,6 +173,50 @@ def test_golden_ecc_match_scaling_down(case):
     assert_stack_parity(stack, g[f"sd_m{motion}_stack8"].astype(np.float32) / np.float32(255.0), warps, motion, 4)
 
 
+def _golden_up_module():
+    src = open(os.path.join(GOLD, "make_golden.py")).read()
+    ns = {}
+    exec(src[src.index("RESIZE_UP_CASES"):src.index("def scale_up_cases")], ns)
+    return ns["RESIZE_UP_CASES"], ns["SCALE_UP_CASES"]
+
+
+def test_golden_resize_area_enlarging():
+    """landscape frame, height < scale_down_width < width: utils::scale_image enlarges and cv::resize(INTER_AREA)
+    runs its 8-bit bilinear kernels in "area mode" (restate.resize_area_up_u8)"""
+    cases, _ = _golden_up_module()
+    g = np.load(os.path.join(GOLD, "scale_up.npz"))
+    for w, h, sd in cases:
+        rng = np.random.default_rng(w * 7 + h)
+        grey = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        want = g[f"resize_{w}x{h}_{int(sd)}"]
+        sw, sh = R.scaled_size(w, h, sd)
+        assert (sh, sw) == want.shape and (sw > w or sh > h)
+        assert np.array_equal(R.resize_area_u8(grey, sw, sh), want)
+
+
+@pytest.mark.parametrize("case", [0, 1])
+def test_golden_ecc_match_scaling_down_enlarging(case):
+    g = np.load(os.path.join(GOLD, "scale_up.npz"))
+    _, sd_cases = _golden_up_module()
+    motion, w, h, sd, seed = sd_cases[case]
+    frames = synth.Stack(w, h, 4, motion, seed=seed).frames()
+    stack, warps, _ = R.ecc_match_scaling_down(frames, motion, 60, 1e-5, 5, sd)
+    for mine, ref in zip(warps[1:], g[f"sd_m{motion}_warps"]):
+        assert synth.corner_displacement(mine, ref if motion == 3 else ref[:2], w, h) <= 5e-3
+    assert_stack_parity(stack, g[f"sd_m{motion}_stack8"].astype(np.float32) / np.float32(255.0), warps, motion, 4)
+
+
+def test_resize_area_enlarging_exact(cv2):
+    from oracle import cvref
+    rng = np.random.default_rng(14)
+    for w, h, sd in [(64, 48, 50), (1024, 768, 800), (100, 75, 99.5), (640, 480, 481), (37, 21, 30), (333, 250, 250.9)]:
+        grey = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        sw, sh = R.scaled_size(w, h, sd)
+        want = cvref.scale_image(grey, sd)
+        assert want.shape == (sh, sw) and (sw > w or sh > h)
+        assert np.array_equal(R.resize_area_u8(grey, sw, sh), want)
+
+
 def test_golden_sharpness():
     g = np.load(os.path.join(GOLD, "sharpness.npz"))
     rng = np.random.default_rng(21)
@@ -224,3 +268,22 @@ def test_sharpness_metrics_exact(cv2):
         assert R.sharpness_modified_laplacian(g) == cvref.sharpness_modified_laplacian(g)
         assert R.sharpness_variance_of_laplacian(g) == cvref.sharpness_variance_of_laplacian(g)
         assert R.sharpness_normalized_gray_level_variance(g) == cvref.sharpness_normalized_gray_level_variance(g)
+
+
+@pytest.mark.parametrize("mode", [1, 2, 3, 4])
+def test_warp_border_modes_bit_exact(cv2, mode):
+    """KeyPointMatchParameters::border_mode (/root/reference/src/lib.rs:66-68, :297): warpPerspective with
+    BORDER_REPLICATE / REFLECT / WRAP / REFLECT_101 — every tap through borderInterpolate on its own."""
+    rng = np.random.default_rng(40 + mode)
+    for (w, h) in [(97, 61), (64, 48), (33, 200)]:
+        src = rng.random((h, w, 3), dtype=np.float32)
+        for trial in range(6):
+            g = synth.random_warp(rng, 3, w, h)
+            if trial >= 2:            # large parts of the destination sample outside the source
+                g[:2, 2] += rng.uniform(-0.6, 0.6, 2) * (w, h)
+                g[:2, :2] += rng.uniform(-0.2, 0.2, (2, 2))
+            if trial >= 4:            # several image widths away: the reflect loop runs more than once
+                g[:2, 2] += rng.uniform(-3, 3, 2) * (w, h)
+            want = cv2.warpPerspective(src, g, (w, h), flags=cv2.INTER_LINEAR, borderMode=mode)
+            got = R.warp_linear(src, g, w, h, True, False, border_mode=mode)
+            assert np.array_equal(got, want)
