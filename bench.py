@@ -6,7 +6,7 @@
                                                          call-for-call like /root/reference/src/lib.rs:719-847)
 
 A "step" = one whole stack: BASELINE configs[3] — ecc_match MotionType::Homography, max_count 5000, eps 1e-5,
-gauss_filt_size 5, on 64 synthetic 3840x2160 BGR frames (oracle/synth.py, seeds fixed) — reference prep + seed,
+gauss_filt_size 5, on 64 synthetic 3840x2160 BGR frames (synthetic.py, seeds fixed) — reference prep + seed,
 63 x {prep, device ECC loop, final warp + accumulate}, lane sum, [reduce over ranks], divide.
 `value`  : frames/s with every frame already resident in HBM as u8 BGR (CUDA-event time, max over ranks).
 `e2e`    : the same through the host-facing API with frames in pinned HOST memory and the stacked image copied
@@ -59,7 +59,7 @@ def workload_name(a):
 
 
 def make_stack(a):
-    from oracle import synth
+    import synthetic as synth
     return synth.Stack(a.width, a.height, a.frames, a.motion, seed=4)
 
 
@@ -194,7 +194,7 @@ def run_b200(a, rank, local_rank, world):
     import torch
     import torch.distributed as dist
     import __graft_entry__ as ge
-    from oracle import synth
+    import synthetic as synth
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)

@@ -7,7 +7,7 @@ sys.path.insert(0, ROOT)
 import numpy as np
 import torch
 import __graft_entry__ as ge
-from oracle import synth
+import synthetic as synth
 pkg = ge.load_package()
 
 

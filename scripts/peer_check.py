@@ -15,7 +15,7 @@ def main():
     import torch
     import torch.distributed as dist
     import __graft_entry__ as ge
-    from oracle import synth
+    import synthetic as synth
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)

@@ -4,7 +4,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np
 import __graft_entry__ as ge
-from oracle import synth
+import synthetic as synth
 pkg = ge.load_package()
 w, h = 200, 136
 for motion in (0, 1, 2, 3):

@@ -6,7 +6,7 @@ sys.path.insert(0, ROOT)
 import numpy as np
 import torch
 import __graft_entry__ as ge
-from oracle import synth
+import synthetic as synth
 pkg = ge.load_package()
 peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6534.1
 

@@ -4,7 +4,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np
 import __graft_entry__ as ge
-from oracle import synth
+import synthetic as synth
 pkg = ge.load_package()
 w, h = 3840, 2160
 st_ = synth.Stack(w, h, 2, 3, seed=4)
