@@ -236,7 +236,13 @@ def run_b200(a, rank, local_rank, world):
         if not use_peers and rank == 0:
             print(f"peer exchange unavailable, using NCCL: {D.connect_peers.last_failure}", file=sys.stderr)
     peer_out = {}
-    shared_host = D.SharedHostStack((h, w, 3)) if use_peers else None
+    shared_host = None
+    if use_peers:
+        try:
+            shared_host = D.SharedHostStack((h, w, 3))
+        except RuntimeError as e:       # same outcome on every rank: fall back to the root's own copy-out
+            if rank == 0:
+                print(f"shared host stack unavailable ({e}); the root copies the whole stack out", file=sys.stderr)
 
     def peer_result():
         return torch.as_tensor(D.DevicePtrArray(peer_out["ptr"], h * w * 3), device=dev).view(h, w, 3)
@@ -276,13 +282,19 @@ def run_b200(a, rank, local_rank, world):
         st.set_reference(pinned_np[0])
         for i in mine:
             st.submit(pinned_np[i], tag=i, pinned=True)
-        if use_peers:
+        if use_peers and shared_host is not None:
             # every rank keeps its slice of the finished stack and copies it out over its OWN PCIe link into the
             # host stack all ranks map; rank 0 owns the result once every rank's copy has landed
             st.peer_reduce_scatter(n)
             st.peer_slice_to_host(shared_host.ptr)
             st.sync()
             dist.barrier()
+            return
+        if use_peers:
+            peer_out["ptr"] = st.peer_reduce(n)
+            st.sync()
+            if rank == 0:
+                out_host.copy_(peer_result(), non_blocking=False)
             return
         ptr, nfl = st.partial()
         if world > 1:
@@ -348,13 +360,14 @@ def run_b200(a, rank, local_rank, world):
     statuses = sorted({r["status"] for r in res})
 
     e2e = None
+    shared_host_used = shared_host is not None
     if not a.skip_e2e:
         ems, _, _, _ = timed(step_e2e, a.steps, min(a.warmup, 1), False)
         h2d = sum(pinned_np[i].nbytes for i in [0] + mine)
         e2e = {"value": n * a.steps / (ems / 1e3), "unit": UNIT, "ms_per_step": ems / a.steps,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(out_host.numel() * 4) if rank == 0 else 0,
                "api": ("EccStack.set_reference/submit(pinned host frames)/peer_reduce_scatter/peer_slice_to_host: every rank "
-                       "copies its slice of the stack into the shared pinned host stack" if use_peers else
+                       "copies its slice of the stack into the shared pinned host stack" if (use_peers and shared_host_used) else
                        "EccStack.set_reference/submit(pinned host frames)/partial/finish_device + D2H of the stack")}
         if world > 1:
             tot = torch.tensor([float(h2d)], dtype=torch.float64, device=dev)
@@ -366,8 +379,9 @@ def run_b200(a, rank, local_rank, world):
     if use_peers:
         barrier()                 # nobody unmaps while a peer may still be inside an exchange
         if rank == 0 and not a.skip_e2e:
-            e2e_mean = float(shared_host.array.mean(dtype=np.float64))
-        shared_host.close()
+            e2e_mean = float((shared_host.array if shared_host is not None else out_host.numpy()).mean(dtype=np.float64))
+        if shared_host is not None:
+            shared_host.close()
         st.peer_disconnect()
         barrier()
     # ---- roofline of the dominant kernel (ecc_iter_kernel), measured alone: 1 lane, CUDA events per stage ----

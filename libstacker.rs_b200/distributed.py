@@ -130,8 +130,9 @@ class SharedHostStack:
     """The finished stack in HOST memory that every rank of the node maps (POSIX shared memory, page-locked in
     each process): after `EccStack.peer_reduce_scatter` every rank copies its own slice out over its own PCIe
     link (`EccStack.peer_slice_to_host(shared.ptr)`), so the device-to-host copy of the result is spread over
-    all GPUs instead of serialised on the root's link.  Collective constructor; `array` is the H x W x C f32
-    view (read it on any rank after every rank's sync() + a barrier)."""
+    all GPUs instead of serialised on the root's link.  Collective constructor (raises RuntimeError on EVERY rank
+    when /dev/shm has no room); `array` is the H x W x C f32 view (read it on any rank after every rank's sync()
+    + a barrier)."""
 
     def __init__(self, shape, group=None, register: bool = True):
         import numpy as np
@@ -143,10 +144,20 @@ class SharedHostStack:
         for d in shape:
             nbytes *= int(d)
         name = [None]
+        self.shm = None
         if self.rank == 0:
-            self.shm = shared_memory.SharedMemory(create=True, size=nbytes)
-            name[0] = self.shm.name
+            # a full /dev/shm does not fail at creation but with SIGBUS at first touch: check the space first
+            try:
+                import os
+                vfs = os.statvfs("/dev/shm")
+                if vfs.f_bavail * vfs.f_frsize >= nbytes + (64 << 20):
+                    self.shm = shared_memory.SharedMemory(create=True, size=nbytes)
+                    name[0] = self.shm.name
+            except Exception:
+                self.shm = None
         dist.broadcast_object_list(name, src=0, group=group)
+        if name[0] is None:          # the same outcome on every rank
+            raise RuntimeError("no room for the shared host stack in /dev/shm")
         if self.rank != 0:
             self.shm = shared_memory.SharedMemory(name=name[0])
             # only the creator owns the segment: keep this process's resource tracker from unlinking it at exit
