@@ -424,11 +424,14 @@ def _check_colour_frame(img: np.ndarray):
 
 # ---- ecc_match: src/lib.rs:702-847 ----------------------------------------------------------------------
 def ecc_match(files: Iterable, params: EccMatchParameters, scale_down_width: Optional[float] = None, *,
-              device: int = -1, workers: Optional[int] = None, return_details: bool = False):
+              device: int = -1, devices=None, workers: Optional[int] = None, return_details: bool = False):
     """Align every frame to the first with ECC and average them.
 
     `files`: paths (decoded on host threads with cv2.imread(IMREAD_UNCHANGED), as
     utils::read_grey_and_f32 does) or already-decoded HxWxC uint8 arrays.
+    `devices`: several CUDA devices of the box, driven from this one process — one context per device, frames
+    dealt round-robin, one fused exchange + divide over NVLink peer memory (what the Rust crate and
+    `libstacker::ecc_match_on_devices` do); default: the single `device`.
     Returns the stacked image, float32 HxWxC in [0,1] (the reference's CV_32FC3 Mat).
     Errors: NotEnoughFiles (empty input); OpenCvError (no COUNT/EPS criteria, ECC non-convergence, bad
     image type); InvalidParams (scale_down_width out of range)."""
@@ -445,30 +448,41 @@ def ecc_match(files: Iterable, params: EccMatchParameters, scale_down_width: Opt
         ecc_size = scaled_size(w, h, float(np.float32(scale_down_width)))
     if not typ:
         raise OpenCvError("findTransformECC: criteria.type must have COUNT or EPS set")
-    with EccStack(w, h, ch, params, device=device, ecc_size=ecc_size) as st:
-        st.set_reference(first)
+    devs = [int(d) for d in devices] if devices else [int(device)]
+    if len(set(devs)) != len(devs):
+        raise InvalidParams("devices must be distinct")
+    stacks = []
+    try:
+        for k, d in enumerate(devs):
+            # only the first context seeds its accumulator with the unwarped frame 0 (src/lib.rs:752-754)
+            stacks.append(EccStack(w, h, ch, params, device=d, ecc_size=ecc_size, seed_reference=(k == 0)))
+            stacks[-1].set_reference(first)
+        if len(stacks) > 1:
+            EccStack.peer_connect_local(stacks)
+        nd = len(stacks)
         n_workers = workers or min(8, os.cpu_count() or 1)
         rest = items[1:]
         if rest:
             if all(isinstance(i, np.ndarray) for i in rest):
                 for k, fr in enumerate(rest):
                     _check_colour_frame(fr)
-                    st.submit(fr, tag=k + 1)
+                    stacks[(k + 1) % nd].submit(fr, tag=k + 1)
             else:
                 # Rayon: one task per frame (src/lib.rs:746-749).  Each task decodes and copies its frame into a
-                # pinned ring buffer (no library lock held); the main thread hands the buffers over in file order,
-                # so the summation order — and the result — does not depend on thread timing.  The window keeps at
-                # most one ring's worth of tasks alive, so a task can always get its buffer.
-                def load_into_ring(item):
+                # pinned ring buffer of the context it is dealt to (no library lock held); the main thread hands
+                # the buffers over in file order, so the summation order — and the result — does not depend on
+                # thread timing.  The window keeps at most one ring's worth of tasks alive per context, so a task
+                # can always get its buffer.
+                def load_into_ring(k, item):
                     fr = _load(item)
                     _check_colour_frame(fr)
                     if fr.shape != (h, w, ch):
                         raise OpenCvError(f"frame size {fr.shape[1]}x{fr.shape[0]} differs from the stack's {w}x{h}")
-                    buf = st.acquire_buffer()
+                    buf = stacks[(k + 1) % nd].acquire_buffer()
                     np.copyto(buf, fr)
                     return buf
 
-                window = max(1, min(n_workers, 2 * st.lanes))
+                window = max(1, min(n_workers, 2 * stacks[0].lanes))
                 with ThreadPoolExecutor(max_workers=window) as ex:
                     pending = []
                     it = iter(enumerate(rest))
@@ -480,14 +494,29 @@ def ecc_match(files: Iterable, params: EccMatchParameters, scale_down_width: Opt
                             except StopIteration:
                                 done = True
                                 break
-                            pending.append((k, ex.submit(load_into_ring, item)))
+                            pending.append((k, ex.submit(load_into_ring, k, item)))
                         if pending:
                             k, fut = pending.pop(0)
-                            st.submit_acquired(fut.result(), tag=k + 1)
-        out = st.finish(len(items))
+                            stacks[(k + 1) % nd].submit_acquired(fut.result(), tag=k + 1)
+        if nd == 1:
+            out = stacks[0].finish(len(items))
+        else:
+            # Rayon's try_reduce + `/ n` as ONE exchange step: every exchange is queued before the first copy-out
+            # (a copy into pageable memory blocks this thread until its device's exchange has finished)
+            out = np.empty((h, w, ch), np.float32)
+            for st in stacks:
+                st.peer_reduce_scatter(len(items))
+            for st in stacks:
+                st.peer_slice_to_host(out.ctypes.data)
+            for st in stacks:
+                st.sync()                      # also raises a frame's ECC failure (src/lib.rs:777)
         if return_details:
-            return out, st.results()
+            res = sorted((r for st in stacks for r in st.results()), key=lambda r: r["tag"])
+            return out, res
         return out
+    finally:
+        for st in stacks:
+            st.close()
 
 
 # ---- keypoint_match: src/lib.rs:129-353 -----------------------------------------------------------------

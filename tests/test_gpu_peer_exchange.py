@@ -126,3 +126,26 @@ def test_two_processes_ipc_equals_nccl():
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "peer exchange ok" in r.stdout
+
+
+def test_python_ecc_match_on_two_devices(pkg, tmp_path):
+    """The Python mirror's ecc_match(devices=[...]): one process, one context per device, frames dealt round-robin,
+    exchange + divide + per-device copy-out — against the single-device call, for decoded arrays and for files."""
+    if _n_gpus() < 2:
+        pytest.skip("needs two GPUs")
+    import cv2
+    frames, params = _stack(pkg, n=6)
+    one, r1 = pkg.ecc_match(frames, params, device=0, return_details=True)
+    two, r2 = pkg.ecc_match(frames, params, devices=[0, 1], return_details=True)
+    assert [r["tag"] for r in r2] == [r["tag"] for r in r1] == [1, 2, 3, 4, 5]
+    for a, b in zip(r1, r2):
+        assert np.array_equal(a["warp"], b["warp"]) and a["iterations"] == b["iterations"]
+    assert np.abs(one - two).max() <= 1e-6           # f32 summation order only
+    paths = []
+    for i, f in enumerate(frames):
+        paths.append(str(tmp_path / f"f{i}.png"))
+        assert cv2.imwrite(paths[-1], f)
+    three = pkg.ecc_match(paths, params, devices=[0, 1])
+    assert np.abs(three - one).max() <= 1e-6
+    with pytest.raises(pkg.StackerError):
+        pkg.ecc_match(frames, params, devices=[0, 0])
