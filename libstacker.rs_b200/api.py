@@ -503,13 +503,7 @@ def ecc_match(files: Iterable, params: EccMatchParameters, scale_down_width: Opt
         else:
             # Rayon's try_reduce + `/ n` as ONE exchange step: every exchange is queued before the first copy-out
             # (a copy into pageable memory blocks this thread until its device's exchange has finished)
-            out = np.empty((h, w, ch), np.float32)
-            for st in stacks:
-                st.peer_reduce_scatter(len(items))
-            for st in stacks:
-                st.peer_slice_to_host(out.ctypes.data)
-            for st in stacks:
-                st.sync()                      # also raises a frame's ECC failure (src/lib.rs:777)
+            out = _finish_on_devices(stacks, len(items), (h, w, ch))   # its sync() also raises a frame's ECC failure (src/lib.rs:777)
         if return_details:
             res = sorted((r for st in stacks for r in st.results()), key=lambda r: r["tag"])
             return out, res
@@ -571,11 +565,27 @@ def _frame_homography(kp0, des0, img, params: KeyPointMatchParameters, scale_dow
     return hm
 
 
+def _finish_on_devices(stacks, divisor: int, shape) -> np.ndarray:
+    """Rayon's try_reduce + `/ n` over several contexts of this process: ONE exchange step over NVLink peer
+    memory, every device copying its slice of the result out.  Every exchange is queued before the first
+    copy-out (a copy into pageable memory blocks this thread until its device's exchange has finished)."""
+    out = np.empty(shape, np.float32)
+    for st in stacks:
+        st.peer_reduce_scatter(divisor)
+    for st in stacks:
+        st.peer_slice_to_host(out.ctypes.data)
+    for st in stacks:
+        st.sync()
+    return out
+
+
 def keypoint_match(files: Iterable, params: KeyPointMatchParameters = KeyPointMatchParameters(),
-                   scale_down_width: Optional[float] = None, *, device: int = -1,
+                   scale_down_width: Optional[float] = None, *, device: int = -1, devices=None,
                    workers: Optional[int] = None):
     """Returns (dropped, stacked f32 HxWxC).  ORB / BFMatcher / findHomography stay on the host (OpenCV),
-    the final warp_perspective + accumulate + divide run on the GPU.
+    the final warp_perspective + accumulate + divide run on the GPU.  `devices`: several CUDA
+    devices driven from this process (BASELINE configs[4]): the accepted frames are dealt round-robin to one
+    warp-only context per device and the partial stacks meet in one exchange + divide.
 
     Deviation, documented: when frames are dropped the reference's result depends on how Rayon split the
     index range (src/lib.rs:307 seeds a worker's accumulator with a copy of frame 0); here dropped frames
@@ -597,13 +607,43 @@ def keypoint_match(files: Iterable, params: KeyPointMatchParameters = KeyPointMa
     grey0 = cv2.cvtColor(first, cv2.COLOR_BGR2GRAY)
     kp0, des0 = _orb(grey0 if sd is None else _scale_image(grey0, sd))
     dropped = 0
+
+    def work(item):
+        img = _load(item)
+        _check_colour_frame(img)
+        return img, _frame_homography(kp0, des0, img, params, sd)
+
+    devs = [int(d) for d in devices] if devices else None
+    if devs is not None and len(devs) > 1:
+        if len(set(devs)) != len(devs):
+            raise InvalidParams("devices must be distinct")
+        stacks = []
+        try:
+            for k, d in enumerate(devs):
+                stacks.append(EccStack(w, h, ch, None, device=d, seed_reference=(k == 0)))
+                stacks[-1].set_reference(first)
+            EccStack.peer_connect_local(stacks)
+            n_workers = workers or min(8, os.cpu_count() or 1)
+            accepted = 0
+            with ThreadPoolExecutor(max_workers=n_workers) as ex:
+                for k, (img, hm) in enumerate(ex.map(work, items[1:])):
+                    if hm is None:
+                        dropped += 1
+                        continue
+                    if img.shape[:2] != (h, w):
+                        raise NotImplementedError_("frames of differing size")
+                    accepted += 1
+                    stacks[accepted % len(stacks)].submit_warp(img, hm, params.border_mode, params.border_value, tag=k + 1)
+            if len(items) - dropped <= 0:
+                raise InvalidParams("All images discarded: try modifying KeyPointMatchParameters::match_distance_threshold")
+            return dropped, _finish_on_devices(stacks, len(items) - dropped, (h, w, ch))
+        finally:
+            for st in stacks:
+                st.close()
+    if devs:
+        device = devs[0]
     with EccStack(w, h, ch, None, device=device) as st:
         st.set_reference(first)
-
-        def work(item):
-            img = _load(item)
-            _check_colour_frame(img)
-            return img, _frame_homography(kp0, des0, img, params, sd)
 
         n_workers = workers or min(8, os.cpu_count() or 1)
         with ThreadPoolExecutor(max_workers=n_workers) as ex:

@@ -149,3 +149,18 @@ def test_python_ecc_match_on_two_devices(pkg, tmp_path):
     assert np.abs(three - one).max() <= 1e-6
     with pytest.raises(pkg.StackerError):
         pkg.ecc_match(frames, params, devices=[0, 0])
+
+
+def test_python_keypoint_match_on_two_devices(pkg):
+    """keypoint_match(devices=[...]) (BASELINE configs[4]: the warp + stack tail across GPUs): same drops and the
+    same stack as the single-device call, up to f32 summation order."""
+    if _n_gpus() < 2:
+        pytest.skip("needs two GPUs")
+    pytest.importorskip("cv2")
+    from oracle import synth
+    frames = synth.Stack(800, 600, 6, 3, seed=31).frames()
+    params = pkg.KeyPointMatchParameters(method=pkg.RANSAC, ransac_reproj_threshold=5.0, match_keep_ratio=0.8, match_ratio=0.9)
+    d1, one = pkg.keypoint_match(frames, params, device=0)
+    d2, two = pkg.keypoint_match(frames, params, devices=[0, 1])
+    assert d1 == d2 == 0
+    assert np.abs(one - two).max() <= 1e-6
