@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define STK_ABI_VERSION 3
+#define STK_ABI_VERSION 4
 
 /* ---- status codes ------------------------------------------------------------------------- */
 enum {
@@ -144,6 +144,15 @@ int stk_ecc_submit_warp(stk_ecc_ctx* ctx, const uint8_t* bgr, size_t pitch, cons
                         int border_mode, const double border_value[4], int64_t tag);
 int stk_ecc_submit_warp_device(stk_ecc_ctx* ctx, const uint8_t* d_bgr, size_t pitch, const double h[9],
                                int border_mode, const double border_value[4], int64_t tag);
+
+/* The 2x3 form: warp_affine(img_f32, M, size, INTER_LINEAR, border_mode, border_value) + accumulate — the final warp
+   ecc_match applies for Translation / Euclidean / Affine (src/lib.rs:782-790), with a caller-supplied matrix.
+   m is the row-major 2x3 f64 forward map (inverted internally like cv::warpAffine; coordinates in OpenCV's 10-bit
+   fixed point).  Bit-identical to cv2.warpAffine on the CV_32F frame. */
+int stk_ecc_submit_warp_affine(stk_ecc_ctx* ctx, const uint8_t* bgr, size_t pitch, const double m[6],
+                               int border_mode, const double border_value[4], int64_t tag);
+int stk_ecc_submit_warp_affine_device(stk_ecc_ctx* ctx, const uint8_t* d_bgr, size_t pitch, const double m[6],
+                                      int border_mode, const double border_value[4], int64_t tag);
 
 /* wait for every queued frame; returns the first per-frame error (STK_ERR_ECC_*) or STK_OK */
 int stk_ecc_sync(stk_ecc_ctx* ctx);

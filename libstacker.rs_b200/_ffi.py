@@ -14,7 +14,7 @@ STK_OK, STK_ERR_BAD_ARG, STK_ERR_CUDA, STK_ERR_NOT_ENOUGH, STK_ERR_ECC_NOCONV, S
     STK_ERR_CRITERIA, STK_ERR_STATE, STK_ERR_UNSUPPORTED, STK_ERR_NOMEM = range(10)
 STK_TERM_COUNT, STK_TERM_EPS = 1, 2
 STK_BORDER_CONSTANT = 0
-STK_ABI_VERSION = 3
+STK_ABI_VERSION = 4
 
 
 class EccConfig(C.Structure):
@@ -61,6 +61,8 @@ SYMBOLS = {
     "stk_ecc_release_frame_buffer": (C.c_int, [_P, _P]),
     "stk_ecc_submit_warp": (C.c_int, [_P, _P, C.c_size_t, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.c_int64]),
     "stk_ecc_submit_warp_device": (C.c_int, [_P, _P, C.c_size_t, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.c_int64]),
+    "stk_ecc_submit_warp_affine": (C.c_int, [_P, _P, C.c_size_t, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.c_int64]),
+    "stk_ecc_submit_warp_affine_device": (C.c_int, [_P, _P, C.c_size_t, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.c_int64]),
     "stk_ecc_sync": (C.c_int, [_P]),
     "stk_ecc_results": (C.c_int, [_P, C.POINTER(FrameResult), C.c_int, C.POINTER(C.c_int)]),
     "stk_ecc_finish": (C.c_int, [_P, C.c_int, _P, C.c_size_t]),

@@ -238,6 +238,18 @@ class EccStack:
         f, ptr, pitch = self._host_frame(frame)
         _check(lib.stk_ecc_submit_warp(self._ctx, ptr, pitch, hm, int(border_mode), bv, int(tag)))
 
+    def submit_warp_affine(self, frame, m, border_mode: int = BORDER_CONSTANT, border_value=(0, 0, 0, 0), tag: int = 0):
+        """warp_affine(img_f32, M 2x3 f64, ..) + accumulate (src/lib.rs:782-790 with a caller-supplied matrix)."""
+        mm = (C.c_double * 6)(*np.asarray(m, np.float64).reshape(-1)[:6])
+        bv = (C.c_double * 4)(*[float(v) for v in border_value])
+        dv = _device_view(frame)
+        if dv is not None:
+            self._keep.append(frame)
+            _check(lib.stk_ecc_submit_warp_affine_device(self._ctx, dv[0], dv[1], mm, int(border_mode), bv, int(tag)))
+            return
+        f, ptr, pitch = self._host_frame(frame)
+        _check(lib.stk_ecc_submit_warp_affine(self._ctx, ptr, pitch, mm, int(border_mode), bv, int(tag)))
+
     # -- completion
     def sync(self):
         rc = lib.stk_ecc_sync(self._ctx)

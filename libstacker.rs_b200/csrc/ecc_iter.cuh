@@ -69,16 +69,14 @@ struct EccState {
 };
 
 struct alignas(64) EccIterParams {
-  CUtensorMap tm_img;       // I : f32 [H][W], box kBoxW x kBoxH, zero fill outside
-  CUtensorMap tm_tmpl;      // T : f32 [H][W], box kEccStripW x kChunkH
-  CUtensorMap tm_img_p2;    // same planes with the packed-pair kernel's boxes (kBoxW x kP2BoxH, kEccStripW x kP2ChunkH)
-  CUtensorMap tm_tmpl_p2;
+  CUtensorMap tm_img;       // I : f32 [H][W], box kBoxW x (chunk height + 16) of the kernel configuration, zero fill outside
+  CUtensorMap tm_tmpl;      // T : f32 [H][W], box kEccStripW x chunk height
   const float* img;         // same planes, for the general path
   const float* tmpl;
   int pitch;                // floats, both planes
   int width, height;        // template size == image size on this path
   int n_strips;             // 128-column strips
-  int chunks_per_strip;     // ceil(height / kChunkH)
+  int chunks_per_strip;     // ceil(height / chunk height of the kernel configuration)
   double* partials;         // [NV][tiles_pad]: value-major so the cross-block sum reads coalesced
   int tiles_pad;            // gridDim.x rounded up to 32
   EccState* st;
@@ -487,7 +485,8 @@ template <int MOTION> struct Accum {
 // Homography accumulator with the sums stored as register PAIRS so the interior path updates two of them
 // per instruction.  Same sums, same per-sum operation order as Accum<kHomography>; generators are
 // (g0, g1, g2) = (2a, 2b, -2t) (see Accum::emit<TWICE_NEG>).
-//   h[k]  = (p00, p01), (p02, p11), (p12, p22) for k = 0..2, each with moments {1, Y, Y^2}
+//   h[k]  = (p00, p01), (p02, p12), (p11, p22) for k = 0..2, each with moments {1, Y, Y^2}: the first two pairs are
+//           (g0, g1) times a broadcast scalar, the third two scalar squares — no register moves to build them
 //   za/zm/zt[m] = (g0 z, g1 z) for z = w / 1 / t, moments {1, Y} ; zc[m] = (g2 w, g2 t) ; zm2[m] = g2
 //   s1 = (Sw, St), s2 = (Sww, Stt)
 struct AccumH2 {
@@ -513,9 +512,9 @@ struct AccumH2 {
   // interior pixel (mask 1; the caller counts it): g01 = (g0, g1)
   __device__ __forceinline__ void add_packed(float2 g01, float g2, float w_, float t_, float yf) {
     const float2 y2 = f2(yf), yy2 = f2(yf * yf);
-    const float2 q0 = mul2(f2(g01.x), g01);                       // g0 g0, g0 g1
-    const float2 q1 = f2(g01.x * g2, g01.y * g01.y);              // g0 g2, g1 g1
-    const float2 q2 = mul2(f2(g2), f2(g01.y, g2));                // g1 g2, g2 g2
+    const float2 q0 = mul2(g01, f2(g01.x));                       // g0 g0, g0 g1
+    const float2 q1 = mul2(g01, f2(g2));                          // g0 g2, g1 g2
+    const float2 q2 = f2(g01.y * g01.y, g2 * g2);                 // g1 g1, g2 g2
     h[0][0] = add2(h[0][0], q0); h[0][1] = fma2(q0, y2, h[0][1]); h[0][2] = fma2(q0, yy2, h[0][2]);
     h[1][0] = add2(h[1][0], q1); h[1][1] = fma2(q1, y2, h[1][1]); h[1][2] = fma2(q1, yy2, h[1][2]);
     h[2][0] = add2(h[2][0], q2); h[2][1] = fma2(q2, y2, h[2][1]); h[2][2] = fma2(q2, yy2, h[2][2]);
@@ -539,8 +538,8 @@ struct AccumH2 {
     up(h[0][0].x, h[0][1].x, h[0][2].x, g[0] * g[0]);
     up(h[0][0].y, h[0][1].y, h[0][2].y, g[0] * g[1]);
     up(h[1][0].x, h[1][1].x, h[1][2].x, g[0] * g[2]);
-    up(h[1][0].y, h[1][1].y, h[1][2].y, g[1] * g[1]);
-    up(h[2][0].x, h[2][1].x, h[2][2].x, g[1] * g[2]);
+    up(h[1][0].y, h[1][1].y, h[1][2].y, g[1] * g[2]);
+    up(h[2][0].x, h[2][1].x, h[2][2].x, g[1] * g[1]);
     up(h[2][0].y, h[2][1].y, h[2][2].y, g[2] * g[2]);
     const float wm = INTERIOR ? w_ : w_ * mk;
     const float tm = INTERIOR ? t_ : t_ * mk;
@@ -562,12 +561,15 @@ struct AccumH2 {
     const float xx = xf * xf;
     // product order of Layout<>: (0,0) (0,1) (0,2) (1,1) (1,2) (2,2); the sign flips where exactly one factor is g2
     const float pf[6] = {0.25f, 0.25f, -0.25f, 0.25f, -0.25f, 0.25f};
+    // where each product lives: pair index, .y?
+    const int pk[6] = {0, 0, 1, 2, 1, 2};
+    const bool py[6] = {false, true, false, false, true, true};
 #pragma unroll
     for (int idx = 0; idx < 6; ++idx) {
-      const float2 m0 = h[idx >> 1][0], m1 = h[idx >> 1][1], m2 = h[idx >> 1][2];
-      const float p0 = ((idx & 1) ? m0.y : m0.x) * pf[idx];
-      const float p1 = ((idx & 1) ? m1.y : m1.x) * pf[idx];
-      const float p2 = ((idx & 1) ? m2.y : m2.x) * pf[idx];
+      const float2 m0 = h[pk[idx]][0], m1 = h[pk[idx]][1], m2 = h[pk[idx]][2];
+      const float p0 = (py[idx] ? m0.y : m0.x) * pf[idx];
+      const float p1 = (py[idx] ? m1.y : m1.x) * pf[idx];
+      const float p2 = (py[idx] ? m2.y : m2.x) * pf[idx];
       float* o = &v[L::kH + idx * 6];
       o[0] = p0; o[1] = xf * p0; o[2] = p1; o[3] = xx * p0; o[4] = xf * p1; o[5] = p2;
     }
@@ -1188,317 +1190,6 @@ __global__ void __launch_bounds__(kEccThreads, 512 / kEccThreads) ecc_iter_kerne
     g0 += nseg;
   }
   finish_iteration<MOTION, kEccThreads>(p, st, s_accum, s_tot, &s_last);
-}
-
-// ---- Homography, packed pixel pairs -------------------------------------------------------------------
-// Same algorithm and work split as ecc_iter_kernel<kHomography,false>, restructured around Blackwell's
-// packed FP32 instructions (FFMA2 / FADD2 / FMUL2, PTX *.f32x2): every thread walks its column two rows at
-// a time and carries the pair in float2 registers, so one issue slot performs the FP32 op of both pixels.
-// The FP32 pipe does the same work as before (packing halves issue slots, not pipe time — measured,
-// scripts/ffma2_probe.cu); what it removes is the issue bottleneck: ~76 instead of ~150 slots per pixel.
-// Accumulators are float2 too (.x = even rows, .y = odd rows of the run) and are added at the run end.
-// 128-thread blocks, 8-row chunks, 3 blocks per SM.
-constexpr int kP2Threads = 128;
-constexpr int kP2ChunkH = 8;
-constexpr int kP2BoxH = 24;
-constexpr int kP2Stages = 4;
-constexpr int kP2ImgStageBytes = kBoxW * kP2BoxH * 4;            // 13824
-constexpr int kP2TmplStageBytes = kEccStripW * kP2ChunkH * 4;    // 4096
-constexpr int kP2StageBytes = kP2ImgStageBytes + kP2TmplStageBytes;
-constexpr int kP2DynSmem = kP2Stages * kP2StageBytes;            // 71680
-
-
-struct Sample2 { float2 w, gx2, gy2; };
-
-__device__ __forceinline__ Sample2 sample_box2(const float* pa, const float* pb, float2 ax, float2 ay) {
-  const float2 m0 = f2(pa[-kBoxW], pb[-kBoxW]), m1 = f2(pa[-kBoxW + 1], pb[-kBoxW + 1]);
-  const float2 a_1 = f2(pa[-1], pb[-1]), a0 = f2(pa[0], pb[0]), a1 = f2(pa[1], pb[1]), a2 = f2(pa[2], pb[2]);
-  const float2 b_1 = f2(pa[kBoxW - 1], pb[kBoxW - 1]), b0 = f2(pa[kBoxW], pb[kBoxW]);
-  const float2 b1 = f2(pa[kBoxW + 1], pb[kBoxW + 1]), b2 = f2(pa[kBoxW + 2], pb[kBoxW + 2]);
-  const float2 c0 = f2(pa[2 * kBoxW], pb[2 * kBoxW]), c1 = f2(pa[2 * kBoxW + 1], pb[2 * kBoxW + 1]);
-  Sample2 s;
-  s.w = lerp2(lerp2(a0, a1, ax), lerp2(b0, b1, ax), ay);
-  s.gx2 = lerp2(lerp2(sub2(a1, a_1), sub2(a2, a0), ax), lerp2(sub2(b1, b_1), sub2(b2, b0), ax), ay);
-  s.gy2 = lerp2(lerp2(sub2(b0, m0), sub2(b1, m1), ax), lerp2(sub2(c0, a0), sub2(c1, a1), ax), ay);
-  return s;
-}
-
-struct Accum2 {               // Layout<kHomography>, every sum as (even rows, odd rows)
-  float2 n, sw, sww, st, stt, swt;
-  float2 p[6][3];
-  float2 z[3][3][2];
-  __device__ __forceinline__ void clear() {
-    const float2 o = f2(0.f);
-    n = sw = sww = st = stt = swt = o;
-#pragma unroll
-    for (int i = 0; i < 6; ++i)
-#pragma unroll
-      for (int k = 0; k < 3; ++k) p[i][k] = o;
-#pragma unroll
-    for (int a = 0; a < 3; ++a)
-#pragma unroll
-      for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int k = 0; k < 2; ++k) z[a][i][k] = o;
-  }
-  // INTERIOR: both masks are 1 (pixel counts are added by the caller)
-  template <bool INTERIOR>
-  __device__ __forceinline__ void add(const float2 (&g)[3], float2 w_, float2 t_, float2 mk, float2 y, float2 yy) {
-    int idx = 0;
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int j = i; j < 3; ++j) {
-        const float2 pr = mul2(g[i], g[j]);
-        p[idx][0] = add2(p[idx][0], pr);
-        p[idx][1] = fma2(pr, y, p[idx][1]);
-        p[idx][2] = fma2(pr, yy, p[idx][2]);
-        ++idx;
-      }
-    const float2 wm = INTERIOR ? w_ : mul2(w_, mk);
-    const float2 tm = INTERIOR ? t_ : mul2(t_, mk);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const float2 gw = mul2(g[i], w_);
-      const float2 gm = INTERIOR ? g[i] : mul2(g[i], mk);
-      const float2 gt = mul2(g[i], tm);
-      z[0][i][0] = add2(z[0][i][0], gw); z[0][i][1] = fma2(gw, y, z[0][i][1]);
-      z[1][i][0] = add2(z[1][i][0], gm); z[1][i][1] = fma2(gm, y, z[1][i][1]);
-      z[2][i][0] = add2(z[2][i][0], gt); z[2][i][1] = fma2(gt, y, z[2][i][1]);
-    }
-    if (!INTERIOR) n = add2(n, mk);
-    sw = add2(sw, wm); sww = fma2(wm, w_, sww);
-    st = add2(st, tm); stt = fma2(tm, t_, stt);
-    swt = fma2(wm, t_, swt);
-  }
-  // fold the pair lanes together and the column coordinate X into the moments (same layout as Accum::emit)
-  __device__ __forceinline__ void emit(float xf, float (&v)[Layout<kHomography>::NV]) const {
-    using L = Layout<kHomography>;
-    auto h = [](float2 a) { return a.x + a.y; };
-    v[0] = h(n); v[1] = h(sw); v[2] = h(sww); v[3] = h(st); v[4] = h(stt); v[5] = h(swt);
-    const float xx = xf * xf;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      const float p0 = h(p[i][0]), p1 = h(p[i][1]), p2 = h(p[i][2]);
-      float* o = &v[L::kH + i * 6];
-      o[0] = p0; o[1] = xf * p0; o[2] = p1; o[3] = xx * p0; o[4] = xf * p1; o[5] = p2;
-    }
-#pragma unroll
-    for (int a = 0; a < 3; ++a)
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const float z0 = h(z[a][i][0]), z1 = h(z[a][i][1]);
-        float* o = &v[L::kZ + (a * 3 + i) * 3];
-        o[0] = z0; o[1] = xf * z0; o[2] = z1;
-      }
-  }
-};
-
-__global__ void __launch_bounds__(kP2Threads, 3) ecc_iter_pack2_kernel(const __grid_constant__ EccIterParams p) {
-  constexpr int MOTION = kHomography;
-  using L = Layout<MOTION>;
-  constexpr int NV = L::NV;
-  constexpr int kWarps = kP2Threads / 32;
-  extern __shared__ __align__(128) unsigned char dyn[];
-  __shared__ float s_m[9];
-  __shared__ int s_box[kMaxChunks][2];
-  __shared__ alignas(8) uint64_t s_full[kP2Stages];
-  __shared__ alignas(8) uint64_t s_empty[kP2Stages];
-  __shared__ float s_red[kWarps][NV];
-  __shared__ double s_accum[NV];
-  __shared__ int s_last;
-  __shared__ double s_tot[NV];
-
-  EccState* st = p.st;
-  if (st->cont == 0) return;
-
-  const int tid = threadIdx.x;
-  const int lane = tid & 31, wid = tid >> 5;
-  if (p.timing_out && tid == 0) p.timing_out[(size_t)blockIdx.x * 4 + 0] = global_ns();
-  if (tid < 9) s_m[tid] = st->m[tid];
-  if (tid < NV) s_accum[tid] = 0.0;
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < kP2Stages; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], kWarps); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-
-  // chunks are kP2ChunkH rows here; chunks_per_strip in the params counts 16-row chunks
-  const int cps = (p.height + kP2ChunkH - 1) / kP2ChunkH;
-  const long long total = (long long)p.n_strips * cps;
-  int g0 = (int)((long long)blockIdx.x * total / gridDim.x);
-  const int g1 = (int)((long long)(blockIdx.x + 1) * total / gridDim.x);
-  int cc = 0;
-  const int col = tid;       // one column per thread
-
-  while (g0 < g1) {
-    const int strip = g0 / cps, c_first = g0 - strip * cps;
-    const int nseg = min(min(cps - c_first, g1 - g0), kMaxChunks);
-    const int x0 = strip * kEccStripW;
-    const int x1 = min(x0 + kEccStripW, p.width) - 1;
-    const int y0 = c_first * kP2ChunkH;
-    const int y1 = min(y0 + nseg * kP2ChunkH, p.height);
-    __syncthreads();
-
-    if (tid < nseg) {
-      const int cy0 = y0 + tid * kP2ChunkH;
-      const int cy1 = min(cy0 + kP2ChunkH, y1) - 1;
-      double umin, umax, vmin, vmax;
-      bool ok = chunk_bounds<true>(s_m, x0, x1, cy0, cy1, umin, umax, vmin, vmax);
-      int xlo = 0, ylo = 0;
-      if (ok) ok = fabs(umin) < 1e8 && fabs(umax) < 1e8 && fabs(vmin) < 1e8 && fabs(vmax) < 1e8;
-      if (ok) {
-        xlo = ((int)floor(umin) - 2) & ~3;          // TMA: innermost coordinate on a 16-byte boundary
-        ylo = (int)floor(vmin) - 2;
-        ok = ((int)floor(umax) + 3 - xlo < kBoxW) && ((int)floor(vmax) + 3 - ylo < kP2BoxH);
-      }
-      s_box[tid][0] = ok ? xlo : INT_MIN;
-      s_box[tid][1] = ylo;
-    }
-    __syncthreads();
-
-    auto issue = [&](int c) {
-      const int gc = cc + c;
-      const int s = gc % kP2Stages;
-      if (gc >= kP2Stages) mbar_wait(&s_empty[s], (unsigned)(gc / kP2Stages - 1) & 1u);
-      const int xlo = s_box[c][0], ylo = s_box[c][1];
-      const bool boxed = xlo != INT_MIN;
-      unsigned char* stage = dyn + s * kP2StageBytes;
-      mbar_expect_tx(&s_full[s], (boxed ? kP2ImgStageBytes : 0) + kP2TmplStageBytes);
-      if (boxed) tma_load_2d(stage, &p.tm_img_p2, xlo, ylo, &s_full[s]);
-      tma_load_2d(stage + kP2ImgStageBytes, &p.tm_tmpl_p2, x0, y0 + c * kP2ChunkH, &s_full[s]);
-    };
-    if (tid == 0) {
-      for (int c = 0; c < kP2Stages - 1 && c < nseg; ++c) issue(c);
-    }
-
-    const int x = x0 + col;
-    const float xf = (float)x;
-    const bool col_ok = x < p.width;
-    Accum2 acc;
-    acc.clear();
-    int n_safe = 0;
-    FastPersp fp;
-    fp.init(s_m, x);
-    const float2 beta2 = f2(fp.beta), alpha2 = f2(fp.alpha), gamma2 = f2(fp.gamma), delta2 = f2(fp.delta);
-    const float2 wc2 = f2(fp.wc), m212 = f2(fp.m21), nm212 = f2(-fp.m21), xf2 = f2(xf);
-    const float2 c32 = f2(32.f), magic2 = f2(12582912.0f), half2 = f2(0.5f), inv32 = f2(1.f / kInterTab), neg1 = f2(-1.f);
-
-    // one pixel through the exact general path (non-boxed chunks): returns its sample and mask
-    auto slow_sample = [&](int y, Sample& smp, float& mk) {
-      Coord<true> co;
-      co.init(s_m, x);
-      int xq, yq, xn, yn;
-      const bool ok = co.at_with_nearest(y, xq, yq, xn, yn);
-      smp.w = 0.f; smp.gx2 = 0.f; smp.gy2 = 0.f; mk = 0.f;
-      if (ok) {
-        const int sx = xq >> kInterBits, sy = yq >> kInterBits;
-        if (sx >= -1 && sx < p.width && sy >= -1 && sy < p.height) {
-          const float ax = (float)(xq & (kInterTab - 1)) * (1.f / kInterTab);
-          const float ay = (float)(yq & (kInterTab - 1)) * (1.f / kInterTab);
-          smp = sample_general(p.img, p.pitch, p.width, p.height, sx, sy, ax, ay);
-        }
-        mk = ((unsigned)xn < (unsigned)p.width && (unsigned)yn < (unsigned)p.height) ? 1.f : 0.f;
-      }
-    };
-
-    for (int c = 0; c < nseg; ++c) {
-      const int gc = cc + c;
-      const int s = gc % kP2Stages;
-      if (tid == 0 && c + kP2Stages - 1 < nseg) issue(c + kP2Stages - 1);
-      __syncwarp();
-      mbar_wait(&s_full[s], (unsigned)(gc / kP2Stages) & 1u);
-      const float* box = reinterpret_cast<const float*>(dyn + s * kP2StageBytes);
-      const float* tbox = reinterpret_cast<const float*>(dyn + s * kP2StageBytes + kP2ImgStageBytes);
-      const int xlo = s_box[c][0], ylo = s_box[c][1];
-      const bool boxed = xlo != INT_MIN;
-      const int ya = y0 + c * kP2ChunkH;
-      const int yb = min(ya + kP2ChunkH, y1);
-      const unsigned wmask = __ballot_sync(0xffffffffu, col_ok);
-      if (col_ok) {
-        const float* tcol = tbox + col;
-#pragma unroll 2
-        for (int y = ya; y < yb; y += 2) {
-          const bool has_b = y + 1 < yb;                 // odd row count at the bottom of the image
-          const float2 y2 = f2((float)y, (float)(y + 1));
-          const float2 yy2 = mul2(y2, y2);
-          const float2 t2 = f2(tcol[(y - ya) * kEccStripW], has_b ? tcol[(y + 1 - ya) * kEccStripW] : 0.f);
-          // coordinates of both pixels (FastPersp, packed)
-          const float2 w2 = fma2(m212, y2, wc2);
-          const float2 rw2 = f2(rcp_approx(w2.x), rcp_approx(w2.y));
-          const float2 du2 = mul2(fma2(beta2, y2, alpha2), rw2);
-          const float2 dv2 = mul2(fma2(fma2(nm212, y2, delta2), y2, gamma2), rw2);
-          const float2 qxf = fma2(du2, c32, magic2), qyf = fma2(dv2, c32, magic2);
-          const int qxa = __float_as_int(qxf.x) - 0x4B400000, qxb = __float_as_int(qxf.y) - 0x4B400000;
-          const int qya = __float_as_int(qyf.x) - 0x4B400000, qyb = __float_as_int(qyf.y) - 0x4B400000;
-          const int sxa = x + (qxa >> kInterBits), sxb = x + (qxb >> kInterBits);
-          const int sya = y + (qya >> kInterBits), syb = y + 1 + (qyb >> kInterBits);
-          const float2 ax2 = mul2(f2((float)(qxa & (kInterTab - 1)), (float)(qxb & (kInterTab - 1))), inv32);
-          const float2 ay2 = mul2(f2((float)(qya & (kInterTab - 1)), (float)(qyb & (kInterTab - 1))), inv32);
-          Sample2 smp;
-          float2 mk2 = f2(1.f, has_b ? 1.f : 0.f);
-          bool all_safe = false;
-          if (boxed) {
-            const bool safe = (unsigned)(sxa - 1) <= (unsigned)(p.width - 4) && (unsigned)(sya - 1) <= (unsigned)(p.height - 4) &&
-                              (unsigned)(sxb - 1) <= (unsigned)(p.width - 4) && (unsigned)(syb - 1) <= (unsigned)(p.height - 4) && has_b;
-            all_safe = __all_sync(wmask, safe);
-            const float* pa = box + (sya - ylo) * kBoxW + (sxa - xlo);
-            const float* pb = has_b ? box + (syb - ylo) * kBoxW + (sxb - xlo) : pa;
-            if (all_safe) {
-              smp = sample_box2(pa, pb, ax2, ay2);
-            } else {
-              const Sample sa = sample_box_rules(pa, ax2.x, ay2.x, sxa, sya, p.width, p.height);
-              const Sample sb = sample_box_rules(pb, ax2.y, ay2.y, sxb, syb, p.width, p.height);
-              smp.w = f2(sa.w, has_b ? sb.w : 0.f);
-              smp.gx2 = f2(sa.gx2, has_b ? sb.gx2 : 0.f);
-              smp.gy2 = f2(sa.gy2, has_b ? sb.gy2 : 0.f);
-              int xna, yna, xnb, ynb;
-              FastPersp::nearest(du2.x, dv2.x, xna, yna);
-              FastPersp::nearest(du2.y, dv2.y, xnb, ynb);
-              xna += x; yna += y; xnb += x; ynb += y + 1;
-              mk2.x = ((unsigned)xna < (unsigned)p.width && (unsigned)yna < (unsigned)p.height) ? 1.f : 0.f;
-              mk2.y = (has_b && (unsigned)xnb < (unsigned)p.width && (unsigned)ynb < (unsigned)p.height) ? 1.f : 0.f;
-            }
-          } else {
-            Sample sa, sb; sb.w = sb.gx2 = sb.gy2 = 0.f;
-            float ma, mb = 0.f;
-            slow_sample(y, sa, ma);
-            if (has_b) slow_sample(y + 1, sb, mb);
-            smp.w = f2(sa.w, sb.w); smp.gx2 = f2(sa.gx2, sb.gx2); smp.gy2 = f2(sa.gy2, sb.gy2);
-            mk2 = f2(ma, mb);
-          }
-          // Jacobian generators: a = gx / den, b = gy / den, t = hatX a + hatY b, hatX = -u, hatY = -v, den = w
-          float2 g[3];
-          const float2 hr = mul2(rw2, half2);
-          g[0] = mul2(smp.gx2, hr);
-          g[1] = mul2(smp.gy2, hr);
-          const float2 u2 = add2(xf2, du2), v2 = add2(y2, dv2);
-          g[2] = mul2(fma2(u2, g[0], mul2(v2, g[1])), neg1);
-          if (all_safe) { acc.add<true>(g, smp.w, t2, mk2, y2, yy2); n_safe += 2; }
-          else acc.add<false>(g, smp.w, t2, mk2, y2, yy2);
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[s]);
-    }
-    acc.n = add2(acc.n, f2((float)n_safe, 0.f));
-
-    {
-      float v[NV];
-      acc.emit(xf, v);
-      warp_reduce_vector<NV>(v, lane, s_red[wid]);
-    }
-    __syncthreads();
-    if (tid < NV) {
-      double sres = 0.0;
-#pragma unroll
-      for (int w = 0; w < kWarps; ++w) sres += (double)s_red[w][tid];
-      s_accum[tid] += sres;
-    }
-    cc += nseg;
-    g0 += nseg;
-  }
-  finish_iteration<MOTION, kP2Threads>(p, st, s_accum, s_tot, &s_last);
 }
 
 // State initialisation at the head of each frame's loop (identity warp, rho = -1, last_rho = -eps).

@@ -22,6 +22,7 @@
 
 #include "common.cuh"
 #include "ecc_iter.cuh"
+#include "ecc_iter_v2.cuh"
 #include "prep.cuh"
 #include "resize_area.cuh"
 #include "tenengrad.cuh"
@@ -85,6 +86,18 @@ void invert_perspective_host(const double* s, double* o) {
   o[6] = det2(s[3], s[4], s[6], s[7]) * d;
   o[7] = det2(s[1], s[0], s[7], s[6]) * d;
   o[8] = det2(s[0], s[1], s[3], s[4]) * d;
+}
+
+// cv::warpAffine's inverse of the 2x3 forward map (imgwarp.cpp), f64, same operation order; `o` = [iM00 iM01 iM02;
+// iM10 iM11 iM12] followed by the projective row (0 0 1) the kernel's parameter block carries.
+void invert_affine_host(const double* m, double* o) {
+  double d = m[0] * m[4] - m[1] * m[3];
+  d = d != 0.0 ? 1.0 / d : 0.0;
+  const double a11 = m[4] * d, a22 = m[0] * d;
+  o[0] = a11; o[1] = m[1] * (-d); o[3] = m[3] * (-d); o[4] = a22;
+  o[2] = -o[0] * m[2] - o[1] * m[5];
+  o[5] = -o[3] * m[2] - o[4] * m[5];
+  o[6] = 0.0; o[7] = 0.0; o[8] = 1.0;
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point table (no link-time libcuda dependency)
@@ -251,7 +264,6 @@ struct Lane {
   cudaGraphExec_t exec = nullptr;
   cudaGraphConditionalHandle handle = 0;
   CUtensorMap tm_tmpl;
-  CUtensorMap tm_tmpl_p2;
 };
 
 // Host feed: a ring of pinned frame buffers owned by the context.  Decode tasks fill a
@@ -306,13 +318,13 @@ struct stk_ecc_ctx {
   int max_iter = 0;
   double eps = 0;
   CUtensorMap tm_img;
-  CUtensorMap tm_img_p2;
   bool exact_coords = false;
   bool pdl = false;            // programmatic dependent launch between the chained iteration kernels (opt-in STK_ECC_PDL=1: measured no gain on one lane and -5 % with four, the waiting blocks hold SM slots)
   int loop_unroll = 4;         // iteration kernels per WHILE-body pass (STK_ECC_UNROLL)
   int rim_weight = 10;         // cost of a rim-strip chunk in 1/8 of an interior one (STK_ECC_RIM_WEIGHT)
-  bool pack2 = false;          // Homography with FastPersp coordinates runs the packed-pair kernel
-  int iter_threads = 0, iter_smem = 0;
+  void* iter_fn = nullptr;     // the iteration kernel of this context (generation + geometry, see iter_variant)
+  int iter_threads = 0, iter_smem = 0, iter_chunk_h = 0, iter_box_h = 0, iter_min_blocks = 0;
+  int iter_gen = 2, iter_cfg = 0;
   bool host_loop = false;
   bool have_ref = false;
   stk::PrepParams prep_proto;
@@ -334,15 +346,46 @@ struct stk_ecc_ctx {
 
 namespace {
 
-// homography has two instantiations: FastPersp coordinates (default) and exact f64 (STK_ECC_EXACT_COORDS=1)
-void* iter_kernel_for(int motion, bool exact, bool pack2 = false) {
-  if (pack2) return (void*)stk::ecc_iter_pack2_kernel;
+// The iteration kernel of a context: generation 2 (csrc/ecc_iter_v2.cuh) in one of its compiled geometries, or
+// the first-generation kernel (STK_ECC_GEN=1, kept as the measured baseline).  Homography has two coordinate
+// flavours: FastPersp (default) and exact f64 (STK_ECC_EXACT_COORDS=1).  Geometries other than the default are
+// compiled for the default Homography flavour only (STK_ECC_CFG picks one; scripts/k2_variants.py measures them).
+struct IterVariant { void* fn; int threads, smem, chunk_h, box_h, min_blocks; };
+
+template <int MOTION, bool EXACT, class CFG>
+IterVariant v2_variant() {
+  return {(void*)stk::ecc_iter_v2_kernel<MOTION, EXACT, CFG>, CFG::kThreads, CFG::kDynSmem, CFG::kChunkH, CFG::kBoxH, CFG::kMinBlocks};
+}
+
+using DefaultEccCfg = stk::EccCfg0;
+
+IterVariant iter_variant(int motion, bool exact, int gen, int cfg) {
+  if (gen == 1) {
+    void* fn;
+    switch (motion) {
+      case STK_MOTION_TRANSLATION: fn = (void*)stk::ecc_iter_kernel<stk::kTranslation, true>; break;
+      case STK_MOTION_EUCLIDEAN: fn = (void*)stk::ecc_iter_kernel<stk::kEuclidean, true>; break;
+      case STK_MOTION_AFFINE: fn = (void*)stk::ecc_iter_kernel<stk::kAffine, true>; break;
+      default: fn = exact ? (void*)stk::ecc_iter_kernel<stk::kHomography, true> : (void*)stk::ecc_iter_kernel<stk::kHomography, false>;
+    }
+    return {fn, stk::kEccThreads, stk::kEccDynSmem, stk::kChunkH, stk::kBoxH, 2};
+  }
   switch (motion) {
-    case STK_MOTION_TRANSLATION: return (void*)stk::ecc_iter_kernel<stk::kTranslation, true>;
-    case STK_MOTION_EUCLIDEAN: return (void*)stk::ecc_iter_kernel<stk::kEuclidean, true>;
-    case STK_MOTION_AFFINE: return (void*)stk::ecc_iter_kernel<stk::kAffine, true>;
-    default: return exact ? (void*)stk::ecc_iter_kernel<stk::kHomography, true>
-                          : (void*)stk::ecc_iter_kernel<stk::kHomography, false>;
+    case STK_MOTION_TRANSLATION: return v2_variant<stk::kTranslation, true, DefaultEccCfg>();
+    case STK_MOTION_EUCLIDEAN: return v2_variant<stk::kEuclidean, true, DefaultEccCfg>();
+    case STK_MOTION_AFFINE: return v2_variant<stk::kAffine, true, DefaultEccCfg>();
+    default: break;
+  }
+  if (exact) return v2_variant<stk::kHomography, true, DefaultEccCfg>();
+  switch (cfg) {
+    case 1: return v2_variant<stk::kHomography, false, stk::EccCfg1>();
+    case 2: return v2_variant<stk::kHomography, false, stk::EccCfg2>();
+    case 3: return v2_variant<stk::kHomography, false, stk::EccCfg3>();
+    case 4: return v2_variant<stk::kHomography, false, stk::EccCfg4>();
+    case 5: return v2_variant<stk::kHomography, false, stk::EccCfg5>();
+    case 6: return v2_variant<stk::kHomography, false, stk::EccCfg6>();
+    case 7: return v2_variant<stk::kHomography, false, stk::EccCfg7>();
+    default: return v2_variant<stk::kHomography, false, stk::EccCfg0>();
   }
 }
 
@@ -360,8 +403,6 @@ stk::EccIterParams iter_params(stk_ecc_ctx* c, Lane& ln, bool use_handle) {
   memset(&p, 0, sizeof p);
   p.tm_img = c->tm_img;
   p.tm_tmpl = ln.tm_tmpl;
-  p.tm_img_p2 = c->tm_img_p2;
-  p.tm_tmpl_p2 = ln.tm_tmpl_p2;
   p.img = c->img;
   p.tmpl = ln.tmpl;
   p.pitch = c->pitch_f;
@@ -411,7 +452,7 @@ int build_lane_graph(stk_ecc_ctx* c, Lane& ln) {
     stk::EccIterParams ip = iter_params(c, ln, true);
     void* args[] = {&ip};
     cudaKernelNodeParams kp = {};
-    kp.func = iter_kernel_for(c->cfg.motion_type, c->exact_coords, c->pack2);
+    kp.func = c->iter_fn;
     kp.gridDim = dim3(c->n_tiles);
     kp.blockDim = dim3(c->iter_threads);
     kp.sharedMemBytes = c->iter_smem;
@@ -652,7 +693,7 @@ int enqueue_align(stk_ecc_ctx* c, Lane& ln, const uint8_t* d_src, size_t pitch, 
     while (*h_cont && done_iters < c->max_iter) {
       const int chunk = std::min(4, c->max_iter - done_iters);
       for (int i = 0; i < chunk; ++i)
-        CU(cudaLaunchKernel(iter_kernel_for(c->cfg.motion_type, c->exact_coords, c->pack2), dim3(c->n_tiles), dim3(c->iter_threads), args, c->iter_smem, ln.stream));
+        CU(cudaLaunchKernel(c->iter_fn, dim3(c->n_tiles), dim3(c->iter_threads), args, c->iter_smem, ln.stream));
       done_iters += chunk;
       CU(cudaMemcpyAsync(h_cont, &ln.st->cont, sizeof(int), cudaMemcpyDeviceToHost, ln.stream));
       CU(cudaStreamSynchronize(ln.stream));
@@ -835,22 +876,23 @@ int stk_ecc_create(const stk_ecc_config* cfg, stk_ecc_ctx** out) {
 
   if (cfg->align) {
     // work split: 128-column strips x row chunks, dealt evenly to one persistent block per resident slot
-    const char* p2 = getenv("STK_ECC_PACK2");
-    // the packed-pair kernel is opt-in (STK_ECC_PACK2=1): measured 26 % fewer instructions but IPC 0.50 vs
-    // 0.71 at 168 registers / 3 warps per scheduler, i.e. no faster than the scalar kernel
-    c->pack2 = cfg->motion_type == STK_MOTION_HOMOGRAPHY && !c->exact_coords && p2 && strcmp(p2, "1") == 0;
-    c->iter_threads = c->pack2 ? stk::kP2Threads : stk::kEccThreads;
-    c->iter_smem = c->pack2 ? stk::kP2DynSmem : stk::kEccDynSmem;
-    const void* kfn = (const void*)iter_kernel_for(cfg->motion_type, c->exact_coords, c->pack2);
-    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, c->iter_smem) != cudaSuccess)
+    if (const char* g = getenv("STK_ECC_GEN")) c->iter_gen = atoi(g) == 1 ? 1 : 2;
+    if (const char* g = getenv("STK_ECC_CFG")) c->iter_cfg = std::max(0, std::min(stk::kEccCfgCount - 1, atoi(g)));
+    const IterVariant iv = iter_variant(cfg->motion_type, c->exact_coords, c->iter_gen, c->iter_cfg);
+    c->iter_fn = iv.fn;
+    c->iter_threads = iv.threads;
+    c->iter_smem = iv.smem;
+    c->iter_chunk_h = iv.chunk_h;
+    c->iter_box_h = iv.box_h;
+    c->iter_min_blocks = iv.min_blocks;
+    if (cudaFuncSetAttribute(c->iter_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, c->iter_smem) != cudaSuccess)
       return cleanup(fail(STK_ERR_CUDA, "cannot reserve %d bytes of dynamic shared memory for the ECC kernel", c->iter_smem));
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, c->iter_threads, c->iter_smem) != cudaSuccess || occ < 1) occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, c->iter_fn, c->iter_threads, c->iter_smem) != cudaSuccess || occ < 1) occ = 1;
     const int slots = c->sm_count * occ;
     c->n_strips = (c->ew + stk::kEccStripW - 1) / stk::kEccStripW;
-    c->chunks_per_strip = (c->eh + stk::kChunkH - 1) / stk::kChunkH;
-    const int chunk_h = c->pack2 ? stk::kP2ChunkH : stk::kChunkH;
-    const long long total_chunks = (long long)c->n_strips * ((c->eh + chunk_h - 1) / chunk_h);
+    c->chunks_per_strip = (c->eh + c->iter_chunk_h - 1) / c->iter_chunk_h;
+    const long long total_chunks = (long long)c->n_strips * c->chunks_per_strip;
     // at least two chunks per block so the per-run fold/reduction stays amortised on small frames
     c->n_tiles = (int)std::max(1LL, std::min<long long>(slots, total_chunks / 2));
     c->nv = model_nv(cfg->motion_type);
@@ -869,9 +911,7 @@ int stk_ecc_create(const stk_ecc_config* cfg, stk_ecc_ctx** out) {
     }
     if (cudaMalloc((void**)&c->img, (size_t)c->pitch_f * c->eh * sizeof(float)) != cudaSuccess)
       return cleanup(fail(STK_ERR_NOMEM, "cudaMalloc(I plane) failed"));
-    rc = make_plane_tensor_map(&c->tm_img, c->img, c->ew, c->eh, c->pitch_f, stk::kBoxW, stk::kBoxH);
-    if (rc) return cleanup(rc);
-    rc = make_plane_tensor_map(&c->tm_img_p2, c->img, c->ew, c->eh, c->pitch_f, stk::kBoxW, stk::kP2BoxH);
+    rc = make_plane_tensor_map(&c->tm_img, c->img, c->ew, c->eh, c->pitch_f, stk::kBoxW, c->iter_box_h);
     if (rc) return cleanup(rc);
     if (c->scaled) {
       rc = make_area_plan(cfg->width, cfg->height, c->ew, c->eh, c->area);
@@ -886,9 +926,7 @@ int stk_ecc_create(const stk_ecc_config* cfg, stk_ecc_ctx** out) {
     if (cudaMalloc((void**)&ln.acc, c->acc_floats * sizeof(float)) != cudaSuccess) return cleanup(fail(STK_ERR_NOMEM, "cudaMalloc(accumulator) failed"));
     if (cfg->align) {
       if (cudaMalloc((void**)&ln.tmpl, (size_t)c->pitch_f * c->eh * sizeof(float)) != cudaSuccess) return cleanup(fail(STK_ERR_NOMEM, "cudaMalloc(T plane) failed"));
-      rc = make_plane_tensor_map(&ln.tm_tmpl, ln.tmpl, c->ew, c->eh, c->pitch_f, stk::kEccStripW, stk::kChunkH);
-      if (rc) return cleanup(rc);
-      rc = make_plane_tensor_map(&ln.tm_tmpl_p2, ln.tmpl, c->ew, c->eh, c->pitch_f, stk::kEccStripW, stk::kP2ChunkH);
+      rc = make_plane_tensor_map(&ln.tm_tmpl, ln.tmpl, c->ew, c->eh, c->pitch_f, stk::kEccStripW, c->iter_chunk_h);
       if (rc) return cleanup(rc);
       if (c->scaled && cudaMalloc((void**)&ln.small, (size_t)c->small_pitch * c->eh) != cudaSuccess) return cleanup(fail(STK_ERR_NOMEM, "cudaMalloc(downscaled grey) failed"));
       if (cudaMalloc((void**)&ln.st, sizeof(stk::EccState)) != cudaSuccess) return cleanup(fail(STK_ERR_NOMEM, "cudaMalloc(state) failed"));
@@ -995,7 +1033,7 @@ int stk_ecc_set_reference_device(stk_ecc_ctx* c, const uint8_t* d_bgr, size_t pi
 
 // a filled ring buffer: asynchronous upload on the next lane, then align (inv == null) or warp-only; the
 // buffer goes back to the ring at once, guarded by its event
-static int submit_ring(stk_ecc_ctx* c, int idx, int64_t tag, const double* inv, const float* border) {
+static int submit_ring(stk_ecc_ctx* c, int idx, int64_t tag, const double* inv, const float* border, bool persp = true) {
   int rc = STK_OK;
   {
     std::lock_guard<std::mutex> g(c->mu);
@@ -1009,7 +1047,7 @@ static int submit_ring(stk_ecc_ctx* c, int idx, int64_t tag, const double* inv, 
     if (rc == STK_OK && e != cudaSuccess) rc = fail(STK_ERR_CUDA, "frame upload: %s", cudaGetErrorString(e));
     if (rc == STK_OK) {
       if (inv) {
-        rc = launch_warp(c, ln, ln.d_frame, row, true, inv, border, false);
+        rc = launch_warp(c, ln, ln.d_frame, row, persp, inv, border, false);
         if (rc == STK_OK) { ResultSlot slot; slot.tag = tag; slot.host = nullptr; c->results.push_back(slot); }
       } else {
         rc = enqueue_align(c, ln, ln.d_frame, row, tag);
@@ -1084,7 +1122,7 @@ int stk_ecc_submit_acquired(stk_ecc_ctx* c, uint8_t* buf, int64_t tag) {
 }
 
 static int submit_warp(stk_ecc_ctx* c, const uint8_t* buf, size_t pitch, const double* h, int border_mode,
-                       const double* border_value, int64_t tag, bool device) {
+                       const double* border_value, int64_t tag, bool device, bool affine = false) {
   int rc = check_ctx(c);
   if (rc) return rc;
   if (!buf || !h) return fail(STK_ERR_BAD_ARG, "null argument");
@@ -1095,7 +1133,8 @@ static int submit_warp(stk_ecc_ctx* c, const uint8_t* buf, size_t pitch, const d
   const size_t row = (size_t)c->cfg.width * c->cfg.channels;
   if (pitch < row) return fail(STK_ERR_BAD_ARG, "pitch %zu < row bytes %zu", pitch, row);
   double inv[9];
-  invert_perspective_host(h, inv);
+  if (affine) invert_affine_host(h, inv);
+  else invert_perspective_host(h, inv);
   float border[5] = {0, 0, 0, 0, (float)border_mode};
   if (border_value) for (int i = 0; i < 4; ++i) border[i] = (float)border_value[i];
   if (!device) {
@@ -1103,13 +1142,13 @@ static int submit_warp(stk_ecc_ctx* c, const uint8_t* buf, size_t pitch, const d
     rc = ring_acquire(c, &idx);
     if (rc) return rc;
     copy_rows(c->ring[idx].host, buf, pitch, row, c->cfg.height);
-    return submit_ring(c, idx, tag, inv, border);
+    return submit_ring(c, idx, tag, inv, border, !affine);
   }
   std::lock_guard<std::mutex> g(c->mu);
   Lane& ln = pick_lane(c);
   const uint8_t* d_src = buf;
   size_t d_pitch = pitch;
-  rc = launch_warp(c, ln, d_src, d_pitch, true, inv, border, false);
+  rc = launch_warp(c, ln, d_src, d_pitch, !affine, inv, border, false);
   if (rc) return rc;
   { ResultSlot slot; slot.tag = tag; slot.host = nullptr; c->results.push_back(slot); }
   return STK_OK;
@@ -1122,6 +1161,15 @@ int stk_ecc_submit_warp(stk_ecc_ctx* c, const uint8_t* bgr, size_t pitch, const 
 int stk_ecc_submit_warp_device(stk_ecc_ctx* c, const uint8_t* d_bgr, size_t pitch, const double h[9], int border_mode,
                                const double border_value[4], int64_t tag) {
   return submit_warp(c, d_bgr, pitch, h, border_mode, border_value, tag, true);
+}
+
+int stk_ecc_submit_warp_affine(stk_ecc_ctx* c, const uint8_t* bgr, size_t pitch, const double m[6], int border_mode,
+                               const double border_value[4], int64_t tag) {
+  return submit_warp(c, bgr, pitch, m, border_mode, border_value, tag, false, true);
+}
+int stk_ecc_submit_warp_affine_device(stk_ecc_ctx* c, const uint8_t* d_bgr, size_t pitch, const double m[6], int border_mode,
+                                      const double border_value[4], int64_t tag) {
+  return submit_warp(c, d_bgr, pitch, m, border_mode, border_value, tag, true, true);
 }
 
 int stk_ecc_sync(stk_ecc_ctx* c) {
@@ -1582,7 +1630,7 @@ int stk_ecc_debug_iteration(stk_ecc_ctx* c, const uint8_t* bgr, size_t pitch, co
   stk::EccIterParams ip = iter_params(c, ln, false);
   ip.totals_out = d_tot;
   void* args[] = {&ip};
-  cudaError_t e = cudaLaunchKernel(iter_kernel_for(c->cfg.motion_type, c->exact_coords, c->pack2), dim3(c->n_tiles), dim3(c->iter_threads), args, c->iter_smem, ln.stream);
+  cudaError_t e = cudaLaunchKernel(c->iter_fn, dim3(c->n_tiles), dim3(c->iter_threads), args, c->iter_smem, ln.stream);
   stk::EccState hs;
   if (e == cudaSuccess) e = cudaMemcpyAsync(totals, d_tot, sizeof(double) * c->nv, cudaMemcpyDeviceToHost, ln.stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(&hs, ln.st, sizeof hs, cudaMemcpyDeviceToHost, ln.stream);
@@ -1625,7 +1673,7 @@ int stk_ecc_debug_timing(stk_ecc_ctx* c, const uint8_t* bgr, size_t pitch, const
   void* args[] = {&ip};
   cudaError_t e = cudaSuccess;
   for (int i = 0; i < std::max(1, iters) && e == cudaSuccess; ++i)
-    e = cudaLaunchKernel(iter_kernel_for(c->cfg.motion_type, c->exact_coords, c->pack2), dim3(c->n_tiles), dim3(c->iter_threads), args, c->iter_smem, ln.stream);
+    e = cudaLaunchKernel(c->iter_fn, dim3(c->n_tiles), dim3(c->iter_threads), args, c->iter_smem, ln.stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(stamps, d_t, sizeof(unsigned long long) * need, cudaMemcpyDeviceToHost, ln.stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ln.stream);
   cudaFree(d_t);

@@ -16,10 +16,15 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 from oracle import synth, cvref  # noqa: E402
 
 
+# every golden stack has 5 frames: the north-star bar (8-bit max-abs-diff <= 1) is asserted literally on stacks of
+# >= 5 frames (a zero-blended rim pixel of ONE frame moves by ~3 levels per 1/32-px coordinate quantum; / n)
+N_STACK = 5
+
+
 def ecc_cases():
     out = {}
     for motion in (0, 1, 2, 3):
-        st = synth.Stack(256, 192, 3, motion, seed=100 + motion)
+        st = synth.Stack(256, 192, N_STACK, motion, seed=100 + motion)
         frames = st.frames()
         stack, warps, rhos = cvref.ecc_match(frames, motion, 5000, 1e-5, 5, workers=1)
         out[f"m{motion}_warps"] = np.stack([np.vstack([w, [0, 0, 1]]) if w.shape[0] == 2 else w for w in warps[1:]]).astype(np.float32)
@@ -65,7 +70,7 @@ def scale_down_cases():
         grey = rng.integers(0, 256, (h, w), dtype=np.uint8)
         out[f"resize_{w}x{h}_{int(sd)}"] = cvref.scale_image(grey, sd)
     for motion, w, h, sd, seed in SCALE_DOWN_CASES:
-        frames = synth.Stack(w, h, 4, motion, seed=seed).frames()
+        frames = synth.Stack(w, h, N_STACK, motion, seed=seed).frames()
         stack, warps, _ = cvref.ecc_match_scaling_down(frames, motion, 60, 1e-5, 5, sd)
         out[f"sd_m{motion}_warps"] = np.stack([np.vstack([m, [0, 0, 1]]) if m.shape[0] == 2 else m for m in warps[1:]]).astype(np.float32)
         out[f"sd_m{motion}_stack8"] = np.rint(stack * 255.0).astype(np.uint8)
@@ -87,7 +92,7 @@ def scale_up_cases():
         grey = rng.integers(0, 256, (h, w), dtype=np.uint8)
         out[f"resize_{w}x{h}_{int(sd)}"] = cvref.scale_image(grey, sd)
     for motion, w, h, sd, seed in SCALE_UP_CASES:
-        frames = synth.Stack(w, h, 4, motion, seed=seed).frames()
+        frames = synth.Stack(w, h, N_STACK, motion, seed=seed).frames()
         stack, warps, _ = cvref.ecc_match_scaling_down(frames, motion, 60, 1e-5, 5, sd)
         out[f"sd_m{motion}_warps"] = np.stack([np.vstack([m, [0, 0, 1]]) if m.shape[0] == 2 else m for m in warps[1:]]).astype(np.float32)
         out[f"sd_m{motion}_stack8"] = np.rint(stack * 255.0).astype(np.uint8)

@@ -26,15 +26,11 @@ def coverage(warps, motion, width, height):
 
 
 def assert_stack_parity(got_f32, want_f32, warps, motion, n_frames):
+    """The north-star bars, literally: 8-bit max-abs-diff <= 1 and PSNR >= 50 dB.  Every parity stack has at least
+    5 frames: one frame's zero-blended rim pixel moves by ~3 grey levels per 1/32-px coordinate quantum, and the
+    bars are stated for stacks, where that is divided by n."""
+    assert n_frames >= 5, "parity stacks have at least 5 frames"
     g8, w8 = np.rint(got_f32 * 255.0), np.rint(want_f32 * 255.0)
     d = np.abs(g8 - w8)
     assert psnr8(g8, w8) >= 50.0, psnr8(g8, w8)
-    if n_frames >= 5:
-        assert d.max() <= 1, d.max()
-        return
-    # tiny stacks: one frame's rim pixel weighs 1/n of ~100 levels; hold the <= 1 bar where all frames
-    # cover, and <= 2 on the rims
-    h, w = got_f32.shape[:2]
-    cov = coverage(warps, motion, w, h)
-    assert d[cov].max() <= 1, d[cov].max()
-    assert d.max() <= 2, d.max()
+    assert d.max() <= 1, d.max()

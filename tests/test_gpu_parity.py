@@ -128,6 +128,42 @@ def test_warp_only_border_modes_bit_exact(pkg, mode, chan):
     assert np.array_equal(got, acc * np.float32(0.25))
 
 
+@pytest.mark.parametrize("size", [(320, 240), (333, 97), (1921, 1083)])
+@pytest.mark.parametrize("chan", [3, 4])
+def test_warp_affine_bit_exact_vs_oracle_and_cv2(pkg, have_cv2, size, chan):
+    """The 2x3 final warp of ecc_match (warp_affine, src/lib.rs:782-790; OpenCV's 10-bit fixed-point coordinates)
+    through its own entry point: `array_equal` against the oracle and against cv2.warpAffine on the CV_32F frame."""
+    w, h = size
+    rng = np.random.default_rng(w * 7 + chan)
+    n = 5
+    frames = [rng.integers(0, 256, (h, w, chan), dtype=np.uint8) for _ in range(n)]
+    ms = []
+    for i in range(n - 1):
+        g = synth.random_warp(rng, 2, w, h)[:2].copy()
+        if i % 2:                                           # large motions: rims, taps outside, whole rows of border
+            g[:, 2] += rng.uniform(-0.3, 0.3, 2) * (w, h)
+            g[:, :2] += rng.uniform(-0.1, 0.1, (2, 2))
+        ms.append(g)
+    bv = (0.0, 0.0, 0.0, 0.0) if chan == 3 else (0.1, 0.2, 0.3, 0.4)
+    with pkg.EccStack(w, h, chan, None, device=0, lanes=1) as st:     # one lane: fixed summation order
+        st.set_reference(frames[0])
+        for f, m in zip(frames[1:], ms):
+            st.submit_warp_affine(f, m, pkg.BORDER_CONSTANT, bv)
+        got = st.finish(n)
+    acc = R.to_f32_unit(frames[0])
+    for f, m in zip(frames[1:], ms):
+        acc = acc + R.warp_linear(R.to_f32_unit(f), m, w, h, perspective=False, inverse_map=False, border_value=np.array(bv[:chan]))
+    assert np.array_equal(got, acc * np.float32(1.0 / n))
+    if have_cv2:
+        import cv2
+        k255 = np.float32(1 / 255.0)
+        acc = frames[0].astype(np.float32) * k255
+        for f, m in zip(frames[1:], ms):
+            acc = acc + cv2.warpAffine(f.astype(np.float32) * k255, m, (w, h), flags=cv2.INTER_LINEAR,
+                                       borderMode=cv2.BORDER_CONSTANT, borderValue=bv)
+        assert np.array_equal(got, acc * np.float32(1.0 / n))
+
+
 def test_warp_only_transparent_border_unsupported(pkg):
     frame = np.zeros((16, 16, 3), np.uint8)
     with pkg.EccStack(16, 16, 3, None, device=0, lanes=1) as st:
@@ -236,18 +272,18 @@ def test_iteration_sums_match_oracle(pkg, motion, size):
 @pytest.mark.parametrize("motion", MOTIONS)
 def test_ecc_match_small_vs_oracle(pkg, motion):
     w, h = 320, 240
-    stack = synth.Stack(w, h, 4, motion, seed=47 + motion)
+    stack = synth.Stack(w, h, 6, motion, seed=47 + motion)
     frames = stack.frames()
     params = pkg.EccMatchParameters(pkg.MotionType(motion), 5000, 1e-5, 5)
     got, res = pkg.ecc_match(frames, params, None, device=0, return_details=True)
     want, warps, iters = R.ecc_match(frames, motion, 5000, 1e-5, 5)
-    assert [r["status"] for r in res] == [0, 0, 0]
+    assert [r["status"] for r in res] == [0] * 5
     for r, wm, it in zip(res, warps[1:], iters[1:]):
         mine = r["warp"] if motion == 3 else r["warp"][:2]
         assert synth.corner_displacement(mine, wm, w, h) <= 0.05
         # the eps test on rho may trip an iteration or three apart; the matrix and stack bars above decide
         assert it > 40 or abs(r["iterations"] - it) <= 4
-    assert_stack_parity(got, want, warps, motion, 4)
+    assert_stack_parity(got, want, warps, motion, 6)
 
 
 def test_ecc_match_config1_vs_cv2(pkg, have_cv2):
@@ -268,17 +304,17 @@ def test_ecc_match_config1_vs_cv2(pkg, have_cv2):
 
 
 def test_ecc_match_config2_shape_vs_cv2(pkg, have_cv2):
-    """BASELINE config 2 (Euclidean 1920x1080) on 4 of its 16 frames."""
+    """BASELINE config 2 (Euclidean 1920x1080) on 5 of its 16 frames (all 16: tests/test_gpu_fullsize.py)."""
     if not have_cv2:
         pytest.skip("cv2 not installed")
     from oracle import cvref
-    frames = synth.config_stack(2, n_frames=4).frames()
+    frames = synth.config_stack(2, n_frames=5).frames()
     params = pkg.EccMatchParameters(pkg.MotionType.Euclidean, 5000, 1e-5, 5)
     got, res = pkg.ecc_match(frames, params, None, device=0, return_details=True)
     want, warps, _ = cvref.ecc_match(frames, 1, 5000, 1e-5, 5)
     for r, wm in zip(res, warps[1:]):
         assert synth.corner_displacement(r["warp"][:2], wm, 1920, 1080) <= 0.05
-    assert_stack_parity(got, want, warps, 1, 4)
+    assert_stack_parity(got, want, warps, 1, 5)
 
 
 def test_fixed_iteration_count_and_eps_only(pkg):
@@ -334,21 +370,32 @@ def test_lanes_and_device_resident_input(pkg):
 
 
 def test_kernel_variants_agree(pkg, monkeypatch):
-    """The homography iteration kernel has three instantiations: FastPersp coordinates (default), exact f64
-    coordinates (STK_ECC_EXACT_COORDS=1) and packed pixel pairs (STK_ECC_PACK2=1).  Same stack, same bars."""
+    """The homography iteration kernel exists in several builds: FastPersp coordinates (default), exact f64
+    coordinates (STK_ECC_EXACT_COORDS=1), the compiled block geometries of the second-generation kernel
+    (STK_ECC_CFG, csrc/ecc_iter_v2.cuh), the first-generation kernel (STK_ECC_GEN=1) and the host-driven loop
+    (STK_LOOP_MODE=host).  Same stack, same bars; the geometries must also agree with each other to rounding."""
     w, h = 400, 300
-    frames = synth.Stack(w, h, 4, 3, seed=50).frames()
+    frames = synth.Stack(w, h, 5, 3, seed=50).frames()
     want, warps, _ = R.ecc_match(frames, 3, 5000, 1e-5, 5)
     params = pkg.EccMatchParameters(pkg.MotionType.Homography, 5000, 1e-5, 5)
-    for env in ({}, {"STK_ECC_EXACT_COORDS": "1"}, {"STK_ECC_PACK2": "1"}, {"STK_LOOP_MODE": "host"}):
-        for k in ("STK_ECC_EXACT_COORDS", "STK_ECC_PACK2", "STK_LOOP_MODE"):
+    keys = ("STK_ECC_EXACT_COORDS", "STK_ECC_GEN", "STK_ECC_CFG", "STK_LOOP_MODE")
+    envs = [{}, {"STK_ECC_EXACT_COORDS": "1"}, {"STK_ECC_GEN": "1"}, {"STK_LOOP_MODE": "host"}]
+    envs += [{"STK_ECC_CFG": str(k)} for k in range(1, 8)]
+    first = None
+    for env in envs:
+        for k in keys:
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         got, res = pkg.ecc_match(frames, params, None, device=0, return_details=True)
         for r, wm in zip(res, warps[1:]):
             assert synth.corner_displacement(r["warp"], wm, w, h) <= 0.05, env
-        assert_stack_parity(got, want, warps, 3, 4)
+        assert_stack_parity(got, want, warps, 3, 5)
+        if "STK_ECC_EXACT_COORDS" not in env:
+            if first is None:
+                first = res
+            for a, b in zip(first, res):
+                assert synth.corner_displacement(a["warp"], b["warp"], w, h) <= 2e-3, env
 
 
 # ---- K6: Tenengrad, bit-identical ------------------------------------------------------------------------
@@ -420,20 +467,20 @@ def test_grey_resize_area_enlarging_bit_exact(pkg, case):
 def test_ecc_match_scaling_down_enlarging_vs_oracle_and_golden(pkg, case):
     import os
     motion, w, h, sd, seed = case
-    frames = synth.Stack(w, h, 4, motion, seed=seed).frames()
+    frames = synth.Stack(w, h, 5, motion, seed=seed).frames()
     params = pkg.EccMatchParameters(pkg.MotionType(motion), 60, 1e-5, 5)
     got, res = pkg.ecc_match(frames, params, sd, device=0, return_details=True)
     want, warps, _ = R.ecc_match_scaling_down(frames, motion, 60, 1e-5, 5, sd)
-    assert [r["status"] for r in res] == [0, 0, 0]
+    assert [r["status"] for r in res] == [0] * 4
     for r, wm in zip(res, warps[1:]):
         mine = r["warp"] if motion == 3 else r["warp"][:2]
         assert synth.corner_displacement(mine, wm, w, h) <= 0.05
-    assert_stack_parity(got, want, warps, motion, 4)
+    assert_stack_parity(got, want, warps, motion, 5)
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "scale_up.npz"))
     for r, ref in zip(res, g[f"sd_m{motion}_warps"]):
         mine = r["warp"] if motion == 3 else r["warp"][:2]
         assert synth.corner_displacement(mine, ref if motion == 3 else ref[:2], w, h) <= 0.05
-    assert_stack_parity(got, g[f"sd_m{motion}_stack8"].astype(np.float32) / np.float32(255.0), warps, motion, 4)
+    assert_stack_parity(got, g[f"sd_m{motion}_stack8"].astype(np.float32) / np.float32(255.0), warps, motion, 5)
 
 
 def test_grey_resize_area_golden(pkg):
@@ -455,20 +502,20 @@ def test_ecc_match_scaling_down_vs_oracle_and_golden(pkg, case):
     rules, full-size warp: against the restatement and against the committed cv2 vectors."""
     import os
     motion, w, h, sd, seed = case
-    frames = synth.Stack(w, h, 4, motion, seed=seed).frames()
+    frames = synth.Stack(w, h, 5, motion, seed=seed).frames()
     params = pkg.EccMatchParameters(pkg.MotionType(motion), 60, 1e-5, 5)
     got, res = pkg.ecc_match(frames, params, sd, device=0, return_details=True)
     want, warps, iters = R.ecc_match_scaling_down(frames, motion, 60, 1e-5, 5, sd)
-    assert [r["status"] for r in res] == [0, 0, 0]
+    assert [r["status"] for r in res] == [0] * 4
     for r, wm in zip(res, warps[1:]):
         mine = r["warp"] if motion == 3 else r["warp"][:2]
         assert synth.corner_displacement(mine, wm, w, h) <= 0.05
-    assert_stack_parity(got, want, warps, motion, 4)
+    assert_stack_parity(got, want, warps, motion, 5)
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "scale_down.npz"))
     for r, ref in zip(res, g[f"sd_m{motion}_warps"]):
         mine = r["warp"] if motion == 3 else r["warp"][:2]
         assert synth.corner_displacement(mine, ref if motion == 3 else ref[:2], w, h) <= 0.05
-    assert_stack_parity(got, g[f"sd_m{motion}_stack8"].astype(np.float32) / np.float32(255.0), warps, motion, 4)
+    assert_stack_parity(got, g[f"sd_m{motion}_stack8"].astype(np.float32) / np.float32(255.0), warps, motion, 5)
 
 
 def test_ecc_match_scaling_down_config1_vs_cv2(pkg, have_cv2):
