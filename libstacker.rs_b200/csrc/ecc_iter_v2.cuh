@@ -227,6 +227,7 @@ __global__ void __launch_bounds__(CFG::kThreads, CFG::kMinBlocks) ecc_iter_v2_ke
         if (fast_coords) fp.init(s_m, x);
       }
       mbar_wait(&s_full[s], (unsigned)(gc / kStages) & 1u);
+      if (p.timing_out && tid == 0 && gc == 0) p.timing_out[(size_t)blockIdx.x * 4 + 3] = global_ns();   // first chunk landed
       const float* box = reinterpret_cast<const float*>(dyn + s * kStageBytes);
       const float* tbox = reinterpret_cast<const float*>(dyn + s * kStageBytes + kImgBytes);
       const bool boxed = xlo != INT_MIN;
