@@ -120,16 +120,32 @@ def term_criteria(params: EccMatchParameters):
 
 
 # ---- low-level stack context ---------------------------------------------------------------------------
-def _device_view(obj):
+def _device_view(obj, expect_shape=None):
     """(ptr, pitch_bytes) of an array living on the GPU (anything with __cuda_array_interface__, e.g. a
-    torch CUDA tensor of shape HxWxC uint8), or None for host arrays."""
+    torch CUDA tensor of shape HxWxC uint8), or None for host arrays.  The array must be 8-bit with dense
+    pixels (only the row pitch may be padded) and, when `expect_shape` is given, of exactly that shape: the
+    library reads height * pitch bytes from the pointer, so anything else would be an out-of-bounds device read.
+    Stream contract: the library's lane streams are non-blocking, so the producer of the array must have finished
+    writing it (synchronise the producing stream, or record/wait an event) before the frame is submitted."""
     iface = getattr(obj, "__cuda_array_interface__", None)
     if iface is None:
         return None
-    shape = iface["shape"]
+    shape = tuple(int(v) for v in iface["shape"])
+    if iface.get("typestr") not in ("|u1", "<u1", ">u1"):
+        raise OpenCvError(f"device frame must be 8-bit unsigned (got typestr {iface.get('typestr')!r})")
+    if expect_shape is not None and shape != tuple(expect_shape):
+        raise OpenCvError(f"device frame has shape {shape}, the stack expects {tuple(expect_shape)}")
     strides = iface.get("strides")
-    pitch = strides[0] if strides else int(np.prod(shape[1:]))
-    return int(iface["data"][0]), int(pitch)
+    dense = [1]
+    for d in reversed(shape[1:]):
+        dense.insert(0, dense[0] * d)
+    if strides:
+        if tuple(int(v) for v in strides[1:]) != tuple(dense[1:]):
+            raise OpenCvError(f"device frame must have dense pixels (strides {tuple(strides)})")
+        if int(strides[0]) < dense[0]:
+            raise OpenCvError("device frame rows overlap")
+    pitch = int(strides[0]) if strides else dense[0]
+    return int(iface["data"][0]), pitch
 
 
 class EccStack:
@@ -190,7 +206,7 @@ class EccStack:
         return frame, frame.ctypes.data, frame.strides[0]
 
     def set_reference(self, frame):
-        dv = _device_view(frame)
+        dv = _device_view(frame, (self.height, self.width, self.channels))
         if dv is not None:
             _check(lib.stk_ecc_set_reference_device(self._ctx, dv[0], dv[1]))
             self._keep.append(frame)
@@ -199,7 +215,7 @@ class EccStack:
             _check(lib.stk_ecc_set_reference(self._ctx, ptr, pitch))
 
     def submit(self, frame, tag: int = 0, pinned: bool = False):
-        dv = _device_view(frame)
+        dv = _device_view(frame, (self.height, self.width, self.channels))
         if dv is not None:
             self._keep.append(frame)
             _check(lib.stk_ecc_submit_frame_device(self._ctx, dv[0], dv[1], int(tag)))
@@ -230,7 +246,7 @@ class EccStack:
     def submit_warp(self, frame, h, border_mode: int = BORDER_CONSTANT, border_value=(0, 0, 0, 0), tag: int = 0):
         hm = (C.c_double * 9)(*np.asarray(h, np.float64).reshape(9))
         bv = (C.c_double * 4)(*[float(v) for v in border_value])
-        dv = _device_view(frame)
+        dv = _device_view(frame, (self.height, self.width, self.channels))
         if dv is not None:
             self._keep.append(frame)
             _check(lib.stk_ecc_submit_warp_device(self._ctx, dv[0], dv[1], hm, int(border_mode), bv, int(tag)))
@@ -242,7 +258,7 @@ class EccStack:
         """warp_affine(img_f32, M 2x3 f64, ..) + accumulate (src/lib.rs:782-790 with a caller-supplied matrix)."""
         mm = (C.c_double * 6)(*np.asarray(m, np.float64).reshape(-1)[:6])
         bv = (C.c_double * 4)(*[float(v) for v in border_value])
-        dv = _device_view(frame)
+        dv = _device_view(frame, (self.height, self.width, self.channels))
         if dv is not None:
             self._keep.append(frame)
             _check(lib.stk_ecc_submit_warp_affine_device(self._ctx, dv[0], dv[1], mm, int(border_mode), bv, int(tag)))
@@ -539,6 +555,14 @@ def _scale_image(img, scale_down: float):
     return cv2.resize(img, (int(w * factor), int(h * factor)), interpolation=cv2.INTER_AREA)
 
 
+def _keep_count(n_good: int, keep_ratio: float) -> int:
+    """`(filtered_matches.len() as f32 * params.match_keep_ratio).round() as usize` (src/lib.rs:235, :472): f32 product, halves rounded
+    AWAY from zero as Rust's f32::round does (6 matches at 0.75 keep 5; Python's round() would keep 4 and drop
+    the frame below the 5-match minimum)."""
+    x = np.float32(n_good) * np.float32(keep_ratio)
+    return int(np.floor(x + np.float32(0.5))) if x >= 0 else 0
+
+
 def _frame_homography(kp0, des0, img, params: KeyPointMatchParameters, scale_down: Optional[float] = None):
     """Host stages of src/lib.rs:200-287 (scale_down: :424-547, features on the INTER_AREA-downscaled grey and
     the homography taken back to full size with adjust_homography_for_scale_f64, src/utils.rs:218-248);
@@ -555,8 +579,7 @@ def _frame_homography(kp0, des0, img, params: KeyPointMatchParameters, scale_dow
     good = [m[0] for m in knn
             if len(m) == 2 and m[0].distance < np.float32(params.match_ratio) * m[1].distance]
     good.sort(key=lambda m: m.distance)
-    keep = int(round(float(np.float32(len(good)) * np.float32(params.match_keep_ratio))))
-    good = good[:keep]
+    good = good[:_keep_count(len(good), params.match_keep_ratio)]
     if len(good) < 5:
         return None
     src = np.float32([kp0[m.queryIdx].pt for m in good]).reshape(-1, 1, 2)

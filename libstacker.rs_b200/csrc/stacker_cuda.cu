@@ -251,7 +251,13 @@ int launch_resize(const AreaPlan& a, const uint8_t* d_src, size_t pitch, int cha
 struct Lane {
   cudaStream_t stream = nullptr;
   float* tmpl = nullptr;            // T plane
-  uint8_t* d_frame = nullptr;       // device staging for host-submitted frames
+  uint8_t* d_frames[stk::kWarpBatch] = {};  // device staging for host-submitted frames: one per slot of the warp batch
+                                            // (a frame's bytes must outlive its deferred final warp)
+  stk::EccState* pend_st = nullptr;         // [kWarpBatch] copies of the finished ECC state (inverse map, status) per pending frame
+  stk::WarpFrame pend[stk::kWarpBatch];     // frames whose final warp + accumulate is queued for the next batched launch
+  int n_pend = 0;
+  unsigned staging_used = 0;                // bit k: d_frames[k] holds a pending frame
+  bool pend_persp = true;
   uint8_t* small = nullptr;         // downscaled grey (ecc_match_scaling_down), ew x eh, small_pitch bytes per row
   uint8_t* h_stage = nullptr;       // pinned staging for pageable host buffers
   cudaEvent_t stage_free = nullptr; // H2D out of h_stage finished
@@ -321,6 +327,7 @@ struct stk_ecc_ctx {
   bool exact_coords = false;
   bool pdl = false;            // programmatic dependent launch between the chained iteration kernels (opt-in STK_ECC_PDL=1: measured no gain on one lane and -5 % with four, the waiting blocks hold SM slots)
   int loop_unroll = 4;         // iteration kernels per WHILE-body pass (STK_ECC_UNROLL)
+  int warp_batch = stk::kWarpBatch;   // frames per final-warp launch, 1..kWarpBatch (STK_WARP_BATCH)
   int rim_weight = 10;         // cost of a rim-strip chunk in 1/8 of an interior one (STK_ECC_RIM_WEIGHT)
   void* iter_fn = nullptr;     // the iteration kernel of this context (generation + geometry, see iter_variant)
   int iter_threads = 0, iter_smem = 0, iter_chunk_h = 0, iter_box_h = 0, iter_min_blocks = 0;
@@ -544,35 +551,61 @@ int launch_prep(stk_ecc_ctx* c, const uint8_t* d_src, size_t pitch, uint8_t* sma
   return STK_OK;
 }
 
-int launch_warp(stk_ecc_ctx* c, Lane& ln, const uint8_t* d_src, size_t pitch, bool persp,
-                const double* inv_host, const float* border, bool from_state) {
+// K4 for the frames queued on a lane: ONE launch gathers up to kWarpBatch frames and touches the accumulator once
+int flush_warps(stk_ecc_ctx* c, Lane& ln) {
+  if (ln.n_pend == 0) return STK_OK;
   stk::WarpAccParams p = {};
-  p.src = d_src;
-  p.src_pitch = pitch;
+  for (int j = 0; j < ln.n_pend; ++j) p.f[j] = ln.pend[j];
+  p.n = ln.n_pend;
   p.acc = ln.acc;
   p.width = c->cfg.width;
   p.height = c->cfg.height;
   p.src_width = c->cfg.width;
   p.src_height = c->cfg.height;
-  p.inv_ptr = from_state ? ln.st->inv : nullptr;   // device address arithmetic only
-  p.status_ptr = from_state ? &ln.st->status : nullptr;
-  if (inv_host) for (int i = 0; i < 9; ++i) p.inv[i] = inv_host[i];
-  for (int i = 0; i < 4; ++i) p.border[i] = border ? border[i] : 0.f;
-  p.border_mode = border ? (int)border[4] : STK_BORDER_CONSTANT;      // border[4]: the cv::BorderTypes value
   p.store = ln.acc_used ? 0 : 1;
   dim3 block(stk::kWarpBX, stk::kWarpBY);
   dim3 grid((p.width + stk::kWarpBX - 1) / stk::kWarpBX, (p.height + stk::kWarpTH - 1) / stk::kWarpTH);
   const int ch = c->cfg.channels;
   if (ch == 3) {
-    if (persp) stk::warp_accumulate_kernel<3, true><<<grid, block, 0, ln.stream>>>(p);
+    if (ln.pend_persp) stk::warp_accumulate_kernel<3, true><<<grid, block, 0, ln.stream>>>(p);
     else stk::warp_accumulate_kernel<3, false><<<grid, block, 0, ln.stream>>>(p);
   } else {
-    if (persp) stk::warp_accumulate_kernel<4, true><<<grid, block, 0, ln.stream>>>(p);
+    if (ln.pend_persp) stk::warp_accumulate_kernel<4, true><<<grid, block, 0, ln.stream>>>(p);
     else stk::warp_accumulate_kernel<4, false><<<grid, block, 0, ln.stream>>>(p);
   }
   c->launches++;
+  ln.n_pend = 0;
+  ln.staging_used = 0;
   CU(cudaGetLastError());
   ln.acc_used = true;
+  return STK_OK;
+}
+
+// Queue one frame's final warp + accumulate on its lane (launched when kWarpBatch frames are waiting, or at the next
+// sync / finish / exchange).  from_state: the matrix and status are the lane's ECC state as of this point of the
+// stream (a device-side copy is taken, the lane's state is reused by the next frame).  The frame's bytes (d_src) must
+// stay valid until the batch is launched and has run: the lane's staging slots / the caller's device buffer.
+int launch_warp(stk_ecc_ctx* c, Lane& ln, const uint8_t* d_src, size_t pitch, bool persp,
+                const double* inv_host, const float* border, bool from_state) {
+  if (ln.n_pend > 0 && ln.pend_persp != persp) { int rc = flush_warps(c, ln); if (rc) return rc; }
+  const int max_batch = c->warp_batch;
+  const int j = ln.n_pend;
+  stk::WarpFrame& f = ln.pend[j];
+  memset(&f, 0, sizeof f);
+  f.src = d_src;
+  f.src_pitch = pitch;
+  if (from_state) {
+    CU(cudaMemcpyAsync(ln.pend_st + j, ln.st, sizeof(stk::EccState), cudaMemcpyDeviceToDevice, ln.stream));
+    f.inv_ptr = ln.pend_st[j].inv;            // device address arithmetic only
+    f.status_ptr = &ln.pend_st[j].status;
+  }
+  if (inv_host) for (int i = 0; i < 9; ++i) f.inv[i] = inv_host[i];
+  for (int i = 0; i < 4; ++i) f.border[i] = border ? border[i] : 0.f;
+  f.border_mode = border ? (int)border[4] : STK_BORDER_CONSTANT;      // border[4]: the cv::BorderTypes value
+  for (int k = 0; k < stk::kWarpBatch; ++k) if (d_src == ln.d_frames[k] && d_src) ln.staging_used |= 1u << k;
+  ln.pend_persp = persp;
+  ln.n_pend = j + 1;
+  if (ln.n_pend >= max_batch) return flush_warps(c, ln);
   return STK_OK;
 }
 
@@ -591,10 +624,10 @@ int alloc_result_state(stk_ecc_ctx* c, stk::EccState** out) {
 
 // Stage a host frame into the lane's device buffer (dense rows).  `pinned` = the caller's buffer is
 // page-locked and stays valid until sync, so it is copied from directly.
-int upload_frame(stk_ecc_ctx* c, Lane& ln, const uint8_t* host, size_t pitch, bool pinned) {
+int upload_frame(stk_ecc_ctx* c, Lane& ln, uint8_t* d_frame, const uint8_t* host, size_t pitch, bool pinned) {
   const size_t row = (size_t)c->cfg.width * c->cfg.channels;
   if (pinned) {
-    CU(cudaMemcpy2DAsync(ln.d_frame, row, host, pitch, row, c->cfg.height, cudaMemcpyHostToDevice, ln.stream));
+    CU(cudaMemcpy2DAsync(d_frame, row, host, pitch, row, c->cfg.height, cudaMemcpyHostToDevice, ln.stream));
     return STK_OK;
   }
   CU(cudaEventSynchronize(ln.stage_free));
@@ -603,7 +636,7 @@ int upload_frame(stk_ecc_ctx* c, Lane& ln, const uint8_t* host, size_t pitch, bo
   } else {
     for (int y = 0; y < c->cfg.height; ++y) memcpy(ln.h_stage + (size_t)y * row, host + (size_t)y * pitch, row);
   }
-  CU(cudaMemcpyAsync(ln.d_frame, ln.h_stage, row * c->cfg.height, cudaMemcpyHostToDevice, ln.stream));
+  CU(cudaMemcpyAsync(d_frame, ln.h_stage, row * c->cfg.height, cudaMemcpyHostToDevice, ln.stream));
   CU(cudaEventRecord(ln.stage_free, ln.stream));
   return STK_OK;
 }
@@ -711,7 +744,13 @@ int enqueue_align(stk_ecc_ctx* c, Lane& ln, const uint8_t* d_src, size_t pitch, 
   return STK_OK;
 }
 
+int flush_all(stk_ecc_ctx* c) {
+  for (auto& ln : c->lanes) { int rc = flush_warps(c, ln); if (rc) return rc; }
+  return STK_OK;
+}
+
 int sync_all(stk_ecc_ctx* c) {
+  { int rc = flush_all(c); if (rc) return rc; }
   for (auto& ln : c->lanes) CU(cudaStreamSynchronize(ln.stream));
   // account for the device-launched iteration kernels and surface per-frame failures
   int first_err = STK_OK;
@@ -868,6 +907,7 @@ int stk_ecc_create(const stk_ecc_config* cfg, stk_ecc_ctx** out) {
   if (const char* pd = getenv("STK_ECC_PDL")) c->pdl = strcmp(pd, "0") != 0;
   if (const char* un = getenv("STK_ECC_UNROLL")) c->loop_unroll = std::max(1, std::min(16, atoi(un)));
   if (const char* rw = getenv("STK_ECC_RIM_WEIGHT")) c->rim_weight = std::max(8, std::min(32, atoi(rw)));
+  if (const char* wb = getenv("STK_WARP_BATCH")) c->warp_batch = std::max(1, std::min(stk::kWarpBatch, atoi(wb)));
   const char* lm = getenv("STK_LOOP_MODE");
   c->host_loop = lm && strcmp(lm, "host") == 0;
 
@@ -930,6 +970,7 @@ int stk_ecc_create(const stk_ecc_config* cfg, stk_ecc_ctx** out) {
       if (rc) return cleanup(rc);
       if (c->scaled && cudaMalloc((void**)&ln.small, (size_t)c->small_pitch * c->eh) != cudaSuccess) return cleanup(fail(STK_ERR_NOMEM, "cudaMalloc(downscaled grey) failed"));
       if (cudaMalloc((void**)&ln.st, sizeof(stk::EccState)) != cudaSuccess) return cleanup(fail(STK_ERR_NOMEM, "cudaMalloc(state) failed"));
+      if (cudaMalloc((void**)&ln.pend_st, sizeof(stk::EccState) * stk::kWarpBatch) != cudaSuccess) return cleanup(fail(STK_ERR_NOMEM, "cudaMalloc(pending states) failed"));
       {
         // the rescale factors are the only fields the init kernel leaves alone
         stk::EccState zero;
@@ -964,7 +1005,8 @@ int stk_ecc_destroy(stk_ecc_ctx* c) {
     if (ln.stream) cudaStreamSynchronize(ln.stream);
     if (ln.exec) cudaGraphExecDestroy(ln.exec);
     if (ln.graph) cudaGraphDestroy(ln.graph);
-    cudaFree(ln.tmpl); cudaFree(ln.d_frame); cudaFree(ln.small); cudaFree(ln.st); cudaFree(ln.partials); cudaFree(ln.acc);
+    cudaFree(ln.tmpl); cudaFree(ln.small); cudaFree(ln.st); cudaFree(ln.pend_st); cudaFree(ln.partials); cudaFree(ln.acc);
+    for (auto* d : ln.d_frames) cudaFree(d);
     if (ln.h_stage) cudaFreeHost(ln.h_stage);
     if (ln.stage_free) cudaEventDestroy(ln.stage_free);
     if (ln.drained) cudaEventDestroy(ln.drained);
@@ -981,9 +1023,15 @@ int stk_ecc_destroy(stk_ecc_ctx* c) {
   return STK_OK;
 }
 
-static int ensure_host_staging(stk_ecc_ctx* c, Lane& ln, bool need_pinned_stage) {
-  if (!ln.d_frame) CU(cudaMalloc((void**)&ln.d_frame, c->frame_bytes));
+// a staging buffer for the NEXT frame submitted to this lane: one that holds no frame whose warp is still queued
+// (at most kWarpBatch - 1 are, so one is always free)
+static int ensure_host_staging(stk_ecc_ctx* c, Lane& ln, bool need_pinned_stage, uint8_t** d_frame) {
+  int k = 0;
+  while (k < stk::kWarpBatch - 1 && (ln.staging_used >> k) & 1u) ++k;
+  uint8_t*& slot = ln.d_frames[k];
+  if (!slot) CU(cudaMalloc((void**)&slot, c->frame_bytes));
   if (need_pinned_stage && !ln.h_stage) CU(cudaHostAlloc((void**)&ln.h_stage, c->frame_bytes, cudaHostAllocDefault));
+  *d_frame = slot;
   return STK_OK;
 }
 
@@ -1040,17 +1088,18 @@ static int submit_ring(stk_ecc_ctx* c, int idx, int64_t tag, const double* inv, 
     Lane& ln = pick_lane(c);
     RingBuf& rb = c->ring[idx];
     const size_t row = (size_t)c->cfg.width * c->cfg.channels;
-    rc = ensure_host_staging(c, ln, false);
+    uint8_t* d_frame = nullptr;
+    rc = ensure_host_staging(c, ln, false, &d_frame);
     cudaError_t e = cudaSuccess;
-    if (rc == STK_OK) e = cudaMemcpyAsync(ln.d_frame, rb.host, c->frame_bytes, cudaMemcpyHostToDevice, ln.stream);
+    if (rc == STK_OK) e = cudaMemcpyAsync(d_frame, rb.host, c->frame_bytes, cudaMemcpyHostToDevice, ln.stream);
     if (rc == STK_OK && e == cudaSuccess) e = cudaEventRecord(rb.uploaded, ln.stream);
     if (rc == STK_OK && e != cudaSuccess) rc = fail(STK_ERR_CUDA, "frame upload: %s", cudaGetErrorString(e));
     if (rc == STK_OK) {
       if (inv) {
-        rc = launch_warp(c, ln, ln.d_frame, row, persp, inv, border, false);
+        rc = launch_warp(c, ln, d_frame, row, persp, inv, border, false);
         if (rc == STK_OK) { ResultSlot slot; slot.tag = tag; slot.host = nullptr; c->results.push_back(slot); }
       } else {
-        rc = enqueue_align(c, ln, ln.d_frame, row, tag);
+        rc = enqueue_align(c, ln, d_frame, row, tag);
       }
     }
   }
@@ -1079,11 +1128,12 @@ static int submit_align(stk_ecc_ctx* c, const uint8_t* buf, size_t pitch, int64_
   if (!c->have_ref) return fail(STK_ERR_STATE, "stk_ecc_set_reference must come first");
   Lane& ln = pick_lane(c);
   if (kind == 2) return enqueue_align(c, ln, buf, pitch, tag);
-  rc = ensure_host_staging(c, ln, false);
+  uint8_t* d_frame = nullptr;
+  rc = ensure_host_staging(c, ln, false, &d_frame);
   if (rc) return rc;
-  rc = upload_frame(c, ln, buf, pitch, true);
+  rc = upload_frame(c, ln, d_frame, buf, pitch, true);
   if (rc) return rc;
-  return enqueue_align(c, ln, ln.d_frame, row, tag);
+  return enqueue_align(c, ln, d_frame, row, tag);
 }
 
 int stk_ecc_submit_frame(stk_ecc_ctx* c, const uint8_t* bgr, size_t pitch, int64_t tag) { return submit_align(c, bgr, pitch, tag, 0); }
@@ -1184,6 +1234,7 @@ int stk_ecc_results(stk_ecc_ctx* c, stk_frame_result* out, int capacity, int* co
   if (rc) return rc;
   if (!count || (capacity > 0 && !out)) return fail(STK_ERR_BAD_ARG, "null argument");
   std::lock_guard<std::mutex> g(c->mu);
+  if ((rc = flush_all(c))) return rc;
   for (auto& ln : c->lanes) CU(cudaStreamSynchronize(ln.stream));
   int n = 0;
   for (auto& r : c->results) {
@@ -1439,6 +1490,7 @@ int peer_exchange(stk_ecc_ctx* c, int divisor, bool scatter) {
   std::lock_guard<std::mutex> g(c->mu);
   PeerLink& pl = c->peer;
   if (!pl.connected) return fail(STK_ERR_STATE, "stk_ecc_peer_reduce before stk_ecc_peer_connect");
+  if ((rc = flush_all(c))) return rc;
   Lane& l0 = c->lanes[0];
   // join the lanes on the device (no host synchronisation), then sum them into lane 0's accumulator
   const float* ordered[16];
@@ -1535,7 +1587,7 @@ int stk_ecc_reset(stk_ecc_ctx* c) {
   int rc = check_ctx(c);
   if (rc) return rc;
   std::lock_guard<std::mutex> g(c->mu);
-  for (auto& ln : c->lanes) { CU(cudaStreamSynchronize(ln.stream)); ln.acc_used = false; }
+  for (auto& ln : c->lanes) { CU(cudaStreamSynchronize(ln.stream)); ln.acc_used = false; ln.n_pend = 0; ln.staging_used = 0; }
   for (auto& r : c->results) for (auto& e : r.ev) if (e) cudaEventDestroy(e);
   c->results.clear();
   c->states_used = 0;
@@ -1564,6 +1616,7 @@ int stk_ecc_stage_times(stk_ecc_ctx* c, double ms[3], int64_t* frames, int64_t* 
   if (rc) return rc;
   if (!ms) return fail(STK_ERR_BAD_ARG, "null argument");
   std::lock_guard<std::mutex> g(c->mu);
+  if ((rc = flush_all(c))) return rc;
   for (auto& ln : c->lanes) CU(cudaStreamSynchronize(ln.stream));
   ms[0] = ms[1] = ms[2] = 0.0;
   int64_t nf = 0, it = 0;
@@ -1614,12 +1667,13 @@ int stk_ecc_debug_iteration(stk_ecc_ctx* c, const uint8_t* bgr, size_t pitch, co
   std::lock_guard<std::mutex> g(c->mu);
   if (!c->have_ref) return fail(STK_ERR_STATE, "stk_ecc_set_reference must come first");
   Lane& ln = c->lanes[0];
-  rc = ensure_host_staging(c, ln, true);
+  uint8_t* d_frame = nullptr;
+  rc = ensure_host_staging(c, ln, true, &d_frame);
   if (rc) return rc;
-  rc = upload_frame(c, ln, bgr, pitch, false);
+  rc = upload_frame(c, ln, d_frame, bgr, pitch, false);
   if (rc) return rc;
   const size_t row = (size_t)c->cfg.width * c->cfg.channels;
-  rc = launch_prep(c, ln.d_frame, row, ln.small, ln.tmpl, ln.stream);
+  rc = launch_prep(c, d_frame, row, ln.small, ln.tmpl, ln.stream);
   if (rc) return rc;
   const bool persp = c->cfg.motion_type == STK_MOTION_HOMOGRAPHY;
   stk::ecc_init_kernel<<<1, 32, 0, ln.stream>>>(ln.st, persp ? 1 : 0, 1 << 30, -1.0, 0, 0);
@@ -1655,12 +1709,13 @@ int stk_ecc_debug_timing(stk_ecc_ctx* c, const uint8_t* bgr, size_t pitch, const
   std::lock_guard<std::mutex> g(c->mu);
   if (!c->have_ref) return fail(STK_ERR_STATE, "stk_ecc_set_reference must come first");
   Lane& ln = c->lanes[0];
-  rc = ensure_host_staging(c, ln, true);
+  uint8_t* d_frame = nullptr;
+  rc = ensure_host_staging(c, ln, true, &d_frame);
   if (rc) return rc;
-  rc = upload_frame(c, ln, bgr, pitch, false);
+  rc = upload_frame(c, ln, d_frame, bgr, pitch, false);
   if (rc) return rc;
   const size_t row = (size_t)c->cfg.width * c->cfg.channels;
-  rc = launch_prep(c, ln.d_frame, row, ln.small, ln.tmpl, ln.stream);
+  rc = launch_prep(c, d_frame, row, ln.small, ln.tmpl, ln.stream);
   if (rc) return rc;
   const bool persp = c->cfg.motion_type == STK_MOTION_HOMOGRAPHY;
   stk::ecc_init_kernel<<<1, 32, 0, ln.stream>>>(ln.st, persp ? 1 : 0, 1 << 30, -1.0, 0, 0);

@@ -19,18 +19,26 @@
 
 namespace stk {
 
-struct WarpAccParams {
+constexpr int kWarpBatch = 4;             // frames gathered per launch: the accumulator is read and written once per batch
+
+struct WarpFrame {
   const uint8_t* src;     // u8 interleaved
   size_t src_pitch;
-  float* acc;             // f32 interleaved, width*channels floats per row, dense
-  int width, height;      // destination size (== accumulator size)
-  int src_width, src_height;
   const double* inv_ptr;  // device pointer to the inverse map (ECC path), or null -> inv[]
-  const int* status_ptr;  // device pointer to the frame's ECC status (skip when != 0), or null
+  const int* status_ptr;  // device pointer to the frame's ECC status (frame skipped when != 0), or null
   double inv[9];
   float border[4];
   int border_mode;        // cv::BorderTypes: 0 CONSTANT, 1 REPLICATE, 2 REFLECT, 3 WRAP, 4 REFLECT_101
-  int store;              // 1: acc = v (first frame on this lane), 0: acc += v
+  int pad;
+};
+
+struct WarpAccParams {
+  WarpFrame f[kWarpBatch];
+  int n;                  // frames in this launch, 1..kWarpBatch, added in index order
+  float* acc;             // f32 interleaved, width*channels floats per row, dense
+  int width, height;      // destination size (== accumulator size)
+  int src_width, src_height;
+  int store;              // 1: acc = sum of the batch (first batch on this lane), 0: acc += ...
 };
 
 // Correctly rounded 1/w for w in the normal range (|w| in [2^-500, 2^500]): the instruction sequence of
@@ -65,48 +73,59 @@ constexpr int kWarpBX = 32, kWarpBY = 8;   // thread block
 constexpr int kWarpRows = 4;               // destination rows per thread: the block tile is 32 x 32 pixels
 constexpr int kWarpTH = kWarpBY * kWarpRows;
 
-// 32 x 32 destination tile per 256-thread block, four rows per thread (so the per-thread column terms of the
-// coordinate transform, the parameter loads and the index math are paid once per four pixels).  The C
-// interpolated values of the tile are staged in shared memory and the accumulator read-modify-write is done
-// as coalesced 128-bit accesses (a tile row is 32*C contiguous floats).  ncu (profiles/) showed the first
-// versions to be issue-bound (390, then 234 instructions per pixel), so the per-pixel path is kept lean: the
-// inverse map is staged once per block, the 64-px column block start is a mask, the reciprocal replaces
-// the f64 divide (32/W == 32 * (1/W) exactly: a power-of-two scaling commutes with rounding),
-// __double2int_rn supplies the saturation, and pixels whose four taps are inside the source skip all
-// border selects.
-template <int C, bool PERSP>
-__global__ void __launch_bounds__(kWarpBX * kWarpBY, 8) warp_accumulate_kernel(const WarpAccParams p) {
-  __shared__ __align__(16) float s_val[kWarpTH][kWarpBX * C];
-  __shared__ double s_m[9];
-  if (p.status_ptr && *p.status_ptr != 0) return;
-  const int tid = threadIdx.y * kWarpBX + threadIdx.x;
-  if (tid < 9) {
-    double mv = p.inv[0];
+// value = s00*w00 + s01*w01 + s10*w10 + s11*w11, left to right in f32 (OpenCV's remapBilinear order), for the C channels
+// of one pixel; taps are raw bytes, converted as fl(byte * fl(1/255)).  Channel pairs ride the packed f32x2 forms (each
+// half is an IEEE round-to-nearest op, so the values are those of the scalar sequence).
+template <int C>
+__device__ __forceinline__ void blend_taps(const unsigned (&t00)[C], const unsigned (&t01)[C], const unsigned (&t10)[C],
+                                           const unsigned (&t11)[C], float w00, float w01, float w10, float w11, float* out) {
+  const float k255 = (float)(1.0 / 255.0);
+  constexpr int P = C / 2;
 #pragma unroll
-    for (int i = 1; i < 9; ++i) if (tid == i) mv = p.inv[i];
-    if (p.inv_ptr) mv = p.inv_ptr[tid];
-    s_m[tid] = mv;
+  for (int q = 0; q < P; ++q) {
+    const float2 k2 = make_float2(k255, k255);
+    const float2 s00 = __fmul2_rn(make_float2((float)t00[2 * q], (float)t00[2 * q + 1]), k2);
+    const float2 s01 = __fmul2_rn(make_float2((float)t01[2 * q], (float)t01[2 * q + 1]), k2);
+    const float2 s10 = __fmul2_rn(make_float2((float)t10[2 * q], (float)t10[2 * q + 1]), k2);
+    const float2 s11 = __fmul2_rn(make_float2((float)t11[2 * q], (float)t11[2 * q + 1]), k2);
+    float2 v = __fmul2_rn(s00, make_float2(w00, w00));
+    v = __fadd2_rn(v, __fmul2_rn(s01, make_float2(w01, w01)));
+    v = __fadd2_rn(v, __fmul2_rn(s10, make_float2(w10, w10)));
+    v = __fadd2_rn(v, __fmul2_rn(s11, make_float2(w11, w11)));
+    out[2 * q] = v.x;
+    out[2 * q + 1] = v.y;
   }
-  __syncthreads();
+  if (C & 1) {
+    constexpr int c = C - 1;
+    const float s00 = __fmul_rn((float)t00[c], k255), s01 = __fmul_rn((float)t01[c], k255);
+    const float s10 = __fmul_rn((float)t10[c], k255), s11 = __fmul_rn((float)t11[c], k255);
+    out[c] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s00, w00), __fmul_rn(s01, w01)), __fmul_rn(s10, w10)), __fmul_rn(s11, w11));
+  }
+}
+
+// One frame's contribution to the block's 32 x 32 tile: the C interpolated values of every pixel, into s_val
+// (tile row r at s_val + r * 32 * C).  mtx = the frame's inverse map (9 doubles, shared memory).
+template <int C, bool PERSP>
+__device__ __forceinline__ void warp_tile(const WarpFrame& f, const double* mtx, float* s_val, int width, int height,
+                                          int sw, int sh) {
   const int x = blockIdx.x * kWarpBX + threadIdx.x;
   const int y_base = blockIdx.y * kWarpTH + threadIdx.y;
-  const float k255 = (float)(1.0 / 255.0);
-  const int sw = p.src_width, sh = p.src_height;
+  constexpr int kRow = kWarpBX * C;
 
   // per-thread (column) terms
   double cx0 = 0, cx1 = 0, cy0 = 0, cy1 = 0, cw0 = 0, cw1 = 0;
   int adelta = 0, bdelta = 0;
   if (PERSP) {
     // WarpPerspectiveInvoker: X0/Y0/W0 at the start of the 64-px column block, then + M*x1
-    const int xb = p.width >= 64 ? (x & ~63) : 0;
+    const int xb = width >= 64 ? (x & ~63) : 0;
     const double xbd = (double)xb, x1 = (double)(x - xb);
-    cx0 = __dmul_rn(s_m[0], xbd); cx1 = __dmul_rn(s_m[0], x1);
-    cy0 = __dmul_rn(s_m[3], xbd); cy1 = __dmul_rn(s_m[3], x1);
-    cw0 = __dmul_rn(s_m[6], xbd); cw1 = __dmul_rn(s_m[6], x1);
+    cx0 = __dmul_rn(mtx[0], xbd); cx1 = __dmul_rn(mtx[0], x1);
+    cy0 = __dmul_rn(mtx[3], xbd); cy1 = __dmul_rn(mtx[3], x1);
+    cw0 = __dmul_rn(mtx[6], xbd); cw1 = __dmul_rn(mtx[6], x1);
   } else {
     const double xd = (double)x;
-    adelta = __double2int_rn(__dmul_rn(__dmul_rn(s_m[0], xd), kAbScale));
-    bdelta = __double2int_rn(__dmul_rn(__dmul_rn(s_m[3], xd), kAbScale));
+    adelta = __double2int_rn(__dmul_rn(__dmul_rn(mtx[0], xd), kAbScale));
+    bdelta = __double2int_rn(__dmul_rn(__dmul_rn(mtx[3], xd), kAbScale));
   }
 
   // Interior tiles (the bulk of a frame): when the four corners of the tile land inside
@@ -115,13 +134,13 @@ __global__ void __launch_bounds__(kWarpBX * kWarpBY, 8) warp_accumulate_kernel(c
   // covers the 1/32-px quantisation), so the pixel loop needs no bounds test, clamp or border select, the
   // reciprocal no special cases and cvRound no saturation.  Decided per warp (lanes 0-3 take one corner each,
   // inequalities multiplied through by w: no division), no extra barrier.
-  bool lean = blockIdx.x * kWarpBX + kWarpBX <= p.width && blockIdx.y * kWarpTH + kWarpTH <= p.height;
+  bool lean = blockIdx.x * kWarpBX + kWarpBX <= width && blockIdx.y * kWarpTH + kWarpTH <= height;
   {
     const int k = threadIdx.x & 3;
     const double cxk = (double)(blockIdx.x * kWarpBX + ((k & 1) ? kWarpBX - 1 : 0));
     const double cyk = (double)(blockIdx.y * kWarpTH + ((k & 2) ? kWarpTH - 1 : 0));
-    const double nu = s_m[0] * cxk + s_m[1] * cyk + s_m[2], nv = s_m[3] * cxk + s_m[4] * cyk + s_m[5];
-    const double ww = PERSP ? s_m[6] * cxk + s_m[7] * cyk + s_m[8] : 1.0;
+    const double nu = mtx[0] * cxk + mtx[1] * cyk + mtx[2], nv = mtx[3] * cxk + mtx[4] * cyk + mtx[5];
+    const double ww = PERSP ? mtx[6] * cxk + mtx[7] * cyk + mtx[8] : 1.0;
     const double lo = 0.0625 * ww, uhi = ((double)(sw - 1) - 0.0625) * ww, vhi = ((double)(sh - 1) - 0.0625) * ww;
     lean = __all_sync(0xffffffffu, lean && ww > 1e-9 && ww < 1e9 && nu >= lo && nu < uhi && nv >= lo && nv < vhi);
   }
@@ -133,15 +152,15 @@ __global__ void __launch_bounds__(kWarpBX * kWarpBY, 8) warp_accumulate_kernel(c
       const double yd = (double)(y_base + rr * kWarpBY);
       int xq, yq;
       if (PERSP) {
-        const double X0 = __dadd_rn(__dadd_rn(cx0, __dmul_rn(s_m[1], yd)), s_m[2]);
-        const double Y0 = __dadd_rn(__dadd_rn(cy0, __dmul_rn(s_m[4], yd)), s_m[5]);
-        const double W0 = __dadd_rn(__dadd_rn(cw0, __dmul_rn(s_m[7], yd)), s_m[8]);
+        const double X0 = __dadd_rn(__dadd_rn(cx0, __dmul_rn(mtx[1], yd)), mtx[2]);
+        const double Y0 = __dadd_rn(__dadd_rn(cy0, __dmul_rn(mtx[4], yd)), mtx[5]);
+        const double W0 = __dadd_rn(__dadd_rn(cw0, __dmul_rn(mtx[7], yd)), mtx[8]);
         const double W32 = __dmul_rn(rcp_rn_normal(__dadd_rn(W0, cw1)), (double)kInterTab);
         xq = rint_magic(__dmul_rn(__dadd_rn(X0, cx1), W32));
         yq = rint_magic(__dmul_rn(__dadd_rn(Y0, cy1), W32));
       } else {
-        const int X0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(s_m[1], yd), s_m[2]), kAbScale)) + 16;
-        const int Y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(s_m[4], yd), s_m[5]), kAbScale)) + 16;
+        const int X0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(mtx[1], yd), mtx[2]), kAbScale)) + 16;
+        const int Y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(mtx[4], yd), mtx[5]), kAbScale)) + 16;
         xq = (int)((unsigned)X0 + (unsigned)adelta) >> (kAbBits - kInterBits);
         yq = (int)((unsigned)Y0 + (unsigned)bdelta) >> (kAbBits - kInterBits);
       }
@@ -149,41 +168,36 @@ __global__ void __launch_bounds__(kWarpBX * kWarpBY, 8) warp_accumulate_kernel(c
       const float ay = (float)(yq & (kInterTab - 1)) * (1.f / kInterTab);
       const float w00 = __fmul_rn(1.f - ay, 1.f - ax), w01 = __fmul_rn(1.f - ay, ax);
       const float w10 = __fmul_rn(ay, 1.f - ax), w11 = __fmul_rn(ay, ax);
-      const uint8_t* r0 = p.src + (ptrdiff_t)(yq >> kInterBits) * (ptrdiff_t)p.src_pitch + (xq >> kInterBits) * C;
-      const uint8_t* r1 = r0 + p.src_pitch;
+      const uint8_t* r0 = f.src + (ptrdiff_t)(yq >> kInterBits) * (ptrdiff_t)f.src_pitch + (xq >> kInterBits) * C;
+      const uint8_t* r1 = r0 + f.src_pitch;
       unsigned t00[C], t01[C], t10[C], t11[C];
 #pragma unroll
       for (int c = 0; c < C; ++c) { t00[c] = __ldg(r0 + c); t01[c] = __ldg(r0 + C + c); t10[c] = __ldg(r1 + c); t11[c] = __ldg(r1 + C + c); }
-#pragma unroll
-      for (int c = 0; c < C; ++c) {
-        const float s00 = __fmul_rn((float)t00[c], k255), s01 = __fmul_rn((float)t01[c], k255);
-        const float s10 = __fmul_rn((float)t10[c], k255), s11 = __fmul_rn((float)t11[c], k255);
-        s_val[ry][threadIdx.x * C + c] =
-            __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s00, w00), __fmul_rn(s01, w01)), __fmul_rn(s10, w10)), __fmul_rn(s11, w11));
-      }
+      blend_taps<C>(t00, t01, t10, t11, w00, w01, w10, w11, s_val + ry * kRow + threadIdx.x * C);
     }
-  } else {
+    return;
+  }
 #pragma unroll
   for (int rr = 0; rr < kWarpRows; ++rr) {
     const int y = y_base + rr * kWarpBY;
     float v[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) v[c] = 0.f;
-    if (x < p.width && y < p.height) {
+    if (x < width && y < height) {
       const double yd = (double)y;
       int xq, yq;
       if (PERSP) {
-        const double X0 = __dadd_rn(__dadd_rn(cx0, __dmul_rn(s_m[1], yd)), s_m[2]);
-        const double Y0 = __dadd_rn(__dadd_rn(cy0, __dmul_rn(s_m[4], yd)), s_m[5]);
-        const double W0 = __dadd_rn(__dadd_rn(cw0, __dmul_rn(s_m[7], yd)), s_m[8]);
+        const double X0 = __dadd_rn(__dadd_rn(cx0, __dmul_rn(mtx[1], yd)), mtx[2]);
+        const double Y0 = __dadd_rn(__dadd_rn(cy0, __dmul_rn(mtx[4], yd)), mtx[5]);
+        const double W0 = __dadd_rn(__dadd_rn(cw0, __dmul_rn(mtx[7], yd)), mtx[8]);
         const double W = __dadd_rn(W0, cw1);
         const double W32 = (W != 0.0) ? __dmul_rn(__drcp_rn(W), (double)kInterTab) : 0.0;      // == INTER_TAB_SIZE / W
         // cvRound with saturation == clamp to [INT_MIN, INT_MAX] then round half to even
         xq = __double2int_rn(__dmul_rn(__dadd_rn(X0, cx1), W32));
         yq = __double2int_rn(__dmul_rn(__dadd_rn(Y0, cy1), W32));
       } else {
-        const int X0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(s_m[1], yd), s_m[2]), kAbScale)) + 16;
-        const int Y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(s_m[4], yd), s_m[5]), kAbScale)) + 16;
+        const int X0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(mtx[1], yd), mtx[2]), kAbScale)) + 16;
+        const int Y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(mtx[4], yd), mtx[5]), kAbScale)) + 16;
         xq = (int)((unsigned)X0 + (unsigned)adelta) >> (kAbBits - kInterBits);
         yq = (int)((unsigned)Y0 + (unsigned)bdelta) >> (kAbBits - kInterBits);
       }
@@ -194,26 +208,21 @@ __global__ void __launch_bounds__(kWarpBX * kWarpBY, 8) warp_accumulate_kernel(c
       const float ay = (float)(yq & (kInterTab - 1)) * (1.f / kInterTab);
       const float w00 = __fmul_rn(1.f - ay, 1.f - ax), w01 = __fmul_rn(1.f - ay, ax);
       const float w10 = __fmul_rn(ay, 1.f - ax), w11 = __fmul_rn(ay, ax);
-      const uint8_t* r0 = p.src + (ptrdiff_t)sy * (ptrdiff_t)p.src_pitch + (ptrdiff_t)sx * C;
-      const uint8_t* r1 = r0 + p.src_pitch;
+      const float k255 = (float)(1.0 / 255.0);
+      const uint8_t* r0 = f.src + (ptrdiff_t)sy * (ptrdiff_t)f.src_pitch + (ptrdiff_t)sx * C;
+      const uint8_t* r1 = r0 + f.src_pitch;
       if ((unsigned)sx < (unsigned)(sw - 1) && (unsigned)sy < (unsigned)(sh - 1)) {
         // all four taps inside the source: the common case, no border logic
         unsigned t00[C], t01[C], t10[C], t11[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) { t00[c] = __ldg(r0 + c); t01[c] = __ldg(r0 + C + c); t10[c] = __ldg(r1 + c); t11[c] = __ldg(r1 + C + c); }
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-          const float s00 = __fmul_rn((float)t00[c], k255), s01 = __fmul_rn((float)t01[c], k255);
-          const float s10 = __fmul_rn((float)t10[c], k255), s11 = __fmul_rn((float)t11[c], k255);
-          v[c] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s00, w00), __fmul_rn(s01, w01)), __fmul_rn(s10, w10)),
-                           __fmul_rn(s11, w11));
-        }
-      } else if (p.border_mode != 0) {
+        blend_taps<C>(t00, t01, t10, t11, w00, w01, w10, w11, v);
+      } else if (f.border_mode != 0) {
         // REPLICATE / REFLECT / WRAP / REFLECT_101: each tap's coordinates go through borderInterpolate on their own
-        const int x0 = border_index(sx, sw, p.border_mode), x1 = border_index(sx + 1, sw, p.border_mode);
-        const int y0 = border_index(sy, sh, p.border_mode), y1 = border_index(sy + 1, sh, p.border_mode);
-        const uint8_t* q0 = p.src + (size_t)y0 * p.src_pitch;
-        const uint8_t* q1 = p.src + (size_t)y1 * p.src_pitch;
+        const int x0 = border_index(sx, sw, f.border_mode), x1 = border_index(sx + 1, sw, f.border_mode);
+        const int y0 = border_index(sy, sh, f.border_mode), y1 = border_index(sy + 1, sh, f.border_mode);
+        const uint8_t* q0 = f.src + (size_t)y0 * f.src_pitch;
+        const uint8_t* q1 = f.src + (size_t)y1 * f.src_pitch;
 #pragma unroll
         for (int c = 0; c < C; ++c) {
           const float s00 = __fmul_rn((float)__ldg(q0 + x0 * C + c), k255), s01 = __fmul_rn((float)__ldg(q0 + x1 * C + c), k255);
@@ -223,64 +232,119 @@ __global__ void __launch_bounds__(kWarpBX * kWarpBY, 8) warp_accumulate_kernel(c
         }
       } else if (sx >= sw || sx + 1 < 0 || sy >= sh || sy + 1 < 0) {
 #pragma unroll
-        for (int c = 0; c < C; ++c) v[c] = p.border[c];
+        for (int c = 0; c < C; ++c) v[c] = f.border[c];
       } else {
         const bool x0in = (unsigned)sx < (unsigned)sw, x1in = (unsigned)(sx + 1) < (unsigned)sw;
         const bool y0in = (unsigned)sy < (unsigned)sh, y1in = (unsigned)(sy + 1) < (unsigned)sh;
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-          const float s00 = (y0in && x0in) ? __fmul_rn((float)__ldg(r0 + c), k255) : p.border[c];
-          const float s01 = (y0in && x1in) ? __fmul_rn((float)__ldg(r0 + C + c), k255) : p.border[c];
-          const float s10 = (y1in && x0in) ? __fmul_rn((float)__ldg(r1 + c), k255) : p.border[c];
-          const float s11 = (y1in && x1in) ? __fmul_rn((float)__ldg(r1 + C + c), k255) : p.border[c];
+          const float s00 = (y0in && x0in) ? __fmul_rn((float)__ldg(r0 + c), k255) : f.border[c];
+          const float s01 = (y0in && x1in) ? __fmul_rn((float)__ldg(r0 + C + c), k255) : f.border[c];
+          const float s10 = (y1in && x0in) ? __fmul_rn((float)__ldg(r1 + c), k255) : f.border[c];
+          const float s11 = (y1in && x1in) ? __fmul_rn((float)__ldg(r1 + C + c), k255) : f.border[c];
           v[c] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s00, w00), __fmul_rn(s01, w01)), __fmul_rn(s10, w10)),
                            __fmul_rn(s11, w11));
         }
       }
     }
 #pragma unroll
-    for (int c = 0; c < C; ++c) s_val[threadIdx.y + rr * kWarpBY][threadIdx.x * C + c] = v[c];
+    for (int c = 0; c < C; ++c) s_val[(threadIdx.y + rr * kWarpBY) * kRow + threadIdx.x * C + c] = v[c];
   }
+}
+
+// 32 x 32 destination tile per 256-thread block, four rows per thread (so the per-thread column terms of the
+// coordinate transform, the parameter loads and the index math are paid once per four pixels).  The C
+// interpolated values of the tile are staged in shared memory and the accumulator is touched as coalesced 128-bit
+// accesses (a tile row is 32*C contiguous floats).  BATCHED: up to kWarpBatch frames per launch — the block keeps its
+// slice of the accumulator in REGISTERS, adds frame after frame in index order (the same f32 sequence as one launch
+// per frame, so results are bit-identical to the unbatched form) and writes it back once: 3N + 24N/k bytes per frame
+// instead of 27N.  The staging tile is double-buffered, so a frame costs one block barrier.
+// ncu (profiles/) showed the first versions to be issue-bound (390, then 234 instructions per pixel), so the
+// per-pixel path is kept lean: the inverse maps are staged once per block, the 64-px column block start is a mask,
+// the reciprocal replaces the f64 divide (32/W == 32 * (1/W) exactly: a power-of-two scaling commutes with
+// rounding), __double2int_rn supplies the saturation, pixels whose four taps are inside the source skip all border
+// selects, and channel pairs are converted and blended with packed f32x2 instructions.
+// A frame whose ECC status is non-zero contributes nothing (the reference aborts the whole stack, src/lib.rs:777);
+// in store mode the accumulator is still written (zeros + the other frames), never left uninitialised.
+template <int C, bool PERSP>
+__global__ void __launch_bounds__(kWarpBX * kWarpBY, 5) warp_accumulate_kernel(const __grid_constant__ WarpAccParams p) {
+  constexpr int kRow = kWarpBX * C;                 // floats per tile row
+  constexpr int kVecPerRow = kRow / 4;
+  constexpr int kVecs = kWarpTH * kVecPerRow;
+  constexpr int kThreads = kWarpBX * kWarpBY;
+  constexpr int kPerThread = kVecs / kThreads;      // 3 (C = 3) or 4 (C = 4) float4 per thread
+  static_assert(kVecs % kThreads == 0, "tile vectors must divide evenly over the block");
+  __shared__ __align__(16) float s_val[2][kWarpTH * kRow];
+  __shared__ double s_m[kWarpBatch][9];
+  __shared__ int s_skip[kWarpBatch];
+  const int tid = threadIdx.y * kWarpBX + threadIdx.x;
+  if (tid < 9 * p.n) {
+    const int j = tid / 9, i = tid - 9 * j;
+    s_m[j][i] = p.f[j].inv_ptr ? p.f[j].inv_ptr[i] : p.f[j].inv[i];
   }
+  if (tid < p.n) s_skip[tid] = (p.f[tid].status_ptr && *p.f[tid].status_ptr != 0) ? 1 : 0;
   __syncthreads();
 
-  // coalesced accumulate: tile row r holds floats [x_tile0*C, x_tile0*C + 32*C) of accumulator row y0 + r
   const int tx0 = blockIdx.x * kWarpBX;
   const int ty0 = blockIdx.y * kWarpTH;
   const int row_elems = min(kWarpBX, p.width - tx0) * C;        // valid floats in this tile row
   const size_t row_base = (size_t)tx0 * C;                       // float offset of the tile inside a row
-  const bool vec_ok = (((size_t)p.width * C) % 4 == 0) && (row_base % 4 == 0);
+  const bool vec_ok = (((size_t)p.width * C) % 4 == 0);          // then every float4 of the tile is all in or all out
+
   if (vec_ok) {
-    constexpr int kVecPerRow = kWarpBX * C / 4;
-    constexpr int kVecs = kWarpTH * kVecPerRow;
-#pragma unroll
-    for (int i0 = 0; i0 < kVecs; i0 += kWarpBX * kWarpBY) {
-      const int i = i0 + tid;
-      if (i >= kVecs) break;
+    float4 a[kPerThread];
+    auto slot = [&](int k) -> float* {            // this thread's k-th float4 of the tile in the accumulator, or null
+      const int i = k * kThreads + tid;
       const int r = i / kVecPerRow, q = i - r * kVecPerRow;
-      const int yy = ty0 + r;
-      if (yy >= p.height || q * 4 >= row_elems) continue;
-      float* a = p.acc + (size_t)yy * p.width * C + row_base + q * 4;
-      const float4 nv = *reinterpret_cast<const float4*>(&s_val[r][q * 4]);
-      if (q * 4 + 4 <= row_elems) {
-        float4 o = nv;
-        if (!p.store) {
-          const float4 cur = *reinterpret_cast<const float4*>(a);
-          o.x = __fadd_rn(cur.x, nv.x); o.y = __fadd_rn(cur.y, nv.y); o.z = __fadd_rn(cur.z, nv.z); o.w = __fadd_rn(cur.w, nv.w);
-        }
-        *reinterpret_cast<float4*>(a) = o;
-      } else {
-        const float e[4] = {nv.x, nv.y, nv.z, nv.w};
-        for (int k = 0; k < 4 && q * 4 + k < row_elems; ++k) a[k] = p.store ? e[k] : __fadd_rn(a[k], e[k]);
-      }
+      const bool in = ty0 + r < p.height && q * 4 < row_elems;
+      return in ? p.acc + (size_t)(ty0 + r) * p.width * C + row_base + q * 4 : nullptr;
+    };
+#pragma unroll
+    for (int k = 0; k < kPerThread; ++k) {
+      a[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!p.store) { const float* ap = slot(k); if (ap) a[k] = *reinterpret_cast<const float4*>(ap); }
     }
-  } else {
-    for (int i = tid; i < kWarpTH * kWarpBX * C; i += kWarpBX * kWarpBY) {
-      const int r = i / (kWarpBX * C), q = i - r * (kWarpBX * C);
+    int buf = 0;
+    for (int j = 0; j < p.n; ++j) {
+      if (s_skip[j]) continue;                                   // block-uniform
+      warp_tile<C, PERSP>(p.f[j], s_m[j], s_val[buf], p.width, p.height, p.src_width, p.src_height);
+      __syncthreads();      // tile j complete; every thread has also finished reading buffer buf^1 (tile j-1) before
+                            // it started computing tile j, so tile j+1 may overwrite that buffer
+#pragma unroll
+      for (int k = 0; k < kPerThread; ++k) {
+        const float4 nv = *reinterpret_cast<const float4*>(&s_val[buf][(k * kThreads + tid) * 4]);
+        a[k].x = __fadd_rn(a[k].x, nv.x); a[k].y = __fadd_rn(a[k].y, nv.y);
+        a[k].z = __fadd_rn(a[k].z, nv.z); a[k].w = __fadd_rn(a[k].w, nv.w);
+      }
+      buf ^= 1;
+    }
+#pragma unroll
+    for (int k = 0; k < kPerThread; ++k) { float* ap = slot(k); if (ap) *reinterpret_cast<float4*>(ap) = a[k]; }
+    return;
+  }
+
+  // rows that do not start on 16-byte boundaries (width*C not a multiple of 4): scalar read-modify-write per frame
+  bool first = p.store != 0;
+  for (int j = 0; j < p.n; ++j) {
+    if (s_skip[j]) continue;
+    warp_tile<C, PERSP>(p.f[j], s_m[j], s_val[0], p.width, p.height, p.src_width, p.src_height);
+    __syncthreads();
+    for (int i = tid; i < kWarpTH * kRow; i += kThreads) {
+      const int r = i / kRow, q = i - r * kRow;
       const int yy = ty0 + r;
       if (yy >= p.height || q >= row_elems) continue;
       float* a = p.acc + (size_t)yy * p.width * C + row_base + q;
-      *a = p.store ? s_val[r][q] : __fadd_rn(*a, s_val[r][q]);
+      *a = first ? s_val[0][i] : __fadd_rn(*a, s_val[0][i]);
+    }
+    __syncthreads();
+    first = false;
+  }
+  if (first) {          // store mode and every frame of the batch skipped: the accumulator still becomes defined
+    for (int i = tid; i < kWarpTH * kRow; i += kThreads) {
+      const int r = i / kRow, q = i - r * kRow;
+      const int yy = ty0 + r;
+      if (yy >= p.height || q >= row_elems) continue;
+      p.acc[(size_t)yy * p.width * C + row_base + q] = 0.f;
     }
   }
 }

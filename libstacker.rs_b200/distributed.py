@@ -194,6 +194,29 @@ class SharedHostStack:
         self.shm = None
 
 
+def agree_on_failure(err, group=None):
+    """The reference aborts the WHOLE stack when one frame fails (`?` on find_transform_ecc,
+    /root/reference/src/lib.rs:777).  With the frames sharded over ranks only the rank that owns the failing frame
+    sees the error, so the ranks agree on it here (collective; `err` = this rank's exception or None): if any rank
+    failed, EVERY rank raises — the failing ranks their own error, the others an OpenCvError naming it — and nobody
+    enters a collective the failing rank will never reach."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        if err is not None:
+            raise err
+        return
+    mine = None if err is None else (dist.get_rank(group), type(err).__name__, str(err))
+    votes = [None] * dist.get_world_size(group)
+    dist.all_gather_object(votes, mine, group=group)
+    first = next((v for v in votes if v is not None), None)
+    if first is None:
+        return
+    if err is not None:
+        raise err
+    from .api import OpenCvError
+    raise OpenCvError(f"the stack was aborted: rank {first[0]} failed with {first[1]}: {first[2]}")
+
+
 def stack_on_ranks(stack, frames_by_index, n_frames: int, rank: int, world: int, device=None, peers: bool = False):
     """Run this rank's shard through `stack` (an EccStack whose reference is already set; rank 0's was
     created with seed_reference=True, the others with False), reduce, and return the final HxWxC f32 torch
@@ -203,14 +226,27 @@ def stack_on_ranks(stack, frames_by_index, n_frames: int, rank: int, world: int,
     import torch
     for i in shard_frames(n_frames, rank, world):
         stack.submit(frames_by_index[i], tag=i)
+    from .api import StackerError
+    err = None
     if peers:
+        # the exchange is queued on every rank whatever happened to the frames (a failed frame contributes nothing),
+        # so no rank is left waiting for a peer; the per-frame errors surface at sync() and are agreed on afterwards
         d_out = stack.peer_reduce(n_frames)
-        stack.sync()
+        try:
+            stack.sync()
+        except StackerError as e:
+            err = e
+        agree_on_failure(err)
         if rank != 0:
             return None
         n = stack.height * stack.width * stack.channels
         return torch.as_tensor(DevicePtrArray(d_out, n), device=device).view(stack.height, stack.width, stack.channels)
-    ptr, n = stack.partial()
+    ptr = n = None
+    try:
+        ptr, n = stack.partial()
+    except StackerError as e:
+        err = e
+    agree_on_failure(err)        # before the reduce: a rank that failed must not leave the others inside the collective
     part = torch.as_tensor(DevicePtrArray(ptr, n), device=device)
     reduce_partial_stack(part, 0)
     if rank != 0:

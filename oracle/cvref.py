@@ -179,6 +179,13 @@ def sharpness_normalized_gray_level_variance(grey_u8):
     return float(sigma[0, 0]) ** 2 / max(float(mu[0, 0]), float(np.finfo(np.float64).eps))
 
 
+def keep_count(n_good: int, keep_ratio: float) -> int:
+    """src/lib.rs:235: `(filtered_matches.len() as f32 * params.match_keep_ratio).round() as usize` — Rust's f32::round rounds
+    halves AWAY from zero (Python's round() goes to even: 6 * 0.75 = 4.5 must keep 5, not 4)."""
+    x = np.float32(n_good) * np.float32(keep_ratio)
+    return int(np.floor(x + np.float32(0.5))) if x >= 0 else 0
+
+
 def keypoint_homography(grey0_kp_des, grey_i, method, reproj, match_ratio, keep_ratio):
     """src/lib.rs:200-287: ORB -> BF kNN(2) -> Lowe ratio -> sort -> keep -> findHomography(dst->src).
     Returns a 3x3 f64 matrix or None when the reference would drop the frame."""
@@ -191,8 +198,7 @@ def keypoint_homography(grey0_kp_des, grey_i, method, reproj, match_ratio, keep_
     knn = matcher.knnMatch(des0, des, k=2)
     good = [m[0] for m in knn if len(m) == 2 and m[0].distance < np.float32(match_ratio) * m[1].distance]
     good.sort(key=lambda m: m.distance)
-    keep = int(round(float(np.float32(len(good)) * np.float32(keep_ratio))))
-    good = good[:keep]
+    good = good[:keep_count(len(good), keep_ratio)]
     if len(good) < 5:
         return None
     src = np.float32([kp0[m.queryIdx].pt for m in good]).reshape(-1, 1, 2)

@@ -170,3 +170,43 @@ def test_shared_host_stack_collects_every_ranks_slice(pkg):
     for world in (1, 2, 3, 8):
         edges = [D.scatter_bounds(n, r, world) for r in range(world)]
         assert edges[0][0] == 0 and edges[-1][1] == n and all(a[1] == b[0] for a, b in zip(edges, edges[1:]))
+
+
+def _failure_worker(rank, world, port, failing_rank, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as ge
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pkg = ge.load_package()
+    err = pkg.OpenCvError("findTransformECC: the algorithm stopped before its convergence") if rank == failing_rank else None
+    try:
+        pkg.distributed.agree_on_failure(err)
+        q.put((rank, None))
+    except pkg.StackerError as e:
+        q.put((rank, str(e)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("failing_rank", [1, None])
+def test_a_failed_frame_aborts_the_stack_on_every_rank(failing_rank):
+    """src/lib.rs:777: one frame's ECC failure fails the whole call.  Sharded over ranks, every rank must raise (and
+    none may be left inside the reduce): distributed.agree_on_failure, used by stack_on_ranks before the exchange."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_failure_worker, args=(r, 2, port, failing_rank, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    if failing_rank is None:
+        assert results == {0: None, 1: None}
+    else:
+        assert "stopped before its convergence" in results[0] and "rank 1" in results[0]
+        assert "stopped before its convergence" in results[1]

@@ -114,3 +114,30 @@ def test_rank_by_sharpness_order():
     from oracle import restate as R
     # examples/main.rs:53-64: ascending sort, drop the worst, reverse -> sharpest first
     assert R.rank_by_sharpness([5.0, 1.0, 9.0, 3.0]) == [2, 0, 3]
+
+
+def test_keep_count_rounds_half_away_from_zero(pkg):
+    """src/lib.rs:235: `(len as f32 * match_keep_ratio).round() as usize` — Rust's f32::round rounds halves away
+    from zero.  With the default ratio 0.75 the product lands on .5 whenever len % 4 == 2: 6 -> 5 (Python's
+    round() would give 4, below the 5-match minimum, and drop a frame the reference keeps), 14 -> 11, 22 -> 17."""
+    from oracle import cvref
+    for fn in (pkg.api._keep_count, cvref.keep_count):
+        assert [fn(n, 0.75) for n in (6, 14, 22, 4, 5, 7, 0)] == [5, 11, 17, 3, 4, 5, 0]
+        assert fn(10, 0.8) == 8 and fn(3, 0.5) == 2 and fn(1, 0.5) == 1
+
+
+def test_device_frame_validation(pkg):
+    """Frames handed over through __cuda_array_interface__ are checked before the library sees the pointer."""
+    class Fake:
+        def __init__(self, shape, typestr="|u1", strides=None):
+            self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (4096, False), "version": 3,
+                                             "strides": strides}
+    dv = pkg.api._device_view
+    assert dv(Fake((4, 8, 3)), (4, 8, 3)) == (4096, 24)
+    assert dv(Fake((4, 8, 3), strides=(32, 3, 1)), (4, 8, 3)) == (4096, 32)
+    with pytest.raises(pkg.OpenCvError):
+        dv(Fake((4, 8, 3), typestr="<f4"), (4, 8, 3))
+    with pytest.raises(pkg.OpenCvError):
+        dv(Fake((4, 9, 3)), (4, 8, 3))
+    with pytest.raises(pkg.OpenCvError):
+        dv(Fake((4, 8, 3), strides=(48, 6, 2)), (4, 8, 3))
