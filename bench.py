@@ -146,9 +146,41 @@ def cpu_sample_run(a, n_sample: int):
     frames = [stack.frame(i) for i in range(n_sample)]
     workers = min(os.cpu_count() or 1, max(1, n_sample - 1))
     t0 = time.perf_counter()
-    cvref.ecc_match(frames, a.motion, 5000, 1e-5, 5, workers=workers)
+    _, warps, _ = cvref.ecc_match(frames, a.motion, 5000, 1e-5, 5, workers=workers)
     dt = time.perf_counter() - t0
+    cpu_sample_run.warps = {i: w for i, w in enumerate(warps) if w is not None}      # the checker's matrices, tag -> warp
     return n_sample / dt, dt, workers, n_sample
+
+
+cpu_sample_run.warps = {}
+
+
+def oracle_warp_error(a, res, tags):
+    """max corner displacement (px) between this run's recovered matrices and the reference engine's
+    (cv2.findTransformECC driven as src/lib.rs:769-777, oracle/cvref.py) for the given frame tags — the checker
+    leg of the bench (outside every timed region)."""
+    import synthetic as synth
+    from oracle import cvref
+    stack = make_stack(a)
+    have = cpu_sample_run.warps
+    g0 = None
+    worst, n = 0.0, 0
+    by_tag = {r["tag"]: r["warp"] for r in res}
+    for t in tags:
+        if t not in by_tag:
+            continue
+        if t in have:
+            m_ref = have[t]
+        else:
+            import cv2
+            if g0 is None:
+                g0 = cv2.cvtColor(stack.frame(0), cv2.COLOR_BGR2GRAY)
+            _, m_ref = cvref.align_frame(cv2.cvtColor(stack.frame(t), cv2.COLOR_BGR2GRAY), g0, a.motion,
+                                         cvref.term_criteria(5000, 1e-5), 5)
+        mine = by_tag[t] if a.motion == 3 else by_tag[t][:2]
+        worst = max(worst, synth.corner_displacement(mine, m_ref, a.width, a.height))
+        n += 1
+    return worst, n
 
 
 def default_cpu_sample(a):
@@ -374,7 +406,79 @@ def run_b200(a, rank, local_rank, world):
             dist.all_reduce(tot)
             e2e["h2d_bytes_per_step"] = int(tot.item())
 
+    # bare host->device ceiling for this run's pinned frame buffers (all ranks at once, like the e2e leg)
+    h2d_probe = None
+    if not a.skip_e2e:
+        scratch = torch.empty_like(dev_frames[0])
+        order = [0] + mine
+
+        def h2d_only():
+            for i in order:
+                scratch.copy_(pinned[i], non_blocking=True)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h2d_only()
+        barrier()
+        e0.record()
+        for _ in range(3):
+            h2d_only()
+        e1.record()
+        torch.cuda.synchronize()
+        t_ms = torch.tensor([e0.elapsed_time(e1) / 3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        h2d_probe = {"ms_per_step": float(t_ms.item()), "GBps_aggregate": e2e["h2d_bytes_per_step"] / (float(t_ms.item()) * 1e-3) / 1e9,
+                     "frames_per_s_ceiling": n / (float(t_ms.item()) * 1e-3),
+                     "how": "the same pinned frame buffers copied to the device with nothing else running, every rank at once, max over ranks"}
+        e2e["frac_of_h2d_ceiling"] = e2e["value"] / h2d_probe["frames_per_s_ceiling"]
+        e2e["h2d_probe"] = h2d_probe
+        del scratch
+
+    # the plugin call itself, one-shot, as a user of the reference would make it: ecc_match(frames, params, None)
+    # (creates and destroys its context inside the call, like the reference allocates per call)
+    e2e_api = None
+    if world == 1 and not a.skip_e2e:
+        frames_list = [pinned_np[i] for i in range(n)]
+        api_out = out_host.numpy()
+        pkg.ecc_match(frames_list, params, None, device=local_rank, pinned=True, out=api_out)      # warm-up
+        t0 = time.perf_counter()
+        reps = max(1, min(a.steps, 3))
+        for _ in range(reps):
+            pkg.ecc_match(frames_list, params, None, device=local_rank, pinned=True, out=api_out)
+        dt = (time.perf_counter() - t0) / reps
+        e2e_api = {"value": n / dt, "unit": UNIT, "ms_per_call": dt * 1e3,
+                   "api": "ecc_match(list of pinned host arrays, EccMatchParameters, None, out=pinned) — one call per stack, "
+                          "context creation and destruction inside the call, wall clock",
+                   "stack_mean": float(api_out.mean(dtype=np.float64))}
+
     stack_mean = float((peer_result() if use_peers else out_dev).mean().item()) if rank == 0 else None
+    # ---- correctness of THIS run (outside every timed region) ------------------------------------------------------
+    # N > 1: rank 0 redoes the whole stack on its one device and compares the 8-bit stacks and every matrix with what
+    # the ranks produced together; all N: one or more matrices against the reference engine (cv2, oracle/cvref.py)
+    multi_check = None
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, [(r["tag"], r["warp"].tolist(), r["iterations"]) for r in res])
+        if rank == 0:
+            multi = (peer_result() if use_peers else out_dev).clone()
+            with pkg.EccStack(w, h, 3, params, device=local_rank, lanes=a.lanes, seed_reference=True) as s1:
+                s1.set_reference(dev_frames[0])
+                for i in range(1, n):
+                    fr = dev_frames[i] if i in dev_frames else torch.from_numpy(stack_src.frame(i)).to(dev)
+                    s1.submit(fr, tag=i)
+                    if i not in dev_frames:
+                        s1.sync()             # the temporary frame is released right after its alignment
+                single = torch.from_numpy(s1.finish(n)).to(dev)
+                single_res = {r["tag"]: r for r in s1.results()}
+            d8 = (torch.round(multi * 255.0) - torch.round(single * 255.0)).abs().max().item()
+            worst, seen = 0.0, set()
+            for shard in gathered:
+                for tag, wm, it in shard:
+                    seen.add(tag)
+                    worst = max(worst, synth.corner_displacement(np.array(wm, np.float32), single_res[tag]["warp"], w, h))
+            multi_check = {"max_abs_diff_8bit_vs_single_gpu": float(d8), "max_abs_diff_f32_vs_single_gpu": float((multi - single).abs().max().item()),
+                           "max_corner_diff_vs_single_gpu_px": worst, "frames_covered": len(seen), "frames_expected": n - 1}
+            del multi, single
     e2e_mean = None
     if use_peers:
         barrier()                 # nobody unmaps while a peer may still be inside an exchange
@@ -384,7 +488,14 @@ def run_b200(a, rank, local_rank, world):
             shared_host.close()
         st.peer_disconnect()
         barrier()
-    # ---- roofline of the dominant kernel (ecc_iter_kernel), measured alone: 1 lane, CUDA events per stage ----
+    if world > 1:
+        pr = torch.zeros(world, dtype=torch.float64, device=dev)
+        pr[rank] = float(sum(iters))
+        dist.all_reduce(pr)
+        iters_per_rank_pre = [int(v) for v in pr.tolist()]
+    else:
+        iters_per_rank_pre = [sum(iters)]
+    # ---- roofline of the dominant kernel (the ECC iteration kernel), measured alone: 1 lane, CUDA events per stage ----
     st.close()
     roof = stages = None
     peaks = {}
@@ -412,13 +523,25 @@ def run_b200(a, rank, local_rank, world):
                 traffic = json.load(open(os.path.join(ROOT, "profiles", "ecc_iter_traffic.json"))).get("dram_bytes_per_launch")
             except Exception:
                 pass
-            roof = {"bound": "hbm", "kernel": "ecc_iter_kernel<Homography>" if a.motion == 3 else f"ecc_iter_kernel<{a.motion}>",
+            # in the timed step the lanes overlap one frame's serial tail and relaunch gap with other frames' pixel phases:
+            # what one iteration costs THERE = (device time of the step - the other kernels' own times) / iterations
+            other_ms = (t["prep_ms"] + t["warp_ms"]) / t["frames"] * (n - 1) / world
+            step_ms = ms / a.steps
+            iters_here = max(iters_per_rank_pre) if iters_per_rank_pre else 0
+            in_step_us = 1e3 * (step_ms - other_ms) / iters_here if iters_here else None
+            roof = {"bound": "hbm", "kernel": "ecc_iter_v2_kernel<Homography>" if a.motion == 3 else f"ecc_iter_v2_kernel<{a.motion}>",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                     "algorithmic_bytes_per_launch": 8 * n_px, "us_per_launch": per_iter_ms * 1e3,
                     "peak_source": peak_src,
-                    "how": "1 lane, CUDA events on the lane stream around each frame's device loop (init + all "
-                           "iterations of the graph WHILE node, relaunch gaps included) / iterations; "
-                           f"{t['frames']} frames, {t['iterations']} iterations"}
+                    "how": "ONE LANE (the conservative figure): CUDA events on the lane stream around each frame's device loop "
+                           "(init + all iterations of the graph WHILE node, serial tail and relaunch gaps included) / iterations; "
+                           f"{t['frames']} frames, {t['iterations']} iterations",
+                    "in_step": None if in_step_us is None else {
+                        "us_per_launch": in_step_us, "achieved": 8.0 * n_px / (in_step_us * 1e-6) / 1e9,
+                        "frac": 8.0 * n_px / (in_step_us * 1e-6) / 1e9 / peak,
+                        "dominant_kernel_ms_per_step": in_step_us * iters_here * 1e-3, "ms_per_step": step_ms,
+                        "how": f"inside the timed {a.lanes}-lane step: (ms_per_step - (prep + warp) per frame measured on one lane x frames "
+                               "of the slowest rank) / ECC iterations of the slowest rank; <= ms_per_step by construction"}}
             stages = {
                 "prep": {"ms_per_frame": t["prep_ms"] / t["frames"], "GBps": 7.0 * n_px / (t["prep_ms"] / t["frames"] * 1e-3) / 1e9},
                 "ecc_loop": {"ms_per_frame": t["loop_ms"] / t["frames"], "iterations_per_frame": t["iterations"] / t["frames"]},
@@ -453,6 +576,18 @@ def run_b200(a, rank, local_rank, world):
         except Exception as e:  # pragma: no cover
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
 
+    oracle_check = None
+    if rank == 0 and not a.skip_cpu:
+        try:
+            # N = 1: every frame of the CPU sample (its matrices are a by-product of the cpu_baseline leg); N > 1: one
+            # frame through cv2.findTransformECC (~20 s on the host cores)
+            tags = sorted(cpu_sample_run.warps) if cpu_sample_run.warps else [mine[0] if mine else 1]
+            err, cnt = oracle_warp_error(a, res, tags)
+            oracle_check = {"max_corner_error_vs_oracle_px": err, "frames": cnt,
+                            "oracle": "cv2.findTransformECC driven as src/lib.rs:769-777 (oracle/cvref.py)"}
+        except Exception as e:  # pragma: no cover
+            oracle_check = {"error": str(e)}
+
     if rank == 0:
         # algorithmic bytes of the whole step: per frame (34 + 8K)N, per stack 43N per GPU
         alg_bytes = (34 * (n - 1) + 8 * total_iters + 43 * world) * n_px
@@ -467,10 +602,11 @@ def run_b200(a, rank, local_rank, world):
                        "numa_bound": bool(numa_bound), "ecc_iterations_per_step": total_iters, "ecc_iterations_per_rank": iters_per_rank, "wall_ms_per_step": wall_ms / a.steps},
             "whole_step": {"algorithmic_GBps_per_gpu": alg_bytes / (ms / a.steps * 1e-3) / 1e9 / world,
                            "frac_of_hbm_peak": alg_bytes / (ms / a.steps * 1e-3) / 1e9 / world / peak},
-            "roofline": roof, "stages": stages, "cpu_baseline": cpu, "e2e": e2e,
+            "roofline": roof, "stages": stages, "cpu_baseline": cpu, "e2e": e2e, "e2e_api": e2e_api,
             "gpu_launches": launches, "clocks": clocks,
             "check": {"max_corner_error_vs_ground_truth_px": truth_err, "ecc_status_codes": statuses,
-                      "stack_mean": stack_mean, "e2e_stack_mean": e2e_mean},
+                      "stack_mean": stack_mean, "e2e_stack_mean": e2e_mean,
+                      "oracle": oracle_check, "multi_gpu": multi_check},
         }
         print(json.dumps(line))
     if world > 1:

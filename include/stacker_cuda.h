@@ -189,7 +189,10 @@ int stk_ecc_finish_device(stk_ecc_ctx* ctx, const float* d_sum, int divisor, flo
    summed, exchanged.  On rank 0 *d_out receives the device pointer of the finished stack (height*width*channels
    floats, library-owned, valid after stk_ecc_sync until the next peer_reduce); elsewhere NULL.  stk_ecc_sync
    afterwards returns per-frame ECC errors, and STK_ERR_CUDA if a rank did not show up within
-   STK_PEER_TIMEOUT_MS (default 10000) — the kernels never spin forever. */
+   STK_PEER_TIMEOUT_MS (environment, default 30000) — the kernels never spin forever; raise it when ranks can reach the
+   exchange further apart than that (e.g. decode imbalance).  connect resets the exchange step count and the flag
+   block of the context: no rank may start an exchange before EVERY rank has returned from connect (a barrier or, as
+   distributed.connect_peers does, a vote all ranks take part in). */
 typedef struct stk_peer_handle { unsigned char bytes[256]; } stk_peer_handle;
 int stk_ecc_peer_export(stk_ecc_ctx* ctx, stk_peer_handle* out);
 int stk_ecc_peer_connect(stk_ecc_ctx* ctx, int rank, int world, const stk_peer_handle* handles /* [world] */);

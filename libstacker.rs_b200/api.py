@@ -284,8 +284,14 @@ class EccStack:
                             iterations=r.iterations, status=r.status))
         return out
 
-    def finish(self, divisor: int) -> np.ndarray:
-        out = np.empty((self.height, self.width, self.channels), np.float32)
+    def finish(self, divisor: int, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """`out`: an HxWxC float32 array to receive the stack (e.g. page-locked memory: the device-to-host copy of a
+        4K stack is 2 ms into pinned memory, several times that into pageable memory)."""
+        shape = (self.height, self.width, self.channels)
+        if out is None:
+            out = np.empty(shape, np.float32)
+        elif out.dtype != np.float32 or out.shape != shape or out.strides[1:] != (4 * self.channels, 4):
+            raise InvalidParams(f"out must be a float32 array of shape {shape} with dense rows")
         _check(lib.stk_ecc_finish(self._ctx, int(divisor), out.ctypes.data, out.strides[0]))
         self._keep.clear()
         return out
@@ -452,7 +458,8 @@ def _check_colour_frame(img: np.ndarray):
 
 # ---- ecc_match: src/lib.rs:702-847 ----------------------------------------------------------------------
 def ecc_match(files: Iterable, params: EccMatchParameters, scale_down_width: Optional[float] = None, *,
-              device: int = -1, devices=None, workers: Optional[int] = None, return_details: bool = False):
+              device: int = -1, devices=None, workers: Optional[int] = None, return_details: bool = False,
+              pinned: bool = False, out: Optional[np.ndarray] = None):
     """Align every frame to the first with ECC and average them.
 
     `files`: paths (decoded on host threads with cv2.imread(IMREAD_UNCHANGED), as
@@ -460,6 +467,10 @@ def ecc_match(files: Iterable, params: EccMatchParameters, scale_down_width: Opt
     `devices`: several CUDA devices of the box, driven from this one process — one context per device, frames
     dealt round-robin, one fused exchange + divide over NVLink peer memory (what the Rust crate and
     `libstacker::ecc_match_on_devices` do); default: the single `device`.
+    `pinned=True`: the caller's arrays live in page-locked memory (stk_pinned_alloc, torch pin_memory): they are
+    uploaded from where they are, no staging copy; they must stay untouched until the call returns.  Pageable
+    arrays and files go through the context's pinned ring, filled by `workers` host threads.
+    `out`: optional HxWxC float32 array (ideally page-locked) that receives the stack on a single device.
     Returns the stacked image, float32 HxWxC in [0,1] (the reference's CV_32FC3 Mat).
     Errors: NotEnoughFiles (empty input); OpenCvError (no COUNT/EPS criteria, ECC non-convergence, bad
     image type); InvalidParams (scale_down_width out of range)."""
@@ -491,10 +502,10 @@ def ecc_match(files: Iterable, params: EccMatchParameters, scale_down_width: Opt
         n_workers = workers or min(8, os.cpu_count() or 1)
         rest = items[1:]
         if rest:
-            if all(isinstance(i, np.ndarray) for i in rest):
+            if pinned and all(isinstance(i, np.ndarray) for i in rest):
                 for k, fr in enumerate(rest):
                     _check_colour_frame(fr)
-                    stacks[(k + 1) % nd].submit(fr, tag=k + 1)
+                    stacks[(k + 1) % nd].submit(fr, tag=k + 1, pinned=True)
             else:
                 # Rayon: one task per frame (src/lib.rs:746-749).  Each task decodes and copies its frame into a
                 # pinned ring buffer of the context it is dealt to (no library lock held); the main thread hands
@@ -527,7 +538,7 @@ def ecc_match(files: Iterable, params: EccMatchParameters, scale_down_width: Opt
                             k, fut = pending.pop(0)
                             stacks[(k + 1) % nd].submit_acquired(fut.result(), tag=k + 1)
         if nd == 1:
-            out = stacks[0].finish(len(items))
+            out = stacks[0].finish(len(items), out)
         else:
             # Rayon's try_reduce + `/ n` as ONE exchange step: every exchange is queued before the first copy-out
             # (a copy into pageable memory blocks this thread until its device's exchange has finished)

@@ -260,6 +260,7 @@ struct Lane {
   bool pend_persp = true;
   uint8_t* small = nullptr;         // downscaled grey (ecc_match_scaling_down), ew x eh, small_pitch bytes per row
   uint8_t* h_stage = nullptr;       // pinned staging for pageable host buffers
+  int* h_cont = nullptr;            // pinned "loop continues" word of the host-driven loop (STK_LOOP_MODE=host)
   cudaEvent_t stage_free = nullptr; // H2D out of h_stage finished
   cudaEvent_t drained = nullptr;    // lane's queued work finished (peer exchange joins the lanes on the device)
   stk::EccState* st = nullptr;
@@ -720,8 +721,8 @@ int enqueue_align(stk_ecc_ctx* c, Lane& ln, const uint8_t* d_src, size_t pitch, 
     stk::EccIterParams ip = iter_params(c, ln, false);
     void* args[] = {&ip};
     int done_iters = 0;
-    int* h_cont = nullptr;
-    CU(cudaHostAlloc((void**)&h_cont, sizeof(int), cudaHostAllocDefault));
+    if (!ln.h_cont) CU(cudaHostAlloc((void**)&ln.h_cont, sizeof(int), cudaHostAllocDefault));   // once per lane
+    int* h_cont = ln.h_cont;
     *h_cont = 1;
     while (*h_cont && done_iters < c->max_iter) {
       const int chunk = std::min(4, c->max_iter - done_iters);
@@ -731,7 +732,6 @@ int enqueue_align(stk_ecc_ctx* c, Lane& ln, const uint8_t* d_src, size_t pitch, 
       CU(cudaMemcpyAsync(h_cont, &ln.st->cont, sizeof(int), cudaMemcpyDeviceToHost, ln.stream));
       CU(cudaStreamSynchronize(ln.stream));
     }
-    cudaFreeHost(h_cont);
   }
   if ((rc = mark(2))) return rc;
   rc = launch_warp(c, ln, d_src, pitch, persp, nullptr, nullptr, true);
@@ -1008,6 +1008,7 @@ int stk_ecc_destroy(stk_ecc_ctx* c) {
     cudaFree(ln.tmpl); cudaFree(ln.small); cudaFree(ln.st); cudaFree(ln.pend_st); cudaFree(ln.partials); cudaFree(ln.acc);
     for (auto* d : ln.d_frames) cudaFree(d);
     if (ln.h_stage) cudaFreeHost(ln.h_stage);
+    if (ln.h_cont) cudaFreeHost(ln.h_cont);
     if (ln.stage_free) cudaEventDestroy(ln.stage_free);
     if (ln.drained) cudaEventDestroy(ln.drained);
     if (ln.stream) cudaStreamDestroy(ln.stream);
@@ -1430,6 +1431,10 @@ int stk_ecc_peer_connect(stk_ecc_ctx* c, int rank, int world, const stk_peer_han
   pl.rank = rank;
   pl.world = world;
   pl.connected = true;
+  // a (re)connect starts the step count afresh on EVERY rank (connect is collective): a context that already
+  // exchanged in another group would otherwise disagree with a fresh one and spin into the timeout
+  pl.step = 0;
+  CU(cudaMemset(pl.flags, 0, stk::kPeerFlagWords * sizeof(uint32_t)));
   return STK_OK;
 }
 
@@ -1466,6 +1471,9 @@ int stk_ecc_peer_connect_local(stk_ecc_ctx* const* ctxs, int world) {
     pl.rank = r;
     pl.world = world;
     pl.connected = true;
+    pl.step = 0;
+    CU(cudaSetDevice(ctxs[r]->device));
+    CU(cudaMemset(pl.flags, 0, stk::kPeerFlagWords * sizeof(uint32_t)));
   }
   return STK_OK;
 }
@@ -1534,7 +1542,7 @@ int peer_exchange(stk_ecc_ctx* c, int divisor, bool scatter) {
   p.world = pl.world;
   p.step = ++pl.step;
   p.scale = (float)(1.0 / (double)divisor);
-  static const unsigned long long timeout_ms = [] { const char* e = getenv("STK_PEER_TIMEOUT_MS"); return e ? strtoull(e, nullptr, 10) : 10000ull; }();
+  static const unsigned long long timeout_ms = [] { const char* e = getenv("STK_PEER_TIMEOUT_MS"); return e ? strtoull(e, nullptr, 10) : 30000ull; }();
   p.timeout_ns = timeout_ms * 1000000ull;
   const int blocks = c->sm_count * 4;
   switch (pl.world) {

@@ -73,9 +73,20 @@ constexpr int kWarpBX = 32, kWarpBY = 8;   // thread block
 constexpr int kWarpRows = 4;               // destination rows per thread: the block tile is 32 x 32 pixels
 constexpr int kWarpTH = kWarpBY * kWarpRows;
 
+// Packed f32x2 multiply, written as PTX.  Only the MULTIPLIES of the blend are packed: ptxas fuses a packed multiply
+// feeding a packed add into FFMA2 even for the `.rn` forms (seen in the SASS of the first batched build, with or
+// without -fmad=false, and as a bit mismatch against cv2 at 6000x4000), so the adds stay scalar __fadd_rn, which is
+// never fused.
+__device__ __forceinline__ float2 mul2_rn_exact(float2 a, float2 b) {
+  float2 d;
+  asm("{\n .reg .b64 ra, rb, rd;\n mov.b64 ra, {%2, %3};\n mov.b64 rb, {%4, %5};\n mul.rn.f32x2 rd, ra, rb;\n mov.b64 {%0, %1}, rd;\n}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+
 // value = s00*w00 + s01*w01 + s10*w10 + s11*w11, left to right in f32 (OpenCV's remapBilinear order), for the C channels
-// of one pixel; taps are raw bytes, converted as fl(byte * fl(1/255)).  Channel pairs ride the packed f32x2 forms (each
-// half is an IEEE round-to-nearest op, so the values are those of the scalar sequence).
+// of one pixel; taps are raw bytes, converted as fl(byte * fl(1/255)).  The multiplies of a channel pair ride the packed
+// f32x2 form (each half is an IEEE round-to-nearest multiply, so the values are those of the scalar sequence).
 template <int C>
 __device__ __forceinline__ void blend_taps(const unsigned (&t00)[C], const unsigned (&t01)[C], const unsigned (&t10)[C],
                                            const unsigned (&t11)[C], float w00, float w01, float w10, float w11, float* out) {
@@ -84,14 +95,15 @@ __device__ __forceinline__ void blend_taps(const unsigned (&t00)[C], const unsig
 #pragma unroll
   for (int q = 0; q < P; ++q) {
     const float2 k2 = make_float2(k255, k255);
-    const float2 s00 = __fmul2_rn(make_float2((float)t00[2 * q], (float)t00[2 * q + 1]), k2);
-    const float2 s01 = __fmul2_rn(make_float2((float)t01[2 * q], (float)t01[2 * q + 1]), k2);
-    const float2 s10 = __fmul2_rn(make_float2((float)t10[2 * q], (float)t10[2 * q + 1]), k2);
-    const float2 s11 = __fmul2_rn(make_float2((float)t11[2 * q], (float)t11[2 * q + 1]), k2);
-    float2 v = __fmul2_rn(s00, make_float2(w00, w00));
-    v = __fadd2_rn(v, __fmul2_rn(s01, make_float2(w01, w01)));
-    v = __fadd2_rn(v, __fmul2_rn(s10, make_float2(w10, w10)));
-    v = __fadd2_rn(v, __fmul2_rn(s11, make_float2(w11, w11)));
+    const float2 s00 = mul2_rn_exact(make_float2((float)t00[2 * q], (float)t00[2 * q + 1]), k2);
+    const float2 s01 = mul2_rn_exact(make_float2((float)t01[2 * q], (float)t01[2 * q + 1]), k2);
+    const float2 s10 = mul2_rn_exact(make_float2((float)t10[2 * q], (float)t10[2 * q + 1]), k2);
+    const float2 s11 = mul2_rn_exact(make_float2((float)t11[2 * q], (float)t11[2 * q + 1]), k2);
+    const float2 p00 = mul2_rn_exact(s00, make_float2(w00, w00)), p01 = mul2_rn_exact(s01, make_float2(w01, w01));
+    const float2 p10 = mul2_rn_exact(s10, make_float2(w10, w10)), p11 = mul2_rn_exact(s11, make_float2(w11, w11));
+    float2 v;
+    v.x = __fadd_rn(__fadd_rn(__fadd_rn(p00.x, p01.x), p10.x), p11.x);
+    v.y = __fadd_rn(__fadd_rn(__fadd_rn(p00.y, p01.y), p10.y), p11.y);
     out[2 * q] = v.x;
     out[2 * q + 1] = v.y;
   }

@@ -185,6 +185,8 @@ ImageF32 stack_with_homographies(const std::vector<ImageU8>& frames, const std::
   check(stk_ecc_set_reference(ctx.c, first.data.data(), (size_t)first.width * first.channels));
   for (size_t i = 1; i < frames.size(); ++i) {
     check_colour(frames[i]);
+    if (frames[i].width != first.width || frames[i].height != first.height || frames[i].channels != first.channels)
+      throw NotImplemented("frames of differing size");         // the library would read first.height rows from this buffer
     check(stk_ecc_submit_warp(ctx.c, frames[i].data.data(), (size_t)frames[i].width * frames[i].channels,
                               homographies[i - 1].data(), params.border_mode, params.border_value, (int64_t)i));
   }

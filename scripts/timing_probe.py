@@ -26,5 +26,9 @@ for v in (sys.argv[1:] or ["1:0", "2:0", "2:2"]):
             print("  first chunk landed us after start:", q(rel[:, 3] - rel[:, 0]))
         print("  pixels+folds done  us:", q(rel[:, 1]))
         print("  block main loop duration us:", q(rel[:, 1] - rel[:, 0]))
+        dur = rel[:, 1] - rel[:, 0]
+        hist, edges = np.histogram(dur, bins=np.arange(16, 64, 4))
+        print("  duration histogram (us: blocks):", " ".join(f"{int(e)}-{int(e) + 4}:{c}" for e, c in zip(edges, hist) if c))
+        print("  durations by block id (us):", " ".join(str(int(round(float(d)))) for d in dur))
         tl = (tail[:3].astype(np.int64) - int(t0)) / 1e3
         print("  tail: cross-block sum done %.1f, solve done %.1f, end %.1f  (last block %d)" % (tl[0], tl[1], tl[2], int(tail[3])))
