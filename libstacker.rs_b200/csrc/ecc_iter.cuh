@@ -379,6 +379,32 @@ __device__ bool chunk_bounds(const float* m, int x0, int x1, int y0, int y1, dou
   return ok;
 }
 
+// The same bounding box in f32 (second-generation kernel): the table is on every block's start-up path, and the f64
+// divides made it ~1 us of the ~3 us a block needs before its first chunk lands.  |error| <~ 1e-3 px at 4K-class
+// coordinates — absorbed by the 2-px box margin and the 1/16-px slack of the interior test (callers add it).
+template <bool PERSP>
+__device__ bool chunk_bounds_f32(const float* m, int x0, int x1, int y0, int y1, float& umin, float& umax,
+                                 float& vmin, float& vmax) {
+  bool ok = true;
+  umin = vmin = 3.0e38f; umax = vmax = -3.0e38f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float x = (k & 1) ? (float)x1 : (float)x0;
+    const float y = (k & 2) ? (float)y1 : (float)y0;
+    float u = fmaf(m[0], x, fmaf(m[1], y, m[2]));
+    float v = fmaf(m[3], x, fmaf(m[4], y, m[5]));
+    if (PERSP) {
+      const float ww = fmaf(m[6], x, fmaf(m[7], y, m[8]));
+      if (!(ww > 1e-6f)) { ok = false; continue; }
+      const float rw = 1.0f / ww;
+      u *= rw; v *= rw;
+    }
+    if (!(u == u) || !(v == v)) ok = false;
+    umin = fminf(umin, u); umax = fmaxf(umax, u); vmin = fminf(vmin, v); vmax = fmaxf(vmax, v);
+  }
+  return ok;
+}
+
 // ---- accumulation ----------------------------------------------------------------------------------
 template <int MOTION> struct Accum {
   using L = Layout<MOTION>;

@@ -22,7 +22,7 @@
 
 namespace stk {
 
-template <int THREADS, int RPT, int UNROLL, int STAGES, int MINB>
+template <int THREADS, int RPT, int UNROLL, int STAGES, int MINB, int PACK = 1>
 struct EccCfg {
   static_assert(THREADS % kEccStripW == 0 && RPT % UNROLL == 0, "bad ECC kernel geometry");
   static constexpr int kThreads = THREADS;
@@ -31,6 +31,7 @@ struct EccCfg {
   static constexpr int kUnroll = UNROLL;        // rows per straight-line group of the lean body
   static constexpr int kStages = STAGES;
   static constexpr int kMinBlocks = MINB;
+  static constexpr int kPack = PACK;            // lean Homography body: 1 = packed f32x2 arithmetic, 0 = scalar, 2 = packed sums only
   static constexpr int kWarps = THREADS / 32;
   static constexpr int kChunkH = RPT * kRowParts;
   static constexpr int kBoxH = kChunkH + 16;    // same 16-row drift/halo margin as the first-generation kernel
@@ -156,19 +157,21 @@ __global__ void __launch_bounds__(CFG::kThreads, CFG::kMinBlocks) ecc_iter_v2_ke
       const int strip = gi / cps, crow = gi - strip * cps;
       const int x0 = strip * kEccStripW, x1 = min(x0 + kEccStripW, p.width) - 1;
       const int cy0 = crow * kCH, cy1 = min(cy0 + kCH, p.height) - 1;
-      double umin, umax, vmin, vmax;
-      bool ok = chunk_bounds<Md::persp>(s_m, x0, x1, cy0, cy1, umin, umax, vmin, vmax);
+      float umin, umax, vmin, vmax;
+      bool ok = chunk_bounds_f32<Md::persp>(s_m, x0, x1, cy0, cy1, umin, umax, vmin, vmax);
       int xlo = 0, ylo = 0;
-      if (ok) ok = fabs(umin) < 1e8 && fabs(umax) < 1e8 && fabs(vmin) < 1e8 && fabs(vmax) < 1e8;
+      if (ok) ok = fabsf(umin) < 1e6f && fabsf(umax) < 1e6f && fabsf(vmin) < 1e6f && fabsf(vmax) < 1e6f;
       if (ok) {
-        xlo = ((int)floor(umin) - 2) & ~3;      // TMA: innermost coordinate on a 16-byte boundary
-        ylo = (int)floor(vmin) - 2;
-        ok = ((int)floor(umax) + 3 - xlo < kBoxW) && ((int)floor(vmax) + 3 - ylo < kBH);
+        // f32 bounds: widen by 1/32 px before flooring; the box keeps its 2-px margin on the low side and one more
+        // column/row than the taps need on the high side
+        xlo = ((int)floorf(umin - 0.03125f) - 2) & ~3;      // TMA: innermost coordinate on a 16-byte boundary
+        ylo = (int)floorf(vmin - 0.03125f) - 2;
+        ok = ((int)floorf(umax + 0.03125f) + 3 - xlo < kBoxW) && ((int)floorf(vmax + 0.03125f) + 3 - ylo < kBH);
       }
       s_box[tid][0] = ok ? xlo : INT_MIN;
       s_box[tid][1] = ylo;
-      s_box[tid][2] = (ok && floor(umin - 0.0625) >= 1.0 && floor(umax + 0.0625) <= (double)(p.width - 3) &&
-                       floor(vmin - 0.0625) >= 1.0 && floor(vmax + 0.0625) <= (double)(p.height - 3)) ? 1 : 0;
+      s_box[tid][2] = (ok && floorf(umin - 0.0625f) >= 1.0f && floorf(umax + 0.0625f) <= (float)(p.width - 3) &&
+                       floorf(vmin - 0.0625f) >= 1.0f && floorf(vmax + 0.0625f) <= (float)(p.height - 3)) ? 1 : 0;
       s_box[tid][3] = (strip << 16) | crow;
     }
     __syncthreads();
@@ -241,7 +244,36 @@ __global__ void __launch_bounds__(CFG::kThreads, CFG::kMinBlocks) ecc_iter_v2_ke
         if (boxed && s_box[c][2] != 0 && yb - ya == kRpt) {
           // lean path (interior chunk, full height): straight-line groups of kUnr rows — no border rule, no mask,
           // no vote, no branch — so the rows of a group interleave freely in the schedule
-          if constexpr (fast_coords) {
+          if constexpr (fast_coords && CFG::kPack != 1) {
+            // scalar arithmetic (kPack 0) / scalar sampling with packed sums (kPack 2): a packed f32x2 instruction with
+            // three distinct register-pair operands holds the FP32 pipe for ~4 cycles, not 2 (scripts/pipe_probe.cu),
+            // so packing only pays where the loop is issue-bound
+            const float* bp0 = box + (ya - ylo) * kBoxW + (x - xlo);
+            float yf0 = (float)ya;
+#pragma unroll 1
+            for (int rg = 0; rg < kRpt; rg += kUnr) {
+#pragma unroll
+              for (int r = 0; r < kUnr; ++r) {
+                const float yf = yf0 + (float)r;
+                const float t_ = trow[r * kEccStripW];
+                int qx, qy;
+                float du, dv, rw;
+                fp.at(yf, qx, qy, du, dv, rw);
+                const float* bp = bp0 + ((qy >> kInterBits) + r) * kBoxW + (qx >> kInterBits);
+                const float ax = (float)(qx & (kInterTab - 1)) * (1.f / kInterTab);
+                const float ay = (float)(qy & (kInterTab - 1)) * (1.f / kInterTab);
+                const Sample smp = sample_box(bp, ax, ay);
+                float g[G];
+                g[0] = smp.gx2 * rw; g[1] = smp.gy2 * rw;                       // 2a, 2b
+                g[G - 1] = fmaf(xf + du, g[0], (yf + dv) * g[1]);               // -2t
+                if constexpr (CFG::kPack == 2) acc.add_packed(f2(g[0], g[1]), g[G - 1], smp.w, t_, yf);
+                else acc.template add<true>(g, smp.w, t_, 1.f, yf);
+              }
+              trow += kUnr * kEccStripW;
+              bp0 += kUnr * kBoxW;
+              yf0 += (float)kUnr;
+            }
+          } else if constexpr (fast_coords) {
             // ((q - M) >> 5) == (q >> 5) - (M >> 5) for the magic M = 0x4B400000 (its low 5 bits are zero): the
             // subtraction is folded into the box pointer
             // (unsigned arithmetic: the intermediate values wrap mod 2^32, the final index is the small true one)
@@ -399,6 +431,10 @@ using EccCfg4 = EccCfg<512, 8, 8, 4, 1>;     // one 16-warp block per SM, 128x32
 using EccCfg5 = EccCfg<384, 8, 4, 2, 2>;     // 2 x 12 warps per SM, 128x24 chunks
 using EccCfg6 = EccCfg<256, 8, 4, 4, 2>;     // geometry 0 with 4-row groups (isolates the unroll depth)
 using EccCfg7 = EccCfg<128, 8, 8, 2, 5>;     // five independent 4-warp blocks per SM, 128x8 chunks
-constexpr int kEccCfgCount = 8;
+using EccCfg8 = EccCfg<256, 16, 8, 2, 2, 0>; // geometry 2, SCALAR lean body
+using EccCfg9 = EccCfg<256, 16, 8, 2, 2, 2>; // geometry 2, scalar sampling + packed sums
+using EccCfg10 = EccCfg<256, 16, 4, 2, 3, 0>;// scalar body at 3 blocks/SM (<= 85 registers; chunk 128x32 needs 2 stages of 43.6 KB: 2 blocks by smem)
+using EccCfg11 = EccCfg<256, 8, 4, 2, 3, 0>; // scalar body, 128x16 chunks, 3 blocks/SM
+constexpr int kEccCfgCount = 12;
 
 }  // namespace stk

@@ -393,6 +393,10 @@ IterVariant iter_variant(int motion, bool exact, int gen, int cfg) {
     case 5: return v2_variant<stk::kHomography, false, stk::EccCfg5>();
     case 6: return v2_variant<stk::kHomography, false, stk::EccCfg6>();
     case 7: return v2_variant<stk::kHomography, false, stk::EccCfg7>();
+    case 8: return v2_variant<stk::kHomography, false, stk::EccCfg8>();
+    case 9: return v2_variant<stk::kHomography, false, stk::EccCfg9>();
+    case 10: return v2_variant<stk::kHomography, false, stk::EccCfg10>();
+    case 11: return v2_variant<stk::kHomography, false, stk::EccCfg11>();
     default: return v2_variant<stk::kHomography, false, stk::EccCfg0>();
   }
 }
@@ -929,6 +933,10 @@ int stk_ecc_create(const stk_ecc_config* cfg, stk_ecc_ctx** out) {
       return cleanup(fail(STK_ERR_CUDA, "cannot reserve %d bytes of dynamic shared memory for the ECC kernel", c->iter_smem));
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, c->iter_fn, c->iter_threads, c->iter_smem) != cudaSuccess || occ < 1) occ = 1;
+    // persistent blocks per SM and launch: the kernel's occupancy, unless STK_ECC_BLOCKS_PER_SM asks for fewer (with
+    // several lanes the other slot is taken by another frame's kernel, and a block that owns twice the chunks pays its
+    // start-up and its fold once for twice the work)
+    if (const char* bps = getenv("STK_ECC_BLOCKS_PER_SM")) occ = std::max(1, std::min(occ, atoi(bps)));
     const int slots = c->sm_count * occ;
     c->n_strips = (c->ew + stk::kEccStripW - 1) / stk::kEccStripW;
     c->chunks_per_strip = (c->eh + c->iter_chunk_h - 1) / c->iter_chunk_h;

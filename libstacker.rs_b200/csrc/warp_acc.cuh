@@ -115,10 +115,25 @@ __device__ __forceinline__ void blend_taps(const unsigned (&t00)[C], const unsig
   }
 }
 
-// One frame's contribution to the block's 32 x 32 tile: the C interpolated values of every pixel, into s_val
-// (tile row r at s_val + r * 32 * C).  mtx = the frame's inverse map (9 doubles, shared memory).
+// acc[c] = fl(acc[c] + v[c]) on the thread's OWN pixel slot of the block's accumulator tile in shared memory (lane
+// stride C floats: conflict-free for C = 3; one 128-bit access for C = 4)
+template <int C>
+__device__ __forceinline__ void tile_add(float* slot, const float (&v)[C]) {
+  if constexpr (C == 4) {
+    float4 a = *reinterpret_cast<float4*>(slot);
+    a.x = __fadd_rn(a.x, v[0]); a.y = __fadd_rn(a.y, v[1]); a.z = __fadd_rn(a.z, v[2]); a.w = __fadd_rn(a.w, v[3]);
+    *reinterpret_cast<float4*>(slot) = a;
+  } else {
+#pragma unroll
+    for (int c = 0; c < C; ++c) slot[c] = __fadd_rn(slot[c], v[c]);
+  }
+}
+
+// One frame's contribution to the block's 32 x 32 tile: the C interpolated values of each of the thread's four pixels
+// are ADDED to the accumulator tile s_acc (tile row r at s_acc + r * 32 * C).  Every thread owns its pixels' slots for
+// the whole launch, so consecutive frames need no barrier.  mtx = the frame's inverse map (9 doubles, shared memory).
 template <int C, bool PERSP>
-__device__ __forceinline__ void warp_tile(const WarpFrame& f, const double* mtx, float* s_val, int width, int height,
+__device__ __forceinline__ void warp_tile(const WarpFrame& f, const double* mtx, float* s_acc, int width, int height,
                                           int sw, int sh) {
   const int x = blockIdx.x * kWarpBX + threadIdx.x;
   const int y_base = blockIdx.y * kWarpTH + threadIdx.y;
@@ -185,7 +200,9 @@ __device__ __forceinline__ void warp_tile(const WarpFrame& f, const double* mtx,
       unsigned t00[C], t01[C], t10[C], t11[C];
 #pragma unroll
       for (int c = 0; c < C; ++c) { t00[c] = __ldg(r0 + c); t01[c] = __ldg(r0 + C + c); t10[c] = __ldg(r1 + c); t11[c] = __ldg(r1 + C + c); }
-      blend_taps<C>(t00, t01, t10, t11, w00, w01, w10, w11, s_val + ry * kRow + threadIdx.x * C);
+      float v[C];
+      blend_taps<C>(t00, t01, t10, t11, w00, w01, w10, w11, v);
+      tile_add<C>(s_acc + ry * kRow + threadIdx.x * C, v);
     }
     return;
   }
@@ -258,35 +275,34 @@ __device__ __forceinline__ void warp_tile(const WarpFrame& f, const double* mtx,
                            __fmul_rn(s11, w11));
         }
       }
+      tile_add<C>(s_acc + (threadIdx.y + rr * kWarpBY) * kRow + threadIdx.x * C, v);
     }
-#pragma unroll
-    for (int c = 0; c < C; ++c) s_val[(threadIdx.y + rr * kWarpBY) * kRow + threadIdx.x * C + c] = v[c];
   }
 }
 
 // 32 x 32 destination tile per 256-thread block, four rows per thread (so the per-thread column terms of the
-// coordinate transform, the parameter loads and the index math are paid once per four pixels).  The C
-// interpolated values of the tile are staged in shared memory and the accumulator is touched as coalesced 128-bit
-// accesses (a tile row is 32*C contiguous floats).  BATCHED: up to kWarpBatch frames per launch — the block keeps its
-// slice of the accumulator in REGISTERS, adds frame after frame in index order (the same f32 sequence as one launch
-// per frame, so results are bit-identical to the unbatched form) and writes it back once: 3N + 24N/k bytes per frame
-// instead of 27N.  The staging tile is double-buffered, so a frame costs one block barrier.
+// coordinate transform, the parameter loads and the index math are paid once per four pixels).
+// BATCHED: up to kWarpBatch frames per launch.  The block loads its tile of the accumulator into shared memory once
+// (coalesced 128-bit accesses: a tile row is 32*C contiguous floats), every thread then adds frame after frame, in
+// index order, into the slots of its own four pixels — the same f32 sequence as one launch per frame, so results are
+// bit-identical to the unbatched form — and the tile is written back once: 3N + 24N/k bytes per frame instead of 27N.
+// Between frames there is NO barrier (a thread touches only its own slots), so the warps of a block drift apart and
+// the byte gathers of one overlap the arithmetic of the others; the accumulator costs no registers, which keeps the
+// kernel at 8 blocks per SM (ncu r2: the register-resident form ran at 5 blocks per SM with `long_scoreboard` on the
+// gathers as the top stall).
 // ncu (profiles/) showed the first versions to be issue-bound (390, then 234 instructions per pixel), so the
 // per-pixel path is kept lean: the inverse maps are staged once per block, the 64-px column block start is a mask,
 // the reciprocal replaces the f64 divide (32/W == 32 * (1/W) exactly: a power-of-two scaling commutes with
 // rounding), __double2int_rn supplies the saturation, pixels whose four taps are inside the source skip all border
-// selects, and channel pairs are converted and blended with packed f32x2 instructions.
+// selects, and the multiplies of a channel pair are packed f32x2 instructions.
 // A frame whose ECC status is non-zero contributes nothing (the reference aborts the whole stack, src/lib.rs:777);
 // in store mode the accumulator is still written (zeros + the other frames), never left uninitialised.
 template <int C, bool PERSP>
-__global__ void __launch_bounds__(kWarpBX * kWarpBY, 5) warp_accumulate_kernel(const __grid_constant__ WarpAccParams p) {
+__global__ void __launch_bounds__(kWarpBX * kWarpBY, 8) warp_accumulate_kernel(const __grid_constant__ WarpAccParams p) {
   constexpr int kRow = kWarpBX * C;                 // floats per tile row
-  constexpr int kVecPerRow = kRow / 4;
-  constexpr int kVecs = kWarpTH * kVecPerRow;
+  constexpr int kTile = kWarpTH * kRow;
   constexpr int kThreads = kWarpBX * kWarpBY;
-  constexpr int kPerThread = kVecs / kThreads;      // 3 (C = 3) or 4 (C = 4) float4 per thread
-  static_assert(kVecs % kThreads == 0, "tile vectors must divide evenly over the block");
-  __shared__ __align__(16) float s_val[2][kWarpTH * kRow];
+  __shared__ __align__(16) float s_acc[kTile];
   __shared__ double s_m[kWarpBatch][9];
   __shared__ int s_skip[kWarpBatch];
   const int tid = threadIdx.y * kWarpBX + threadIdx.x;
@@ -295,7 +311,6 @@ __global__ void __launch_bounds__(kWarpBX * kWarpBY, 5) warp_accumulate_kernel(c
     s_m[j][i] = p.f[j].inv_ptr ? p.f[j].inv_ptr[i] : p.f[j].inv[i];
   }
   if (tid < p.n) s_skip[tid] = (p.f[tid].status_ptr && *p.f[tid].status_ptr != 0) ? 1 : 0;
-  __syncthreads();
 
   const int tx0 = blockIdx.x * kWarpBX;
   const int ty0 = blockIdx.y * kWarpTH;
@@ -303,60 +318,39 @@ __global__ void __launch_bounds__(kWarpBX * kWarpBY, 5) warp_accumulate_kernel(c
   const size_t row_base = (size_t)tx0 * C;                       // float offset of the tile inside a row
   const bool vec_ok = (((size_t)p.width * C) % 4 == 0);          // then every float4 of the tile is all in or all out
 
+  // accumulator tile: global -> shared (zeros in store mode and outside the image)
   if (vec_ok) {
-    float4 a[kPerThread];
-    auto slot = [&](int k) -> float* {            // this thread's k-th float4 of the tile in the accumulator, or null
-      const int i = k * kThreads + tid;
-      const int r = i / kVecPerRow, q = i - r * kVecPerRow;
-      const bool in = ty0 + r < p.height && q * 4 < row_elems;
-      return in ? p.acc + (size_t)(ty0 + r) * p.width * C + row_base + q * 4 : nullptr;
-    };
-#pragma unroll
-    for (int k = 0; k < kPerThread; ++k) {
-      a[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (!p.store) { const float* ap = slot(k); if (ap) a[k] = *reinterpret_cast<const float4*>(ap); }
+    for (int i = tid; i < kTile / 4; i += kThreads) {
+      const int r = i / (kRow / 4), q = i - r * (kRow / 4);
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!p.store && ty0 + r < p.height && q * 4 < row_elems)
+        a = *reinterpret_cast<const float4*>(p.acc + (size_t)(ty0 + r) * p.width * C + row_base + q * 4);
+      *reinterpret_cast<float4*>(&s_acc[i * 4]) = a;
     }
-    int buf = 0;
-    for (int j = 0; j < p.n; ++j) {
-      if (s_skip[j]) continue;                                   // block-uniform
-      warp_tile<C, PERSP>(p.f[j], s_m[j], s_val[buf], p.width, p.height, p.src_width, p.src_height);
-      __syncthreads();      // tile j complete; every thread has also finished reading buffer buf^1 (tile j-1) before
-                            // it started computing tile j, so tile j+1 may overwrite that buffer
-#pragma unroll
-      for (int k = 0; k < kPerThread; ++k) {
-        const float4 nv = *reinterpret_cast<const float4*>(&s_val[buf][(k * kThreads + tid) * 4]);
-        a[k].x = __fadd_rn(a[k].x, nv.x); a[k].y = __fadd_rn(a[k].y, nv.y);
-        a[k].z = __fadd_rn(a[k].z, nv.z); a[k].w = __fadd_rn(a[k].w, nv.w);
-      }
-      buf ^= 1;
+  } else {
+    for (int i = tid; i < kTile; i += kThreads) {
+      const int r = i / kRow, q = i - r * kRow;
+      s_acc[i] = (!p.store && ty0 + r < p.height && q < row_elems) ? p.acc[(size_t)(ty0 + r) * p.width * C + row_base + q] : 0.f;
     }
-#pragma unroll
-    for (int k = 0; k < kPerThread; ++k) { float* ap = slot(k); if (ap) *reinterpret_cast<float4*>(ap) = a[k]; }
-    return;
   }
+  __syncthreads();
 
-  // rows that do not start on 16-byte boundaries (width*C not a multiple of 4): scalar read-modify-write per frame
-  bool first = p.store != 0;
   for (int j = 0; j < p.n; ++j) {
-    if (s_skip[j]) continue;
-    warp_tile<C, PERSP>(p.f[j], s_m[j], s_val[0], p.width, p.height, p.src_width, p.src_height);
-    __syncthreads();
-    for (int i = tid; i < kWarpTH * kRow; i += kThreads) {
-      const int r = i / kRow, q = i - r * kRow;
-      const int yy = ty0 + r;
-      if (yy >= p.height || q >= row_elems) continue;
-      float* a = p.acc + (size_t)yy * p.width * C + row_base + q;
-      *a = first ? s_val[0][i] : __fadd_rn(*a, s_val[0][i]);
-    }
-    __syncthreads();
-    first = false;
+    if (s_skip[j]) continue;                                   // block-uniform
+    warp_tile<C, PERSP>(p.f[j], s_m[j], s_acc, p.width, p.height, p.src_width, p.src_height);
   }
-  if (first) {          // store mode and every frame of the batch skipped: the accumulator still becomes defined
-    for (int i = tid; i < kWarpTH * kRow; i += kThreads) {
+  __syncthreads();
+
+  if (vec_ok) {
+    for (int i = tid; i < kTile / 4; i += kThreads) {
+      const int r = i / (kRow / 4), q = i - r * (kRow / 4);
+      if (ty0 + r < p.height && q * 4 < row_elems)
+        *reinterpret_cast<float4*>(p.acc + (size_t)(ty0 + r) * p.width * C + row_base + q * 4) = *reinterpret_cast<const float4*>(&s_acc[i * 4]);
+    }
+  } else {
+    for (int i = tid; i < kTile; i += kThreads) {
       const int r = i / kRow, q = i - r * kRow;
-      const int yy = ty0 + r;
-      if (yy >= p.height || q >= row_elems) continue;
-      p.acc[(size_t)yy * p.width * C + row_base + q] = 0.f;
+      if (ty0 + r < p.height && q < row_elems) p.acc[(size_t)(ty0 + r) * p.width * C + row_base + q] = s_acc[i];
     }
   }
 }

@@ -7,7 +7,7 @@
               and the stack's frames/s;
 
 and check that every variant recovers the same warps (max corner displacement against variant gen1) with the
-same iteration counts.  Usage:  python scripts/k2_variants.py [n_frames] [variant ...]   (variant = gen:cfg)
+same iteration counts.  Usage:  python scripts/k2_variants.py [n_frames] [variant ...]   (variant = gen:cfg[:blocks per SM per launch])
 """
 import json
 import os
@@ -32,8 +32,13 @@ params = pkg.EccMatchParameters(pkg.MotionType.Homography, 5000, 1e-5, 5)
 base = None
 rows = []
 for v in variants:
-    gen, cfg = v.split(":")
+    parts = v.split(":")
+    gen, cfg = parts[0], parts[1]
     os.environ["STK_ECC_GEN"], os.environ["STK_ECC_CFG"] = gen, cfg
+    if len(parts) > 2:
+        os.environ["STK_ECC_BLOCKS_PER_SM"] = parts[2]       # gen:cfg:blocks-per-SM-per-launch
+    else:
+        os.environ.pop("STK_ECC_BLOCKS_PER_SM", None)
     rec = {"variant": v}
     try:
         with pkg.EccStack(w, h, 3, params, device=0, lanes=1) as s1:
