@@ -435,6 +435,8 @@ using EccCfg8 = EccCfg<256, 16, 8, 2, 2, 0>; // geometry 2, SCALAR lean body
 using EccCfg9 = EccCfg<256, 16, 8, 2, 2, 2>; // geometry 2, scalar sampling + packed sums
 using EccCfg10 = EccCfg<256, 16, 4, 2, 3, 0>;// scalar body at 3 blocks/SM (<= 85 registers; chunk 128x32 needs 2 stages of 43.6 KB: 2 blocks by smem)
 using EccCfg11 = EccCfg<256, 8, 4, 2, 3, 0>; // scalar body, 128x16 chunks, 3 blocks/SM
-constexpr int kEccCfgCount = 12;
+using EccCfg12 = EccCfg<256, 12, 4, 3, 2>;   // 128x24 chunks, THREE stages at 2 blocks/SM (106 KB): one more chunk of slack against warp skew
+using EccCfg13 = EccCfg<256, 12, 6, 3, 2>;   // the same with 6-row groups
+constexpr int kEccCfgCount = 14;
 
 }  // namespace stk

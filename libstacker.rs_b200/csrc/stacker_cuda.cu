@@ -397,6 +397,8 @@ IterVariant iter_variant(int motion, bool exact, int gen, int cfg) {
     case 9: return v2_variant<stk::kHomography, false, stk::EccCfg9>();
     case 10: return v2_variant<stk::kHomography, false, stk::EccCfg10>();
     case 11: return v2_variant<stk::kHomography, false, stk::EccCfg11>();
+    case 12: return v2_variant<stk::kHomography, false, stk::EccCfg12>();
+    case 13: return v2_variant<stk::kHomography, false, stk::EccCfg13>();
     default: return v2_variant<stk::kHomography, false, stk::EccCfg0>();
   }
 }
@@ -1805,6 +1807,39 @@ int stk_tenengrad_batch_device(const uint8_t* d_imgs, size_t frame_stride, size_
   if (channels != 1 && channels != 3 && channels != 4) return fail(STK_ERR_UNSUPPORTED, "channels must be 1, 3 or 4");
   if (pitch < (size_t)width * channels) return fail(STK_ERR_BAD_ARG, "pitch too small");
   if (device >= 0) CU(cudaSetDevice(device));
+  if (ksize == 3 && channels == 1 && width % stk::kTsCols == 0 && height >= 2 && pitch % 16 == 0 && frame_stride % 16 == 0 &&
+      ((uintptr_t)d_imgs) % 16 == 0 && getenv("STK_TENENGRAD_STREAM") == nullptr) {
+    // k = 3 on 16-byte aligned grey planes: the dedicated streaming kernel, the whole batch in one launch
+    unsigned long long* d_sums = nullptr;
+    const size_t sum_bytes = sizeof(unsigned long long) * stk::kSumSlots * (size_t)n;
+    int cur_dev = 0;
+    CU(cudaGetDevice(&cur_dev));
+    std::lock_guard<std::mutex> scratch_lock(g_scratch.mu);
+    rc = scratch_for(cur_dev, sum_bytes, &d_sums);
+    if (rc) return rc;
+    cudaError_t e = cudaMemsetAsync(d_sums, 0, sum_bytes, 0);
+    stk::TenStreamParams q = {};
+    q.src = d_imgs; q.frame_stride = frame_stride; q.pitch = pitch; q.width = width; q.height = height;
+    // bands of up to kTsBand rows, shortened on small batches so that the grid still fills the device
+    q.bands = (height + stk::kTsBand - 1) / stk::kTsBand;
+    q.col_blocks = (width + stk::kTsThreads * stk::kTsCols - 1) / (stk::kTsThreads * stk::kTsCols);
+    q.sums = d_sums;
+    std::vector<unsigned long long> h((size_t)n * stk::kSumSlots);
+    if (e == cudaSuccess) {
+      const long long blocks = (long long)n * q.bands * q.col_blocks;
+      stk::tenengrad_stream_kernel<<<(unsigned)blocks, stk::kTsThreads>>>(q);
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(h.data(), d_sums, sum_bytes, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return fail(STK_ERR_CUDA, "tenengrad: %s", cudaGetErrorString(e));
+    const double scale = 1.0 / ((double)width * (double)height);
+    for (int i = 0; i < n; ++i) {
+      unsigned long long t = 0;
+      for (int k = 0; k < stk::kSumSlots; ++k) t += h[(size_t)i * stk::kSumSlots + k];
+      out[i] = (double)t * scale;   // cv::mean: exact integer sum * (1.0 / N)
+    }
+    return STK_OK;
+  }
   if (ksize == 3 && channels == 1 && width % 4 == 0 && width >= 8 && height >= 2 && pitch % 4 == 0 && frame_stride % 4 == 0 &&
       ((uintptr_t)d_imgs) % 4 == 0) {
     // k = 3 on grey planes: the streaming kernel (same exact integer sum, ~4x faster than the tiled one)

@@ -240,4 +240,124 @@ __global__ void __launch_bounds__(kStreamThreads) sharpness_stream_kernel(const 
   }
 }
 
+// ---- Tenengrad(3) alone, streaming, for batches of 8-bit grey planes ---------------------------------------------
+// What sharpness_tenengrad (ksize 3) needs is ONE sum per frame, and ranking a stack asks for it on every frame
+// (examples/main.rs:37-64).  Round-1 ncu put the fused four-metric kernel at 16-26 us per 4K plane — 6-8 % of HBM,
+// ~26 integer operations per pixel behind three 1-4-byte loads per row — so the ranking metric gets its own kernel:
+//   * a thread owns 16 adjacent columns: ONE 128-bit load per row; the two halo columns come from the neighbouring
+//     lanes by shuffle (BORDER_REFLECT_101 at the plane's edges is a select of the lane's own second/second-last byte);
+//   * rows stream through a 3-row register window that is ROTATED BY NAME (the loop is unrolled three times), so no
+//     register is ever copied; the next two rows' loads are always in flight;
+//   * per column and row the vertical terms s = up + 2 mid + down and d = down - up are formed once and shared by the
+//     three pixels that use them: ~8 integer operations per pixel (gx = s[c+1] - s[c-1], gy = d[c-1] + 2 d[c] + d[c+1],
+//     two multiply-adds into a 32-bit band sum, widened to 64 bits once per band);
+//   * the whole batch is one launch; a block adds ONE 64-bit value to its frame's slot.
+// Same exact integer sum as tenengrad_kernel, so the f64 result is bit-identical to the OpenCV CV_64F pipeline.
+// Requirements (else the tiled kernels run): channels == 1, width % 16 == 0, pitch % 16 == 0, 16-byte aligned planes.
+constexpr int kTsThreads = 128, kTsCols = 16, kTsBand = 48;     // 48 rows x 16 cols x 2 x 1020^2 < 2^32
+
+struct TenStreamParams {
+  const uint8_t* src;
+  size_t frame_stride, pitch;
+  int width, height;
+  int bands;                    // ceil(height / kTsBand)
+  int col_blocks;               // ceil(width / (kTsThreads * kTsCols))
+  unsigned long long* sums;     // [n_frames][kSumSlots]
+};
+
+__device__ __forceinline__ void ts_unpack(const uint4 q, unsigned left, unsigned right, int (&v)[kTsCols + 2]) {
+  const unsigned w[4] = {q.x, q.y, q.z, q.w};
+  v[0] = (int)left;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    v[1 + 4 * k] = (int)(w[k] & 0xffu);
+    v[2 + 4 * k] = (int)((w[k] >> 8) & 0xffu);
+    v[3 + 4 * k] = (int)((w[k] >> 16) & 0xffu);
+    v[4 + 4 * k] = (int)(w[k] >> 24);
+  }
+  v[kTsCols + 1] = (int)right;
+}
+
+__global__ void __launch_bounds__(kTsThreads) tenengrad_stream_kernel(const TenStreamParams p) {
+  __shared__ unsigned long long s_part[kTsThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31;
+  // blockIdx.x = (frame, band, column block) flattened, column block fastest
+  int b = blockIdx.x;
+  const int cb = b % p.col_blocks; b /= p.col_blocks;
+  const int band = b % p.bands;
+  const int frame = b / p.bands;
+  const int w = p.width, h = p.height;
+  const int x0 = (cb * kTsThreads + tid) * kTsCols;
+  const int y0 = band * kTsBand;
+  const int y_end = min(y0 + kTsBand, h);
+  const uint8_t* src = p.src + (size_t)frame * p.frame_stride;
+  const bool active = x0 < w;
+  const bool edge_l = x0 == 0, edge_r = x0 + kTsCols == w;
+  const int xa = active ? x0 : 0;                 // idle threads load column block 0 again (they only feed shuffles)
+
+  auto load = [&](int y) -> uint4 {
+    return __ldg(reinterpret_cast<const uint4*>(src + (size_t)reflect101(y, h) * p.pitch + xa));
+  };
+  // the row as 18 ints: [halo left, 16 own columns, halo right]
+  auto expand = [&](const uint4 q, int (&v)[kTsCols + 2]) {
+    // neighbours' edge bytes: lane-1's last byte, lane+1's first byte (a warp's lanes are adjacent 16-column groups)
+    unsigned from_l = __shfl_up_sync(0xffffffffu, q.w >> 24, 1);
+    unsigned from_r = __shfl_down_sync(0xffffffffu, q.x & 0xffu, 1);
+    // warp boundaries inside the plane: one byte load each (lanes 0 and 31 only); plane edges: REFLECT_101
+    // = column 1 / column w-2, i.e. this thread's own second / second-last byte
+    unsigned left = edge_l ? ((q.x >> 8) & 0xffu) : from_l;
+    unsigned right = edge_r ? ((q.w >> 16) & 0xffu) : from_r;
+    ts_unpack(q, left, right, v);
+  };
+
+  unsigned int acc = 0;
+  // halo bytes across warp boundaries (lane 0's left, lane 31's right) cannot come from a shuffle: they are loaded
+  // as single bytes per row below
+  const bool need_l = lane == 0 && !edge_l && active, need_r = lane == 31 && !edge_r && active && x0 + kTsCols < w;
+
+  auto row_terms = [&](const int (&up)[kTsCols + 2], const int (&mid)[kTsCols + 2], const int (&dn)[kTsCols + 2]) {
+    int sv[kTsCols + 2], dv[kTsCols + 2];
+#pragma unroll
+    for (int j = 0; j < kTsCols + 2; ++j) { sv[j] = up[j] + 2 * mid[j] + dn[j]; dv[j] = dn[j] - up[j]; }
+#pragma unroll
+    for (int i = 0; i < kTsCols; ++i) {
+      const int gx = sv[i + 2] - sv[i];
+      const int gy = dv[i] + 2 * dv[i + 1] + dv[i + 2];
+      acc += (unsigned)(gx * gx) + (unsigned)(gy * gy);
+    }
+  };
+
+  auto finish = [&](int y, const uint4 q, int (&v)[kTsCols + 2]) {
+    expand(q, v);
+    if (need_l) v[0] = (int)__ldg(src + (size_t)reflect101(y, h) * p.pitch + x0 - 1);
+    if (need_r) v[kTsCols + 1] = (int)__ldg(src + (size_t)reflect101(y, h) * p.pitch + x0 + kTsCols);
+  };
+
+  int ra[kTsCols + 2], rb[kTsCols + 2], rc[kTsCols + 2];
+  finish(y0 - 1, load(y0 - 1), ra);
+  finish(y0, load(y0), rb);
+  int y = y0;
+  // three rows per trip, the window rotating by name: (ra, rb, rc) -> (rb, rc, ra) -> (rc, ra, rb); the trip's three
+  // loads are issued before the first row is touched
+  for (; y + 3 <= y_end; y += 3) {
+    const uint4 q1 = load(y + 1), q2 = load(y + 2), q3 = load(y + 3);
+    finish(y + 1, q1, rc); if (active) row_terms(ra, rb, rc);
+    finish(y + 2, q2, ra); if (active) row_terms(rb, rc, ra);
+    finish(y + 3, q3, rb); if (active) row_terms(rc, ra, rb);
+  }
+  if (y < y_end) { finish(y + 1, load(y + 1), rc); if (active) row_terms(ra, rb, rc); ++y; }
+  if (y < y_end) { finish(y + 1, load(y + 1), ra); if (active) row_terms(rb, rc, ra); ++y; }
+
+  unsigned long long t = warp_sum((unsigned long long)acc);
+  if (lane == 0) s_part[tid >> 5] = t;
+  __syncthreads();
+  if (tid == 0) {
+    unsigned long long tot = 0;
+#pragma unroll
+    for (int k = 0; k < kTsThreads / 32; ++k) tot += s_part[k];
+    const int slot = (band * p.col_blocks + cb) % kSumSlots;
+    atomicAdd(p.sums + (size_t)frame * kSumSlots + slot, tot);       // integer: order-independent, deterministic
+  }
+}
+
 }  // namespace stk

@@ -408,6 +408,26 @@ def test_tenengrad_exact(pkg, k, size):
     assert pkg.sharpness_tenengrad(grey, k, device=0) == R.sharpness_tenengrad(grey, k)
 
 
+@pytest.mark.parametrize("size", [(16, 2), (32, 3), (512, 49), (528, 97), (2064, 50), (4112, 5), (3840, 2160)])
+def test_tenengrad_stream_kernel_exact(pkg, size):
+    """Tenengrad(3) on 16-byte aligned grey planes runs the dedicated streaming kernel (16 columns per thread, halo
+    by shuffle, 48-row bands): plane edges, warp and block boundaries, band tails of 1 and 2 rows, a batch."""
+    import ctypes as C
+    import torch
+    w, h = size
+    rng = np.random.default_rng(w * 3 + h)
+    n = 3
+    greys = rng.integers(0, 256, (n, h, w), dtype=np.uint8)
+    greys[1] = 255                                           # saturated plane: zero gradient everywhere
+    greys[2, :, ::2] = 0
+    greys[2, :, 1::2] = 255                                  # maximum horizontal gradient
+    dev = torch.from_numpy(greys).cuda()
+    out = (C.c_double * n)()
+    assert pkg._ffi.lib.stk_tenengrad_batch_device(dev.data_ptr(), h * w, w, w, h, 1, 3, n, 0, out) == 0
+    assert list(out) == [R.sharpness_tenengrad(g, 3) for g in greys]
+    assert pkg.sharpness_tenengrad(greys[0], 3, device=0) == out[0]
+
+
 def test_tenengrad_vs_cv2_and_ordering(pkg, have_cv2):
     """config 3's ranking step: identical sharpness ORDER (ties included) as the reference."""
     if not have_cv2:
