@@ -332,7 +332,7 @@ struct stk_ecc_ctx {
   int rim_weight = 10;         // cost of a rim-strip chunk in 1/8 of an interior one (STK_ECC_RIM_WEIGHT)
   void* iter_fn = nullptr;     // the iteration kernel of this context (generation + geometry, see iter_variant)
   int iter_threads = 0, iter_smem = 0, iter_chunk_h = 0, iter_box_h = 0, iter_min_blocks = 0;
-  int iter_gen = 2, iter_cfg = 0;
+  int iter_gen = 2, iter_cfg = -1;          // -1: the default geometry of iter_variant
   bool host_loop = false;
   bool have_ref = false;
   stk::PrepParams prep_proto;
@@ -365,7 +365,9 @@ IterVariant v2_variant() {
   return {(void*)stk::ecc_iter_v2_kernel<MOTION, EXACT, CFG>, CFG::kThreads, CFG::kDynSmem, CFG::kChunkH, CFG::kBoxH, CFG::kMinBlocks};
 }
 
-using DefaultEccCfg = stk::EccCfg0;
+// default geometry: 128x32 chunks (16 rows per thread), 2 TMA stages, 2 blocks per SM — the fastest of the measured
+// geometries on one lane and on four (scripts/k2_variants.py, profiles/r2_summary.md)
+using DefaultEccCfg = stk::EccCfg2;
 
 IterVariant iter_variant(int motion, bool exact, int gen, int cfg) {
   if (gen == 1) {
@@ -399,7 +401,8 @@ IterVariant iter_variant(int motion, bool exact, int gen, int cfg) {
     case 11: return v2_variant<stk::kHomography, false, stk::EccCfg11>();
     case 12: return v2_variant<stk::kHomography, false, stk::EccCfg12>();
     case 13: return v2_variant<stk::kHomography, false, stk::EccCfg13>();
-    default: return v2_variant<stk::kHomography, false, stk::EccCfg0>();
+    case 0: return v2_variant<stk::kHomography, false, stk::EccCfg0>();
+    default: return v2_variant<stk::kHomography, false, DefaultEccCfg>();
   }
 }
 
@@ -923,7 +926,7 @@ int stk_ecc_create(const stk_ecc_config* cfg, stk_ecc_ctx** out) {
   if (cfg->align) {
     // work split: 128-column strips x row chunks, dealt evenly to one persistent block per resident slot
     if (const char* g = getenv("STK_ECC_GEN")) c->iter_gen = atoi(g) == 1 ? 1 : 2;
-    if (const char* g = getenv("STK_ECC_CFG")) c->iter_cfg = std::max(0, std::min(stk::kEccCfgCount - 1, atoi(g)));
+    if (const char* g = getenv("STK_ECC_CFG")) c->iter_cfg = std::max(-1, std::min(stk::kEccCfgCount - 1, atoi(g)));
     const IterVariant iv = iter_variant(cfg->motion_type, c->exact_coords, c->iter_gen, c->iter_cfg);
     c->iter_fn = iv.fn;
     c->iter_threads = iv.threads;
@@ -938,7 +941,10 @@ int stk_ecc_create(const stk_ecc_config* cfg, stk_ecc_ctx** out) {
     // persistent blocks per SM and launch: the kernel's occupancy, unless STK_ECC_BLOCKS_PER_SM asks for fewer (with
     // several lanes the other slot is taken by another frame's kernel, and a block that owns twice the chunks pays its
     // start-up and its fold once for twice the work)
+    // Measured (4K Homography, 13-frame stacks): four lanes 3 181 -> 3 430 frames/s with ONE block per SM and launch,
+    // one lane 55.7 -> 64.1 us per iteration — so the grid follows the lane count of the context.
     if (const char* bps = getenv("STK_ECC_BLOCKS_PER_SM")) occ = std::max(1, std::min(occ, atoi(bps)));
+    else if (c->n_lanes >= 3) occ = 1;
     const int slots = c->sm_count * occ;
     c->n_strips = (c->ew + stk::kEccStripW - 1) / stk::kEccStripW;
     c->chunks_per_strip = (c->eh + c->iter_chunk_h - 1) / c->iter_chunk_h;
@@ -1822,12 +1828,14 @@ int stk_tenengrad_batch_device(const uint8_t* d_imgs, size_t frame_stride, size_
     q.src = d_imgs; q.frame_stride = frame_stride; q.pitch = pitch; q.width = width; q.height = height;
     // bands of up to kTsBand rows, shortened on small batches so that the grid still fills the device
     q.bands = (height + stk::kTsBand - 1) / stk::kTsBand;
-    q.col_blocks = (width + stk::kTsThreads * stk::kTsCols - 1) / (stk::kTsThreads * stk::kTsCols);
+    static const int cols = [] { const char* e = getenv("STK_TENENGRAD_COLS"); return (e && atoi(e) == 8) ? 8 : 16; }();
+    q.col_blocks = (width + stk::kTsThreads * cols - 1) / (stk::kTsThreads * cols);
     q.sums = d_sums;
     std::vector<unsigned long long> h((size_t)n * stk::kSumSlots);
     if (e == cudaSuccess) {
       const long long blocks = (long long)n * q.bands * q.col_blocks;
-      stk::tenengrad_stream_kernel<<<(unsigned)blocks, stk::kTsThreads>>>(q);
+      if (cols == 8) stk::tenengrad_stream_kernel<8><<<(unsigned)blocks, stk::kTsThreads>>>(q);
+      else stk::tenengrad_stream_kernel<16><<<(unsigned)blocks, stk::kTsThreads>>>(q);
       e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpy(h.data(), d_sums, sum_bytes, cudaMemcpyDeviceToHost);

@@ -261,24 +261,19 @@ struct TenStreamParams {
   size_t frame_stride, pitch;
   int width, height;
   int bands;                    // ceil(height / kTsBand)
-  int col_blocks;               // ceil(width / (kTsThreads * kTsCols))
+  int col_blocks;               // ceil(width / (kTsThreads * COLS))
   unsigned long long* sums;     // [n_frames][kSumSlots]
 };
 
-__device__ __forceinline__ void ts_unpack(const uint4 q, unsigned left, unsigned right, int (&v)[kTsCols + 2]) {
-  const unsigned w[4] = {q.x, q.y, q.z, q.w};
-  v[0] = (int)left;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    v[1 + 4 * k] = (int)(w[k] & 0xffu);
-    v[2 + 4 * k] = (int)((w[k] >> 8) & 0xffu);
-    v[3 + 4 * k] = (int)((w[k] >> 16) & 0xffu);
-    v[4 + 4 * k] = (int)(w[k] >> 24);
-  }
-  v[kTsCols + 1] = (int)right;
-}
+// COLS = 16 (one 128-bit load per row and thread) or 8 (64-bit loads, half the registers, twice the warps)
+template <int COLS> struct TsRow;
+template <> struct TsRow<16> { using type = uint4; };
+template <> struct TsRow<8> { using type = uint2; };
 
+template <int COLS>
 __global__ void __launch_bounds__(kTsThreads) tenengrad_stream_kernel(const TenStreamParams p) {
+  using Row = typename TsRow<COLS>::type;
+  constexpr int NW = COLS / 4;
   __shared__ unsigned long long s_part[kTsThreads / 32];
   const int tid = threadIdx.x, lane = tid & 31;
   // blockIdx.x = (frame, band, column block) flattened, column block fastest
@@ -287,66 +282,80 @@ __global__ void __launch_bounds__(kTsThreads) tenengrad_stream_kernel(const TenS
   const int band = b % p.bands;
   const int frame = b / p.bands;
   const int w = p.width, h = p.height;
-  const int x0 = (cb * kTsThreads + tid) * kTsCols;
+  const int x0 = (cb * kTsThreads + tid) * COLS;
   const int y0 = band * kTsBand;
   const int y_end = min(y0 + kTsBand, h);
   const uint8_t* src = p.src + (size_t)frame * p.frame_stride;
   const bool active = x0 < w;
-  const bool edge_l = x0 == 0, edge_r = x0 + kTsCols == w;
+  const bool edge_l = x0 == 0, edge_r = x0 + COLS == w;
   const int xa = active ? x0 : 0;                 // idle threads load column block 0 again (they only feed shuffles)
+  // halo bytes across warp boundaries (lane 0's left, lane 31's right) cannot come from a shuffle: one byte load each
+  const bool need_l = lane == 0 && !edge_l && active, need_r = lane == 31 && !edge_r && active;
+  const int xl = need_l ? x0 - 1 : xa, xr = need_r ? x0 + COLS : xa;
 
-  auto load = [&](int y) -> uint4 {
-    return __ldg(reinterpret_cast<const uint4*>(src + (size_t)reflect101(y, h) * p.pitch + xa));
+  // BORDER_REFLECT_101 row (|overshoot| is at most 2 here and height >= 2): no loop, no branch
+  auto row_of = [&](int y) -> const uint8_t* {
+    const int yy = y < 0 ? -y : (y >= h ? 2 * h - 2 - y : y);
+    return src + (size_t)yy * p.pitch;
   };
-  // the row as 18 ints: [halo left, 16 own columns, halo right]
-  auto expand = [&](const uint4 q, int (&v)[kTsCols + 2]) {
-    // neighbours' edge bytes: lane-1's last byte, lane+1's first byte (a warp's lanes are adjacent 16-column groups)
-    unsigned from_l = __shfl_up_sync(0xffffffffu, q.w >> 24, 1);
-    unsigned from_r = __shfl_down_sync(0xffffffffu, q.x & 0xffu, 1);
-    // warp boundaries inside the plane: one byte load each (lanes 0 and 31 only); plane edges: REFLECT_101
-    // = column 1 / column w-2, i.e. this thread's own second / second-last byte
-    unsigned left = edge_l ? ((q.x >> 8) & 0xffu) : from_l;
-    unsigned right = edge_r ? ((q.w >> 16) & 0xffu) : from_r;
-    ts_unpack(q, left, right, v);
+  struct Raw { Row q; unsigned l, r; };
+  auto load = [&](int y) -> Raw {
+    const uint8_t* row = row_of(y);
+    Raw t;
+    t.q = __ldg(reinterpret_cast<const Row*>(row + xa));
+    t.l = (lane == 0) ? (unsigned)__ldg(row + xl) : 0u;          // predicated single-byte loads on the warp's end lanes
+    t.r = (lane == 31) ? (unsigned)__ldg(row + xr) : 0u;
+    return t;
+  };
+  // the row as COLS + 2 ints: [halo left, own columns, halo right]
+  auto expand = [&](const Raw& t, int (&v)[COLS + 2]) {
+    unsigned wds[NW];
+    if constexpr (COLS == 16) { wds[0] = t.q.x; wds[1] = t.q.y; wds[2] = t.q.z; wds[3] = t.q.w; }
+    else { wds[0] = t.q.x; wds[1] = t.q.y; }
+    // neighbours' edge bytes: lane-1's last byte, lane+1's first byte (a warp's lanes are adjacent column groups)
+    const unsigned from_l = __shfl_up_sync(0xffffffffu, wds[NW - 1] >> 24, 1);
+    const unsigned from_r = __shfl_down_sync(0xffffffffu, wds[0] & 0xffu, 1);
+    // plane edges: REFLECT_101 = column 1 / column w-2, i.e. this thread's own second / second-last byte
+    const unsigned left = edge_l ? ((wds[0] >> 8) & 0xffu) : (need_l ? t.l : from_l);
+    const unsigned right = edge_r ? ((wds[NW - 1] >> 16) & 0xffu) : (need_r ? t.r : from_r);
+    v[0] = (int)left;
+#pragma unroll
+    for (int k = 0; k < NW; ++k) {
+      v[1 + 4 * k] = (int)(wds[k] & 0xffu);
+      v[2 + 4 * k] = (int)((wds[k] >> 8) & 0xffu);
+      v[3 + 4 * k] = (int)((wds[k] >> 16) & 0xffu);
+      v[4 + 4 * k] = (int)(wds[k] >> 24);
+    }
+    v[COLS + 1] = (int)right;
   };
 
   unsigned int acc = 0;
-  // halo bytes across warp boundaries (lane 0's left, lane 31's right) cannot come from a shuffle: they are loaded
-  // as single bytes per row below
-  const bool need_l = lane == 0 && !edge_l && active, need_r = lane == 31 && !edge_r && active && x0 + kTsCols < w;
-
-  auto row_terms = [&](const int (&up)[kTsCols + 2], const int (&mid)[kTsCols + 2], const int (&dn)[kTsCols + 2]) {
-    int sv[kTsCols + 2], dv[kTsCols + 2];
+  auto row_terms = [&](const int (&up)[COLS + 2], const int (&mid)[COLS + 2], const int (&dn)[COLS + 2]) {
+    int sv[COLS + 2], dv[COLS + 2];
 #pragma unroll
-    for (int j = 0; j < kTsCols + 2; ++j) { sv[j] = up[j] + 2 * mid[j] + dn[j]; dv[j] = dn[j] - up[j]; }
+    for (int j = 0; j < COLS + 2; ++j) { sv[j] = up[j] + 2 * mid[j] + dn[j]; dv[j] = dn[j] - up[j]; }
 #pragma unroll
-    for (int i = 0; i < kTsCols; ++i) {
+    for (int i = 0; i < COLS; ++i) {
       const int gx = sv[i + 2] - sv[i];
       const int gy = dv[i] + 2 * dv[i + 1] + dv[i + 2];
       acc += (unsigned)(gx * gx) + (unsigned)(gy * gy);
     }
   };
 
-  auto finish = [&](int y, const uint4 q, int (&v)[kTsCols + 2]) {
-    expand(q, v);
-    if (need_l) v[0] = (int)__ldg(src + (size_t)reflect101(y, h) * p.pitch + x0 - 1);
-    if (need_r) v[kTsCols + 1] = (int)__ldg(src + (size_t)reflect101(y, h) * p.pitch + x0 + kTsCols);
-  };
-
-  int ra[kTsCols + 2], rb[kTsCols + 2], rc[kTsCols + 2];
-  finish(y0 - 1, load(y0 - 1), ra);
-  finish(y0, load(y0), rb);
+  int ra[COLS + 2], rb[COLS + 2], rc[COLS + 2];
+  expand(load(y0 - 1), ra);
+  expand(load(y0), rb);
   int y = y0;
   // three rows per trip, the window rotating by name: (ra, rb, rc) -> (rb, rc, ra) -> (rc, ra, rb); the trip's three
   // loads are issued before the first row is touched
   for (; y + 3 <= y_end; y += 3) {
-    const uint4 q1 = load(y + 1), q2 = load(y + 2), q3 = load(y + 3);
-    finish(y + 1, q1, rc); if (active) row_terms(ra, rb, rc);
-    finish(y + 2, q2, ra); if (active) row_terms(rb, rc, ra);
-    finish(y + 3, q3, rb); if (active) row_terms(rc, ra, rb);
+    const Raw q1 = load(y + 1), q2 = load(y + 2), q3 = load(y + 3);
+    expand(q1, rc); if (active) row_terms(ra, rb, rc);
+    expand(q2, ra); if (active) row_terms(rb, rc, ra);
+    expand(q3, rb); if (active) row_terms(rc, ra, rb);
   }
-  if (y < y_end) { finish(y + 1, load(y + 1), rc); if (active) row_terms(ra, rb, rc); ++y; }
-  if (y < y_end) { finish(y + 1, load(y + 1), ra); if (active) row_terms(rb, rc, ra); ++y; }
+  if (y < y_end) { expand(load(y + 1), rc); if (active) row_terms(ra, rb, rc); ++y; }
+  if (y < y_end) { expand(load(y + 1), ra); if (active) row_terms(rb, rc, ra); ++y; }
 
   unsigned long long t = warp_sum((unsigned long long)acc);
   if (lane == 0) s_part[tid >> 5] = t;
