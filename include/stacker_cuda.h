@@ -122,7 +122,12 @@ int stk_ecc_set_reference_device(stk_ecc_ctx* ctx, const uint8_t* d_bgr, size_t 
    warp_perspective, acc + warped                         (src/lib.rs:756-814)
    Asynchronous: returns once the frame is queued on a lane.  The host buffer may be reused as soon as
    the call returns unless it is pinned (stk_pinned_alloc), in which case it must stay valid until
-   stk_ecc_sync()/finish.  Thread-safe. */
+   stk_ecc_sync()/finish.  Thread-safe.
+   The frame's final warp + accumulate is DEFERRED: it is launched together with up to three other frames of the
+   same lane (one pass over the f32 accumulator for four frames, in submission order — bit-identical to one launch
+   per frame) when four are waiting, or at the next sync / results / partial / finish / exchange.  A DEVICE buffer
+   (_device variants) must therefore stay valid and unmodified until one of those calls has returned, and whoever
+   produced it must have finished writing it before the submit call (the library's streams are non-blocking). */
 int stk_ecc_submit_frame(stk_ecc_ctx* ctx, const uint8_t* bgr, size_t pitch, int64_t tag);
 int stk_ecc_submit_frame_pinned(stk_ecc_ctx* ctx, const uint8_t* pinned_bgr, size_t pitch, int64_t tag);
 int stk_ecc_submit_frame_device(stk_ecc_ctx* ctx, const uint8_t* d_bgr, size_t pitch, int64_t tag);

@@ -24,7 +24,8 @@ fn main() {
     println!("cargo:rustc-link-search=native={cuda}/lib64");
     println!("cargo:rustc-link-lib=dylib=cudart");
     println!("cargo:rustc-link-lib=dylib=stdc++");
-    for f in ["stacker_cuda.cu", "common.cuh", "prep.cuh", "ecc_iter.cuh", "warp_acc.cuh", "tenengrad.cuh"] {
+    for f in ["stacker_cuda.cu", "common.cuh", "prep.cuh", "ecc_iter.cuh", "ecc_iter_v2.cuh", "warp_acc.cuh", "tenengrad.cuh",
+              "resize_area.cuh", "peer_reduce.cuh"] {
         println!("cargo:rerun-if-changed={}", csrc.join(f).display());
     }
     println!("cargo:rerun-if-changed={}", include.join("stacker_cuda.h").display());

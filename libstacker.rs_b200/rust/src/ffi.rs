@@ -1,4 +1,4 @@
-//! Thin `extern "C"` layer over include/stacker_cuda.h (ABI version 3).  One declaration per entry point the
+//! Thin `extern "C"` layer over include/stacker_cuda.h (ABI version 4).  One declaration per entry point the
 //! Rust wrappers use; see the header for ownership and threading rules.
 #![allow(non_camel_case_types)]
 use std::os::raw::{c_char, c_int, c_void};
@@ -66,6 +66,10 @@ unsafe extern "C" {
     pub fn stk_ecc_release_frame_buffer(ctx: *mut stk_ecc_ctx, buf: *mut u8) -> c_int;
     pub fn stk_ecc_submit_warp(
         ctx: *mut stk_ecc_ctx, bgr: *const u8, pitch: usize, h: *const f64, border_mode: c_int,
+        border_value: *const f64, tag: i64,
+    ) -> c_int;
+    pub fn stk_ecc_submit_warp_affine(
+        ctx: *mut stk_ecc_ctx, bgr: *const u8, pitch: usize, m: *const f64, border_mode: c_int,
         border_value: *const f64, tag: i64,
     ) -> c_int;
     pub fn stk_ecc_sync(ctx: *mut stk_ecc_ctx) -> c_int;

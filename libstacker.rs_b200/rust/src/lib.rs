@@ -26,6 +26,10 @@ pub enum StackerError {
     NotImplemented,
     #[error(transparent)]
     IoError(#[from] std::io::Error),
+    // kept for source compatibility with callers that match on it (reference src/lib.rs:37-38); this crate holds no
+    // MatExpr behind a lock, so it is never produced here
+    #[error(transparent)]
+    PoisonError(#[from] std::sync::PoisonError<core::MatExprResult<core::MatExpr>>),
     #[error("Invalid path encoding {0}")]
     InvalidPathEncoding(PathBuf),
     #[error("Invalid parameter(s) {0}")]
@@ -81,10 +85,6 @@ fn devices() -> Result<Vec<i32>, StackerError> {
     check(unsafe { ffi::stk_device_count(&mut n) })?;
     let want = std::env::var("STACKER_GPUS").ok().and_then(|v| v.parse::<i32>().ok()).unwrap_or(n);
     Ok((0..n.min(want).max(1)).collect())
-}
-
-fn new_ctx(first: &Mat, ecc: Option<(EccMatchParameters, core::TermCriteria)>, ecc_size: Option<(i32, i32)>) -> Result<ffi::Ctx, StackerError> {
-    new_ctx_on(first, ecc, ecc_size, -1, true)
 }
 
 fn new_ctx_on(first: &Mat, ecc: Option<(EccMatchParameters, core::TermCriteria)>, ecc_size: Option<(i32, i32)>,
@@ -156,35 +156,49 @@ where
         check(unsafe { ffi::stk_ecc_peer_connect_local(raw.as_ptr(), raw.len() as i32) })?;
     }
     let ctxs = &ctxs;
-    // decode on the Rayon pool, one task per frame (reference: src/lib.rs:746-749); submission is thread-safe
-    // and asynchronous
-    (1..files.len()).into_par_iter().with_min_len(1).try_for_each(|i| -> Result<(), StackerError> {
-        let img = utils::read_frame(&files[i])?;
-        if img.size()? != first.size()? || img.channels() != first.channels() {
-            return Err(StackerError::InvalidParams(format!("{:?}: size differs from the first frame", files[i])));
+    // Decode on the Rayon pool, one task per frame (reference: src/lib.rs:746-749).  A task decodes its frame and copies
+    // the rows into a pinned ring buffer of the context the frame is dealt to (no library lock is held while it copies;
+    // `imgcodecs::imdecode_to` on a Mat wrapped around `buf` would save this copy too).  The buffers are handed over in
+    // FILE ORDER by this thread, window by window, so the f32 summation order — and therefore the result — does not
+    // depend on thread timing (the reference's own order is whatever Rayon's split gives).  A window never exceeds one
+    // ring (2 buffers per lane, 4 lanes), so every task of a window gets its buffer.
+    struct Filled(*mut u8);
+    unsafe impl Send for Filled {}
+    let window = 8usize;
+    let order: Vec<usize> = (1..files.len()).collect();
+    for chunk in order.chunks(window * ctxs.len()) {
+        let filled: Vec<Filled> = chunk.par_iter().with_min_len(1).map(|&i| -> Result<Filled, StackerError> {
+            let img = utils::read_frame(&files[i])?;
+            if img.size()? != first.size()? || img.channels() != first.channels() {
+                return Err(StackerError::InvalidParams(format!("{:?}: size differs from the first frame", files[i])));
+            }
+            let (mut buf, mut pitch) = (std::ptr::null_mut::<u8>(), 0usize);
+            let ctx = &ctxs[i % ctxs.len()];
+            check(unsafe { ffi::stk_ecc_acquire_frame_buffer(ctx.0, &mut buf, &mut pitch) })?;
+            let step = img.mat_step().get(0);
+            for y in 0..img.rows() as usize {
+                unsafe { std::ptr::copy_nonoverlapping(img.data().add(y * step), buf.add(y * pitch), pitch) };
+            }
+            Ok(Filled(buf))
+        }).collect::<Result<Vec<_>, _>>()?;
+        for (&i, f) in chunk.iter().zip(filled.iter()) {
+            check(unsafe { ffi::stk_ecc_submit_acquired(ctxs[i % ctxs.len()].0, f.0, i as i64) })?;
         }
-        // host feed: copy the decoded rows into a pinned ring buffer of the context (no library lock is held
-        // while this task copies) and hand it over; the upload is asynchronous and the buffer is recycled by
-        // the library.  (`imgcodecs::imdecode_to` on a Mat wrapped around `buf` would save this copy too.)
-        let (mut buf, mut pitch) = (std::ptr::null_mut::<u8>(), 0usize);
-        let ctx = &ctxs[i % ctxs.len()];
-        check(unsafe { ffi::stk_ecc_acquire_frame_buffer(ctx.0, &mut buf, &mut pitch) })?;
-        let step = img.mat_step().get(0);
-        for y in 0..img.rows() as usize {
-            unsafe { std::ptr::copy_nonoverlapping(img.data().add(y * step), buf.add(y * pitch), pitch) };
-        }
-        check(unsafe { ffi::stk_ecc_submit_acquired(ctx.0, buf, i as i64) })
-    })?;
+    }
     if ctxs.len() == 1 {
         return finish(&ctxs[0], &first, files.len());
     }
-    // Rayon's try_reduce + `/ n` (reference src/lib.rs:819-839) as ONE exchange step over NVLink peer memory: every
-    // device reduces and scales its slice of the stack and copies it into the result Mat over its own PCIe link.
-    // All exchanges are queued before the first copy-out (a copy into pageable memory blocks this thread).
+    finish_on_devices(ctxs, &first, files.len())
+}
+
+/// Rayon's try_reduce + `/ n` (reference src/lib.rs:819-839, :319-346) as ONE exchange step over NVLink peer memory:
+/// every device reduces and scales its slice of the stack and copies it into the result Mat over its own PCIe link.
+/// All exchanges are queued before the first copy-out (a copy into pageable memory blocks this thread).
+fn finish_on_devices(ctxs: &[ffi::Ctx], first: &Mat, divisor: usize) -> Result<Mat, StackerError> {
     let typ = core::CV_MAKETYPE(core::CV_32F, first.channels());
     let mut out = unsafe { Mat::new_rows_cols(first.rows(), first.cols(), typ)? };
     for c in ctxs.iter() {
-        check(unsafe { ffi::stk_ecc_peer_reduce_scatter(c.0, files.len() as i32, std::ptr::null_mut(), std::ptr::null_mut(), std::ptr::null_mut()) })?;
+        check(unsafe { ffi::stk_ecc_peer_reduce_scatter(c.0, divisor as i32, std::ptr::null_mut(), std::ptr::null_mut(), std::ptr::null_mut()) })?;
     }
     for c in ctxs.iter() {
         check(unsafe { ffi::stk_ecc_peer_slice_to_host(c.0, out.data_mut() as *mut f32) })?;
@@ -230,8 +244,20 @@ where
         Ok((kp, des))
     };
     let (kp0, des0) = orb(&grey(&first)?)?;
-    let ctx = new_ctx(&first, None, None)?;
-    check(unsafe { ffi::stk_ecc_set_reference(ctx.0, first.data(), first.mat_step().get(0)) })?;
+    // one warp-only context per GPU of the box (BASELINE configs[4]): every device gets frame 0 (only the first seeds
+    // its accumulator with it), accepted frames are dealt by index, the partial stacks meet in ONE exchange + divide
+    let devs = devices()?;
+    let mut ctxs = Vec::with_capacity(devs.len());
+    for (k, d) in devs.iter().enumerate() {
+        let c = new_ctx_on(&first, None, None, *d, k == 0)?;
+        check(unsafe { ffi::stk_ecc_set_reference(c.0, first.data(), first.mat_step().get(0)) })?;
+        ctxs.push(c);
+    }
+    if ctxs.len() > 1 {
+        let raw: Vec<*mut ffi::stk_ecc_ctx> = ctxs.iter().map(|c| c.0).collect();
+        check(unsafe { ffi::stk_ecc_peer_connect_local(raw.as_ptr(), raw.len() as i32) })?;
+    }
+    let ctxs = &ctxs;
     let border = [params.border_value[0], params.border_value[1], params.border_value[2], params.border_value[3]];
     let dropped: i32 = (1..files.len()).into_par_iter().with_min_len(1).map(|i| -> Result<i32, StackerError> {
         let img = utils::read_frame(&files[i])?;
@@ -274,14 +300,18 @@ where
             hv[7] /= sy;
         }
         check(unsafe {
-            ffi::stk_ecc_submit_warp(ctx.0, img.data(), img.mat_step().get(0), hv.as_ptr(), params.border_mode, border.as_ptr(), i as i64)
+            ffi::stk_ecc_submit_warp(ctxs[i % ctxs.len()].0, img.data(), img.mat_step().get(0), hv.as_ptr(), params.border_mode, border.as_ptr(), i as i64)
         })?;
         Ok(0)
     }).try_reduce(|| 0, |a, b| Ok(a + b))?;
     if files.len() as i32 - dropped <= 0 {
         return Err(StackerError::InvalidParams("All images discarded: try modifying KeyPointMatchParameters::match_distance_threshold".into()));
     }
-    Ok((dropped, finish(&ctx, &first, files.len() - dropped as usize)?))
+    let kept = files.len() - dropped as usize;
+    if ctxs.len() == 1 {
+        return Ok((dropped, finish(&ctxs[0], &first, kept)?));
+    }
+    Ok((dropped, finish_on_devices(ctxs, &first, kept)?))
 }
 
 /// Tenengrad sharpness (Krotkov86) of an 8-bit single-channel image; bit-identical to the reference's

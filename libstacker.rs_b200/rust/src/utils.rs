@@ -1,7 +1,47 @@
-//! Host-side helpers kept from the reference crate's `utils` module (same signatures): checked `imread`,
-//! the `EccMatchParameters -> TermCriteria` conversion and the `KeyPointMatchParameters` defaults.
+//! Host-side helpers kept from the reference crate's `utils` module (same signatures): `MatExt`, `SetMValue`, checked
+//! `imread`, the `EccMatchParameters -> TermCriteria` conversion and the `KeyPointMatchParameters` defaults.
 use crate::{EccMatchParameters, StackerError};
 use opencv::{imgcodecs, prelude::*};
+
+/// Extension trait for more ergonomic Mat conversions (reference: src/utils.rs:9-23; part of the public `utils`
+/// surface, so it stays — the GPU path itself never materialises the converted frame).
+pub trait MatExt {
+    /// Convert matrix to specified type with scaling: `dst = self * alpha + beta` as `rtype`.
+    fn convert(&self, rtype: i32, alpha: f64, beta: f64) -> Result<Mat, StackerError>;
+}
+
+impl MatExt for Mat {
+    fn convert(&self, rtype: i32, alpha: f64, beta: f64) -> Result<Mat, StackerError> {
+        let mut dst = Mat::default();
+        self.convert_to(&mut dst, rtype, alpha, beta)?;
+        Ok(dst)
+    }
+}
+
+/// Trait for setting a value in a 2d `Mat<T>` (reference: src/utils.rs:39-71).
+pub trait SetMValue {
+    fn set_2d<T: opencv::prelude::DataType>(&mut self, row: i32, col: i32, value: T) -> Result<(), StackerError>;
+}
+
+impl SetMValue for Mat {
+    #[inline]
+    /// ```
+    /// # use libstacker::{prelude::*, opencv::prelude::*, opencv::prelude::MatTraitConst};
+    /// # use crate::libstacker::utils::SetMValue;
+    /// let mut m = unsafe { opencv::core::Mat::new_rows_cols(1, 3, opencv::core::CV_64FC1).unwrap() };
+    /// m.set_2d::<f64>(0, 0, -1.0).unwrap();
+    /// m.set_2d::<f64>(0, 1, -2.0).unwrap();
+    /// m.set_2d::<f64>(0, 2, -3.0).unwrap();
+    /// assert_eq!(-1.0, *m.at_2d::<f64>(0, 0).unwrap());
+    /// assert_eq!(-2.0, *m.at_2d::<f64>(0, 1).unwrap());
+    /// assert_eq!(-3.0, *m.at_2d::<f64>(0, 2).unwrap());
+    /// ```
+    fn set_2d<T: opencv::prelude::DataType>(&mut self, row: i32, col: i32, value: T) -> Result<(), StackerError> {
+        let v = self.at_2d_mut::<T>(row, col)?;
+        *v = value;
+        Ok(())
+    }
+}
 
 /// `imread` with a checked path (reference: src/utils.rs:111-117).
 #[inline(always)]
