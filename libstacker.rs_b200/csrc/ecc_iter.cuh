@@ -82,6 +82,7 @@ struct alignas(64) EccIterParams {
   EccState* st;
   cudaGraphConditionalHandle handle;
   int use_handle;
+  unsigned frac_magic;      // 0x4B400000 (1.5 * 2^23): kept in a register by the lean pixel body (ecc_iter_v2.cuh::lean_pixel)
   int rim_weight;           // cost of a chunk of the first/last strip in 1/8 of an interior chunk (8 = no bias)
   double* totals_out;       // optional: the NV reduced sums of this iteration (test hook), else null
   unsigned long long* timing_out;   // optional: %globaltimer stamps per tile [n_tiles][4] + tail [4] (profiling hook)
@@ -600,6 +601,113 @@ struct AccumH2 {
       o[0] = p0; o[1] = xf * p0; o[2] = p1; o[3] = xx * p0; o[4] = xf * p1; o[5] = p2;
     }
     // projections: z in {w, m, m t} x g_i, moments {1, X, Y}
+    const float z0[3][3] = {{za[0].x, za[0].y, zc[0].x}, {zm[0].x, zm[0].y, zm2[0]}, {zt[0].x, zt[0].y, zc[0].y}};
+    const float z1[3][3] = {{za[1].x, za[1].y, zc[1].x}, {zm[1].x, zm[1].y, zm2[1]}, {zt[1].x, zt[1].y, zc[1].y}};
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const float f = i == 2 ? -0.5f : 0.5f;
+        const float v0 = z0[a][i] * f, v1 = z1[a][i] * f;
+        float* o = &v[L::kZ + (a * 3 + i) * 3];
+        o[0] = v0; o[1] = xf * v0; o[2] = v1;
+      }
+  }
+};
+
+// Third form of the Homography accumulator ("premultiplied"): the same 41 sums with the row coordinate folded into the
+// GENERATORS instead of into the products.  With gy_i = g_i * Y (3 multiplies per pixel),
+//     sum g_i g_j        = fma(g_i,  g_j,  .)      sum g_i z     = fma(g_i,  z, .)
+//     sum g_i g_j Y      = fma(gy_i, g_j,  .)      sum g_i z Y   = fma(gy_i, z, .)
+//     sum g_i g_j Y^2    = fma(gy_i, gy_j, .)      sum g_i, sum g_i Y : plain adds
+// every sum is ONE instruction and no product g_i g_j / g_i z is ever formed on its own: 44 FP32-pipe cycles per pixel
+// instead of 54 (AccumH2: 15 products + 39 accumulations), 27 issue slots instead of 30.  Each update rounds once
+// (fused) where AccumH2 rounded the product first — at least as accurate.
+//   hA[m] = (p00, p11), hB[m] = (p02, p12): packed; hC[m] = (p01, p22): two scalar chains; m = moment {1, Y, Y^2}
+//   za/zt/zm[m] = (g0 z, g1 z) for z = w / t / 1; zc[m] = (g2 w, g2 t); zm2[m] = g2; s1 = (Sw, St), s2 = (Sww, Stt)
+struct AccumH3 {
+  using L = Layout<kHomography>;
+  static constexpr int G = 3;
+  float n, swt;
+  float2 s1, s2;
+  float2 hA[3], hB[3], hC[3];
+  float2 za[2], zm[2], zt[2], zc[2];
+  float zm2[2];
+
+  __device__ __forceinline__ void clear() {
+    const float2 o = f2(0.f);
+    n = swt = 0.f; s1 = s2 = o;
+#pragma unroll
+    for (int m = 0; m < 3; ++m) hA[m] = hB[m] = hC[m] = o;
+#pragma unroll
+    for (int m = 0; m < 2; ++m) { za[m] = zm[m] = zt[m] = zc[m] = o; zm2[m] = 0.f; }
+  }
+
+  // interior pixel (mask 1; the caller counts it): g01 = (g0, g1)
+  __device__ __forceinline__ void add_packed(float2 g01, float g2, float w_, float t_, float yf) {
+    const float2 gy01 = mul2(g01, f2(yf));
+    const float gy2 = g2 * yf;
+    hA[0] = fma2(g01, g01, hA[0]); hA[1] = fma2(gy01, g01, hA[1]); hA[2] = fma2(gy01, gy01, hA[2]);
+    hB[0] = fma2(g01, f2(g2), hB[0]); hB[1] = fma2(gy01, f2(g2), hB[1]); hB[2] = fma2(gy01, f2(gy2), hB[2]);
+    hC[0].x = fmaf(g01.x, g01.y, hC[0].x); hC[1].x = fmaf(gy01.x, g01.y, hC[1].x); hC[2].x = fmaf(gy01.x, gy01.y, hC[2].x);
+    hC[0].y = fmaf(g2, g2, hC[0].y); hC[1].y = fmaf(gy2, g2, hC[1].y); hC[2].y = fmaf(gy2, gy2, hC[2].y);
+    const float2 wt = f2(w_, t_);
+    za[0] = fma2(g01, f2(w_), za[0]); za[1] = fma2(gy01, f2(w_), za[1]);
+    zt[0] = fma2(g01, f2(t_), zt[0]); zt[1] = fma2(gy01, f2(t_), zt[1]);
+    zc[0] = fma2(f2(g2), wt, zc[0]);  zc[1] = fma2(f2(gy2), wt, zc[1]);
+    zm[0] = add2(zm[0], g01);         zm[1] = add2(zm[1], gy01);
+    zm2[0] += g2; zm2[1] += gy2;
+    s1 = add2(s1, wt);
+    s2 = fma2(wt, wt, s2);
+    swt = fmaf(w_, t_, swt);
+  }
+
+  // general pixel (rim / careful / slow paths): scalar arithmetic on the same registers
+  template <bool INTERIOR>
+  __device__ __forceinline__ void add(const float (&g)[3], float w_, float t_, float mk, float yf) {
+    const float y0 = g[0] * yf, y1 = g[1] * yf, y2 = g[2] * yf;
+    auto up = [&](float& a0, float& a1, float& a2, float gi, float gj, float yi, float yj) {
+      a0 = fmaf(gi, gj, a0); a1 = fmaf(yi, gj, a1); a2 = fmaf(yi, yj, a2);
+    };
+    up(hA[0].x, hA[1].x, hA[2].x, g[0], g[0], y0, y0);
+    up(hA[0].y, hA[1].y, hA[2].y, g[1], g[1], y1, y1);
+    up(hB[0].x, hB[1].x, hB[2].x, g[0], g[2], y0, y2);
+    up(hB[0].y, hB[1].y, hB[2].y, g[1], g[2], y1, y2);
+    up(hC[0].x, hC[1].x, hC[2].x, g[0], g[1], y0, y1);
+    up(hC[0].y, hC[1].y, hC[2].y, g[2], g[2], y2, y2);
+    const float wm = INTERIOR ? w_ : w_ * mk;
+    const float tm = INTERIOR ? t_ : t_ * mk;
+    auto uz = [&](float& a0, float& a1, float gi, float yi, float z) { a0 = fmaf(gi, z, a0); a1 = fmaf(yi, z, a1); };
+    uz(za[0].x, za[1].x, g[0], y0, w_); uz(za[0].y, za[1].y, g[1], y1, w_); uz(zc[0].x, zc[1].x, g[2], y2, w_);
+    uz(zt[0].x, zt[1].x, g[0], y0, tm); uz(zt[0].y, zt[1].y, g[1], y1, tm); uz(zc[0].y, zc[1].y, g[2], y2, tm);
+    if (INTERIOR) {
+      zm[0].x += g[0]; zm[1].x += y0; zm[0].y += g[1]; zm[1].y += y1; zm2[0] += g[2]; zm2[1] += y2;
+    } else {
+      uz(zm[0].x, zm[1].x, g[0], y0, mk); uz(zm[0].y, zm[1].y, g[1], y1, mk); uz(zm2[0], zm2[1], g[2], y2, mk);
+      n += mk;
+    }
+    s1.x += wm; s2.x = fmaf(wm, w_, s2.x);
+    s1.y += tm; s2.y = fmaf(tm, t_, s2.y);
+    swt = fmaf(wm, t_, swt);
+  }
+
+  template <bool TWICE_NEG>
+  __device__ __forceinline__ void emit(float xf, float (&v)[L::NV]) const {
+    static_assert(TWICE_NEG, "AccumH3 holds (2a, 2b, -2t) sums");
+    v[0] = n; v[1] = s1.x; v[2] = s2.x; v[3] = s1.y; v[4] = s2.y; v[5] = swt;
+    const float xx = xf * xf;
+    // product order of Layout<>: (0,0) (0,1) (0,2) (1,1) (1,2) (2,2); the sign flips where exactly one factor is g2
+    const float pf[6] = {0.25f, 0.25f, -0.25f, 0.25f, -0.25f, 0.25f};
+#pragma unroll
+    for (int idx = 0; idx < 6; ++idx) {
+      float m[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        m[k] = idx == 0 ? hA[k].x : idx == 1 ? hC[k].x : idx == 2 ? hB[k].x : idx == 3 ? hA[k].y : idx == 4 ? hB[k].y : hC[k].y;
+      const float p0 = m[0] * pf[idx], p1 = m[1] * pf[idx], p2 = m[2] * pf[idx];
+      float* o = &v[L::kH + idx * 6];
+      o[0] = p0; o[1] = xf * p0; o[2] = p1; o[3] = xx * p0; o[4] = xf * p1; o[5] = p2;
+    }
     const float z0[3][3] = {{za[0].x, za[0].y, zc[0].x}, {zm[0].x, zm[0].y, zm2[0]}, {zt[0].x, zt[0].y, zc[0].y}};
     const float z1[3][3] = {{za[1].x, za[1].y, zc[1].x}, {zm[1].x, zm[1].y, zm2[1]}, {zt[1].x, zt[1].y, zc[1].y}};
 #pragma unroll

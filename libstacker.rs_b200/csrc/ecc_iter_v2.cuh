@@ -18,11 +18,13 @@
 //   * the pixel body sheds its integer<->float conversions (fraction bits spliced under the 1.5*2^23
 //     magic exponent, one packed FFMA) and the magic-constant subtractions (folded into the box pointer).
 #pragma once
+#include <type_traits>
+
 #include "ecc_iter.cuh"
 
 namespace stk {
 
-template <int THREADS, int RPT, int UNROLL, int STAGES, int MINB, int PACK = 1>
+template <int THREADS, int RPT, int UNROLL, int STAGES, int MINB, int PACK = 1, int BODY = 0>
 struct EccCfg {
   static_assert(THREADS % kEccStripW == 0 && RPT % UNROLL == 0, "bad ECC kernel geometry");
   static constexpr int kThreads = THREADS;
@@ -31,7 +33,9 @@ struct EccCfg {
   static constexpr int kUnroll = UNROLL;        // rows per straight-line group of the lean body
   static constexpr int kStages = STAGES;
   static constexpr int kMinBlocks = MINB;
-  static constexpr int kPack = PACK;            // lean Homography body: 1 = packed f32x2 arithmetic, 0 = scalar, 2 = packed sums only
+  static constexpr int kPack = PACK;            // lean Homography body: 1 = packed f32x2 arithmetic, 0 = scalar, 2 = packed sums only,
+                                                // 3 = packed with the premultiplied accumulator (AccumH3)
+  static constexpr int kBody = BODY;            // lean_pixel variant (packed bodies only)
   static constexpr int kWarps = THREADS / 32;
   static constexpr int kChunkH = RPT * kRowParts;
   static constexpr int kBoxH = kChunkH + 16;    // same 16-row drift/halo margin as the first-generation kernel
@@ -76,6 +80,45 @@ __device__ __forceinline__ void warp_reduce_accumulate(float (&v)[NV], int lane,
       if (lane == 0) acc[i] += (double)t;
     }
   }
+}
+
+// One interior pixel of the Homography lean body (FastPersp coordinates, 12 taps from the shared-memory box, Jacobian
+// generators (2a, 2b, -2t), sums): everything between the template value t_ and the accumulator update.
+//   bi      index of the thread's box element for row r of the group with the magic offsets folded in:
+//           ((q - M) >> 5) == (q >> 5) - (M >> 5) for M = 0x4B400000 (its low 5 bits are zero), unsigned wrap-around
+//   magic   0x4B400000 held in a REGISTER (the caller gets it from the kernel parameters): (q & 31) | magic is then ONE
+//           LOP3 per coordinate; as an immediate it takes two (LOP3 has a single immediate slot).
+// V = 0: the round-2 first-session body; V = 1: fused LOP3, scalar (u, v) — a packed instruction holds the issue
+// port for two cycles (scripts/pipe_probe.cu), so a packed op that needs a pair-forming move costs more than two scalars.
+template <int V, class ACC>
+__device__ __forceinline__ void lean_pixel(const FastPersp& fp, float xf, float yf, float t_, const float* box, unsigned bi,
+                                           unsigned magic, ACC& acc) {
+  const float rw = rcp_approx(fmaf(fp.m21, yf, fp.wc));
+  const float2 d = mul2(f2(fmaf(fp.beta, yf, fp.alpha), fmaf(fmaf(-fp.m21, yf, fp.delta), yf, fp.gamma)), f2(rw));
+  const float2 qf = fma2(d, f2(32.0f), f2(12582912.0f));
+  const int qxb = __float_as_int(qf.x), qyb = __float_as_int(qf.y);    // M + rint(32 du), M + rint(32 dv)
+  const float* bp = box + (bi + (unsigned)(qyb >> kInterBits) * (unsigned)kBoxW + (unsigned)(qxb >> kInterBits));
+  // fractions k/32: splice the 5 low bits under the magic exponent (a float equal to 2^23*1.5 + k), one packed FFMA
+  float2 axy;
+  if constexpr (V == 0) {
+    axy = fma2(f2(__int_as_float((qxb & (kInterTab - 1)) | 0x4B400000), __int_as_float((qyb & (kInterTab - 1)) | 0x4B400000)),
+               f2(1.f / kInterTab), f2(-12582912.0f / kInterTab));
+  } else {
+    axy = fma2(f2(__int_as_float((qxb & (kInterTab - 1)) | magic), __int_as_float((qyb & (kInterTab - 1)) | magic)),
+               f2(1.f / kInterTab), f2(-12582912.0f / kInterTab));
+  }
+  float w_;
+  float2 gxy2;
+  sample_box_packed(bp, axy.x, axy.y, w_, gxy2);
+  const float2 g01 = mul2(gxy2, f2(rw));                          // 2a, 2b
+  float g2;                                                       // -2t  (t = hatX a + hatY b, hat = -(u, v))
+  if constexpr (V == 0) {
+    const float2 uv = add2(f2(xf, yf), d);                        // sample position (u, v)
+    g2 = fmaf(uv.x, g01.x, uv.y * g01.y);
+  } else {
+    g2 = fmaf(xf + d.x, g01.x, (yf + d.y) * g01.y);
+  }
+  acc.add_packed(g01, g2, w_, t_, yf);
 }
 
 template <class ACC, int NV, bool TWICE_NEG>
@@ -128,20 +171,22 @@ __global__ void __launch_bounds__(CFG::kThreads, CFG::kMinBlocks) ecc_iter_v2_ke
   const int part = tid / kEccStripW;
   constexpr bool fast_coords = Md::persp && !EXACT;
 
-  typename AccumFor<MOTION, fast_coords>::type acc;
+  using AccT = typename std::conditional<fast_coords && CFG::kPack == 3, AccumH3, typename AccumFor<MOTION, fast_coords>::type>::type;
+  AccT acc;
   acc.clear();
   int n_safe = 0;
   int cur_strip = -1, x = 0;
   float xf = 0.f;
   bool col_ok = false;
   FastPersp fp;
+  const unsigned frac_magic = p.frac_magic;     // 0x4B400000 in a register: see lean_pixel
 
   // column sums of the strip this thread just left -> its warp's f64 row (warp-collective, no block barrier).
   // The fold itself is an out-of-line call (fold_columns): it is rare (once per strip change) and its 130
   // temporaries must not take part in the register allocation of the pixel loop.
   auto fold = [&]() {
     acc.n += (float)n_safe;
-    fold_columns<typename AccumFor<MOTION, fast_coords>::type, NV, fast_coords>(acc, xf, lane, s_acc[wid]);
+    fold_columns<AccT, NV, fast_coords>(acc, xf, lane, s_acc[wid]);
     acc.clear();
     n_safe = 0;
   };
@@ -244,7 +289,7 @@ __global__ void __launch_bounds__(CFG::kThreads, CFG::kMinBlocks) ecc_iter_v2_ke
         if (boxed && s_box[c][2] != 0 && yb - ya == kRpt) {
           // lean path (interior chunk, full height): straight-line groups of kUnr rows — no border rule, no mask,
           // no vote, no branch — so the rows of a group interleave freely in the schedule
-          if constexpr (fast_coords && CFG::kPack != 1) {
+          if constexpr (fast_coords && (CFG::kPack == 0 || CFG::kPack == 2)) {
             // scalar arithmetic (kPack 0) / scalar sampling with packed sums (kPack 2): a packed f32x2 instruction with
             // three distinct register-pair operands holds the FP32 pipe for ~4 cycles, not 2 (scripts/pipe_probe.cu),
             // so packing only pays where the loop is issue-bound
@@ -274,35 +319,15 @@ __global__ void __launch_bounds__(CFG::kThreads, CFG::kMinBlocks) ecc_iter_v2_ke
               yf0 += (float)kUnr;
             }
           } else if constexpr (fast_coords) {
-            // ((q - M) >> 5) == (q >> 5) - (M >> 5) for the magic M = 0x4B400000 (its low 5 bits are zero): the
-            // subtraction is folded into the box pointer
-            // (unsigned arithmetic: the intermediate values wrap mod 2^32, the final index is the small true one)
+            // the magic offsets of the float->int splice are folded into the box index (see lean_pixel)
             constexpr unsigned kMagicHi = 0x4B400000u >> kInterBits;
             unsigned bi0 = (unsigned)((ya - ylo) * kBoxW + (x - xlo)) - kMagicHi * (unsigned)(kBoxW + 1);
             float yf0 = (float)ya;
 #pragma unroll 1
             for (int rg = 0; rg < kRpt; rg += kUnr) {
 #pragma unroll
-              for (int r = 0; r < kUnr; ++r) {
-                const float yf = yf0 + (float)r;
-                const float t_ = trow[r * kEccStripW];
-                // FastPersp::at with the two coordinates carried as a pair
-                const float rw = rcp_approx(fmaf(fp.m21, yf, fp.wc));
-                const float2 d = mul2(f2(fmaf(fp.beta, yf, fp.alpha), fmaf(fmaf(-fp.m21, yf, fp.delta), yf, fp.gamma)), f2(rw));
-                const float2 qf = fma2(d, f2(32.0f), f2(12582912.0f));
-                const int qxb = __float_as_int(qf.x), qyb = __float_as_int(qf.y);    // M + rint(32 du), M + rint(32 dv)
-                const float* bp = box + (bi0 + (unsigned)((qyb >> kInterBits) + r) * (unsigned)kBoxW + (unsigned)(qxb >> kInterBits));
-                // fractions k/32: splice the 5 low bits under the magic exponent (a float equal to 2^23*1.5 + k), one packed FFMA
-                const float2 axy = fma2(f2(__int_as_float((qxb & (kInterTab - 1)) | 0x4B400000), __int_as_float((qyb & (kInterTab - 1)) | 0x4B400000)),
-                                        f2(1.f / kInterTab), f2(-12582912.0f / kInterTab));
-                float w_;
-                float2 gxy2;
-                sample_box_packed(bp, axy.x, axy.y, w_, gxy2);
-                const float2 g01 = mul2(gxy2, f2(rw));                          // 2a, 2b
-                const float2 uv = add2(f2(xf, yf), d);                          // sample position (u, v)
-                const float g2 = fmaf(uv.x, g01.x, uv.y * g01.y);               // -2t  (t = hatX a + hatY b, hat = -(u, v))
-                acc.add_packed(g01, g2, w_, t_, yf);
-              }
+              for (int r = 0; r < kUnr; ++r)
+                lean_pixel<CFG::kBody>(fp, xf, yf0 + (float)r, trow[r * kEccStripW], box, bi0 + (unsigned)(r * kBoxW), frac_magic, acc);
               trow += kUnr * kEccStripW;
               bi0 += kUnr * kBoxW;
               yf0 += (float)kUnr;
@@ -437,6 +462,10 @@ using EccCfg10 = EccCfg<256, 16, 4, 2, 3, 0>;// scalar body at 3 blocks/SM (<= 8
 using EccCfg11 = EccCfg<256, 8, 4, 2, 3, 0>; // scalar body, 128x16 chunks, 3 blocks/SM
 using EccCfg12 = EccCfg<256, 12, 4, 3, 2>;   // 128x24 chunks, THREE stages at 2 blocks/SM (106 KB): one more chunk of slack against warp skew
 using EccCfg13 = EccCfg<256, 12, 6, 3, 2>;   // the same with 6-row groups
-constexpr int kEccCfgCount = 14;
+using EccCfg14 = EccCfg<256, 16, 8, 2, 2, 3>; // geometry 2 with the premultiplied accumulator (44 instead of 54 FP32-pipe cycles of sums per pixel)
+using EccCfg15 = EccCfg<256, 8, 8, 4, 2, 3>;  // geometry 0 with the premultiplied accumulator
+using EccCfg16 = EccCfg<256, 16, 8, 2, 2, 3, 1>; // cfg 14 with the leaner pixel body (fused LOP3, scalar (u, v))
+using EccCfg17 = EccCfg<256, 16, 4, 2, 2, 3, 1>; // the same in 4-row groups
+constexpr int kEccCfgCount = 18;
 
 }  // namespace stk

@@ -6,12 +6,13 @@
 //   build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I libstacker.rs_b200/csrc -o scripts/pipe_probe scripts/pipe_probe.cu
 #include <cuda_runtime.h>
 #include <cstdio>
-#include "ecc_iter.cuh"
+#include <type_traits>
+#include "ecc_iter_v2.cuh"
 
 using namespace stk;
 
 template <int MODE>
-__global__ void __launch_bounds__(256, 2) probe(float* out, int iters, float a, float b) {
+__global__ void __launch_bounds__(256, 2) probe(float* out, int iters, float a, float b, unsigned magic) {
   __shared__ float box[kBoxW * 32];
   for (int i = threadIdx.x; i < kBoxW * 32; i += 256) box[i] = (float)(i % 97) * 0.01f;
   __syncthreads();
@@ -71,6 +72,35 @@ __global__ void __launch_bounds__(256, 2) probe(float* out, int iters, float a, 
       }
     }
     for (int i = 0; i < 18; ++i) r += h[i];
+  } else if (MODE == 5 || MODE == 6) {   // the premultiplied accumulator: packed interior form (5), scalar form (6)
+    AccumH3 acc; acc.clear();
+    float2 g01 = f2(a + lane, b - lane); float g2 = a * b, w_ = a + 1.f, t_ = b + 2.f, yf = 3.f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (MODE == 5) acc.add_packed(g01, g2, w_, t_, yf);
+        else { const float g[3] = {g01.x, g01.y, g2}; acc.add<true>(g, w_, t_, 1.f, yf); }
+        g01.x += a; g01.y += b; g2 += a; w_ += b; t_ += a; yf += 1.f;
+      }
+    }
+    float v[AccumH3::L::NV]; acc.emit<true>(1.f, v);
+    for (int i = 0; i < AccumH3::L::NV; ++i) r += v[i];
+  } else if (MODE >= 7 && MODE <= 10) {  // the whole interior pixel (ecc_iter_v2.cuh::lean_pixel): 7 = AccumH2, 8 = AccumH3, 9 = AccumH3 + leaner body, 10 = 9 in 4-row groups
+    typename std::conditional<MODE == 7, AccumH2, AccumH3>::type acc; acc.clear();
+    FastPersp fp; fp.alpha = a * 0.3f; fp.beta = 1e-4f * b; fp.gamma = 0.2f * b; fp.delta = 1e-4f * a; fp.wc = 1.f + 1e-6f * lane; fp.m21 = 1e-7f;
+    const float xf = (float)lane;
+    float yf0 = 0.f;
+    constexpr unsigned kMagicHi = 0x4B400000u >> kInterBits;
+    const unsigned bi0 = (unsigned)(2 * kBoxW + 2 + lane) - kMagicHi * (unsigned)(kBoxW + 1);
+    constexpr int U = MODE == 10 ? 4 : 8;
+    for (int it = 0; it < iters * (8 / U); ++it) {
+#pragma unroll
+      for (int k = 0; k < U; ++k)
+        lean_pixel<(MODE >= 9) ? 1 : 0>(fp, xf, yf0 + (float)k, box[(k + 20) * kBoxW + lane], box, bi0 + (unsigned)(k * kBoxW), magic, acc);
+      yf0 = (yf0 < 8.f) ? yf0 + (float)U : 0.f;           // stay inside the 32-row box
+    }
+    float v[AccumH2::L::NV]; acc.template emit<true>(1.f, v);
+    for (int i = 0; i < AccumH2::L::NV; ++i) r += v[i];
   } else if (MODE == 4) {                // packed FMA, accumulator pair only varying (the ffma2_probe case)
     float2 x[9]; for (int i = 0; i < 9; ++i) x[i] = f2(a + i, b + i);
     const float2 aa = f2(a), bb = f2(b);
@@ -92,7 +122,7 @@ void run(const char* name, float* out, double pipe_cycles_expected) {
   float best = 1e9f;
   for (int rep = 0; rep < 4; ++rep) {
     cudaEventRecord(e0);
-    probe<MODE><<<148 * 2, 256>>>(out, iters, 1.0001f, 0.5f);
+    probe<MODE><<<148 * 2, 256>>>(out, iters, 1.0001f, 0.5f, 0x4B400000u);
     cudaEventRecord(e1); cudaEventSynchronize(e1);
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     if (rep && ms < best) best = ms;
@@ -111,5 +141,11 @@ int main() {
   run<2>("9 packed sums, 3 distinct pairs (+yy, 4 FADD)", out, 18 + 5);
   run<3>("18 scalar sums (+yy, 4 FADD)", out, 18 + 5);
   run<4>("9 FFMA2, invariant multiplicand/addend", out, 18);
+  run<5>("accumulate premultiplied packed (AccumH3) + 6 FADD", out, 44 + 6);
+  run<6>("accumulate premultiplied scalar (AccumH3) + 6 FADD", out, 44 + 6);
+  run<7>("whole interior pixel, AccumH2", out, 97);
+  run<8>("whole interior pixel, AccumH3", out, 87);
+  run<9>("whole interior pixel, AccumH3, leaner body", out, 87);
+  run<10>("whole interior pixel, AccumH3, leaner body, 4-row groups", out, 87);
   return 0;
 }
