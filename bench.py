@@ -384,6 +384,30 @@ def run_b200(a, rank, local_rank, world):
 
     ms, wall_ms, launches, clocks = timed(step_resident, a.steps, a.warmup, True)
     value = n * a.steps / (ms / 1e3)
+
+    # diagnostic (untimed): what each rank's own share costs with no exchange at the end — the spread over the ranks is
+    # the frame-granular imbalance, max(rank_work_ms) against ms_per_step is what the exchange and the coupling cost
+    rank_work_ms = None
+    if world > 1:
+        def own_share():
+            st.reset()
+            st.set_reference(dev_frames[0])
+            for i in mine:
+                st.submit(dev_frames[i], tag=i)
+            st.sync()
+        own_share()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            own_share()
+        e1.record()
+        torch.cuda.synchronize()
+        own = torch.zeros(world, dtype=torch.float64, device=dev)
+        own[rank] = e0.elapsed_time(e1) / 3
+        dist.all_reduce(own)
+        rank_work_ms = [round(float(v), 4) for v in own.tolist()]
+        barrier()
     res = st.results()
     iters = [r["iterations"] for r in res]
     # the run must have aligned the frames for real: recovered warps vs the ground truth of the generator
@@ -599,7 +623,7 @@ def run_b200(a, rank, local_rank, world):
                        "l2": "inputs larger than L2: every step reads all frames (%.2f GB u8) from HBM" % (n * n_px * 3 / 1e9),
                        "parallelism": (f"frames sharded over {world} GPU(s), " + ("one fused reduce-scatter+divide kernel per rank over NVLink peer memory"
                                                                                    if use_peers else "one NCCL reduce")) if world > 1 else "1 GPU",
-                       "numa_bound": bool(numa_bound), "ecc_iterations_per_step": total_iters, "ecc_iterations_per_rank": iters_per_rank, "wall_ms_per_step": wall_ms / a.steps},
+                       "numa_bound": bool(numa_bound), "ecc_iterations_per_step": total_iters, "ecc_iterations_per_rank": iters_per_rank, "rank_work_ms_no_exchange": rank_work_ms, "wall_ms_per_step": wall_ms / a.steps},
             "whole_step": {"algorithmic_GBps_per_gpu": alg_bytes / (ms / a.steps * 1e-3) / 1e9 / world,
                            "frac_of_hbm_peak": alg_bytes / (ms / a.steps * 1e-3) / 1e9 / world / peak},
             "roofline": roof, "stages": stages, "cpu_baseline": cpu, "e2e": e2e, "e2e_api": e2e_api,

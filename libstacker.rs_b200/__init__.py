@@ -14,7 +14,7 @@ from .api import (  # noqa: F401
     ecc_match, keypoint_match, sharpness_tenengrad, term_criteria, EccStack, imread,
     BORDER_CONSTANT, RANSAC, prep_grey_blur, scaled_size, grey_resize_area,
     sharpness_all, sharpness_batch, sharpness_modified_laplacian, sharpness_variance_of_laplacian,
-    sharpness_normalized_gray_level_variance,
+    sharpness_normalized_gray_level_variance, clear_context_cache,
 )
 from . import _ffi, distributed  # noqa: F401
 

@@ -9,9 +9,11 @@ in the CUDA library; there is no CPU fallback.
 """
 from __future__ import annotations
 
+import atexit
 import ctypes as C
 import enum
 import os
+import threading
 from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass
 from typing import Iterable, Optional, Sequence
@@ -456,6 +458,59 @@ def _check_colour_frame(img: np.ndarray):
         raise OpenCvError("cvtColor(BGR2GRAY): input must have 3 or 4 channels")
 
 
+# ---- context cache ---------------------------------------------------------------------------------------
+# A context owns ~0.7 GB of device buffers, pinned staging and CUDA graphs for a 4K stack; creating and destroying
+# it costs 50-300 ms (cudaMalloc / cudaHostAlloc / cudaFree), several times the 19 ms the stack itself takes.  The
+# one-shot plugin calls therefore park their single-device context here and the next call with the same geometry and
+# parameters resets and reuses it.  STK_CONTEXT_CACHE=<n> bounds the idle contexts kept per process (default 2,
+# 0 disables); clear_context_cache() releases them.
+_CTX_CACHE = {}
+_CTX_CACHE_LOCK = threading.Lock()
+_CTX_CACHE_MAX = max(0, int(os.environ.get("STK_CONTEXT_CACHE", "2")))
+
+
+def _ctx_key(w, h, ch, params, device, ecc_size, seed_reference, lanes):
+    pk = None if params is None else (int(params.motion_type), params.max_count, float(params.epsilon), int(params.gauss_filt_size))
+    return (int(device), int(w), int(h), int(ch), pk, None if ecc_size is None else tuple(int(v) for v in ecc_size),
+            bool(seed_reference), int(lanes))
+
+
+def _acquire_stack(w, h, ch, params, device, ecc_size=None, seed_reference=True, lanes=0):
+    key = _ctx_key(w, h, ch, params, device, ecc_size, seed_reference, lanes)
+    with _CTX_CACHE_LOCK:
+        idle = _CTX_CACHE.get(key)
+        st = idle.pop() if idle else None
+    if st is not None:
+        try:
+            st.reset()
+            return st, key
+        except StackerError:
+            st.close()
+    return EccStack(w, h, ch, params, device=device, lanes=lanes, seed_reference=seed_reference, ecc_size=ecc_size), key
+
+
+def _release_stack(st, key, reusable: bool):
+    if reusable and _CTX_CACHE_MAX > 0:
+        with _CTX_CACHE_LOCK:
+            if sum(len(v) for v in _CTX_CACHE.values()) < _CTX_CACHE_MAX:
+                st._keep.clear()
+                _CTX_CACHE.setdefault(key, []).append(st)
+                return
+    st.close()
+
+
+def clear_context_cache():
+    """Destroy the idle contexts kept by ecc_match / keypoint_match (frees their device and pinned memory)."""
+    with _CTX_CACHE_LOCK:
+        stacks = [st for v in _CTX_CACHE.values() for st in v]
+        _CTX_CACHE.clear()
+    for st in stacks:
+        st.close()
+
+
+atexit.register(clear_context_cache)
+
+
 # ---- ecc_match: src/lib.rs:702-847 ----------------------------------------------------------------------
 def ecc_match(files: Iterable, params: EccMatchParameters, scale_down_width: Optional[float] = None, *,
               device: int = -1, devices=None, workers: Optional[int] = None, return_details: bool = False,
@@ -491,11 +546,17 @@ def ecc_match(files: Iterable, params: EccMatchParameters, scale_down_width: Opt
     if len(set(devs)) != len(devs):
         raise InvalidParams("devices must be distinct")
     stacks = []
+    cache_key, ok = None, False
     try:
-        for k, d in enumerate(devs):
-            # only the first context seeds its accumulator with the unwarped frame 0 (src/lib.rs:752-754)
-            stacks.append(EccStack(w, h, ch, params, device=d, ecc_size=ecc_size, seed_reference=(k == 0)))
-            stacks[-1].set_reference(first)
+        if len(devs) == 1:
+            st0, cache_key = _acquire_stack(w, h, ch, params, devs[0], ecc_size, True)
+            stacks.append(st0)
+            st0.set_reference(first)
+        else:
+            for k, d in enumerate(devs):
+                # only the first context seeds its accumulator with the unwarped frame 0 (src/lib.rs:752-754)
+                stacks.append(EccStack(w, h, ch, params, device=d, ecc_size=ecc_size, seed_reference=(k == 0)))
+                stacks[-1].set_reference(first)
         if len(stacks) > 1:
             EccStack.peer_connect_local(stacks)
         nd = len(stacks)
@@ -545,11 +606,16 @@ def ecc_match(files: Iterable, params: EccMatchParameters, scale_down_width: Opt
             out = _finish_on_devices(stacks, len(items), (h, w, ch))   # its sync() also raises a frame's ECC failure (src/lib.rs:777)
         if return_details:
             res = sorted((r for st in stacks for r in st.results()), key=lambda r: r["tag"])
+            ok = True
             return out, res
+        ok = True
         return out
     finally:
-        for st in stacks:
-            st.close()
+        if cache_key is not None:
+            _release_stack(stacks[0], cache_key, ok)      # a context that raised is destroyed, not reused
+        else:
+            for st in stacks:
+                st.close()
 
 
 # ---- keypoint_match: src/lib.rs:129-353 -----------------------------------------------------------------
@@ -688,7 +754,9 @@ def keypoint_match(files: Iterable, params: KeyPointMatchParameters = KeyPointMa
                 st.close()
     if devs:
         device = devs[0]
-    with EccStack(w, h, ch, None, device=device) as st:
+    st, cache_key = _acquire_stack(w, h, ch, None, device)
+    ok = False
+    try:
         st.set_reference(first)
 
         n_workers = workers or min(8, os.cpu_count() or 1)
@@ -702,7 +770,11 @@ def keypoint_match(files: Iterable, params: KeyPointMatchParameters = KeyPointMa
                 st.submit_warp(img, hm, params.border_mode, params.border_value, tag=k + 1)
         if len(items) - dropped <= 0:
             raise InvalidParams("All images discarded: try modifying KeyPointMatchParameters::match_distance_threshold")
-        return dropped, st.finish(len(items) - dropped)
+        out = st.finish(len(items) - dropped)
+        ok = True
+        return dropped, out
+    finally:
+        _release_stack(st, cache_key, ok)
 
 
 # ---- sharpness_tenengrad: src/lib.rs:1101-1147 ----------------------------------------------------------

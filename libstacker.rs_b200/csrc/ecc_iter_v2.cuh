@@ -466,6 +466,9 @@ using EccCfg14 = EccCfg<256, 16, 8, 2, 2, 3>; // geometry 2 with the premultipli
 using EccCfg15 = EccCfg<256, 8, 8, 4, 2, 3>;  // geometry 0 with the premultiplied accumulator
 using EccCfg16 = EccCfg<256, 16, 8, 2, 2, 3, 1>; // cfg 14 with the leaner pixel body (fused LOP3, scalar (u, v))
 using EccCfg17 = EccCfg<256, 16, 4, 2, 2, 3, 1>; // the same in 4-row groups
-constexpr int kEccCfgCount = 18;
+using EccCfg18 = EccCfg<512, 8, 8, 4, 1, 3, 1>;  // cfg 16's body in ONE 16-warp block per SM (all warps the same age: no old-block-first
+                                                 // scheduling skew between two co-resident blocks), 128x32 chunks, 4 stages
+using EccCfg19 = EccCfg<512, 16, 8, 2, 1, 3, 1>; // the same with 128x64 chunks, 2 stages
+constexpr int kEccCfgCount = 20;
 
 }  // namespace stk

@@ -329,6 +329,7 @@ struct stk_ecc_ctx {
   bool pdl = false;            // programmatic dependent launch between the chained iteration kernels (opt-in STK_ECC_PDL=1: measured no gain on one lane and -5 % with four, the waiting blocks hold SM slots)
   int loop_unroll = 4;         // iteration kernels per WHILE-body pass (STK_ECC_UNROLL)
   int warp_batch = stk::kWarpBatch;   // frames per final-warp launch, 1..kWarpBatch (STK_WARP_BATCH)
+  int warp_gen = 2;                   // K4 generation: 2 = word loads + guarded f32 coordinates, 1 = the round-1 kernel (STK_WARP_GEN)
   int rim_weight = 10;         // cost of a rim-strip chunk in 1/8 of an interior one (STK_ECC_RIM_WEIGHT)
   void* iter_fn = nullptr;     // the iteration kernel of this context (generation + geometry, see iter_variant)
   int iter_threads = 0, iter_smem = 0, iter_chunk_h = 0, iter_box_h = 0, iter_min_blocks = 0;
@@ -406,6 +407,8 @@ IterVariant iter_variant(int motion, bool exact, int gen, int cfg) {
     case 15: return v2_variant<stk::kHomography, false, stk::EccCfg15>();
     case 16: return v2_variant<stk::kHomography, false, stk::EccCfg16>();
     case 17: return v2_variant<stk::kHomography, false, stk::EccCfg17>();
+    case 18: return v2_variant<stk::kHomography, false, stk::EccCfg18>();
+    case 19: return v2_variant<stk::kHomography, false, stk::EccCfg19>();
     case 0: return v2_variant<stk::kHomography, false, stk::EccCfg0>();
     default: return v2_variant<stk::kHomography, false, DefaultEccCfg>();
   }
@@ -580,14 +583,35 @@ int flush_warps(stk_ecc_ctx* c, Lane& ln) {
   p.src_height = c->cfg.height;
   p.store = ln.acc_used ? 0 : 1;
   dim3 block(stk::kWarpBX, stk::kWarpBY);
-  dim3 grid((p.width + stk::kWarpBX - 1) / stk::kWarpBX, (p.height + stk::kWarpTH - 1) / stk::kWarpTH);
   const int ch = c->cfg.channels;
-  if (ch == 3) {
-    if (ln.pend_persp) stk::warp_accumulate_kernel<3, true><<<grid, block, 0, ln.stream>>>(p);
-    else stk::warp_accumulate_kernel<3, false><<<grid, block, 0, ln.stream>>>(p);
+  if (c->warp_gen == 1) {
+    // first-generation kernel (accumulator tile in shared memory, byte gathers): kept for A/B measurements, STK_WARP_GEN=1
+    dim3 grid((p.width + stk::kWarpBX - 1) / stk::kWarpBX, (p.height + stk::kWarpTH - 1) / stk::kWarpTH);
+    if (ch == 3) {
+      if (ln.pend_persp) stk::warp_accumulate_kernel<3, true><<<grid, block, 0, ln.stream>>>(p);
+      else stk::warp_accumulate_kernel<3, false><<<grid, block, 0, ln.stream>>>(p);
+    } else {
+      if (ln.pend_persp) stk::warp_accumulate_kernel<4, true><<<grid, block, 0, ln.stream>>>(p);
+      else stk::warp_accumulate_kernel<4, false><<<grid, block, 0, ln.stream>>>(p);
+    }
   } else {
-    if (ln.pend_persp) stk::warp_accumulate_kernel<4, true><<<grid, block, 0, ln.stream>>>(p);
-    else stk::warp_accumulate_kernel<4, false><<<grid, block, 0, ln.stream>>>(p);
+    dim3 grid((p.width + stk::kWarpBX - 1) / stk::kWarpBX, (p.height + stk::kWarp2TH - 1) / stk::kWarp2TH);
+    // word-index addressing in 32 bits when every frame of the batch starts and strides on a 4-byte boundary
+    bool aligned = true;
+    for (int j = 0; j < p.n; ++j)
+      aligned = aligned && (reinterpret_cast<uintptr_t>(p.f[j].src) % 4 == 0) && (p.f[j].src_pitch % 4 == 0) &&
+                (p.f[j].src_pitch * (size_t)p.src_height < ((size_t)1 << 32));
+#define STK_LAUNCH_WARP2(C, P)                                                                         \
+    do {                                                                                               \
+      if (aligned) stk::warp_accumulate_v2_kernel<C, P, true><<<grid, block, 0, ln.stream>>>(p);       \
+      else stk::warp_accumulate_v2_kernel<C, P, false><<<grid, block, 0, ln.stream>>>(p);              \
+    } while (0)
+    if (ch == 3) {
+      if (ln.pend_persp) STK_LAUNCH_WARP2(3, true); else STK_LAUNCH_WARP2(3, false);
+    } else {
+      if (ln.pend_persp) STK_LAUNCH_WARP2(4, true); else STK_LAUNCH_WARP2(4, false);
+    }
+#undef STK_LAUNCH_WARP2
   }
   c->launches++;
   ln.n_pend = 0;
@@ -923,6 +947,7 @@ int stk_ecc_create(const stk_ecc_config* cfg, stk_ecc_ctx** out) {
   if (const char* un = getenv("STK_ECC_UNROLL")) c->loop_unroll = std::max(1, std::min(16, atoi(un)));
   if (const char* rw = getenv("STK_ECC_RIM_WEIGHT")) c->rim_weight = std::max(8, std::min(32, atoi(rw)));
   if (const char* wb = getenv("STK_WARP_BATCH")) c->warp_batch = std::max(1, std::min(stk::kWarpBatch, atoi(wb)));
+  if (const char* wg = getenv("STK_WARP_GEN")) c->warp_gen = atoi(wg) == 1 ? 1 : 2;
   const char* lm = getenv("STK_LOOP_MODE");
   c->host_loop = lm && strcmp(lm, "host") == 0;
 

@@ -129,6 +129,76 @@ __device__ __forceinline__ void tile_add(float* slot, const float (&v)[C]) {
   }
 }
 
+// One destination pixel by the general rules (any map, any border mode): coordinates in f64 with OpenCV's operation
+// order and saturation, every tap either inside the source or replaced per the border mode.  (cx0 .. cw1, adelta,
+// bdelta: the per-column terms of the caller.)
+template <int C, bool PERSP>
+__device__ __forceinline__ void general_pixel(const WarpFrame& f, const double* mtx, double cx0, double cx1, double cy0, double cy1,
+                                              double cw0, double cw1, int adelta, int bdelta, int y, int sw, int sh, float (&v)[C]) {
+  const double yd = (double)y;
+  int xq, yq;
+  if (PERSP) {
+    const double X0 = __dadd_rn(__dadd_rn(cx0, __dmul_rn(mtx[1], yd)), mtx[2]);
+    const double Y0 = __dadd_rn(__dadd_rn(cy0, __dmul_rn(mtx[4], yd)), mtx[5]);
+    const double W0 = __dadd_rn(__dadd_rn(cw0, __dmul_rn(mtx[7], yd)), mtx[8]);
+    const double W = __dadd_rn(W0, cw1);
+    const double W32 = (W != 0.0) ? __dmul_rn(__drcp_rn(W), (double)kInterTab) : 0.0;      // == INTER_TAB_SIZE / W
+    // cvRound with saturation == clamp to [INT_MIN, INT_MAX] then round half to even
+    xq = __double2int_rn(__dmul_rn(__dadd_rn(X0, cx1), W32));
+    yq = __double2int_rn(__dmul_rn(__dadd_rn(Y0, cy1), W32));
+  } else {
+    const int X0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(mtx[1], yd), mtx[2]), kAbScale)) + 16;
+    const int Y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(mtx[4], yd), mtx[5]), kAbScale)) + 16;
+    xq = (int)((unsigned)X0 + (unsigned)adelta) >> (kAbBits - kInterBits);
+    yq = (int)((unsigned)Y0 + (unsigned)bdelta) >> (kAbBits - kInterBits);
+  }
+  // integer part is stored as short in OpenCV's map (saturate_cast<short>)
+  const int sx = max(-32768, min(32767, xq >> kInterBits));
+  const int sy = max(-32768, min(32767, yq >> kInterBits));
+  const float ax = (float)(xq & (kInterTab - 1)) * (1.f / kInterTab);
+  const float ay = (float)(yq & (kInterTab - 1)) * (1.f / kInterTab);
+  const float w00 = __fmul_rn(1.f - ay, 1.f - ax), w01 = __fmul_rn(1.f - ay, ax);
+  const float w10 = __fmul_rn(ay, 1.f - ax), w11 = __fmul_rn(ay, ax);
+  const float k255 = (float)(1.0 / 255.0);
+  const uint8_t* r0 = f.src + (ptrdiff_t)sy * (ptrdiff_t)f.src_pitch + (ptrdiff_t)sx * C;
+  const uint8_t* r1 = r0 + f.src_pitch;
+  if ((unsigned)sx < (unsigned)(sw - 1) && (unsigned)sy < (unsigned)(sh - 1)) {
+    // all four taps inside the source: the common case, no border logic
+    unsigned t00[C], t01[C], t10[C], t11[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) { t00[c] = __ldg(r0 + c); t01[c] = __ldg(r0 + C + c); t10[c] = __ldg(r1 + c); t11[c] = __ldg(r1 + C + c); }
+    blend_taps<C>(t00, t01, t10, t11, w00, w01, w10, w11, v);
+  } else if (f.border_mode != 0) {
+    // REPLICATE / REFLECT / WRAP / REFLECT_101: each tap's coordinates go through borderInterpolate on their own
+    const int x0 = border_index(sx, sw, f.border_mode), x1 = border_index(sx + 1, sw, f.border_mode);
+    const int y0 = border_index(sy, sh, f.border_mode), y1 = border_index(sy + 1, sh, f.border_mode);
+    const uint8_t* q0 = f.src + (size_t)y0 * f.src_pitch;
+    const uint8_t* q1 = f.src + (size_t)y1 * f.src_pitch;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float s00 = __fmul_rn((float)__ldg(q0 + x0 * C + c), k255), s01 = __fmul_rn((float)__ldg(q0 + x1 * C + c), k255);
+      const float s10 = __fmul_rn((float)__ldg(q1 + x0 * C + c), k255), s11 = __fmul_rn((float)__ldg(q1 + x1 * C + c), k255);
+      v[c] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s00, w00), __fmul_rn(s01, w01)), __fmul_rn(s10, w10)),
+                       __fmul_rn(s11, w11));
+    }
+  } else if (sx >= sw || sx + 1 < 0 || sy >= sh || sy + 1 < 0) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) v[c] = f.border[c];
+  } else {
+    const bool x0in = (unsigned)sx < (unsigned)sw, x1in = (unsigned)(sx + 1) < (unsigned)sw;
+    const bool y0in = (unsigned)sy < (unsigned)sh, y1in = (unsigned)(sy + 1) < (unsigned)sh;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float s00 = (y0in && x0in) ? __fmul_rn((float)__ldg(r0 + c), k255) : f.border[c];
+      const float s01 = (y0in && x1in) ? __fmul_rn((float)__ldg(r0 + C + c), k255) : f.border[c];
+      const float s10 = (y1in && x0in) ? __fmul_rn((float)__ldg(r1 + c), k255) : f.border[c];
+      const float s11 = (y1in && x1in) ? __fmul_rn((float)__ldg(r1 + C + c), k255) : f.border[c];
+      v[c] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s00, w00), __fmul_rn(s01, w01)), __fmul_rn(s10, w10)),
+                       __fmul_rn(s11, w11));
+    }
+  }
+}
+
 // One frame's contribution to the block's 32 x 32 tile: the C interpolated values of each of the thread's four pixels
 // are ADDED to the accumulator tile s_acc (tile row r at s_acc + r * 32 * C).  Every thread owns its pixels' slots for
 // the whole launch, so consecutive frames need no barrier.  mtx = the frame's inverse map (9 doubles, shared memory).
@@ -209,72 +279,9 @@ __device__ __forceinline__ void warp_tile(const WarpFrame& f, const double* mtx,
 #pragma unroll
   for (int rr = 0; rr < kWarpRows; ++rr) {
     const int y = y_base + rr * kWarpBY;
-    float v[C];
-#pragma unroll
-    for (int c = 0; c < C; ++c) v[c] = 0.f;
     if (x < width && y < height) {
-      const double yd = (double)y;
-      int xq, yq;
-      if (PERSP) {
-        const double X0 = __dadd_rn(__dadd_rn(cx0, __dmul_rn(mtx[1], yd)), mtx[2]);
-        const double Y0 = __dadd_rn(__dadd_rn(cy0, __dmul_rn(mtx[4], yd)), mtx[5]);
-        const double W0 = __dadd_rn(__dadd_rn(cw0, __dmul_rn(mtx[7], yd)), mtx[8]);
-        const double W = __dadd_rn(W0, cw1);
-        const double W32 = (W != 0.0) ? __dmul_rn(__drcp_rn(W), (double)kInterTab) : 0.0;      // == INTER_TAB_SIZE / W
-        // cvRound with saturation == clamp to [INT_MIN, INT_MAX] then round half to even
-        xq = __double2int_rn(__dmul_rn(__dadd_rn(X0, cx1), W32));
-        yq = __double2int_rn(__dmul_rn(__dadd_rn(Y0, cy1), W32));
-      } else {
-        const int X0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(mtx[1], yd), mtx[2]), kAbScale)) + 16;
-        const int Y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(mtx[4], yd), mtx[5]), kAbScale)) + 16;
-        xq = (int)((unsigned)X0 + (unsigned)adelta) >> (kAbBits - kInterBits);
-        yq = (int)((unsigned)Y0 + (unsigned)bdelta) >> (kAbBits - kInterBits);
-      }
-      // integer part is stored as short in OpenCV's map (saturate_cast<short>)
-      const int sx = max(-32768, min(32767, xq >> kInterBits));
-      const int sy = max(-32768, min(32767, yq >> kInterBits));
-      const float ax = (float)(xq & (kInterTab - 1)) * (1.f / kInterTab);
-      const float ay = (float)(yq & (kInterTab - 1)) * (1.f / kInterTab);
-      const float w00 = __fmul_rn(1.f - ay, 1.f - ax), w01 = __fmul_rn(1.f - ay, ax);
-      const float w10 = __fmul_rn(ay, 1.f - ax), w11 = __fmul_rn(ay, ax);
-      const float k255 = (float)(1.0 / 255.0);
-      const uint8_t* r0 = f.src + (ptrdiff_t)sy * (ptrdiff_t)f.src_pitch + (ptrdiff_t)sx * C;
-      const uint8_t* r1 = r0 + f.src_pitch;
-      if ((unsigned)sx < (unsigned)(sw - 1) && (unsigned)sy < (unsigned)(sh - 1)) {
-        // all four taps inside the source: the common case, no border logic
-        unsigned t00[C], t01[C], t10[C], t11[C];
-#pragma unroll
-        for (int c = 0; c < C; ++c) { t00[c] = __ldg(r0 + c); t01[c] = __ldg(r0 + C + c); t10[c] = __ldg(r1 + c); t11[c] = __ldg(r1 + C + c); }
-        blend_taps<C>(t00, t01, t10, t11, w00, w01, w10, w11, v);
-      } else if (f.border_mode != 0) {
-        // REPLICATE / REFLECT / WRAP / REFLECT_101: each tap's coordinates go through borderInterpolate on their own
-        const int x0 = border_index(sx, sw, f.border_mode), x1 = border_index(sx + 1, sw, f.border_mode);
-        const int y0 = border_index(sy, sh, f.border_mode), y1 = border_index(sy + 1, sh, f.border_mode);
-        const uint8_t* q0 = f.src + (size_t)y0 * f.src_pitch;
-        const uint8_t* q1 = f.src + (size_t)y1 * f.src_pitch;
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-          const float s00 = __fmul_rn((float)__ldg(q0 + x0 * C + c), k255), s01 = __fmul_rn((float)__ldg(q0 + x1 * C + c), k255);
-          const float s10 = __fmul_rn((float)__ldg(q1 + x0 * C + c), k255), s11 = __fmul_rn((float)__ldg(q1 + x1 * C + c), k255);
-          v[c] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s00, w00), __fmul_rn(s01, w01)), __fmul_rn(s10, w10)),
-                           __fmul_rn(s11, w11));
-        }
-      } else if (sx >= sw || sx + 1 < 0 || sy >= sh || sy + 1 < 0) {
-#pragma unroll
-        for (int c = 0; c < C; ++c) v[c] = f.border[c];
-      } else {
-        const bool x0in = (unsigned)sx < (unsigned)sw, x1in = (unsigned)(sx + 1) < (unsigned)sw;
-        const bool y0in = (unsigned)sy < (unsigned)sh, y1in = (unsigned)(sy + 1) < (unsigned)sh;
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-          const float s00 = (y0in && x0in) ? __fmul_rn((float)__ldg(r0 + c), k255) : f.border[c];
-          const float s01 = (y0in && x1in) ? __fmul_rn((float)__ldg(r0 + C + c), k255) : f.border[c];
-          const float s10 = (y1in && x0in) ? __fmul_rn((float)__ldg(r1 + c), k255) : f.border[c];
-          const float s11 = (y1in && x1in) ? __fmul_rn((float)__ldg(r1 + C + c), k255) : f.border[c];
-          v[c] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s00, w00), __fmul_rn(s01, w01)), __fmul_rn(s10, w10)),
-                           __fmul_rn(s11, w11));
-        }
-      }
+      float v[C];
+      general_pixel<C, PERSP>(f, mtx, cx0, cx1, cy0, cy1, cw0, cw1, adelta, bdelta, y, sw, sh, v);
       tile_add<C>(s_acc + (threadIdx.y + rr * kWarpBY) * kRow + threadIdx.x * C, v);
     }
   }
@@ -351,6 +358,343 @@ __global__ void __launch_bounds__(kWarpBX * kWarpBY, 8) warp_accumulate_kernel(c
     for (int i = tid; i < kTile; i += kThreads) {
       const int r = i / kRow, q = i - r * kRow;
       if (ty0 + r < p.height && q < row_elems) p.acc[(size_t)(ty0 + r) * p.width * C + row_base + q] = s_acc[i];
+    }
+  }
+}
+
+// ---- K4, second generation ------------------------------------------------------------------------------
+// Same results, bit for bit (same tests), rebuilt around what the round-2 ncu capture of the kernel above showed
+// (profiles/r2_ncu_raw_warp_accumulate.csv): 171 warp-instructions per pixel and the L1 data pipe at 85 % — 12 byte
+// gathers + 12 conversions per pixel, the nine matrix entries re-read from shared memory for every pixel and 12
+// local-memory (spill) accesses per pixel because of the 32-register cap that the occupancy needed, plus 23 FP64
+// operations per pixel for the coordinates.
+//   * taps as aligned 32-bit words: the two horizontal taps of a source row are 2*C contiguous bytes; three aligned
+//     words cover them for any alignment, PRMT shifts them into place and splices each byte under the exponent of
+//     2^23, and ONE fused multiply-add turns that into fl(byte * fl(1/255)) exactly (2^23 * k is exact, so
+//     fma(2^23 + b, k, -2^23 k) rounds b*k once): 6 loads per pixel instead of 12, no conversion instruction;
+//   * perspective coordinates by guarded f32: the displacement (u - x, v - y) of a projective map is a ratio of
+//     per-column polynomials in y (as in the ECC kernel's FastPersp), evaluated in f32 from constants prepared in
+//     f64.  Its error is bounded per column (see FastInv::band); a pixel whose 32*displacement lands closer than that
+//     to a rounding boundary — about one in a thousand — recomputes in f64 with OpenCV's operation order, so the
+//     quantised coordinates are those of cv2.warpPerspective for every pixel;
+//   * the per-column constants and the interior test of every frame of the batch are computed ONCE per block (warp j
+//     does frame j, lane = column) into shared memory, before the block's only barrier — the first build had every
+//     thread redo them per frame: 135 of its 149 instructions per pixel-frame went there and into 64-bit addressing;
+//   * the accumulator slice lives in registers for the whole launch, 64 registers per thread: nothing spills, and the
+//     24 independent word loads of a thread's four pixels hide the L2 latency that the old kernel needed 64 warps per
+//     SM for.
+constexpr int kWarp2Rows = 4;
+constexpr int kWarp2TH = kWarpBY * kWarp2Rows;
+constexpr int kFastInvN = 8;               // floats per column and frame, see FastInv
+
+__device__ __forceinline__ float2 fma2_rn_exact(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n .reg .b64 ra, rb, rc, rd;\n mov.b64 ra, {%2, %3};\n mov.b64 rb, {%4, %5};\n mov.b64 rc, {%6, %7};\n"
+      " fma.rn.f32x2 rd, ra, rb, rc;\n mov.b64 {%0, %1}, rd;\n}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+// PRMT in its default mode; selector nibbles stay below 8 here, so no masking is needed (__byte_perm adds one)
+__device__ __forceinline__ unsigned prmt(unsigned a, unsigned b, unsigned sel) {
+  unsigned d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+
+// Per-column (destination x) constants of one frame's inverse map for the guarded f32 coordinates:
+//   u - x = (alpha + beta y) / W(y),   v - y = (gamma + (delta - m7 y) y) / W(y),   W(y) = wc + m7 y,
+// held pre-multiplied by 32 (exact), so that t = n * rcp(W) is the displacement in 1/32-px quanta.
+struct FastInv {
+  float a32, b32, g32, d32, m7_32, wc, m7, thr;     // thr = 0.5 - band
+  // y_lo, y_hi: the rows of the tile.  band bounds |t_f32 - t_exact| for both coordinates:
+  //   coefficient roundings + the fmas: <= 3 * 2^-24 * S with S = the sum of the absolute terms of the numerator;
+  //   W: two coefficient roundings + one fma, rcp.approx.ftz: 2^-23, the product: 2^-24 — < 9 * 2^-24 relative to |t| <= S / W;
+  // 12 * 2^-24 * S / Wmin covers both with margin; the floor 2^-18 covers the f64 side's own rounding (< 2^-30).
+  // W outside [1/4, 4] (far from the affine-like maps this path is for) or displacements beyond the range of the
+  // magic-constant rounding: thr < 0 sends every pixel of the column through the exact evaluation.
+  __device__ __forceinline__ void init(const double* m, int x, float y_lo, float y_hi) {
+    const double xd = (double)x;
+    const double wcd = m[6] * xd + m[8];
+    a32 = (float)(32.0 * (xd * (m[0] - wcd) + m[2]));
+    b32 = (float)(32.0 * (m[1] - m[7] * xd));
+    g32 = (float)(32.0 * (m[3] * xd + m[5]));
+    d32 = (float)(32.0 * (m[4] - wcd));
+    m7_32 = (float)(32.0 * m[7]);
+    wc = (float)wcd;
+    m7 = (float)m[7];
+    const float su = fabsf(a32) + fabsf(b32) * y_hi;
+    const float sv = fabsf(g32) + (fabsf(d32) + fabsf(m7_32) * y_hi) * y_hi;
+    const float w_lo = fmaf(m7, y_lo, wc), w_hi = fmaf(m7, y_hi, wc);
+    const float wmin = fminf(w_lo, w_hi) * 0.99f;
+    const bool ok = wmin > 0.25f && fmaxf(w_lo, w_hi) < 4.0f && fmaxf(su, sv) < 1.0e6f;
+    thr = ok ? 0.5f - fmaf(fmaxf(su, sv) / wmin, 12.0f / 16777216.0f, 1.0f / 262144.0f) : -1.0f;
+  }
+};
+
+// The two adjacent taps of a source row are 2*C contiguous bytes that start `o` bytes into the aligned word at wp: three
+// words cover them for any o in 0..3 (C == 4 with o == 0 needs two).  Loading and converting are separate steps so that
+// a thread can have the words of all its pixels in flight before it touches the first.
+struct TapWords { unsigned w0, w1, w2; };
+template <int C>
+__device__ __forceinline__ TapWords load_tap_words(const unsigned* wp, unsigned o) {
+  TapWords t;
+  t.w0 = __ldg(wp); t.w1 = __ldg(wp + 1);
+  t.w2 = 0;
+  if (C == 3 || o != 0) t.w2 = __ldg(wp + 2);
+  return t;
+}
+// s0[c], s1[c] = fl(byte * fl(1/255)) of the two taps: PRMT shifts the bytes into place and splices each under the
+// exponent of 2^23; fma(2^23 + b, k, -2^23 k) rounds b*k once because 2^23 k is exact
+template <int C>
+__device__ __forceinline__ void convert_tap_pair(const TapWords& t, unsigned o, float (&s0)[C], float (&s1)[C]) {
+  const unsigned sel = 0x3210u + 0x1111u * o;
+  const unsigned A = prmt(t.w0, t.w1, sel), B = prmt(t.w1, t.w2, sel);      // bytes 0..3 and 4..7 of the pair
+  constexpr unsigned kMagic = 0x4B000000u;                                   // 2^23
+  const float k255 = (float)(1.0 / 255.0);
+  const float kc = -8388608.0f * k255;                                       // exact
+  unsigned b[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { b[i] = prmt(A, kMagic, 0x7540u + i); b[4 + i] = prmt(B, kMagic, 0x7540u + i); }
+  float v[8];
+#pragma unroll
+  for (int i = 0; i + 1 < 2 * C; i += 2) {
+    const float2 r = fma2_rn_exact(make_float2(__uint_as_float(b[i]), __uint_as_float(b[i + 1])), make_float2(k255, k255),
+                                   make_float2(kc, kc));
+    v[i] = r.x; v[i + 1] = r.y;
+  }
+#pragma unroll
+  for (int c = 0; c < C; ++c) { s0[c] = v[c]; s1[c] = v[C + c]; }
+}
+
+// value = s00*w00 + s01*w01 + s10*w10 + s11*w11, left to right in f32, on converted taps (see blend_taps)
+template <int C>
+__device__ __forceinline__ void blend_vals(const float (&s00)[C], const float (&s01)[C], const float (&s10)[C],
+                                           const float (&s11)[C], float w00, float w01, float w10, float w11, float (&out)[C]) {
+  constexpr int P = C / 2;
+#pragma unroll
+  for (int q = 0; q < P; ++q) {
+    const float2 p00 = mul2_rn_exact(make_float2(s00[2 * q], s00[2 * q + 1]), make_float2(w00, w00));
+    const float2 p01 = mul2_rn_exact(make_float2(s01[2 * q], s01[2 * q + 1]), make_float2(w01, w01));
+    const float2 p10 = mul2_rn_exact(make_float2(s10[2 * q], s10[2 * q + 1]), make_float2(w10, w10));
+    const float2 p11 = mul2_rn_exact(make_float2(s11[2 * q], s11[2 * q + 1]), make_float2(w11, w11));
+    out[2 * q] = __fadd_rn(__fadd_rn(__fadd_rn(p00.x, p01.x), p10.x), p11.x);
+    out[2 * q + 1] = __fadd_rn(__fadd_rn(__fadd_rn(p00.y, p01.y), p10.y), p11.y);
+  }
+  if (C & 1) {
+    constexpr int c = C - 1;
+    out[c] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s00[c], w00), __fmul_rn(s01[c], w01)), __fmul_rn(s10[c], w10)), __fmul_rn(s11[c], w11));
+  }
+}
+
+// Interior test of one frame for the block's tile, evaluated by one warp (lanes 0-3 take one corner each): the four
+// corners land inside the source with w > 0 (then every pixel of the tile does: a projective map with w > 0 sends the
+// rectangle into the hull of its corner images; the 1/16 px slack covers the 1/32-px quantisation), with the margins
+// the word loads need — taps from column 1 on (an aligned word may start 3 bytes before the tap) and three columns short
+// of the last one (it may end 6 bytes after the second tap) — and the tile lies inside the destination.
+template <bool PERSP>
+__device__ __forceinline__ bool tile_is_interior(const double* mtx, int lane, int width, int height, int sw, int sh) {
+  bool lean = blockIdx.x * kWarpBX + kWarpBX <= width && blockIdx.y * kWarp2TH + kWarp2TH <= height;
+  const int k = lane & 3;
+  const double cxk = (double)(blockIdx.x * kWarpBX + ((k & 1) ? kWarpBX - 1 : 0));
+  const double cyk = (double)(blockIdx.y * kWarp2TH + ((k & 2) ? kWarp2TH - 1 : 0));
+  const double nu = mtx[0] * cxk + mtx[1] * cyk + mtx[2], nv = mtx[3] * cxk + mtx[4] * cyk + mtx[5];
+  const double ww = PERSP ? mtx[6] * cxk + mtx[7] * cyk + mtx[8] : 1.0;
+  const double ulo = 1.0625 * ww, vlo = 0.0625 * ww;
+  const double uhi = ((double)(sw - 3) - 0.0625) * ww, vhi = ((double)(sh - 1) - 0.0625) * ww;
+  return __all_sync(0xffffffffu, lean && ww > 1e-9 && ww < 1e9 && nu >= ulo && nu < uhi && nv >= vlo && nv < vhi);
+}
+
+// One frame's contribution to the thread's kWarp2Rows pixels (column x, rows y_base + rr * kWarpBY), added to acc.
+//   fic: this column's FastInv constants in shared memory (stride 32 floats), lean: the tile is interior for this frame
+//   ALIGNED: the frame's base address and pitch are multiples of 4 (word index arithmetic in 32 bits)
+template <int C, bool PERSP, bool ALIGNED>
+__device__ __forceinline__ void warp_tile_v2(const WarpFrame& f, const double* __restrict__ mtx, const float* fic, bool lean,
+                                             float (&acc)[kWarp2Rows][C], int width, int height, int sw, int sh) {
+  const int x = blockIdx.x * kWarpBX + threadIdx.x;
+  const int y_base = blockIdx.y * kWarp2TH + threadIdx.y;
+
+  if (lean) {
+    float a32 = 0.f, b32 = 0.f, g32 = 0.f, d32 = 0.f, m7_32 = 0.f, wc = 0.f, m7 = 0.f, thr = 0.f;
+    int adelta = 0, bdelta = 0;
+    if (PERSP) {
+      a32 = fic[0]; b32 = fic[32]; g32 = fic[64]; d32 = fic[96]; m7_32 = fic[128]; wc = fic[160]; m7 = fic[192]; thr = fic[224];
+    } else {
+      adelta = __float_as_int(fic[0]);
+      bdelta = __float_as_int(fic[32]);
+    }
+    const unsigned pitch_w = (unsigned)(f.src_pitch >> 2);
+    // phase 1: quantised source coordinates of the thread's pixels (the only phase with a data-dependent branch)
+    int xq[kWarp2Rows], yq[kWarp2Rows];
+#pragma unroll
+    for (int rr = 0; rr < kWarp2Rows; ++rr) {
+      const int y = y_base + rr * kWarpBY;
+      if (PERSP) {
+        const float yf = (float)y;
+        float r;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(m7, yf, wc)));
+        const float tu = fmaf(b32, yf, a32) * r;
+        const float tv = fmaf(fmaf(-m7_32, yf, d32), yf, g32) * r;
+        const float qu = tu + 12582912.0f, qv = tv + 12582912.0f;      // rint through the 1.5 * 2^23 magic constant
+        const float fu = tu - (qu - 12582912.0f), fv = tv - (qv - 12582912.0f);
+        xq[rr] = (x << kInterBits) + (__float_as_int(qu) - 0x4B400000);
+        yq[rr] = (y << kInterBits) + (__float_as_int(qv) - 0x4B400000);
+        if (fmaxf(fabsf(fu), fabsf(fv)) > thr) {
+          // too close to a rounding boundary for the f32 evaluation (or outside its range): OpenCV's own f64 sequence
+          const int xb = width >= 64 ? (x & ~63) : 0;
+          const double xbd = (double)xb, x1 = (double)(x - xb), yd = (double)y;
+          const double X0 = __dadd_rn(__dadd_rn(__dmul_rn(mtx[0], xbd), __dmul_rn(mtx[1], yd)), mtx[2]);
+          const double Y0 = __dadd_rn(__dadd_rn(__dmul_rn(mtx[3], xbd), __dmul_rn(mtx[4], yd)), mtx[5]);
+          const double W0 = __dadd_rn(__dadd_rn(__dmul_rn(mtx[6], xbd), __dmul_rn(mtx[7], yd)), mtx[8]);
+          const double W32 = __dmul_rn(rcp_rn_normal(__dadd_rn(W0, __dmul_rn(mtx[6], x1))), (double)kInterTab);
+          xq[rr] = rint_magic(__dmul_rn(__dadd_rn(X0, __dmul_rn(mtx[0], x1)), W32));
+          yq[rr] = rint_magic(__dmul_rn(__dadd_rn(Y0, __dmul_rn(mtx[3], x1)), W32));
+        }
+      } else {
+        const double yd = (double)y;
+        const int X0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(mtx[1], yd), mtx[2]), kAbScale)) + 16;
+        const int Y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(mtx[4], yd), mtx[5]), kAbScale)) + 16;
+        xq[rr] = (int)((unsigned)X0 + (unsigned)adelta) >> (kAbBits - kInterBits);
+        yq[rr] = (int)((unsigned)Y0 + (unsigned)bdelta) >> (kAbBits - kInterBits);
+      }
+    }
+    // phase 2: all tap words of all pixels in flight (6 loads per pixel)
+    TapWords t0[kWarp2Rows], t1[kWarp2Rows];
+    unsigned o0[kWarp2Rows], o1[kWarp2Rows];
+#pragma unroll
+    for (int rr = 0; rr < kWarp2Rows; ++rr) {
+      if (ALIGNED) {
+        // interior: both integer positions are non-negative and the frame is < 4 GiB, so 32-bit word indices do
+        const unsigned bx = (unsigned)(xq[rr] >> kInterBits) * C;
+        const unsigned wi = (unsigned)(yq[rr] >> kInterBits) * pitch_w + (bx >> 2);
+        const unsigned* base = reinterpret_cast<const unsigned*>(f.src);
+        o0[rr] = o1[rr] = bx & 3u;
+        t0[rr] = load_tap_words<C>(base + wi, o0[rr]);
+        t1[rr] = load_tap_words<C>(base + (wi + pitch_w), o1[rr]);
+      } else {
+        const uint8_t* r0 = f.src + (ptrdiff_t)(yq[rr] >> kInterBits) * (ptrdiff_t)f.src_pitch + (xq[rr] >> kInterBits) * C;
+        const uintptr_t u0 = reinterpret_cast<uintptr_t>(r0), u1 = u0 + f.src_pitch;
+        o0[rr] = (unsigned)u0 & 3u; o1[rr] = (unsigned)u1 & 3u;
+        t0[rr] = load_tap_words<C>(reinterpret_cast<const unsigned*>(u0 & ~(uintptr_t)3), o0[rr]);
+        t1[rr] = load_tap_words<C>(reinterpret_cast<const unsigned*>(u1 & ~(uintptr_t)3), o1[rr]);
+      }
+    }
+    // phase 3: weights, conversion, blend, accumulate
+#pragma unroll
+    for (int rr = 0; rr < kWarp2Rows; ++rr) {
+      // fractions k/32 spliced under the 1.5 * 2^23 exponent: (2^23 * 1.5 + k) / 32 - 2^23 * 1.5 / 32 is exact
+      const float ax = fmaf(__int_as_float((xq[rr] & (kInterTab - 1)) | 0x4B400000), 1.f / kInterTab, -12582912.0f / kInterTab);
+      const float ay = fmaf(__int_as_float((yq[rr] & (kInterTab - 1)) | 0x4B400000), 1.f / kInterTab, -12582912.0f / kInterTab);
+      const float w00 = __fmul_rn(1.f - ay, 1.f - ax), w01 = __fmul_rn(1.f - ay, ax);
+      const float w10 = __fmul_rn(ay, 1.f - ax), w11 = __fmul_rn(ay, ax);
+      float s00[C], s01[C], s10[C], s11[C], v[C];
+      convert_tap_pair<C>(t0[rr], o0[rr], s00, s01);
+      convert_tap_pair<C>(t1[rr], o1[rr], s10, s11);
+      blend_vals<C>(s00, s01, s10, s11, w00, w01, w10, w11, v);
+#pragma unroll
+      for (int c = 0; c < C; ++c) acc[rr][c] = __fadd_rn(acc[rr][c], v[c]);
+    }
+    return;
+  }
+
+  // rim tiles and maps that leave the source: the general per-pixel path (every tap by its own rule)
+  double cx0 = 0, cx1 = 0, cy0 = 0, cy1 = 0, cw0 = 0, cw1 = 0;
+  int adelta = 0, bdelta = 0;
+  if (PERSP) {
+    const int xb = width >= 64 ? (x & ~63) : 0;
+    const double xbd = (double)xb, x1 = (double)(x - xb);
+    cx0 = __dmul_rn(mtx[0], xbd); cx1 = __dmul_rn(mtx[0], x1);
+    cy0 = __dmul_rn(mtx[3], xbd); cy1 = __dmul_rn(mtx[3], x1);
+    cw0 = __dmul_rn(mtx[6], xbd); cw1 = __dmul_rn(mtx[6], x1);
+  } else {
+    const double xd = (double)x;
+    adelta = __double2int_rn(__dmul_rn(__dmul_rn(mtx[0], xd), kAbScale));
+    bdelta = __double2int_rn(__dmul_rn(__dmul_rn(mtx[3], xd), kAbScale));
+  }
+#pragma unroll 1
+  for (int rr = 0; rr < kWarp2Rows; ++rr) {
+    const int y = y_base + rr * kWarpBY;
+    if (x < width && y < height) {
+      float v[C];
+      general_pixel<C, PERSP>(f, mtx, cx0, cx1, cy0, cy1, cw0, cw1, adelta, bdelta, y, sw, sh, v);
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        // dynamic rr: select the row's slot without indexing the register array
+#pragma unroll
+        for (int q = 0; q < kWarp2Rows; ++q) if (q == rr) acc[q][c] = __fadd_rn(acc[q][c], v[c]);
+      }
+    }
+  }
+}
+
+template <int C, bool PERSP, bool ALIGNED>
+__global__ void __launch_bounds__(kWarpBX * kWarpBY, 4) warp_accumulate_v2_kernel(const __grid_constant__ WarpAccParams p) {
+  __shared__ double s_m[kWarpBatch][9];
+  __shared__ float s_fi[kWarpBatch][kFastInvN][kWarpBX];
+  __shared__ int s_flag[kWarpBatch];              // bit 0: skip the frame (failed ECC), bit 1: interior tile
+  const int tid = threadIdx.y * kWarpBX + threadIdx.x;
+  if (tid < 9 * p.n) {
+    const int j = tid / 9, i = tid - 9 * j;
+    s_m[j][i] = p.f[j].inv_ptr ? p.f[j].inv_ptr[i] : p.f[j].inv[i];
+  }
+  if ((int)threadIdx.y < p.n) {
+    // warp j prepares frame j: interior test of the tile, per-column constants (lane = column)
+    const int j = threadIdx.y, lane = threadIdx.x;
+    double m[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) m[i] = p.f[j].inv_ptr ? p.f[j].inv_ptr[i] : p.f[j].inv[i];
+    const bool lean = tile_is_interior<PERSP>(m, lane, p.width, p.height, p.src_width, p.src_height);
+    const int x = blockIdx.x * kWarpBX + lane;
+    if (PERSP) {
+      FastInv fi;
+      fi.init(m, x, (float)(blockIdx.y * kWarp2TH), (float)(blockIdx.y * kWarp2TH + kWarp2TH - 1));
+      s_fi[j][0][lane] = fi.a32; s_fi[j][1][lane] = fi.b32; s_fi[j][2][lane] = fi.g32; s_fi[j][3][lane] = fi.d32;
+      s_fi[j][4][lane] = fi.m7_32; s_fi[j][5][lane] = fi.wc; s_fi[j][6][lane] = fi.m7; s_fi[j][7][lane] = fi.thr;
+    } else {
+      const double xd = (double)x;
+      s_fi[j][0][lane] = __int_as_float(__double2int_rn(__dmul_rn(__dmul_rn(m[0], xd), kAbScale)));
+      s_fi[j][1][lane] = __int_as_float(__double2int_rn(__dmul_rn(__dmul_rn(m[3], xd), kAbScale)));
+    }
+    if (lane == 0) s_flag[j] = ((p.f[j].status_ptr && *p.f[j].status_ptr != 0) ? 1 : 0) | (lean ? 2 : 0);
+  }
+
+  const int x = blockIdx.x * kWarpBX + threadIdx.x;
+  const int y_base = blockIdx.y * kWarp2TH + threadIdx.y;
+  const size_t row_floats = (size_t)p.width * C;
+  const bool vec4 = C == 4 && ((reinterpret_cast<uintptr_t>(p.acc) & 15) == 0);
+  float acc[kWarp2Rows][C];
+#pragma unroll
+  for (int rr = 0; rr < kWarp2Rows; ++rr) {
+    const int y = y_base + rr * kWarpBY;
+    const bool in = x < p.width && y < p.height && !p.store;
+    const float* src = p.acc + (size_t)y * row_floats + (size_t)x * C;
+    if (C == 4 && vec4) {
+      const float4 a = in ? *reinterpret_cast<const float4*>(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+      acc[rr][0] = a.x; acc[rr][1] = a.y; acc[rr][2] = a.z; acc[rr][C - 1] = a.w;
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) acc[rr][c] = in ? src[c] : 0.f;
+    }
+  }
+  __syncthreads();
+
+  for (int j = 0; j < p.n; ++j) {
+    const int flag = s_flag[j];                                // block-uniform
+    if (flag & 1) continue;
+    warp_tile_v2<C, PERSP, ALIGNED>(p.f[j], s_m[j], &s_fi[j][0][threadIdx.x], (flag & 2) != 0, acc, p.width, p.height,
+                                    p.src_width, p.src_height);
+  }
+
+#pragma unroll
+  for (int rr = 0; rr < kWarp2Rows; ++rr) {
+    const int y = y_base + rr * kWarpBY;
+    if (x < p.width && y < p.height) {
+      float* dst = p.acc + (size_t)y * row_floats + (size_t)x * C;
+      if (C == 4 && vec4) {
+        *reinterpret_cast<float4*>(dst) = make_float4(acc[rr][0], acc[rr][1], acc[rr][2], acc[rr][C - 1]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < C; ++c) dst[c] = acc[rr][c];
+      }
     }
   }
 }

@@ -346,6 +346,32 @@ def test_ecc_errors(pkg):
     assert np.array_equal(out, R.to_f32_unit(frames[0]))
 
 
+def test_context_cache_reuse_and_failure(pkg):
+    """The one-shot plugin calls park their context and reuse it for the next call of the same geometry: identical
+    results, a separate context per parameter set, a context whose call raised is destroyed rather than reused."""
+    api = pkg.api
+    w, h = 256, 192
+    frames = synth.Stack(w, h, 5, 3, seed=12).frames()
+    p1 = pkg.EccMatchParameters(pkg.MotionType.Homography, 5000, 1e-5, 5)
+    p2 = pkg.EccMatchParameters(pkg.MotionType.Affine, 50, 1e-4, 3)
+    pkg.clear_context_cache()
+    a, ra = pkg.ecc_match(frames, p1, None, device=0, return_details=True)
+    assert sum(len(v) for v in api._CTX_CACHE.values()) == 1
+    b, rb = pkg.ecc_match(frames, p1, None, device=0, return_details=True)
+    assert np.array_equal(a, b) and all(np.array_equal(x["warp"], y["warp"]) for x, y in zip(ra, rb))
+    assert sum(len(v) for v in api._CTX_CACHE.values()) == 1          # the same context went back
+    c = pkg.ecc_match(frames, p2, None, device=0)
+    assert len(api._CTX_CACHE) == 2 and not np.array_equal(a, c)
+    flat = np.full((h, w, 3), 7, np.uint8)
+    with pytest.raises(pkg.OpenCvError):
+        pkg.ecc_match([frames[0], flat], p1, None, device=0)
+    assert sum(len(v) for v in api._CTX_CACHE.values()) == 1          # p1's context was destroyed, p2's is still parked
+    d = pkg.ecc_match(frames, p1, None, device=0)
+    assert np.array_equal(a, d)
+    pkg.clear_context_cache()
+    assert not api._CTX_CACHE
+
+
 def test_lanes_and_device_resident_input(pkg):
     """Same stack through 1 lane / 4 lanes, host and device-resident frames: identical warps, stack equal
     up to f32 summation order."""
