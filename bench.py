@@ -309,33 +309,94 @@ def run_b200(a, rank, local_rank, world):
             names = ["reset+set_reference", "submit", "partial(sync+lane sum)", "reduce", "finish"]
             print(f"TRACE rank{rank} " + " ".join(f"{k}={1e3 * (b - a):.3f}ms" for k, a, b in zip(names, t, t[1:])), file=sys.stderr)
 
-    def step_e2e():
-        st.reset()
-        st.set_reference(pinned_np[0])
+    # ---- end-to-end leg: host frames in, finished stack back on the host, through EccStack -------------------------
+    # Two contexts take the stacks alternately: while one stack's tail (last alignments, exchange, copy-out of the result)
+    # is still in flight, the uploads of the next stack are already queued on the other context — PCIe is full duplex and
+    # the host never waits for a stack before feeding the next.  Every stack's result is read back inside the timed
+    # region (the last one by the drain).  N > 1: frame 0 is uploaded by rank 0 only and reaches the other ranks over
+    # NVLink (NCCL broadcast on torch's stream; set_reference orders itself behind that stream, ABI v5).
+    e2e_slots = []
+
+    def make_e2e_slots():
+        stacks = [st]
+        if os.environ.get("STK_E2E_PINGPONG", "1") != "0":
+            st2 = pkg.EccStack(w, h, 3, params, device=local_rank, lanes=a.lanes, seed_reference=(rank == 0))
+            ok2 = (not use_peers) or D.connect_peers(st2)
+            if ok2:
+                stacks.append(st2)
+            else:
+                st2.close()
+        for k, s_ in enumerate(stacks):
+            sh = shared_host if k == 0 else None
+            if use_peers and shared_host is not None and k > 0:
+                try:
+                    sh = D.SharedHostStack((h, w, 3))
+                except RuntimeError:
+                    sh = None
+            e2e_slots.append({"st": s_, "shared": sh, "ref": torch.empty_like(dev_frames[0]) if world > 1 else None,
+                              "out_dev": out_dev if k == 0 else torch.empty_like(out_dev),
+                              "out_host": out_host if k == 0 else torch.empty(h, w, 3, dtype=torch.float32).pin_memory(), "ptr": None})
+        if use_peers and any(sl["shared"] is None for sl in e2e_slots):      # the same copy-out form on every slot
+            for sl in e2e_slots:
+                sl["shared"] = sl["shared"] if all(x["shared"] is not None for x in e2e_slots) else None
+
+    def e2e_queue(sl):
+        c = sl["st"]
+        c.reset()
+        if world > 1:
+            if rank == 0:
+                sl["ref"].copy_(pinned[0], non_blocking=True)
+            dist.broadcast(sl["ref"], src=0)
+            c.set_reference(sl["ref"])
+        else:
+            c.set_reference(pinned_np[0])
         for i in mine:
-            st.submit(pinned_np[i], tag=i, pinned=True)
-        if use_peers and shared_host is not None:
+            c.submit(pinned_np[i], tag=i, pinned=True)
+        if use_peers and sl["shared"] is not None:
             # every rank keeps its slice of the finished stack and copies it out over its OWN PCIe link into the
             # host stack all ranks map; rank 0 owns the result once every rank's copy has landed
-            st.peer_reduce_scatter(n)
-            st.peer_slice_to_host(shared_host.ptr)
-            st.sync()
+            c.peer_reduce_scatter(n)
+            c.peer_slice_to_host(sl["shared"].ptr)
+        elif use_peers:
+            sl["ptr"] = c.peer_reduce(n)
+
+    def e2e_complete(sl):
+        c = sl["st"]
+        if use_peers and sl["shared"] is not None:
+            c.sync()
             dist.barrier()
             return
         if use_peers:
-            peer_out["ptr"] = st.peer_reduce(n)
-            st.sync()
+            c.sync()
             if rank == 0:
-                out_host.copy_(peer_result(), non_blocking=False)
+                sl["out_host"].copy_(torch.as_tensor(D.DevicePtrArray(sl["ptr"], h * w * 3), device=dev).view(h, w, 3), non_blocking=False)
             return
-        ptr, nfl = st.partial()
+        ptr, nfl = c.partial()
         if world > 1:
             part = torch.as_tensor(D.DevicePtrArray(ptr, nfl), device=dev)
             D.reduce_partial_stack(part, 0)
             torch.cuda.synchronize()
         if rank == 0:
-            st.finish_device(ptr, n, out_dev.data_ptr())
-            out_host.copy_(out_dev, non_blocking=False)
+            c.finish_device(ptr, n, sl["out_dev"].data_ptr())
+            sl["out_host"].copy_(sl["out_dev"], non_blocking=False)
+
+    e2e_state = {"k": 0, "pending": None}
+
+    def step_e2e():
+        sl = e2e_slots[e2e_state["k"] % len(e2e_slots)]
+        e2e_state["k"] += 1
+        if e2e_state["pending"] is sl:            # one context only: finish the stack before reusing it
+            e2e_complete(sl)
+            e2e_state["pending"] = None
+        e2e_queue(sl)
+        prev, e2e_state["pending"] = e2e_state["pending"], sl
+        if prev is not None:
+            e2e_complete(prev)
+
+    def drain_e2e():
+        if e2e_state["pending"] is not None:
+            e2e_complete(e2e_state["pending"])
+            e2e_state["pending"] = None
 
     if world > 1 and not use_peers:
         # NCCL sets up channels lazily over its first collectives on a buffer (measured: one 13 ms reduce among
@@ -348,9 +409,11 @@ def run_b200(a, rank, local_rank, world):
         torch.cuda.synchronize()
         dist.barrier()
 
-    def timed(fn, steps, warmup, sample_clocks):
+    def timed(fn, steps, warmup, sample_clocks, drain=None):
         for _ in range(warmup):
             fn()
+        if drain:
+            drain()
         # NVML set-up takes milliseconds: do it BEFORE the barrier, or rank 0 enters the timed region late and
         # every other rank's first exchange waits for it (measured: +1 ms per step on the max-over-ranks time)
         sampler = ClockSampler(local_rank) if (sample_clocks and rank == 0) else None
@@ -365,6 +428,8 @@ def run_b200(a, rank, local_rank, world):
         for _ in range(steps):
             fn()
             launches += st.launch_count()     # reset() zeroes the counter at the start of every step
+        if drain:
+            drain()                           # the last stack's result is read back INSIDE the timed region
         torch.cuda.synchronize()
         e1.record()
         torch.cuda.synchronize()
@@ -418,13 +483,19 @@ def run_b200(a, rank, local_rank, world):
     e2e = None
     shared_host_used = shared_host is not None
     if not a.skip_e2e:
-        ems, _, _, _ = timed(step_e2e, a.steps, min(a.warmup, 1), False)
-        h2d = sum(pinned_np[i].nbytes for i in [0] + mine)
+        make_e2e_slots()
+        shared_host_used = use_peers and e2e_slots[0]["shared"] is not None
+        ems, _, _, _ = timed(step_e2e, a.steps, max(2, min(a.warmup, 2)), False, drain_e2e)
+        h2d = sum(pinned_np[i].nbytes for i in ([0] if (rank == 0 or world == 1) else []) + mine)
         e2e = {"value": n * a.steps / (ems / 1e3), "unit": UNIT, "ms_per_step": ems / a.steps,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(out_host.numel() * 4) if rank == 0 else 0,
+               "contexts": len(e2e_slots),
                "api": ("EccStack.set_reference/submit(pinned host frames)/peer_reduce_scatter/peer_slice_to_host: every rank "
-                       "copies its slice of the stack into the shared pinned host stack" if (use_peers and shared_host_used) else
-                       "EccStack.set_reference/submit(pinned host frames)/partial/finish_device + D2H of the stack")}
+                       "copies its slice of the stack into the shared pinned host stack" if shared_host_used else
+                       "EccStack.set_reference/submit(pinned host frames)/partial/finish_device + D2H of the stack") +
+                      (f"; {len(e2e_slots)} contexts take the stacks alternately (a stack's tail and copy-out overlap the next stack's uploads)"
+                       if len(e2e_slots) > 1 else "") +
+                      ("; frame 0 is uploaded by rank 0 only and broadcast over NVLink (NCCL)" if world > 1 else "")}
         if world > 1:
             tot = torch.tensor([float(h2d)], dtype=torch.float64, device=dev)
             dist.all_reduce(tot)
@@ -504,14 +575,27 @@ def run_b200(a, rank, local_rank, world):
                            "max_corner_diff_vs_single_gpu_px": worst, "frames_covered": len(seen), "frames_expected": n - 1}
             del multi, single
     e2e_mean = None
+    if rank == 0 and e2e_slots:
+        # every slot holds a finished copy of the same stack: check the one written last
+        sl = e2e_slots[(e2e_state["k"] - 1) % len(e2e_slots)]
+        e2e_mean = float((sl["shared"].array if (use_peers and sl["shared"] is not None) else sl["out_host"].numpy()).mean(dtype=np.float64))
     if use_peers:
         barrier()                 # nobody unmaps while a peer may still be inside an exchange
-        if rank == 0 and not a.skip_e2e:
-            e2e_mean = float((shared_host.array if shared_host is not None else out_host.numpy()).mean(dtype=np.float64))
-        if shared_host is not None:
+        closed = set()
+        for sl in e2e_slots:
+            if sl["shared"] is not None and id(sl["shared"]) not in closed:
+                closed.add(id(sl["shared"]))
+                sl["shared"].close()
+        if shared_host is not None and id(shared_host) not in closed:
             shared_host.close()
+        for sl in e2e_slots:
+            if sl["st"] is not st:
+                sl["st"].peer_disconnect()
         st.peer_disconnect()
         barrier()
+    for sl in e2e_slots:
+        if sl["st"] is not st:
+            sl["st"].close()
     if world > 1:
         pr = torch.zeros(world, dtype=torch.float64, device=dev)
         pr[rank] = float(sum(iters))
@@ -623,7 +707,10 @@ def run_b200(a, rank, local_rank, world):
                        "l2": "inputs larger than L2: every step reads all frames (%.2f GB u8) from HBM" % (n * n_px * 3 / 1e9),
                        "parallelism": (f"frames sharded over {world} GPU(s), " + ("one fused reduce-scatter+divide kernel per rank over NVLink peer memory"
                                                                                    if use_peers else "one NCCL reduce")) if world > 1 else "1 GPU",
-                       "numa_bound": bool(numa_bound), "ecc_iterations_per_step": total_iters, "ecc_iterations_per_rank": iters_per_rank, "rank_work_ms_no_exchange": rank_work_ms, "wall_ms_per_step": wall_ms / a.steps},
+                       "numa_bound": bool(numa_bound), "ecc_iterations_per_step": total_iters, "ecc_iterations_per_rank": iters_per_rank, "rank_work_ms_no_exchange": rank_work_ms,
+                       "step_pipelining": ("none (one GPU: every step ends with a host synchronisation)" if world == 1 or not use_peers else
+                                           "no host synchronisation inside the timed region: the exchange of step i runs on its own stream "
+                                           "and overlaps the prep + ECC iterations of step i+1; that step's accumulator writes wait for it"), "wall_ms_per_step": wall_ms / a.steps},
             "whole_step": {"algorithmic_GBps_per_gpu": alg_bytes / (ms / a.steps * 1e-3) / 1e9 / world,
                            "frac_of_hbm_peak": alg_bytes / (ms / a.steps * 1e-3) / 1e9 / world / peak},
             "roofline": roof, "stages": stages, "cpu_baseline": cpu, "e2e": e2e, "e2e_api": e2e_api,

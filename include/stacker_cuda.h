@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define STK_ABI_VERSION 4
+#define STK_ABI_VERSION 5
 
 /* ---- status codes ------------------------------------------------------------------------- */
 enum {
@@ -114,7 +114,10 @@ int stk_ecc_destroy(stk_ecc_ctx* ctx);
 
 /* frame 0: cvt_color + (inside find_transform_ecc) GaussianBlur + gradients of the INPUT image,
    done once per stack instead of once per call          (src/lib.rs:731-738, :769-772)
-   *_device variants take a device pointer on the context's device. */
+   *_device variants take a device pointer on the context's device.
+   Asynchronous (no host synchronisation): lane 0 builds the plane behind whatever the lanes still have queued, the other
+   lanes wait for it on the device.  A page-locked `bgr` is copied asynchronously and must stay unchanged until the next
+   stk_ecc_sync / finish; a pageable one may be reused when the call returns. */
 int stk_ecc_set_reference(stk_ecc_ctx* ctx, const uint8_t* bgr, size_t pitch);
 int stk_ecc_set_reference_device(stk_ecc_ctx* ctx, const uint8_t* d_bgr, size_t pitch);
 
@@ -127,7 +130,17 @@ int stk_ecc_set_reference_device(stk_ecc_ctx* ctx, const uint8_t* d_bgr, size_t 
    same lane (one pass over the f32 accumulator for four frames, in submission order — bit-identical to one launch
    per frame) when four are waiting, or at the next sync / results / partial / finish / exchange.  A DEVICE buffer
    (_device variants) must therefore stay valid and unmodified until one of those calls has returned, and whoever
-   produced it must have finished writing it before the submit call (the library's streams are non-blocking). */
+   produced it must have finished writing it before the submit call (the library's streams are non-blocking), unless the
+   producer's stream was announced with stk_ecc_set_input_stream. */
+/* Stream contract for DEVICE buffers (ABI v5).  The library's lanes are non-blocking streams: by default nothing orders
+   them behind the stream that produced a device frame.  After stk_ecc_set_input_stream(ctx, s, 1) every later *_device
+   call (set_reference_device, submit_frame_device, submit_warp*_device) first records an event on `s` (a cudaStream_t
+   of the context's device, NULL = the legacy default stream) and makes the lane that takes the frame wait for it — a
+   device-side dependency, the host never blocks.  enabled = 0 restores the default.  This is what lets a torch / CuPy /
+   NPP producer hand over a tensor it has only just queued the writes of (the Python mirror passes torch's current
+   stream automatically).  Replaces nothing in the reference, whose Mats live on the host. */
+int stk_ecc_set_input_stream(stk_ecc_ctx* ctx, void* cuda_stream, int enabled);
+
 int stk_ecc_submit_frame(stk_ecc_ctx* ctx, const uint8_t* bgr, size_t pitch, int64_t tag);
 int stk_ecc_submit_frame_pinned(stk_ecc_ctx* ctx, const uint8_t* pinned_bgr, size_t pitch, int64_t tag);
 int stk_ecc_submit_frame_device(stk_ecc_ctx* ctx, const uint8_t* d_bgr, size_t pitch, int64_t tag);

@@ -14,7 +14,7 @@ STK_OK, STK_ERR_BAD_ARG, STK_ERR_CUDA, STK_ERR_NOT_ENOUGH, STK_ERR_ECC_NOCONV, S
     STK_ERR_CRITERIA, STK_ERR_STATE, STK_ERR_UNSUPPORTED, STK_ERR_NOMEM = range(10)
 STK_TERM_COUNT, STK_TERM_EPS = 1, 2
 STK_BORDER_CONSTANT = 0
-STK_ABI_VERSION = 4
+STK_ABI_VERSION = 5
 
 
 class EccConfig(C.Structure):
@@ -53,6 +53,7 @@ SYMBOLS = {
     "stk_ecc_destroy": (C.c_int, [_P]),
     "stk_ecc_set_reference": (C.c_int, [_P, _P, C.c_size_t]),
     "stk_ecc_set_reference_device": (C.c_int, [_P, _P, C.c_size_t]),
+    "stk_ecc_set_input_stream": (C.c_int, [_P, _P, C.c_int]),
     "stk_ecc_submit_frame": (C.c_int, [_P, _P, C.c_size_t, C.c_int64]),
     "stk_ecc_submit_frame_pinned": (C.c_int, [_P, _P, C.c_size_t, C.c_int64]),
     "stk_ecc_submit_frame_device": (C.c_int, [_P, _P, C.c_size_t, C.c_int64]),

@@ -127,8 +127,9 @@ def _device_view(obj, expect_shape=None):
     torch CUDA tensor of shape HxWxC uint8), or None for host arrays.  The array must be 8-bit with dense
     pixels (only the row pitch may be padded) and, when `expect_shape` is given, of exactly that shape: the
     library reads height * pitch bytes from the pointer, so anything else would be an out-of-bounds device read.
-    Stream contract: the library's lane streams are non-blocking, so the producer of the array must have finished
-    writing it (synchronise the producing stream, or record/wait an event) before the frame is submitted."""
+    Stream contract: the library's lane streams are non-blocking; EccStack orders every device frame behind the
+    stream that produced it (`_producer_stream`: torch's current stream for torch tensors, the `stream` entry of the
+    interface otherwise) through stk_ecc_set_input_stream — a device-side dependency, nothing blocks on the host."""
     iface = getattr(obj, "__cuda_array_interface__", None)
     if iface is None:
         return None
@@ -148,6 +149,20 @@ def _device_view(obj, expect_shape=None):
             raise OpenCvError("device frame rows overlap")
     pitch = int(strides[0]) if strides else dense[0]
     return int(iface["data"][0]), pitch
+
+
+def _producer_stream(obj):
+    """The CUDA stream handle (int; 0 = the legacy default stream) whose queued work produces `obj`, or None if unknown:
+    torch's current stream on the tensor's device, else the `stream` entry of __cuda_array_interface__ (v3: 1 = legacy
+    default, 2 = per-thread default — not expressible as a handle here, treated as unknown)."""
+    import sys
+    torch = sys.modules.get("torch")
+    if torch is not None and isinstance(obj, torch.Tensor):
+        return int(torch.cuda.current_stream(obj.device).cuda_stream)
+    st = getattr(obj, "__cuda_array_interface__", {}).get("stream")
+    if st is None or st == 2:
+        return None
+    return 0 if st == 1 else int(st)
 
 
 class EccStack:
@@ -207,19 +222,29 @@ class EccStack:
             frame = np.ascontiguousarray(frame)
         return frame, frame.ctypes.data, frame.strides[0]
 
+    def _order_after(self, frame):
+        """Tell the library which stream produced the device frame about to be submitted (only when it changes)."""
+        ps = _producer_stream(frame)
+        if ps != getattr(self, "_input_stream", -1):
+            _check(lib.stk_ecc_set_input_stream(self._ctx, C.c_void_p(ps or 0), 0 if ps is None else 1))
+            self._input_stream = ps
+
     def set_reference(self, frame):
         dv = _device_view(frame, (self.height, self.width, self.channels))
         if dv is not None:
+            self._order_after(frame)
             _check(lib.stk_ecc_set_reference_device(self._ctx, dv[0], dv[1]))
             self._keep.append(frame)
         else:
             f, ptr, pitch = self._host_frame(frame)
+            self._keep.append(f)      # a page-locked reference is copied asynchronously: keep it until the next sync
             _check(lib.stk_ecc_set_reference(self._ctx, ptr, pitch))
 
     def submit(self, frame, tag: int = 0, pinned: bool = False):
         dv = _device_view(frame, (self.height, self.width, self.channels))
         if dv is not None:
             self._keep.append(frame)
+            self._order_after(frame)
             _check(lib.stk_ecc_submit_frame_device(self._ctx, dv[0], dv[1], int(tag)))
             return
         f, ptr, pitch = self._host_frame(frame)
@@ -251,6 +276,7 @@ class EccStack:
         dv = _device_view(frame, (self.height, self.width, self.channels))
         if dv is not None:
             self._keep.append(frame)
+            self._order_after(frame)
             _check(lib.stk_ecc_submit_warp_device(self._ctx, dv[0], dv[1], hm, int(border_mode), bv, int(tag)))
             return
         f, ptr, pitch = self._host_frame(frame)
@@ -263,6 +289,7 @@ class EccStack:
         dv = _device_view(frame, (self.height, self.width, self.channels))
         if dv is not None:
             self._keep.append(frame)
+            self._order_after(frame)
             _check(lib.stk_ecc_submit_warp_affine_device(self._ctx, dv[0], dv[1], mm, int(border_mode), bv, int(tag)))
             return
         f, ptr, pitch = self._host_frame(frame)
@@ -470,7 +497,7 @@ _CTX_CACHE_MAX = max(0, int(os.environ.get("STK_CONTEXT_CACHE", "2")))
 
 
 def _ctx_key(w, h, ch, params, device, ecc_size, seed_reference, lanes):
-    pk = None if params is None else (int(params.motion_type), params.max_count, float(params.epsilon), int(params.gauss_filt_size))
+    pk = None if params is None else (int(params.motion_type), params.max_count, params.epsilon, int(params.gauss_filt_size))
     return (int(device), int(w), int(h), int(ch), pk, None if ecc_size is None else tuple(int(v) for v in ecc_size),
             bool(seed_reference), int(lanes))
 

@@ -48,6 +48,7 @@ struct PeerReduceParams {
   uint32_t step;
   float scale;                       // float(1 / divisor), as the reference's MatExpr `/ n` evaluates it
   unsigned long long timeout_ns;
+  int pre_waited;                    // 1: peer_announce_wait_kernel already announced and waited on this stream
 };
 
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
@@ -80,14 +81,19 @@ template <int WORLD>   // 0 = run-time world size
 __global__ void __launch_bounds__(256) peer_reduce_scale_kernel(const PeerReduceParams p) {
   const int world = WORLD > 0 ? WORLD : p.world;
   uint32_t* mine = p.flags[p.rank];
-  // (1) my partial was completed by earlier work on this stream: tell everyone (block 0 only)
-  if (blockIdx.x == 0 && threadIdx.x < world) {
-    __threadfence_system();
-    st_release_sys(p.flags[threadIdx.x] + kPeerReady + p.rank, p.step);
-  }
-  // (2) every block waits for every rank's announcement in the LOCAL flag block
   int ok = 1;
-  if (threadIdx.x < world) ok = spin_until(mine + kPeerReady + threadIdx.x, p.step, p.timeout_ns) ? 1 : 0;
+  if (p.pre_waited) {
+    // announced and waited for by the one-warp kernel ahead of this one; a time-out there voids the step
+    if (threadIdx.x == 0) ok = ld_acquire_sys(mine + kPeerError) == p.step ? 0 : 1;
+  } else {
+    // (1) my partial was completed by earlier work on this stream: tell everyone (block 0 only)
+    if (blockIdx.x == 0 && threadIdx.x < world) {
+      __threadfence_system();
+      st_release_sys(p.flags[threadIdx.x] + kPeerReady + p.rank, p.step);
+    }
+    // (2) every block waits for every rank's announcement in the LOCAL flag block
+    if (threadIdx.x < world) ok = spin_until(mine + kPeerReady + threadIdx.x, p.step, p.timeout_ns) ? 1 : 0;
+  }
   ok = __syncthreads_and(ok);
   if (!ok) {
     if (threadIdx.x == 0) mine[kPeerError] = p.step;
@@ -147,6 +153,18 @@ __global__ void __launch_bounds__(256) peer_reduce_scale_kernel(const PeerReduce
   if (s_last && threadIdx.x < world) {
     __threadfence_system();
     st_release_sys(p.flags[threadIdx.x] + kPeerDone + p.rank, p.step);
+  }
+}
+
+// (1) + (2) of the exchange as a kernel of its own (one warp): announce "my partial is complete" to every rank, then wait
+// until every rank has.  A rank that reaches the exchange early spins HERE — 32 threads, not 592 blocks — while its lanes
+// already work on the next stack; the reduce kernel behind it on the stream starts with every partial complete.
+__global__ void peer_announce_wait_kernel(const PeerReduceParams p) {
+  uint32_t* mine = p.flags[p.rank];
+  if (threadIdx.x < p.world) {
+    __threadfence_system();
+    st_release_sys(p.flags[threadIdx.x] + kPeerReady + p.rank, p.step);
+    if (!spin_until(mine + kPeerReady + threadIdx.x, p.step, p.timeout_ns)) mine[kPeerError] = p.step;
   }
 }
 

@@ -262,7 +262,8 @@ struct Lane {
   uint8_t* h_stage = nullptr;       // pinned staging for pageable host buffers
   int* h_cont = nullptr;            // pinned "loop continues" word of the host-driven loop (STK_LOOP_MODE=host)
   cudaEvent_t stage_free = nullptr; // H2D out of h_stage finished
-  cudaEvent_t drained = nullptr;    // lane's queued work finished (peer exchange joins the lanes on the device)
+  cudaEvent_t drained = nullptr;    // lane's queued work finished (set_reference / the peer exchange join the lanes on the device)
+  bool wait_x = false;              // the next accumulator write of this lane must wait for the exchange in flight (x_done)
   stk::EccState* st = nullptr;
   double* partials = nullptr;
   float* acc = nullptr;
@@ -336,6 +337,17 @@ struct stk_ecc_ctx {
   int iter_gen = 2, iter_cfg = -1;          // -1: the default geometry of iter_variant
   bool host_loop = false;
   bool have_ref = false;
+  // Device-side ordering between stacks (no host synchronisation in reset / set_reference / the peer exchange):
+  //   ref_ready  lane 0 finished the reference plane: every other lane waits for it before its first frame;
+  //   x_stream   the multi-GPU exchange (lane sum, announce/wait, reduce-scatter + divide, close) runs here, behind every
+  //              lane's `drained` event, so that the NEXT stack's prep and ECC iterations overlap it; x_done closes it and
+  //              is what the next stack's first accumulator writes (seed, final warps) wait for.
+  cudaEvent_t ref_ready = nullptr, x_done = nullptr;
+  cudaStream_t x_stream = nullptr;
+  // producer stream of device-resident inputs (stk_ecc_set_input_stream): each *_device submission is ordered behind it
+  bool order_inputs = false;
+  cudaStream_t input_stream = nullptr;
+  cudaEvent_t input_ev = nullptr;
   stk::PrepParams prep_proto;
   std::mutex mu;
   std::vector<RingBuf> ring;        // lazily allocated: 2 buffers per lane
@@ -573,6 +585,10 @@ int launch_prep(stk_ecc_ctx* c, const uint8_t* d_src, size_t pitch, uint8_t* sma
 // K4 for the frames queued on a lane: ONE launch gathers up to kWarpBatch frames and touches the accumulator once
 int flush_warps(stk_ecc_ctx* c, Lane& ln) {
   if (ln.n_pend == 0) return STK_OK;
+  if (ln.wait_x) {       // the previous stack's exchange may still read this lane's accumulator
+    CU(cudaStreamWaitEvent(ln.stream, c->x_done, 0));
+    ln.wait_x = false;
+  }
   stk::WarpAccParams p = {};
   for (int j = 0; j < ln.n_pend; ++j) p.f[j] = ln.pend[j];
   p.n = ln.n_pend;
@@ -791,6 +807,7 @@ int flush_all(stk_ecc_ctx* c) {
 int sync_all(stk_ecc_ctx* c) {
   { int rc = flush_all(c); if (rc) return rc; }
   for (auto& ln : c->lanes) CU(cudaStreamSynchronize(ln.stream));
+  CU(cudaStreamSynchronize(c->x_stream));
   // account for the device-launched iteration kernels and surface per-frame failures
   int first_err = STK_OK;
   int64_t iters = 0;
@@ -1007,9 +1024,14 @@ int stk_ecc_create(const stk_ecc_config* cfg, stk_ecc_ctx** out) {
 
   }
   c->lanes.resize(c->n_lanes);
+  if (cudaEventCreateWithFlags(&c->ref_ready, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->x_done, cudaEventDisableTiming) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->x_stream, cudaStreamNonBlocking) != cudaSuccess)
+    return cleanup(fail(STK_ERR_CUDA, "cudaEventCreate / cudaStreamCreate failed"));
   for (auto& ln : c->lanes) {
     if (cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking) != cudaSuccess) return cleanup(fail(STK_ERR_CUDA, "cudaStreamCreate failed"));
-    if (cudaEventCreateWithFlags(&ln.stage_free, cudaEventDisableTiming) != cudaSuccess) return cleanup(fail(STK_ERR_CUDA, "cudaEventCreate failed"));
+    if (cudaEventCreateWithFlags(&ln.stage_free, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ln.drained, cudaEventDisableTiming) != cudaSuccess) return cleanup(fail(STK_ERR_CUDA, "cudaEventCreate failed"));
     if (cudaMalloc((void**)&ln.acc, c->acc_floats * sizeof(float)) != cudaSuccess) return cleanup(fail(STK_ERR_NOMEM, "cudaMalloc(accumulator) failed"));
     if (cfg->align) {
       if (cudaMalloc((void**)&ln.tmpl, (size_t)c->pitch_f * c->eh * sizeof(float)) != cudaSuccess) return cleanup(fail(STK_ERR_NOMEM, "cudaMalloc(T plane) failed"));
@@ -1060,6 +1082,10 @@ int stk_ecc_destroy(stk_ecc_ctx* c) {
     if (ln.drained) cudaEventDestroy(ln.drained);
     if (ln.stream) cudaStreamDestroy(ln.stream);
   }
+  if (c->x_stream) { cudaStreamSynchronize(c->x_stream); cudaStreamDestroy(c->x_stream); }
+  if (c->ref_ready) cudaEventDestroy(c->ref_ready);
+  if (c->input_ev) cudaEventDestroy(c->input_ev);
+  if (c->x_done) cudaEventDestroy(c->x_done);
   for (auto& r : c->results) for (auto& e : r.ev) if (e) cudaEventDestroy(e);
   for (auto& b : c->ring) { if (b.host) cudaFreeHost(b.host); if (b.uploaded) cudaEventDestroy(b.uploaded); }
   for (void* m : c->peer.opened) cudaIpcCloseMemHandle(m);
@@ -1083,13 +1109,44 @@ static int ensure_host_staging(stk_ecc_ctx* c, Lane& ln, bool need_pinned_stage,
   return STK_OK;
 }
 
+// device-resident input: the lane that takes it waits for what its producer's stream has queued so far
+static int order_after_input(stk_ecc_ctx* c, cudaStream_t lane_stream) {
+  if (!c->order_inputs) return STK_OK;
+  if (!c->input_ev) CU(cudaEventCreateWithFlags(&c->input_ev, cudaEventDisableTiming));
+  CU(cudaEventRecord(c->input_ev, c->input_stream));
+  CU(cudaStreamWaitEvent(lane_stream, c->input_ev, 0));
+  return STK_OK;
+}
+
+// lane 0's stream waits until every lane has finished what is queued on it so far
+static int join_lanes_on_lane0(stk_ecc_ctx* c) {
+  Lane& l0 = c->lanes[0];
+  for (auto& ln : c->lanes) {
+    if (&ln == &l0) continue;
+    CU(cudaEventRecord(ln.drained, ln.stream));
+    CU(cudaStreamWaitEvent(l0.stream, ln.drained, 0));
+  }
+  return STK_OK;
+}
+
+// The reference plane is built on lane 0.  No host synchronisation: lane 0 first waits for whatever the other lanes still
+// have queued (frames of an earlier stack read the plane it is about to overwrite), and every other lane then waits for
+// `ref_ready` before its next frame.
 static int set_reference_impl(stk_ecc_ctx* c, const uint8_t* d_bgr, size_t pitch) {
   Lane& l0 = c->lanes[0];
+  int rc = join_lanes_on_lane0(c);
+  if (rc) return rc;
   if (c->cfg.align) {
-    int rc = launch_prep(c, d_bgr, pitch, l0.small, c->img, l0.stream);
+    rc = launch_prep(c, d_bgr, pitch, l0.small, c->img, l0.stream);
     if (rc) return rc;
   }
+  CU(cudaEventRecord(c->ref_ready, l0.stream));
+  for (auto& ln : c->lanes) if (&ln != &l0) CU(cudaStreamWaitEvent(ln.stream, c->ref_ready, 0));
   if (c->cfg.seed_reference) {
+    if (l0.wait_x) {       // the previous stack's exchange may still read lane 0's accumulator
+      CU(cudaStreamWaitEvent(l0.stream, c->x_done, 0));
+      l0.wait_x = false;
+    }
     const int row = c->cfg.width * c->cfg.channels;
     dim3 grid((row + 1023) / 1024, c->cfg.height);
     // 4-byte loads / 16-byte stores need the rows of both buffers to start on those boundaries
@@ -1099,7 +1156,6 @@ static int set_reference_impl(stk_ecc_ctx* c, const uint8_t* d_bgr, size_t pitch
     CU(cudaGetLastError());
     l0.acc_used = true;
   }
-  CU(cudaStreamSynchronize(l0.stream));
   c->have_ref = true;
   return STK_OK;
 }
@@ -1124,7 +1180,18 @@ int stk_ecc_set_reference_device(stk_ecc_ctx* c, const uint8_t* d_bgr, size_t pi
   if (!d_bgr) return fail(STK_ERR_BAD_ARG, "null frame");
   if (pitch < (size_t)c->cfg.width * c->cfg.channels) return fail(STK_ERR_BAD_ARG, "pitch too small");
   std::lock_guard<std::mutex> g(c->mu);
+  rc = order_after_input(c, c->lanes[0].stream);
+  if (rc) return rc;
   return set_reference_impl(c, d_bgr, pitch);
+}
+
+int stk_ecc_set_input_stream(stk_ecc_ctx* c, void* cuda_stream, int enabled) {
+  int rc = check_ctx(c);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> g(c->mu);
+  c->order_inputs = enabled != 0;
+  c->input_stream = enabled ? (cudaStream_t)cuda_stream : nullptr;
+  return STK_OK;
 }
 
 // a filled ring buffer: asynchronous upload on the next lane, then align (inv == null) or warp-only; the
@@ -1175,7 +1242,11 @@ static int submit_align(stk_ecc_ctx* c, const uint8_t* buf, size_t pitch, int64_
   std::lock_guard<std::mutex> g(c->mu);
   if (!c->have_ref) return fail(STK_ERR_STATE, "stk_ecc_set_reference must come first");
   Lane& ln = pick_lane(c);
-  if (kind == 2) return enqueue_align(c, ln, buf, pitch, tag);
+  if (kind == 2) {
+    rc = order_after_input(c, ln.stream);
+    if (rc) return rc;
+    return enqueue_align(c, ln, buf, pitch, tag);
+  }
   uint8_t* d_frame = nullptr;
   rc = ensure_host_staging(c, ln, false, &d_frame);
   if (rc) return rc;
@@ -1246,6 +1317,8 @@ static int submit_warp(stk_ecc_ctx* c, const uint8_t* buf, size_t pitch, const d
   Lane& ln = pick_lane(c);
   const uint8_t* d_src = buf;
   size_t d_pitch = pitch;
+  rc = order_after_input(c, ln.stream);
+  if (rc) return rc;
   rc = launch_warp(c, ln, d_src, d_pitch, !affine, inv, border, false);
   if (rc) return rc;
   { ResultSlot slot; slot.tag = tag; slot.host = nullptr; c->results.push_back(slot); }
@@ -1530,6 +1603,7 @@ int stk_ecc_peer_disconnect(stk_ecc_ctx* c) {
   if (rc) return rc;
   std::lock_guard<std::mutex> g(c->mu);
   for (auto& ln : c->lanes) CU(cudaStreamSynchronize(ln.stream));
+  CU(cudaStreamSynchronize(c->x_stream));
   peer_clear(c);
   return STK_OK;
 }
@@ -1547,22 +1621,23 @@ int peer_exchange(stk_ecc_ctx* c, int divisor, bool scatter) {
   if (!pl.connected) return fail(STK_ERR_STATE, "stk_ecc_peer_reduce before stk_ecc_peer_connect");
   if ((rc = flush_all(c))) return rc;
   Lane& l0 = c->lanes[0];
-  // join the lanes on the device (no host synchronisation), then sum them into lane 0's accumulator
+  cudaStream_t xs = c->x_stream;
+  // join the lanes on the exchange stream (no host synchronisation), then sum them into lane 0's accumulator.  The lanes
+  // themselves stay free: the next stack's prep and ECC iterations run while this exchange is in flight; only its first
+  // accumulator writes wait for x_done (Lane::wait_x).
   const float* ordered[16];
   int m = 0;
   if (l0.acc_used) ordered[m++] = l0.acc;
   for (auto& ln : c->lanes) {
-    if (&ln == &l0) continue;
-    if (!ln.drained) CU(cudaEventCreateWithFlags(&ln.drained, cudaEventDisableTiming));
     CU(cudaEventRecord(ln.drained, ln.stream));
-    CU(cudaStreamWaitEvent(l0.stream, ln.drained, 0));
-    if (ln.acc_used) ordered[m++] = ln.acc;
+    CU(cudaStreamWaitEvent(xs, ln.drained, 0));
+    if (&ln != &l0 && ln.acc_used) ordered[m++] = ln.acc;
   }
   if (!(m == 1 && ordered[0] == l0.acc)) {
-    rc = lane_sum(c, l0.acc, ordered, m, false, 1, l0.stream);
+    rc = lane_sum(c, l0.acc, ordered, m, false, 1, xs);
     if (rc) return rc;
   }
-  for (auto& ln : c->lanes) ln.acc_used = false;
+  for (auto& ln : c->lanes) { ln.acc_used = false; ln.wait_x = true; }
   l0.acc_used = true;
 
   stk::PeerReduceParams p;
@@ -1592,15 +1667,22 @@ int peer_exchange(stk_ecc_ctx* c, int divisor, bool scatter) {
   static const unsigned long long timeout_ms = [] { const char* e = getenv("STK_PEER_TIMEOUT_MS"); return e ? strtoull(e, nullptr, 10) : 30000ull; }();
   p.timeout_ns = timeout_ms * 1000000ull;
   const int blocks = c->sm_count * 4;
+  // announce + wait in a one-warp kernel of its own: a rank that is ahead of the others spins there without holding SM
+  // slots, and the reduce kernel only starts when every partial is complete
+  p.pre_waited = 1;
+  stk::peer_announce_wait_kernel<<<1, 32, 0, xs>>>(p);
+  CU(cudaGetLastError());
   switch (pl.world) {
-    case 2: launch_peer_reduce<2>(p, blocks, l0.stream); break;
-    case 4: launch_peer_reduce<4>(p, blocks, l0.stream); break;
-    case 8: launch_peer_reduce<8>(p, blocks, l0.stream); break;
-    default: launch_peer_reduce<0>(p, blocks, l0.stream); break;
+    case 2: launch_peer_reduce<2>(p, blocks, xs); break;
+    case 4: launch_peer_reduce<4>(p, blocks, xs); break;
+    case 8: launch_peer_reduce<8>(p, blocks, xs); break;
+    default: launch_peer_reduce<0>(p, blocks, xs); break;
   }
   CU(cudaGetLastError());
-  stk::peer_wait_done_kernel<<<1, 32, 0, l0.stream>>>(pl.flags, pl.world, p.step, p.timeout_ns);
+  stk::peer_wait_done_kernel<<<1, 32, 0, xs>>>(pl.flags, pl.world, p.step, p.timeout_ns);
   CU(cudaGetLastError());
+  CU(cudaEventRecord(c->x_done, xs));
+  c->launches += 1;
   c->launches += 2;
   pl.slice_begin = p.begin;
   pl.slice_end = p.end;
@@ -1634,7 +1716,7 @@ int stk_ecc_peer_slice_to_host(stk_ecc_ctx* c, float* out) {
   PeerLink& pl = c->peer;
   if (!pl.connected || !pl.scattered) return fail(STK_ERR_STATE, "stk_ecc_peer_slice_to_host needs a preceding stk_ecc_peer_reduce_scatter");
   const size_t n = pl.slice_end - pl.slice_begin;
-  if (n) CU(cudaMemcpyAsync(out + pl.slice_begin, c->d_out + pl.slice_begin, n * sizeof(float), cudaMemcpyDeviceToHost, c->lanes[0].stream));
+  if (n) CU(cudaMemcpyAsync(out + pl.slice_begin, c->d_out + pl.slice_begin, n * sizeof(float), cudaMemcpyDeviceToHost, c->x_stream));
   return STK_OK;
 }
 
@@ -1642,7 +1724,9 @@ int stk_ecc_reset(stk_ecc_ctx* c) {
   int rc = check_ctx(c);
   if (rc) return rc;
   std::lock_guard<std::mutex> g(c->mu);
-  for (auto& ln : c->lanes) { CU(cudaStreamSynchronize(ln.stream)); ln.acc_used = false; ln.n_pend = 0; ln.staging_used = 0; }
+  // no host synchronisation: the next stk_ecc_set_reference joins the lanes on the device (the pinned result records and
+  // staging buffers are only ever touched in stream order behind that join)
+  for (auto& ln : c->lanes) { ln.acc_used = false; ln.n_pend = 0; ln.staging_used = 0; }
   for (auto& r : c->results) for (auto& e : r.ev) if (e) cudaEventDestroy(e);
   c->results.clear();
   c->states_used = 0;
@@ -1703,6 +1787,8 @@ int stk_prep_grey_blur(const uint8_t* bgr, size_t pitch, int width, int height, 
   int rc = stk_ecc_create(&cfg, &c);
   if (rc) return rc;
   rc = stk_ecc_set_reference(c, bgr, pitch);
+  if (rc == STK_OK && cudaStreamSynchronize(c->lanes[0].stream) != cudaSuccess)     // set_reference is asynchronous
+    rc = fail(STK_ERR_CUDA, "prep failed: %s", cudaGetErrorString(cudaGetLastError()));
   if (rc == STK_OK) {
     cudaError_t e = cudaMemcpy2D(out, out_pitch, c->img, (size_t)c->pitch_f * sizeof(float),
                                  (size_t)width * sizeof(float), height, cudaMemcpyDeviceToHost);

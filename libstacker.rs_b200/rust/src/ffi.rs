@@ -1,4 +1,4 @@
-//! Thin `extern "C"` layer over include/stacker_cuda.h (ABI version 4).  One declaration per entry point the
+//! Thin `extern "C"` layer over include/stacker_cuda.h (ABI version 5).  One declaration per entry point the
 //! Rust wrappers use; see the header for ownership and threading rules.
 #![allow(non_camel_case_types)]
 use std::os::raw::{c_char, c_int, c_void};
@@ -59,6 +59,8 @@ unsafe extern "C" {
     pub fn stk_ecc_create(cfg: *const stk_ecc_config, out: *mut *mut stk_ecc_ctx) -> c_int;
     pub fn stk_ecc_destroy(ctx: *mut stk_ecc_ctx) -> c_int;
     pub fn stk_ecc_set_reference(ctx: *mut stk_ecc_ctx, bgr: *const u8, pitch: usize) -> c_int;
+    /// ABI v5: order every later `*_device` submission behind `cuda_stream` (a `cudaStream_t` of the context's device).
+    pub fn stk_ecc_set_input_stream(ctx: *mut stk_ecc_ctx, cuda_stream: *mut c_void, enabled: c_int) -> c_int;
     pub fn stk_ecc_submit_frame(ctx: *mut stk_ecc_ctx, bgr: *const u8, pitch: usize, tag: i64) -> c_int;
     pub fn stk_ecc_submit_frame_pinned(ctx: *mut stk_ecc_ctx, bgr: *const u8, pitch: usize, tag: i64) -> c_int;
     pub fn stk_ecc_acquire_frame_buffer(ctx: *mut stk_ecc_ctx, buf: *mut *mut u8, pitch: *mut usize) -> c_int;

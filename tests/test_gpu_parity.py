@@ -372,6 +372,34 @@ def test_context_cache_reuse_and_failure(pkg):
     assert not api._CTX_CACHE
 
 
+def test_device_frames_are_ordered_behind_their_producer_stream(pkg):
+    """ABI v5 stream contract: a device frame whose producer has only QUEUED its writes (a side stream that first sleeps,
+    then copies) may be submitted at once — the lane waits for the producer's stream on the device."""
+    import torch
+    w, h = 320, 240
+    frames = synth.Stack(w, h, 5, 3, seed=21).frames()
+    params = pkg.EccMatchParameters(pkg.MotionType.Homography, 5000, 1e-5, 5)
+    want, rw = pkg.ecc_match(frames, params, None, device=0, return_details=True)
+    host = [torch.from_numpy(f).pin_memory() for f in frames]
+    bufs = [torch.zeros(h, w, 3, dtype=torch.uint8, device="cuda:0") for _ in frames]
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream(device=0)
+    with pkg.EccStack(w, h, 3, params, device=0) as st:
+        with torch.cuda.stream(side):
+            for k, (b, hf) in enumerate(zip(bufs, host)):
+                torch.cuda._sleep(10_000_000)          # several ms: the copy below is queued, not done, when submit returns
+                b.copy_(hf, non_blocking=True)
+                if k == 0:
+                    st.set_reference(b)
+                else:
+                    st.submit(b, tag=k)
+        got = st.finish(len(frames))
+        res = st.results()
+    for a, b in zip(sorted(res, key=lambda r: r["tag"]), rw):
+        assert np.array_equal(a["warp"], b["warp"])
+    assert np.abs(got - want).max() <= 1e-6
+
+
 def test_lanes_and_device_resident_input(pkg):
     """Same stack through 1 lane / 4 lanes, host and device-resident frames: identical warps, stack equal
     up to f32 summation order."""

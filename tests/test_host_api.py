@@ -42,7 +42,7 @@ def test_abi_exports_every_declared_symbol(pkg):
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/stacker_cuda.h but not exported"
     assert declared == set(pkg._ffi.SYMBOLS), declared ^ set(pkg._ffi.SYMBOLS)
-    assert lib.stk_abi_version() == 4
+    assert lib.stk_abi_version() == 5
 
 
 def test_struct_layout_matches_header(pkg):
