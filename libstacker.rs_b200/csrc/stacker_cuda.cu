@@ -1666,7 +1666,12 @@ int peer_exchange(stk_ecc_ctx* c, int divisor, bool scatter) {
   p.scale = (float)(1.0 / (double)divisor);
   static const unsigned long long timeout_ms = [] { const char* e = getenv("STK_PEER_TIMEOUT_MS"); return e ? strtoull(e, nullptr, 10) : 30000ull; }();
   p.timeout_ns = timeout_ms * 1000000ull;
-  const int blocks = c->sm_count * 4;
+  // Grid of the reduce kernel (NVLink-bound).  Measured at world 2 on the 4K payload (scripts/peer_check.py,
+  // profiles/r2_peer_blocks.log): 592 blocks 191 us, 148 blocks 191 us, 74 blocks 217 us, 37 blocks 384 us, 16 blocks 832 us —
+  // one block per SM is as fast as four and leaves the other block slot of every SM to the next stack's ECC kernels, which
+  // run beside the exchange.  STK_PEER_BLOCKS overrides.
+  static const int blocks_env = [] { const char* e = getenv("STK_PEER_BLOCKS"); return e ? atoi(e) : 0; }();
+  const int blocks = blocks_env > 0 ? blocks_env : c->sm_count;
   // announce + wait in a one-warp kernel of its own: a rank that is ahead of the others spins there without holding SM
   // slots, and the reduce kernel only starts when every partial is complete
   p.pre_waited = 1;
