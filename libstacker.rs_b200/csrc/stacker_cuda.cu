@@ -598,6 +598,7 @@ int flush_warps(stk_ecc_ctx* c, Lane& ln) {
   p.src_width = c->cfg.width;
   p.src_height = c->cfg.height;
   p.store = ln.acc_used ? 0 : 1;
+  p.frac_magic = 0x4B400000u;
   dim3 block(stk::kWarpBX, stk::kWarpBY);
   const int ch = c->cfg.channels;
   if (c->warp_gen == 1) {

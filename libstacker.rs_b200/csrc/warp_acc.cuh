@@ -39,6 +39,7 @@ struct WarpAccParams {
   int width, height;      // destination size (== accumulator size)
   int src_width, src_height;
   int store;              // 1: acc = sum of the batch (first batch on this lane), 0: acc += ...
+  unsigned frac_magic;    // 0x4B400000 handed over in a REGISTER: (q & 31) | magic is then one LOP3 (two with an immediate)
 };
 
 // Correctly rounded 1/w for w in the normal range (|w| in [2^-500, 2^500]): the instruction sequence of
@@ -394,6 +395,12 @@ __device__ __forceinline__ float2 fma2_rn_exact(float2 a, float2 b, float2 c) {
       : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
   return d;
 }
+__device__ __forceinline__ float2 add2_rn_exact(float2 a, float2 b) {
+  float2 d;
+  asm("{\n .reg .b64 ra, rb, rd;\n mov.b64 ra, {%2, %3};\n mov.b64 rb, {%4, %5};\n add.rn.f32x2 rd, ra, rb;\n mov.b64 {%0, %1}, rd;\n}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
 // PRMT in its default mode; selector nibbles stay below 8 here, so no masking is needed (__byte_perm adds one)
 __device__ __forceinline__ unsigned prmt(unsigned a, unsigned b, unsigned sel) {
   unsigned d;
@@ -466,23 +473,28 @@ __device__ __forceinline__ void convert_tap_pair(const TapWords& t, unsigned o, 
   for (int c = 0; c < C; ++c) { s0[c] = v[c]; s1[c] = v[C + c]; }
 }
 
-// value = s00*w00 + s01*w01 + s10*w10 + s11*w11, left to right in f32, on converted taps (see blend_taps)
+// value = s00*w00 + s01*w01 + s10*w10 + s11*w11, left to right in f32, on converted taps (see blend_taps).  wa = (w00, w01),
+// wb = (w10, w11).  Channel pairs multiply by a broadcast weight; the odd channel's four products ride two packed
+// multiplies across the taps.  Every half of a packed multiply is an IEEE round-to-nearest product, every add a scalar
+// __fadd_rn: the values are those of the scalar sequence.
 template <int C>
 __device__ __forceinline__ void blend_vals(const float (&s00)[C], const float (&s01)[C], const float (&s10)[C],
-                                           const float (&s11)[C], float w00, float w01, float w10, float w11, float (&out)[C]) {
+                                           const float (&s11)[C], float2 wa, float2 wb, float (&out)[C]) {
   constexpr int P = C / 2;
 #pragma unroll
   for (int q = 0; q < P; ++q) {
-    const float2 p00 = mul2_rn_exact(make_float2(s00[2 * q], s00[2 * q + 1]), make_float2(w00, w00));
-    const float2 p01 = mul2_rn_exact(make_float2(s01[2 * q], s01[2 * q + 1]), make_float2(w01, w01));
-    const float2 p10 = mul2_rn_exact(make_float2(s10[2 * q], s10[2 * q + 1]), make_float2(w10, w10));
-    const float2 p11 = mul2_rn_exact(make_float2(s11[2 * q], s11[2 * q + 1]), make_float2(w11, w11));
+    const float2 p00 = mul2_rn_exact(make_float2(s00[2 * q], s00[2 * q + 1]), make_float2(wa.x, wa.x));
+    const float2 p01 = mul2_rn_exact(make_float2(s01[2 * q], s01[2 * q + 1]), make_float2(wa.y, wa.y));
+    const float2 p10 = mul2_rn_exact(make_float2(s10[2 * q], s10[2 * q + 1]), make_float2(wb.x, wb.x));
+    const float2 p11 = mul2_rn_exact(make_float2(s11[2 * q], s11[2 * q + 1]), make_float2(wb.y, wb.y));
     out[2 * q] = __fadd_rn(__fadd_rn(__fadd_rn(p00.x, p01.x), p10.x), p11.x);
     out[2 * q + 1] = __fadd_rn(__fadd_rn(__fadd_rn(p00.y, p01.y), p10.y), p11.y);
   }
   if (C & 1) {
     constexpr int c = C - 1;
-    out[c] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s00[c], w00), __fmul_rn(s01[c], w01)), __fmul_rn(s10[c], w10)), __fmul_rn(s11[c], w11));
+    const float2 pa = mul2_rn_exact(make_float2(s00[c], s01[c]), wa);       // (s00 w00, s01 w01)
+    const float2 pb = mul2_rn_exact(make_float2(s10[c], s11[c]), wb);       // (s10 w10, s11 w11)
+    out[c] = __fadd_rn(__fadd_rn(__fadd_rn(pa.x, pa.y), pb.x), pb.y);
   }
 }
 
@@ -490,18 +502,19 @@ __device__ __forceinline__ void blend_vals(const float (&s00)[C], const float (&
 // corners land inside the source with w > 0 (then every pixel of the tile does: a projective map with w > 0 sends the
 // rectangle into the hull of its corner images; the 1/16 px slack covers the 1/32-px quantisation), with the margins
 // the word loads need — taps from column 1 on (an aligned word may start 3 bytes before the tap) and three columns short
-// of the last one (it may end 6 bytes after the second tap) — and the tile lies inside the destination.
+// of the last one (it may end 6 bytes after the second tap).
 template <bool PERSP>
 __device__ __forceinline__ bool tile_is_interior(const double* mtx, int lane, int width, int height, int sw, int sh) {
-  bool lean = blockIdx.x * kWarpBX + kWarpBX <= width && blockIdx.y * kWarp2TH + kWarp2TH <= height;
+  // a tile that sticks out of the destination on the right / at the bottom is judged on its part inside: the threads
+  // outside compute on the clamped column / row and never store
   const int k = lane & 3;
-  const double cxk = (double)(blockIdx.x * kWarpBX + ((k & 1) ? kWarpBX - 1 : 0));
-  const double cyk = (double)(blockIdx.y * kWarp2TH + ((k & 2) ? kWarp2TH - 1 : 0));
+  const double cxk = (double)min((int)(blockIdx.x * kWarpBX + ((k & 1) ? kWarpBX - 1 : 0)), width - 1);
+  const double cyk = (double)min((int)(blockIdx.y * kWarp2TH + ((k & 2) ? kWarp2TH - 1 : 0)), height - 1);
   const double nu = mtx[0] * cxk + mtx[1] * cyk + mtx[2], nv = mtx[3] * cxk + mtx[4] * cyk + mtx[5];
   const double ww = PERSP ? mtx[6] * cxk + mtx[7] * cyk + mtx[8] : 1.0;
   const double ulo = 1.0625 * ww, vlo = 0.0625 * ww;
   const double uhi = ((double)(sw - 3) - 0.0625) * ww, vhi = ((double)(sh - 1) - 0.0625) * ww;
-  return __all_sync(0xffffffffu, lean && ww > 1e-9 && ww < 1e9 && nu >= ulo && nu < uhi && nv >= vlo && nv < vhi);
+  return __all_sync(0xffffffffu, ww > 1e-9 && ww < 1e9 && nu >= ulo && nu < uhi && nv >= vlo && nv < vhi);
 }
 
 // One frame's contribution to the thread's kWarp2Rows pixels (column x, rows y_base + rr * kWarpBY), added to acc.
@@ -509,11 +522,15 @@ __device__ __forceinline__ bool tile_is_interior(const double* mtx, int lane, in
 //   ALIGNED: the frame's base address and pitch are multiples of 4 (word index arithmetic in 32 bits)
 template <int C, bool PERSP, bool ALIGNED>
 __device__ __forceinline__ void warp_tile_v2(const WarpFrame& f, const double* __restrict__ mtx, const float* fic, bool lean,
-                                             float (&acc)[kWarp2Rows][C], int width, int height, int sw, int sh) {
+                                             float (&acc)[kWarp2Rows][C], int width, int height, int sw, int sh,
+                                             unsigned frac_magic) {
   const int x = blockIdx.x * kWarpBX + threadIdx.x;
   const int y_base = blockIdx.y * kWarp2TH + threadIdx.y;
 
   if (lean) {
+    // threads beyond the right / bottom edge of the destination work on the clamped column / row (their pixels are never
+    // stored): a partial tile runs this path like a full one
+    const int xc = min(x, width - 1);
     float a32 = 0.f, b32 = 0.f, g32 = 0.f, d32 = 0.f, m7_32 = 0.f, wc = 0.f, m7 = 0.f, thr = 0.f;
     int adelta = 0, bdelta = 0;
     if (PERSP) {
@@ -523,25 +540,29 @@ __device__ __forceinline__ void warp_tile_v2(const WarpFrame& f, const double* _
       bdelta = __float_as_int(fic[32]);
     }
     const unsigned pitch_w = (unsigned)(f.src_pitch >> 2);
+    const float2 magic2 = make_float2(12582912.0f, 12582912.0f), neg_magic2 = make_float2(-12582912.0f, -12582912.0f);
     // phase 1: quantised source coordinates of the thread's pixels (the only phase with a data-dependent branch)
     int xq[kWarp2Rows], yq[kWarp2Rows];
 #pragma unroll
     for (int rr = 0; rr < kWarp2Rows; ++rr) {
-      const int y = y_base + rr * kWarpBY;
+      const int y = min(y_base + rr * kWarpBY, height - 1);
       if (PERSP) {
         const float yf = (float)y;
         float r;
         asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(m7, yf, wc)));
-        const float tu = fmaf(b32, yf, a32) * r;
-        const float tv = fmaf(fmaf(-m7_32, yf, d32), yf, g32) * r;
-        const float qu = tu + 12582912.0f, qv = tv + 12582912.0f;      // rint through the 1.5 * 2^23 magic constant
-        const float fu = tu - (qu - 12582912.0f), fv = tv - (qv - 12582912.0f);
-        xq[rr] = (x << kInterBits) + (__float_as_int(qu) - 0x4B400000);
-        yq[rr] = (y << kInterBits) + (__float_as_int(qv) - 0x4B400000);
-        if (fmaxf(fabsf(fu), fabsf(fv)) > thr) {
+        // (tu, tv) = numerators * r: the displacement in 1/32-px quanta; q = rint(t) through the 1.5 * 2^23 magic constant,
+        // res = t - q (both coordinates per packed instruction)
+        const float2 n2 = make_float2(fmaf(b32, yf, a32), fmaf(fmaf(-m7_32, yf, d32), yf, g32));
+        const float2 r2 = make_float2(r, r);
+        const float2 q2 = fma2_rn_exact(n2, r2, magic2);
+        const float2 i2 = add2_rn_exact(q2, neg_magic2);
+        const float2 res = fma2_rn_exact(n2, r2, make_float2(-i2.x, -i2.y));
+        xq[rr] = (xc << kInterBits) + (__float_as_int(q2.x) - 0x4B400000);
+        yq[rr] = (y << kInterBits) + (__float_as_int(q2.y) - 0x4B400000);
+        if (fmaxf(fabsf(res.x), fabsf(res.y)) > thr) {
           // too close to a rounding boundary for the f32 evaluation (or outside its range): OpenCV's own f64 sequence
-          const int xb = width >= 64 ? (x & ~63) : 0;
-          const double xbd = (double)xb, x1 = (double)(x - xb), yd = (double)y;
+          const int xb = width >= 64 ? (xc & ~63) : 0;
+          const double xbd = (double)xb, x1 = (double)(xc - xb), yd = (double)y;
           const double X0 = __dadd_rn(__dadd_rn(__dmul_rn(mtx[0], xbd), __dmul_rn(mtx[1], yd)), mtx[2]);
           const double Y0 = __dadd_rn(__dadd_rn(__dmul_rn(mtx[3], xbd), __dmul_rn(mtx[4], yd)), mtx[5]);
           const double W0 = __dadd_rn(__dadd_rn(__dmul_rn(mtx[6], xbd), __dmul_rn(mtx[7], yd)), mtx[8]);
@@ -581,15 +602,20 @@ __device__ __forceinline__ void warp_tile_v2(const WarpFrame& f, const double* _
     // phase 3: weights, conversion, blend, accumulate
 #pragma unroll
     for (int rr = 0; rr < kWarp2Rows; ++rr) {
-      // fractions k/32 spliced under the 1.5 * 2^23 exponent: (2^23 * 1.5 + k) / 32 - 2^23 * 1.5 / 32 is exact
-      const float ax = fmaf(__int_as_float((xq[rr] & (kInterTab - 1)) | 0x4B400000), 1.f / kInterTab, -12582912.0f / kInterTab);
-      const float ay = fmaf(__int_as_float((yq[rr] & (kInterTab - 1)) | 0x4B400000), 1.f / kInterTab, -12582912.0f / kInterTab);
-      const float w00 = __fmul_rn(1.f - ay, 1.f - ax), w01 = __fmul_rn(1.f - ay, ax);
-      const float w10 = __fmul_rn(ay, 1.f - ax), w11 = __fmul_rn(ay, ax);
+      // fractions k/32 spliced under the 1.5 * 2^23 exponent: (2^23 * 1.5 + k) / 32 - 2^23 * 1.5 / 32 is exact.
+      // axy = (ax, ay); weights as OpenCV forms them: w00 = (1-ay)(1-ax), w01 = (1-ay) ax, w10 = ay (1-ax), w11 = ay ax
+      const float2 axy = fma2_rn_exact(make_float2(__uint_as_float(((unsigned)xq[rr] & (kInterTab - 1)) | frac_magic),
+                                                   __uint_as_float(((unsigned)yq[rr] & (kInterTab - 1)) | frac_magic)),
+                                       make_float2(1.f / kInterTab, 1.f / kInterTab),
+                                       make_float2(-12582912.0f / kInterTab, -12582912.0f / kInterTab));
+      const float2 one_m = add2_rn_exact(make_float2(1.f, 1.f), make_float2(-axy.x, -axy.y));      // (1 - ax, 1 - ay)
+      const float2 xs = make_float2(one_m.x, axy.x);
+      const float2 wa = mul2_rn_exact(make_float2(one_m.y, one_m.y), xs);                            // (w00, w01)
+      const float2 wb = mul2_rn_exact(make_float2(axy.y, axy.y), xs);                                // (w10, w11)
       float s00[C], s01[C], s10[C], s11[C], v[C];
       convert_tap_pair<C>(t0[rr], o0[rr], s00, s01);
       convert_tap_pair<C>(t1[rr], o1[rr], s10, s11);
-      blend_vals<C>(s00, s01, s10, s11, w00, w01, w10, w11, v);
+      blend_vals<C>(s00, s01, s10, s11, wa, wb, v);
 #pragma unroll
       for (int c = 0; c < C; ++c) acc[rr][c] = __fadd_rn(acc[rr][c], v[c]);
     }
@@ -643,10 +669,10 @@ __global__ void __launch_bounds__(kWarpBX * kWarpBY, 4) warp_accumulate_v2_kerne
 #pragma unroll
     for (int i = 0; i < 9; ++i) m[i] = p.f[j].inv_ptr ? p.f[j].inv_ptr[i] : p.f[j].inv[i];
     const bool lean = tile_is_interior<PERSP>(m, lane, p.width, p.height, p.src_width, p.src_height);
-    const int x = blockIdx.x * kWarpBX + lane;
+    const int x = min((int)(blockIdx.x * kWarpBX + lane), p.width - 1);      // columns beyond the edge: see warp_tile_v2
     if (PERSP) {
       FastInv fi;
-      fi.init(m, x, (float)(blockIdx.y * kWarp2TH), (float)(blockIdx.y * kWarp2TH + kWarp2TH - 1));
+      fi.init(m, x, (float)(blockIdx.y * kWarp2TH), (float)min((int)(blockIdx.y * kWarp2TH + kWarp2TH - 1), p.height - 1));
       s_fi[j][0][lane] = fi.a32; s_fi[j][1][lane] = fi.b32; s_fi[j][2][lane] = fi.g32; s_fi[j][3][lane] = fi.d32;
       s_fi[j][4][lane] = fi.m7_32; s_fi[j][5][lane] = fi.wc; s_fi[j][6][lane] = fi.m7; s_fi[j][7][lane] = fi.thr;
     } else {
@@ -681,7 +707,7 @@ __global__ void __launch_bounds__(kWarpBX * kWarpBY, 4) warp_accumulate_v2_kerne
     const int flag = s_flag[j];                                // block-uniform
     if (flag & 1) continue;
     warp_tile_v2<C, PERSP, ALIGNED>(p.f[j], s_m[j], &s_fi[j][0][threadIdx.x], (flag & 2) != 0, acc, p.width, p.height,
-                                    p.src_width, p.src_height);
+                                    p.src_width, p.src_height, p.frac_magic);
   }
 
 #pragma unroll

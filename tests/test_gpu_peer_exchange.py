@@ -71,6 +71,40 @@ def test_world_of_one_equals_finish(pkg):
             st.peer_slice_to_host(host.ctypes.data)
 
 
+def test_stacks_back_to_back_without_host_sync(pkg):
+    """reset / set_reference / the exchange never synchronise with the host (ABI v5): three DIFFERENT stacks are queued
+    on one context one after the other, each result is copied out of the exchange stream into its own host array, and
+    only then does the host synchronise.  Every stack must equal what the same frames give on a fresh context — the
+    next stack's reference prep, ECC iterations and accumulator writes are ordered behind the previous stack on the
+    device (ref_ready / drained / x_done events)."""
+    from oracle import synth
+    w, h, n = 320, 240, 5
+    params = pkg.EccMatchParameters(pkg.MotionType.Affine, 50, 1e-4, 5)
+    stacks = [synth.Stack(w, h, n, 2, seed=s).frames() for s in (41, 42, 43)]
+    want = []
+    for frames in stacks:
+        with pkg.EccStack(w, h, 3, params, device=0, lanes=3) as st:
+            st.set_reference(frames[0])
+            for i, f in enumerate(frames[1:], 1):
+                st.submit(f, tag=i)
+            want.append(st.finish(n))
+    assert not np.array_equal(want[0], want[1])
+    outs = [np.zeros((h, w, 3), np.float32) for _ in stacks]
+    with pkg.EccStack(w, h, 3, params, device=0, lanes=3) as st:
+        st.peer_connect(0, 1, [st.peer_export()])
+        for frames, out in zip(stacks, outs):
+            st.reset()
+            st.set_reference(frames[0])
+            for i, f in enumerate(frames[1:], 1):
+                st.submit(f, tag=i)
+            st.peer_reduce_scatter(n)
+            st.peer_slice_to_host(out.ctypes.data)          # asynchronous, on the exchange stream
+        st.sync()
+        for got, ref in zip(outs, want):
+            assert np.array_equal(got, ref)
+        st.peer_disconnect()
+
+
 def test_peer_reduce_needs_connect(pkg):
     frames, params = _stack(pkg, n=2)
     h, w = frames[0].shape[:2]
