@@ -191,6 +191,7 @@ class EccStack:
         self.lanes = int(lanes) if lanes > 0 else 4        # the library's default
         self._ctx = C.c_void_p()
         self._keep = []          # host arrays that must outlive asynchronous copies
+        self._submitted = 0      # frames handed to the library since the last reset (sizes the results() buffer)
         _check(lib.stk_ecc_create(C.byref(cfg), C.byref(self._ctx)))
 
     # -- lifetime
@@ -246,13 +247,16 @@ class EccStack:
             self._keep.append(frame)
             self._order_after(frame)
             _check(lib.stk_ecc_submit_frame_device(self._ctx, dv[0], dv[1], int(tag)))
+            self._submitted += 1
             return
         f, ptr, pitch = self._host_frame(frame)
         if pinned:
             self._keep.append(f)
             _check(lib.stk_ecc_submit_frame_pinned(self._ctx, ptr, pitch, int(tag)))
+            self._submitted += 1
         else:
             _check(lib.stk_ecc_submit_frame(self._ctx, ptr, pitch, int(tag)))
+            self._submitted += 1
 
     # -- host feed: pinned ring buffers as decode targets
     def acquire_buffer(self) -> np.ndarray:
@@ -266,6 +270,7 @@ class EccStack:
 
     def submit_acquired(self, buf: np.ndarray, tag: int = 0):
         _check(lib.stk_ecc_submit_acquired(self._ctx, buf.ctypes.data, int(tag)))
+        self._submitted += 1
 
     def release_buffer(self, buf: np.ndarray):
         _check(lib.stk_ecc_release_frame_buffer(self._ctx, buf.ctypes.data))
@@ -278,9 +283,11 @@ class EccStack:
             self._keep.append(frame)
             self._order_after(frame)
             _check(lib.stk_ecc_submit_warp_device(self._ctx, dv[0], dv[1], hm, int(border_mode), bv, int(tag)))
+            self._submitted += 1
             return
         f, ptr, pitch = self._host_frame(frame)
         _check(lib.stk_ecc_submit_warp(self._ctx, ptr, pitch, hm, int(border_mode), bv, int(tag)))
+        self._submitted += 1
 
     def submit_warp_affine(self, frame, m, border_mode: int = BORDER_CONSTANT, border_value=(0, 0, 0, 0), tag: int = 0):
         """warp_affine(img_f32, M 2x3 f64, ..) + accumulate (src/lib.rs:782-790 with a caller-supplied matrix)."""
@@ -291,9 +298,11 @@ class EccStack:
             self._keep.append(frame)
             self._order_after(frame)
             _check(lib.stk_ecc_submit_warp_affine_device(self._ctx, dv[0], dv[1], mm, int(border_mode), bv, int(tag)))
+            self._submitted += 1
             return
         f, ptr, pitch = self._host_frame(frame)
         _check(lib.stk_ecc_submit_warp_affine(self._ctx, ptr, pitch, mm, int(border_mode), bv, int(tag)))
+        self._submitted += 1
 
     # -- completion
     def sync(self):
@@ -303,7 +312,7 @@ class EccStack:
 
     def results(self):
         n = C.c_int(0)
-        cap = 1 << 16
+        cap = max(1, self._submitted)
         buf = (_ffi.FrameResult * cap)()
         _check(lib.stk_ecc_results(self._ctx, buf, cap, C.byref(n)))
         out = []
@@ -423,6 +432,7 @@ class EccStack:
     def reset(self):
         _check(lib.stk_ecc_reset(self._ctx))
         self._keep.clear()
+        self._submitted = 0
 
     def launch_count(self) -> int:
         n = C.c_int64()

@@ -141,3 +141,29 @@ def test_device_frame_validation(pkg):
         dv(Fake((4, 9, 3)), (4, 8, 3))
     with pytest.raises(pkg.OpenCvError):
         dv(Fake((4, 8, 3), strides=(48, 6, 2)), (4, 8, 3))
+
+
+def test_context_cache_key_and_producer_stream(pkg):
+    """Host logic of the context cache and of the stream hand-over (no GPU needed): the key separates everything a
+    context is built from; the producer stream comes from __cuda_array_interface__ when the object is not a torch tensor."""
+    api = pkg.api
+    p1 = pkg.EccMatchParameters(pkg.MotionType.Homography, 5000, 1e-5, 5)
+    p2 = pkg.EccMatchParameters(pkg.MotionType.Homography, None, 1e-5, 5)         # EPS only: a different TermCriteria
+    k = api._ctx_key(640, 480, 3, p1, 0, None, True, 0)
+    assert k == api._ctx_key(640, 480, 3, pkg.EccMatchParameters(pkg.MotionType.Homography, 5000, 1e-5, 5), 0, None, True, 0)
+    others = [api._ctx_key(640, 480, 3, p2, 0, None, True, 0), api._ctx_key(640, 480, 4, p1, 0, None, True, 0),
+              api._ctx_key(640, 480, 3, p1, 1, None, True, 0), api._ctx_key(640, 480, 3, p1, 0, (320, 240), True, 0),
+              api._ctx_key(640, 480, 3, None, 0, None, True, 0), api._ctx_key(640, 480, 3, p1, 0, None, False, 0),
+              api._ctx_key(640, 480, 3, p1, 0, None, True, 2)]
+    assert len({k, *others}) == len(others) + 1
+
+    class Fake:
+        def __init__(self, stream):
+            self.__cuda_array_interface__ = {"shape": (2, 2, 3), "typestr": "|u1", "data": (4096, False), "version": 3}
+            if stream != "absent":
+                self.__cuda_array_interface__["stream"] = stream
+    assert api._producer_stream(Fake("absent")) is None        # unknown producer: no ordering is requested
+    assert api._producer_stream(Fake(None)) is None
+    assert api._producer_stream(Fake(1)) == 0                  # 1 = the legacy default stream
+    assert api._producer_stream(Fake(2)) is None               # per-thread default stream: not expressible as a handle
+    assert api._producer_stream(Fake(0x7f00dead)) == 0x7f00dead
