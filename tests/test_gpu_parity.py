@@ -92,6 +92,51 @@ def test_warp_only_matches_oracle_bit_exact(pkg, size, big):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("chan", [3, 4])
+def test_warp_only_unaligned_device_frames_and_strong_perspective(pkg, have_cv2, chan):
+    """The rarely-taken paths of the second-generation K4: device frames whose base address and pitch are NOT 4-byte
+    aligned (byte-granular word addressing), a homography whose w runs from ~0.3 to ~3 over the frame (columns outside
+    the guarded f32 range evaluate every pixel in f64) and one that throws most pixels out of the source — all
+    `array_equal` with cv2.warpPerspective on the CV_32F frame."""
+    import cv2
+    import torch
+    w, h = 401, 302                                   # pitch 401 * chan: odd for chan = 3, and a partial tile on both edges
+    rng = np.random.default_rng(77 + chan)
+    frames = [rng.integers(0, 256, (h, w, chan), dtype=np.uint8) for _ in range(4)]
+    hs = [_rand_h(rng, w, h, True),
+          # inverse map with w falling from 1 to 0.16 across the frame: columns below 1/4 leave the guarded f32 range
+          np.linalg.inv(np.array([[1.1, 0.0, 5.0], [0.0, 1.1, -4.0], [-2.1e-3, 0.0, 1.0]])),
+          # inverse map whose w changes sign inside the frame (cv2: W ? 32 / W : 0, saturating casts): general path
+          np.array([[1.0, 0.02, -3.0], [0.01, 1.0, 2.0], [4.0e-3, -1.5e-3, 1.0]])]
+    k255 = np.float32(1.0 / 255.0)
+    want = frames[0].astype(np.float32) * k255
+    for f, hm in zip(frames[1:], hs):
+        want = want + cv2.warpPerspective(f.astype(np.float32) * k255, hm, (w, h), flags=cv2.INTER_LINEAR)
+    want = want * np.float32(1.0 / 4)
+    # device copies at an odd byte offset inside a larger buffer (base % 4 == 1 or 3)
+    devs = []
+    for k, f in enumerate(frames):
+        raw = torch.zeros(f.size + 8, dtype=torch.uint8, device="cuda:0")
+        off = 1 + 2 * (k % 2)
+        view = raw[off:off + f.size].view(h, w, chan)
+        view.copy_(torch.from_numpy(f))
+        assert view.data_ptr() % 4 != 0
+        devs.append(view)
+    with pkg.EccStack(w, h, chan, None, device=0, lanes=1) as st:
+        st.set_reference(devs[0])
+        for d, hm in zip(devs[1:], hs):
+            st.submit_warp(d, hm)
+        got = st.finish(4)
+    assert np.array_equal(got, want)
+    # the same through host frames (aligned staging: the 32-bit word-index form)
+    with pkg.EccStack(w, h, chan, None, device=0, lanes=1) as st:
+        st.set_reference(frames[0])
+        for f, hm in zip(frames[1:], hs):
+            st.submit_warp(f, hm)
+        got = st.finish(4)
+    assert np.array_equal(got, want)
+
+
 def test_warp_only_border_value_and_bgra(pkg):
     w, h = 120, 90
     rng = np.random.default_rng(3)
