@@ -338,7 +338,7 @@ def run_b200(a, rank, local_rank, world):
                               "out_host": out_host if k == 0 else torch.empty(h, w, 3, dtype=torch.float32).pin_memory(), "ptr": None})
         if use_peers and any(sl["shared"] is None for sl in e2e_slots):      # the same copy-out form on every slot
             for sl in e2e_slots:
-                sl["shared"] = sl["shared"] if all(x["shared"] is not None for x in e2e_slots) else None
+                sl["shared"] = None
 
     def e2e_queue(sl):
         c = sl["st"]
