@@ -262,14 +262,22 @@ def run_b200(a, rank, local_rank, world):
 
     # the exchange step: the library's fused reduce-scatter + divide over NVLink peer memory (default), or the
     # NCCL reduce + scale kernel it replaces (STK_REDUCE=nccl, and the fallback when peers cannot be mapped)
+    def connect(stack):
+        """Map the peers (N > 1, collective) — or, on one GPU, make the context a world of one: its "exchange" is the lane
+        sum fused with the divide on the exchange stream, so that consecutive stacks queue back to back like at N > 1."""
+        if world > 1:
+            return D.connect_peers(stack)
+        stack.peer_connect(0, 1, [stack.peer_export()])
+        return True
+
     use_peers = False
-    if world > 1 and os.environ.get("STK_REDUCE", "peer") != "nccl":
-        use_peers = D.connect_peers(st)
+    if os.environ.get("STK_REDUCE", "peer") != "nccl":
+        use_peers = connect(st)
         if not use_peers and rank == 0:
             print(f"peer exchange unavailable, using NCCL: {D.connect_peers.last_failure}", file=sys.stderr)
     peer_out = {}
     shared_host = None
-    if use_peers:
+    if use_peers and world > 1:
         try:
             shared_host = D.SharedHostStack((h, w, 3))
         except RuntimeError as e:       # same outcome on every rank: fall back to the root's own copy-out
@@ -321,7 +329,7 @@ def run_b200(a, rank, local_rank, world):
         stacks = [st]
         if os.environ.get("STK_E2E_PINGPONG", "1") != "0":
             st2 = pkg.EccStack(w, h, 3, params, device=local_rank, lanes=a.lanes, seed_reference=(rank == 0))
-            ok2 = (not use_peers) or D.connect_peers(st2)
+            ok2 = (not use_peers) or connect(st2)
             if ok2:
                 stacks.append(st2)
             else:
@@ -708,7 +716,7 @@ def run_b200(a, rank, local_rank, world):
                        "parallelism": (f"frames sharded over {world} GPU(s), " + ("one fused reduce-scatter+divide kernel per rank over NVLink peer memory"
                                                                                    if use_peers else "one NCCL reduce")) if world > 1 else "1 GPU",
                        "numa_bound": bool(numa_bound), "ecc_iterations_per_step": total_iters, "ecc_iterations_per_rank": iters_per_rank, "rank_work_ms_no_exchange": rank_work_ms,
-                       "step_pipelining": ("none (one GPU: every step ends with a host synchronisation)" if world == 1 or not use_peers else
+                       "step_pipelining": ("none (every step ends with a host synchronisation)" if not use_peers else
                                            "no host synchronisation inside the timed region: the exchange of step i runs on its own stream "
                                            "and overlaps the prep + ECC iterations of step i+1; that step's accumulator writes wait for it"), "wall_ms_per_step": wall_ms / a.steps},
             "whole_step": {"algorithmic_GBps_per_gpu": alg_bytes / (ms / a.steps * 1e-3) / 1e9 / world,

@@ -1634,6 +1634,19 @@ int peer_exchange(stk_ecc_ctx* c, int divisor, bool scatter) {
     CU(cudaStreamWaitEvent(xs, ln.drained, 0));
     if (&ln != &l0 && ln.acc_used) ordered[m++] = ln.acc;
   }
+  if (pl.world == 1) {
+    // a world of one: the "exchange" is the lane sum fused with the divide (what stk_ecc_finish_device does), but on the
+    // exchange stream and without a host synchronisation — consecutive stacks of ONE device queue back to back as well
+    rc = lane_sum(c, scatter ? c->d_out : pl.root_out, ordered, m, true, divisor, xs);
+    if (rc) return rc;
+    CU(cudaEventRecord(c->x_done, xs));
+    for (auto& ln : c->lanes) { ln.acc_used = false; ln.wait_x = true; }
+    ++pl.step;
+    pl.slice_begin = 0;
+    pl.slice_end = c->acc_floats;
+    pl.scattered = scatter;
+    return STK_OK;
+  }
   if (!(m == 1 && ordered[0] == l0.acc)) {
     rc = lane_sum(c, l0.acc, ordered, m, false, 1, xs);
     if (rc) return rc;
