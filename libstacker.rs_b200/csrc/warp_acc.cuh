@@ -559,8 +559,9 @@ __device__ __forceinline__ void warp_tile_v2(const WarpFrame& f, const double* _
         const float2 res = fma2_rn_exact(n2, r2, make_float2(-i2.x, -i2.y));
         xq[rr] = (xc << kInterBits) + (__float_as_int(q2.x) - 0x4B400000);
         yq[rr] = (y << kInterBits) + (__float_as_int(q2.y) - 0x4B400000);
-        if (fmaxf(fabsf(res.x), fabsf(res.y)) > thr) {
-          // too close to a rounding boundary for the f32 evaluation (or outside its range): OpenCV's own f64 sequence
+        if (!(fabsf(res.x) <= thr && fabsf(res.y) <= thr)) {
+          // too close to a rounding boundary for the f32 evaluation, outside its range (thr < 0) or not a number (a
+          // comparison with NaN is false, so the negated form sends it here too): OpenCV's own f64 sequence
           const int xb = width >= 64 ? (xc & ~63) : 0;
           const double xbd = (double)xb, x1 = (double)(xc - xb), yd = (double)y;
           const double X0 = __dadd_rn(__dadd_rn(__dmul_rn(mtx[0], xbd), __dmul_rn(mtx[1], yd)), mtx[2]);
