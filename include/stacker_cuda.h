@@ -210,7 +210,11 @@ int stk_ecc_finish_device(stk_ecc_ctx* ctx, const float* d_sum, int divisor, flo
    STK_PEER_TIMEOUT_MS (environment, default 30000) — the kernels never spin forever; raise it when ranks can reach the
    exchange further apart than that (e.g. decode imbalance).  connect resets the exchange step count and the flag
    block of the context: no rank may start an exchange before EVERY rank has returned from connect (a barrier or, as
-   distributed.connect_peers does, a vote all ranks take part in). */
+   distributed.connect_peers does, a vote all ranks take part in).
+   The exchange runs on a stream of its own behind every lane's queued work: a rank that is early waits in a one-warp
+   kernel, and the frames of the NEXT stack may be submitted (after stk_ecc_reset + stk_ecc_set_reference) while it is in
+   flight.  A world of ONE is legal (connect with the context's own handle): the exchange is then the lane sum fused with
+   the divide, and the stacks of a single device queue back to back the same way. */
 typedef struct stk_peer_handle { unsigned char bytes[256]; } stk_peer_handle;
 int stk_ecc_peer_export(stk_ecc_ctx* ctx, stk_peer_handle* out);
 int stk_ecc_peer_connect(stk_ecc_ctx* ctx, int rank, int world, const stk_peer_handle* handles /* [world] */);
@@ -228,7 +232,12 @@ int stk_ecc_peer_reduce_scatter(stk_ecc_ctx* ctx, int divisor, const float** d_s
 int stk_ecc_peer_slice_to_host(stk_ecc_ctx* ctx, float* out);
 int stk_ecc_peer_disconnect(stk_ecc_ctx* ctx);
 
-/* start a new stack on the same context (same geometry/parameters): clears accumulators/results */
+/* start a new stack on the same context (same geometry/parameters): clears accumulators/results.
+   Asynchronous (ABI v5): nothing waits on the host.  Whatever the previous stack still has queued — frames, an exchange,
+   a slice copy — completes in stream order; the next stk_ecc_set_reference joins the lanes on the device before it
+   overwrites the reference plane, and the next stack's first accumulator writes wait for an exchange in flight.  Results
+   and the output of the previous stack must be read (stk_ecc_results / stk_ecc_sync + the exchange's pointer) before the
+   NEXT exchange overwrites them, not before reset. */
 int stk_ecc_reset(stk_ecc_ctx* ctx);
 
 /* counters for benchmarks: kernels launched by this context since creation / last reset */
