@@ -349,7 +349,9 @@ __global__ void __launch_bounds__(kTsThreads) tenengrad_stream_kernel(const TenS
   // three rows per trip, the window rotating by name: (ra, rb, rc) -> (rb, rc, ra) -> (rc, ra, rb); the trip's three
   // loads are issued before the first row is touched.  (Measured in round 2: prefetching the NEXT trip's rows as well —
   // 111 registers, 4 blocks per SM instead of 5 — is slower, 7.6 against 6.8 us per 4K plane: occupancy hides the load
-  // latency better than a deeper per-thread pipeline does here.)
+  // latency better than a deeper per-thread pipeline does here.  Forcing 6 or 7 blocks per SM through launch bounds — 80 / 72
+  // registers — changes nothing either: 6.9 / 6.9 / 6.6 us per plane for 5 / 6 / 7 blocks; of the 6.8 us per plane 5.4 are the
+  // kernel, the rest the call's own memset, copy-back and host sum.)
   for (; y + 3 <= y_end; y += 3) {
     const Raw q1 = load(y + 1), q2 = load(y + 2), q3 = load(y + 3);
     expand(q1, rc); if (active) row_terms(ra, rb, rc);
