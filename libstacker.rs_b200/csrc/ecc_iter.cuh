@@ -722,6 +722,96 @@ struct AccumH3 {
   }
 };
 
+// Affine accumulator in the premultiplied packed form of AccumH3 (round 2, last session: the 2x3 models still ran the
+// scalar body — 113 warp-instructions per pixel against Homography's 79, ncu on BASELINE configs[2]'s motion model).
+// Generators are accumulated as (g0, g1) = (2 gx, 2 gy) — what the sampler returns — and the exact factors 1/4 (products)
+// and 1/2 (projections) are undone once per run in emit().  26 sums, 16 instructions per interior pixel:
+//   hA[m] = (p00, p11), hC[m] = p01 for the moments m = {1, Y, Y^2}; za/zm/zt[m] = (g0 z, g1 z) for z = w / 1 / t, m = {1, Y}
+struct AccumA3 {
+  using L = Layout<kAffine>;
+  static constexpr int G = 2;
+  static constexpr bool kTwice = true;
+  float n, swt;
+  float2 s1, s2;
+  float2 hA[3];
+  float hC[3];
+  float2 za[2], zm[2], zt[2];
+
+  __device__ __forceinline__ void clear() {
+    const float2 o = f2(0.f);
+    n = swt = 0.f; s1 = s2 = o;
+#pragma unroll
+    for (int m = 0; m < 3; ++m) { hA[m] = o; hC[m] = 0.f; }
+#pragma unroll
+    for (int m = 0; m < 2; ++m) za[m] = zm[m] = zt[m] = o;
+  }
+
+  // interior pixel (mask 1; the caller counts it): g01 = (2 gx, 2 gy)
+  __device__ __forceinline__ void add_packed(float2 g01, float w_, float t_, float yf) {
+    const float2 gy01 = mul2(g01, f2(yf));
+    hA[0] = fma2(g01, g01, hA[0]); hA[1] = fma2(gy01, g01, hA[1]); hA[2] = fma2(gy01, gy01, hA[2]);
+    hC[0] = fmaf(g01.x, g01.y, hC[0]); hC[1] = fmaf(gy01.x, g01.y, hC[1]); hC[2] = fmaf(gy01.x, gy01.y, hC[2]);
+    const float2 wt = f2(w_, t_);
+    za[0] = fma2(g01, f2(w_), za[0]); za[1] = fma2(gy01, f2(w_), za[1]);
+    zt[0] = fma2(g01, f2(t_), zt[0]); zt[1] = fma2(gy01, f2(t_), zt[1]);
+    zm[0] = add2(zm[0], g01);         zm[1] = add2(zm[1], gy01);
+    s1 = add2(s1, wt);
+    s2 = fma2(wt, wt, s2);
+    swt = fmaf(w_, t_, swt);
+  }
+
+  // general pixel (rim / careful / slow paths), scalar arithmetic on the same registers; g = (2 gx, 2 gy)
+  template <bool INTERIOR>
+  __device__ __forceinline__ void add(const float (&g)[2], float w_, float t_, float mk, float yf) {
+    const float y0 = g[0] * yf, y1 = g[1] * yf;
+    hA[0].x = fmaf(g[0], g[0], hA[0].x); hA[1].x = fmaf(y0, g[0], hA[1].x); hA[2].x = fmaf(y0, y0, hA[2].x);
+    hA[0].y = fmaf(g[1], g[1], hA[0].y); hA[1].y = fmaf(y1, g[1], hA[1].y); hA[2].y = fmaf(y1, y1, hA[2].y);
+    hC[0] = fmaf(g[0], g[1], hC[0]); hC[1] = fmaf(y0, g[1], hC[1]); hC[2] = fmaf(y0, y1, hC[2]);
+    const float wm = INTERIOR ? w_ : w_ * mk;
+    const float tm = INTERIOR ? t_ : t_ * mk;
+    za[0].x = fmaf(g[0], w_, za[0].x); za[1].x = fmaf(y0, w_, za[1].x);
+    za[0].y = fmaf(g[1], w_, za[0].y); za[1].y = fmaf(y1, w_, za[1].y);
+    zt[0].x = fmaf(g[0], tm, zt[0].x); zt[1].x = fmaf(y0, tm, zt[1].x);
+    zt[0].y = fmaf(g[1], tm, zt[0].y); zt[1].y = fmaf(y1, tm, zt[1].y);
+    if (INTERIOR) {
+      zm[0].x += g[0]; zm[1].x += y0; zm[0].y += g[1]; zm[1].y += y1;
+    } else {
+      zm[0].x = fmaf(g[0], mk, zm[0].x); zm[1].x = fmaf(y0, mk, zm[1].x);
+      zm[0].y = fmaf(g[1], mk, zm[0].y); zm[1].y = fmaf(y1, mk, zm[1].y);
+      n += mk;
+    }
+    s1.x += wm; s2.x = fmaf(wm, w_, s2.x);
+    s1.y += tm; s2.y = fmaf(tm, t_, s2.y);
+    swt = fmaf(wm, t_, swt);
+  }
+
+  template <bool UNUSED>
+  __device__ __forceinline__ void emit(float xf, float (&v)[L::NV]) const {
+    v[0] = n; v[1] = s1.x; v[2] = s2.x; v[3] = s1.y; v[4] = s2.y; v[5] = swt;
+    const float xx = xf * xf;
+    // product order of Layout<>: (0,0) (0,1) (1,1)
+#pragma unroll
+    for (int idx = 0; idx < 3; ++idx) {
+      float m[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) m[k] = idx == 0 ? hA[k].x : idx == 1 ? hC[k] : hA[k].y;
+      const float p0 = m[0] * 0.25f, p1 = m[1] * 0.25f, p2 = m[2] * 0.25f;
+      float* o = &v[L::kH + idx * 6];
+      o[0] = p0; o[1] = xf * p0; o[2] = p1; o[3] = xx * p0; o[4] = xf * p1; o[5] = p2;
+    }
+    const float z0[3][2] = {{za[0].x, za[0].y}, {zm[0].x, zm[0].y}, {zt[0].x, zt[0].y}};
+    const float z1[3][2] = {{za[1].x, za[1].y}, {zm[1].x, zm[1].y}, {zt[1].x, zt[1].y}};
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float v0 = z0[a][i] * 0.5f, v1 = z1[a][i] * 0.5f;
+        float* o = &v[L::kZ + (a * 2 + i) * 3];
+        o[0] = v0; o[1] = xf * v0; o[2] = v1;
+      }
+  }
+};
+
 // ---- Jacobian generators (OpenCV evaluates them on f32 grids with the f32 matrix) --------------------
 template <int MOTION> struct Jac {
   static constexpr int G = Model<MOTION>::G;

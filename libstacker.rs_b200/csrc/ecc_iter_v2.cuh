@@ -171,7 +171,10 @@ __global__ void __launch_bounds__(CFG::kThreads, CFG::kMinBlocks) ecc_iter_v2_ke
   const int part = tid / kEccStripW;
   constexpr bool fast_coords = Md::persp && !EXACT;
 
-  using AccT = typename std::conditional<fast_coords && CFG::kPack == 3, AccumH3, typename AccumFor<MOTION, fast_coords>::type>::type;
+  // packed premultiplied accumulators: AccumH3 (Homography, FastPersp coordinates), AccumA3 (Affine, exact coordinates)
+  constexpr bool affine_packed = MOTION == kAffine && CFG::kPack == 3;
+  using AccT = typename std::conditional<fast_coords && CFG::kPack == 3, AccumH3,
+               typename std::conditional<affine_packed, AccumA3, typename AccumFor<MOTION, fast_coords>::type>::type>::type;
   AccT acc;
   acc.clear();
   int n_safe = 0;
@@ -258,6 +261,7 @@ __global__ void __launch_bounds__(CFG::kThreads, CFG::kMinBlocks) ecc_iter_v2_ke
       const float yf = (float)y;
       jac.eval(smp, yf, g);
       if (fast_coords) { g[0] *= 2.f; g[1] *= 2.f; g[G - 1] *= -2.f; }     // the run accumulates (2a, 2b, -2t)
+      if (affine_packed) { g[0] *= 2.f; g[1] *= 2.f; }                       // the run accumulates (2 gx, 2 gy)
       acc.template add<false>(g, smp.w, t_, mk, yf);
     };
 
@@ -331,6 +335,29 @@ __global__ void __launch_bounds__(CFG::kThreads, CFG::kMinBlocks) ecc_iter_v2_ke
               trow += kUnr * kEccStripW;
               bi0 += kUnr * kBoxW;
               yf0 += (float)kUnr;
+            }
+          } else if constexpr (affine_packed) {
+            // Affine: OpenCV's exact 10-bit fixed-point coordinates, the packed sampler and the packed sums
+            Coord<false> co;
+            co.init(s_m, x);
+#pragma unroll 1
+            for (int rg = 0; rg < kRpt; rg += kUnr) {
+#pragma unroll
+              for (int r = 0; r < kUnr; ++r) {
+                const int y = ya + rg + r;
+                const float t_ = trow[(rg + r) * kEccStripW];
+                int xq, yq;
+                co.at(y, xq, yq);
+                const float* bp = box + ((yq >> kInterBits) - ylo) * kBoxW + ((xq >> kInterBits) - xlo);
+                // fractions k/32: the 5 low bits spliced under the 1.5 * 2^23 exponent, one packed FFMA
+                const float2 axy = fma2(f2(__uint_as_float(((unsigned)xq & (kInterTab - 1)) | frac_magic),
+                                           __uint_as_float(((unsigned)yq & (kInterTab - 1)) | frac_magic)),
+                                        f2(1.f / kInterTab), f2(-12582912.0f / kInterTab));
+                float w_;
+                float2 gxy2;
+                sample_box_packed(bp, axy.x, axy.y, w_, gxy2);
+                acc.add_packed(gxy2, w_, t_, (float)y);
+              }
             }
           } else {
             // the other instantiations (2x3 models with OpenCV's exact 10-bit fixed point, homography with exact
@@ -408,6 +435,7 @@ __global__ void __launch_bounds__(CFG::kThreads, CFG::kMinBlocks) ecc_iter_v2_ke
               g[G - 1] = fmaf(xf + du, g[0], (yf + dv) * g[1]);
             } else {
               jac.eval(smp, yf, g);
+              if (affine_packed) { g[0] *= 2.f; g[1] *= 2.f; }
             }
             if (all_safe) { acc.template add<true>(g, smp.w, t_, 1.f, yf); ++n_safe; }
             else acc.template add<false>(g, smp.w, t_, mk, yf);
