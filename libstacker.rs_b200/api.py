@@ -501,7 +501,8 @@ def _check_colour_frame(img: np.ndarray):
 # one-shot plugin calls therefore park their single-device context here and the next call with the same geometry and
 # parameters resets and reuses it.  STK_CONTEXT_CACHE=<n> bounds the idle contexts kept per process (default 2,
 # 0 disables); clear_context_cache() releases them.
-_CTX_CACHE = {}
+_CTX_CACHE = {}            # key -> idle contexts of that geometry, most recently parked last
+_CTX_CACHE_ORDER = []      # (key, stack) in parking order: the front is evicted first (LRU)
 _CTX_CACHE_LOCK = threading.Lock()
 _CTX_CACHE_MAX = max(0, int(os.environ.get("STK_CONTEXT_CACHE", "2")))
 
@@ -517,6 +518,8 @@ def _acquire_stack(w, h, ch, params, device, ecc_size=None, seed_reference=True,
     with _CTX_CACHE_LOCK:
         idle = _CTX_CACHE.get(key)
         st = idle.pop() if idle else None
+        if st is not None:
+            _CTX_CACHE_ORDER.remove((key, st))
     if st is not None:
         try:
             st.reset()
@@ -527,20 +530,32 @@ def _acquire_stack(w, h, ch, params, device, ecc_size=None, seed_reference=True,
 
 
 def _release_stack(st, key, reusable: bool):
-    if reusable and _CTX_CACHE_MAX > 0:
-        with _CTX_CACHE_LOCK:
-            if sum(len(v) for v in _CTX_CACHE.values()) < _CTX_CACHE_MAX:
-                st._keep.clear()
-                _CTX_CACHE.setdefault(key, []).append(st)
-                return
-    st.close()
+    """Park a context for the next call of the same geometry; beyond STK_CONTEXT_CACHE idle contexts the least recently
+    parked one is destroyed (a service whose frame size changes does not keep the first sizes it ever saw)."""
+    if not (reusable and _CTX_CACHE_MAX > 0):
+        st.close()
+        return
+    evicted = []
+    with _CTX_CACHE_LOCK:
+        st._keep.clear()
+        _CTX_CACHE.setdefault(key, []).append(st)
+        _CTX_CACHE_ORDER.append((key, st))
+        while len(_CTX_CACHE_ORDER) > _CTX_CACHE_MAX:
+            k, old = _CTX_CACHE_ORDER.pop(0)
+            _CTX_CACHE[k].remove(old)
+            if not _CTX_CACHE[k]:
+                del _CTX_CACHE[k]
+            evicted.append(old)
+    for old in evicted:
+        old.close()
 
 
 def clear_context_cache():
     """Destroy the idle contexts kept by ecc_match / keypoint_match (frees their device and pinned memory)."""
     with _CTX_CACHE_LOCK:
-        stacks = [st for v in _CTX_CACHE.values() for st in v]
+        stacks = [st for _, st in _CTX_CACHE_ORDER]
         _CTX_CACHE.clear()
+        del _CTX_CACHE_ORDER[:]
     for st in stacks:
         st.close()
 

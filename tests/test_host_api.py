@@ -167,3 +167,31 @@ def test_context_cache_key_and_producer_stream(pkg):
     assert api._producer_stream(Fake(1)) == 0                  # 1 = the legacy default stream
     assert api._producer_stream(Fake(2)) is None               # per-thread default stream: not expressible as a handle
     assert api._producer_stream(Fake(0x7f00dead)) == 0x7f00dead
+
+
+def test_context_cache_evicts_least_recently_parked(pkg, monkeypatch):
+    """Bookkeeping of the context cache with stand-in contexts (no GPU): at most STK_CONTEXT_CACHE idle contexts, the
+    least recently parked one is destroyed first, a context that raised is destroyed at once."""
+    api = pkg.api
+
+    class Stand:
+        def __init__(self, name):
+            self.name, self._keep, self.closed = name, [1], False
+
+        def close(self):
+            self.closed = True
+
+        def reset(self):
+            pass
+
+    api.clear_context_cache()
+    monkeypatch.setattr(api, "_CTX_CACHE_MAX", 2)
+    a, b, c, d = Stand("a"), Stand("b"), Stand("c"), Stand("d")
+    api._release_stack(a, "k1", True)
+    api._release_stack(b, "k2", True)
+    api._release_stack(c, "k1", True)                # third idle context: the oldest (a) goes
+    assert (a.closed, b.closed, c.closed) == (True, False, False) and c._keep == []
+    api._release_stack(d, "k3", False)               # a context whose call raised is never parked
+    assert d.closed and [s.name for _, s in api._CTX_CACHE_ORDER] == ["b", "c"]
+    api.clear_context_cache()
+    assert b.closed and c.closed and not api._CTX_CACHE and not api._CTX_CACHE_ORDER
