@@ -712,7 +712,9 @@ def run_b200(a, rank, local_rank, world):
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(a), "lanes": a.lanes,
-                       "l2": "inputs larger than L2: every step reads all frames (%.2f GB u8) from HBM" % (n * n_px * 3 / 1e9),
+                       "l2": ("inputs larger than L2: every step reads all frames (%.2f GB u8) from HBM" % (n * n_px * 3 / 1e9)) if world == 1 else
+                             ("inputs larger than L2 on every GPU: a step reads all %d frames (%.2f GB u8), %d MB per GPU against 126 MB of L2"
+                              % (n, n * n_px * 3 / 1e9, round((len(mine) + 1) * n_px * 3 / 1e6))),
                        "parallelism": (f"frames sharded over {world} GPU(s), " + ("one fused reduce-scatter+divide kernel per rank over NVLink peer memory"
                                                                                    if use_peers else "one NCCL reduce")) if world > 1 else "1 GPU",
                        "numa_bound": bool(numa_bound), "ecc_iterations_per_step": total_iters, "ecc_iterations_per_rank": iters_per_rank, "rank_work_ms_no_exchange": rank_work_ms,
