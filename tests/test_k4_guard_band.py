@@ -86,3 +86,21 @@ def test_stack_like_motion_rarely_needs_the_exact_path():
         tot_acc += acc
         tot += n
     assert tot_acc > 0.99 * tot
+
+
+def test_byte_splice_conversion_is_exact():
+    """K4 turns a tap byte b into fl(b * fl(1/255)) without a conversion instruction: PRMT splices b under the exponent of
+    2^23 (the float 2^23 + b) and ONE fused multiply-add computes fma(2^23 + b, k, -(2^23 k)).  2^23 k is exact (a power-of-two
+    multiple of k), so the FMA's single rounding is that of b * k: the value OpenCV's convertTo(CV_32F, 1/255) produces."""
+    k = f32(1.0 / 255.0)
+    c = f32(8388608.0) * k
+    assert float(c) == 8388608.0 * float(k)                                   # exact: no rounding in 2^23 * k
+    b = np.arange(256)
+    spliced = (np.uint32(0x4B000000) | b.astype(np.uint32)).view(f32)
+    assert np.array_equal(spliced, (8388608.0 + b).astype(f32))
+    fused = (spliced.astype(np.float64) * float(k) - float(c)).astype(f32)    # exact in f64, rounded once
+    assert np.array_equal(fused, b.astype(f32) * k)
+    # the fraction splice: (1.5 * 2^23 + q) / 32 - 1.5 * 2^23 / 32 == q / 32 for the 5-bit fractions
+    q = np.arange(32)
+    sp = (np.uint32(0x4B400000) | q.astype(np.uint32)).view(f32)
+    assert np.array_equal((sp.astype(np.float64) * (1.0 / 32) - 12582912.0 / 32).astype(f32), (q / 32.0).astype(f32))
