@@ -55,3 +55,37 @@ def test_tenengrad_band_sum_fits_32_bits():
     """K6 (csrc/tenengrad.cuh): a thread accumulates gx^2 + gy^2 of 48 rows x 16 columns in 32 bits before widening.
     |gx|, |gy| <= 4 * 255 for the 3x3 Sobel on 8-bit input."""
     assert 48 * 16 * 2 * (4 * 255) ** 2 < 1 << 32
+
+
+def test_fastpersp_coordinates_move_few_quanta():
+    """K2 (csrc/ecc_iter.cuh, FastPersp): Homography sample positions are evaluated as x + (alpha + beta y) / w in f32 from
+    per-column constants prepared in f64, then quantised to 1/32 px.  DESIGN states that against OpenCV's f64 evaluation
+    this moves the quantum for ~1e-4 of the pixels, by one step: emulate the f32 arithmetic and count."""
+    def fma32(a, b, c):
+        return (np.asarray(a, np.float64) * np.asarray(b, np.float64) + np.asarray(c, np.float64)).astype(f32)
+
+    rng = np.random.default_rng(4)
+    w, h, n = 3840, 2160, 20000
+    moved = total = 0
+    worst = 0
+    for _ in range(40):
+        m = (np.eye(3) + rng.uniform(-1, 1, (3, 3)) * np.array([[2e-3, 2e-3, 6.0], [2e-3, 2e-3, 6.0], [2e-7, 2e-7, 0.0]])).astype(f32)
+        md = m.astype(np.float64)                     # the kernel reads the f32 matrix and prepares constants in f64
+        xs = rng.integers(0, w, n).astype(np.float64)
+        ys = rng.integers(0, h, n).astype(np.float64)
+        alpha = (xs * (md[0, 0] - md[2, 2] - md[2, 0] * xs) + md[0, 2]).astype(f32)
+        beta = (md[0, 1] - md[2, 1] * xs).astype(f32)
+        wc = (md[2, 0] * xs + md[2, 2]).astype(f32)
+        yf = ys.astype(f32)
+        wf = fma32(np.full(n, m[2, 1]), yf, wc)
+        rw = (1.0 / wf.astype(np.float64)).astype(f32)
+        du = (fma32(beta, yf, alpha).astype(np.float64) * rw.astype(np.float64)).astype(f32)
+        q_fast = np.rint(du.astype(np.float64) * 32.0) + 32.0 * xs
+        u = (md[0, 0] * xs + md[0, 1] * ys + md[0, 2]) / (md[2, 0] * xs + md[2, 1] * ys + md[2, 2])
+        q_exact = np.rint(32.0 * u)
+        d = np.abs(q_fast - q_exact)
+        moved += int((d != 0).sum())
+        worst = max(worst, int(d.max()))
+        total += n
+    assert worst <= 1                                  # never more than one 1/32-px step
+    assert moved / total < 1e-3                        # measured ~1e-4
